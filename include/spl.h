@@ -1,0 +1,154 @@
+/*
+ * spl.h — C ABI of libspalinalg_b200.so: the B200 (sm_100a) implementation of
+ * spalinalg's data-parallel sparse hot path.
+ *
+ * The reference (Rust crate spalinalg v0.0.2) has no FFI layer: its boundary is
+ * the crate's public API reached by static trait dispatch.  Each
+ * entry point below names the reference item (file:line under /root/reference)
+ * it stands in for; INTEGRATION.md shows the Rust `extern "C"` block and the
+ * `impl From/Add/Sub/Mul/Neg` shims a maintainer would add on top.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Host index arrays are uint64_t (Rust usize);
+ *    device index arrays are uint32_t.  Values are float or double, selected by
+ *    spl_dtype.  All matrices live in device memory behind an opaque spl_mat.
+ *  - Every function returns an spl_status.  Nothing unwinds across the ABI; the
+ *    Rust shim turns a non-zero status into panic!, the reference's convention
+ *    (assert!/assert_eq!, e.g. src/csr.rs:144-156, src/csr/ops/add.rs:9-10).
+ *  - One spl_ctx per host thread (it owns a stream and the last-error text).
+ *    spl_mat objects are immutable after creation and may be shared read-only.
+ *  - There is no CPU fallback: without a CUDA device spl_ctx_create fails.
+ *  - Limits: dims and nnz below 2^32 (device indices are 32 bit), else
+ *    SPL_ERR_UNSUPPORTED.
+ */
+#ifndef SPL_H
+#define SPL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spl_ctx spl_ctx;
+typedef struct spl_mat spl_mat;
+
+typedef enum {
+    SPL_OK = 0,
+    SPL_ERR_SHAPE = 1,       /* operand shapes disagree (assert_eq! on dims) */
+    SPL_ERR_INVALID = 2,     /* CsrMatrix::new / CscMatrix::new would panic; see spl_invalid_reason */
+    SPL_ERR_CUDA = 3,
+    SPL_ERR_UNSUPPORTED = 4,
+    SPL_ERR_OOM = 5,
+    SPL_ERR_ARG = 6          /* NULL handle, unknown enum, index out of range in COO input */
+} spl_status;
+
+typedef enum { SPL_CSR = 0, SPL_CSC = 1 } spl_format;
+typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:55-57 */
+
+/* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics. */
+typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2 } spl_spmv_kernel;
+
+/* ---- context ------------------------------------------------------------ */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. the caller's
+ * current stream), or NULL to let the context create its own. */
+int spl_ctx_create(int device, void *stream, spl_ctx **out);
+int spl_ctx_destroy(spl_ctx *ctx);
+int spl_ctx_sync(spl_ctx *ctx);
+const char *spl_last_error(const spl_ctx *ctx);
+/* After SPL_ERR_INVALID: 1-based ordinal of the failing assertion of
+ * CsrMatrix::new (src/csr.rs:144-156) / CscMatrix::new (src/csc.rs:144-156):
+ * 1 nrows>0, 2 ncols>0, 3 ptr.len()==n+1, 4 ptr[0]==0, 5 ind.len()==ptr[n],
+ * 6 values.len()==ptr[n], 7 ptr sorted, 8 index in range, 9 indices strictly
+ * increasing inside a row/column. */
+int spl_invalid_reason(const spl_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t spl_launch_count(const spl_ctx *ctx);
+
+/* ---- construction --------------------------------------------------------- */
+
+/* COO -> CSR/CSC assembly.
+ *   impl From<&CooMatrix<T>> for CsrMatrix<T>   src/csr/conv/coo.rs:3-116
+ *   impl From<&CooMatrix<T>> for CscMatrix<T>   src/csc/conv/coo.rs:3-116
+ * Entries sorted by (row, col) [(col, row) for CSC]; duplicates of a cell summed
+ * sequentially in insertion order; sums == 0 dropped.  Bit-exact against the
+ * reference in structure and values.  dedup=0, dropzero=0 gives
+ *   impl From<&DokMatrix<T>> for CsrMatrix<T>   src/csr/conv/dok.rs:3-76
+ *   impl From<&DokMatrix<T>> for CscMatrix<T>   src/csc/conv/dok.rs:3-76
+ * (keys unique, explicit zeros kept).  Host SoA arrays of length len; the bound
+ * checks of CooMatrix::push (src/coo.rs:431-435) are re-checked on the device
+ * (SPL_ERR_ARG).  nrows, ncols must be > 0 (src/coo.rs:105-106). */
+int spl_mat_from_coo(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                     uint64_t len, const uint64_t *row, const uint64_t *col, const void *val,
+                     int dedup, int dropzero, spl_mat **out);
+/* Same with device-resident uint32 SoA input (inputs are not modified). */
+int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                         uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                         const void *val_dev, int dedup, int dropzero, spl_mat **out);
+
+/* CsrMatrix::new (src/csr.rs:137-164) / CscMatrix::new (src/csc.rs:137-164):
+ * validating constructor from host arrays.  ptr is rowptr (CSR) or colptr (CSC). */
+int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t ptr_len, const uint64_t *ptr,
+                            uint64_t ind_len, const uint64_t *ind,
+                            uint64_t val_len, const void *val, spl_mat **out);
+/* Same from device uint32 arrays (copied); validate=0 skips the checks. */
+int spl_mat_from_compressed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                                uint64_t nnz, const uint32_t *ptr_dev, const uint32_t *ind_dev,
+                                const void *val_dev, int validate, spl_mat **out);
+/* CsrMatrix::eye (src/csr.rs:179-188) / CscMatrix::eye (src/csc.rs:179-188). */
+int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **out);
+
+/* ---- the hot path --------------------------------------------------------- */
+
+/* From<&CsrMatrix> for CscMatrix (src/csc/conv/csr.rs:3-53) and
+ * From<&CscMatrix> for CsrMatrix (src/csr/conv/csc.rs:3-53): same matrix, other
+ * format.  format == the input's format yields a copy. */
+int spl_mat_convert(spl_ctx *ctx, const spl_mat *in, int format, spl_mat **out);
+/* CsrMatrix::transpose (src/csr.rs:358-406), CscMatrix::transpose (src/csc.rs:358-406). */
+int spl_mat_transpose(spl_ctx *ctx, const spl_mat *in, spl_mat **out);
+/* impl Add / Sub for &CsrMatrix (src/csr/ops/add.rs:5-75, sub.rs:5-75) and
+ * &CscMatrix (src/csc/ops/add.rs:5-70, sub.rs:5-70).  Pattern union, explicit
+ * zeros kept, one IEEE op per overlap: bit-exact. */
+int spl_mat_add(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out);
+int spl_mat_sub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out);
+/* impl Mul for &CsrMatrix (src/csr/ops/mul.rs:5-60) / &CscMatrix
+ * (src/csc/ops/mul.rs:5-61): C = A*B, each C[i,j] accumulated over ascending k
+ * with the product rounded before the add; structural union, no zero drop. */
+int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out);
+/* impl Neg (src/csr/ops/neg.rs:5-18, src/csc/ops/neg.rs:5-18). */
+int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out);
+
+/* y = A*x with dense device vectors (extension; the reference's only route is
+ * `&A * &X` with X n x 1, src/csr/ops/mul.rs:5-60, whose values this matches to
+ * 1e-12 (f64) / 1e-5 (f32) relative; rows without entries give 0).  A must be
+ * CSR.  x has ncols elements, y nrows. */
+int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev);
+int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel);
+/* Host-buffer form: uploads x, runs spl_spmv, downloads y, synchronises. */
+int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host);
+/* Which kernel AUTO resolves to for this matrix (SPL_SPMV_VECTOR / _MERGE). */
+int spl_spmv_choice(spl_ctx *ctx, const spl_mat *a, int *kernel, int *lanes_per_row);
+
+/* ---- access --------------------------------------------------------------- */
+
+/* nrows/ncols/nnz accessors (src/csr.rs:200-289). Any out pointer may be NULL. */
+int spl_mat_info(const spl_mat *m, int *format, int *dtype, uint64_t *nrows, uint64_t *ncols,
+                 uint64_t *nnz);
+/* rowptr()/colind()/values() (src/csr.rs:228-258) as host copies, indices widened
+ * to usize.  ptr needs nmajor+1 slots, ind and val nnz.  Synchronises. */
+int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *ind, void *val);
+/* Borrow the device arrays (uint32 ptr[nmajor+1], uint32 ind[nnz], T val[nnz]). */
+int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32_t **ind_dev,
+                        const void **val_dev);
+/* From<&CsrMatrix>/<&CscMatrix> for CooMatrix (src/coo.rs:629-705): expand to
+ * host triplets in storage order.  Arrays need nnz slots.  Synchronises. */
+int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val);
+int spl_mat_free(spl_ctx *ctx, spl_mat *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPL_H */

@@ -1,0 +1,71 @@
+"""ctypes binding of include/spl.h (libspalinalg_b200.so).  This is the only way the Python host
+mirror reaches the device; there is no fallback: if the library is missing or no CUDA device is
+present, imports succeed but every operation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspalinalg_b200.so")
+
+SPL_OK, SPL_ERR_SHAPE, SPL_ERR_INVALID, SPL_ERR_CUDA, SPL_ERR_UNSUPPORTED, SPL_ERR_OOM, SPL_ERR_ARG = range(7)
+SPL_CSR, SPL_CSC = 0, 1
+SPL_F32, SPL_F64 = 0, 1
+SPL_SPMV_AUTO, SPL_SPMV_VECTOR, SPL_SPMV_MERGE = 0, 1, 2
+
+STATUS_NAMES = {0: "SPL_OK", 1: "SPL_ERR_SHAPE", 2: "SPL_ERR_INVALID", 3: "SPL_ERR_CUDA",
+                4: "SPL_ERR_UNSUPPORTED", 5: "SPL_ERR_OOM", 6: "SPL_ERR_ARG"}
+
+_vp, _u64, _i = C.c_void_p, C.c_uint64, C.c_int
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every symbol include/spl.h declares
+SIGNATURES = {
+    "spl_ctx_create": (_i, [_i, _vp, _pp]),
+    "spl_ctx_destroy": (_i, [_vp]),
+    "spl_ctx_sync": (_i, [_vp]),
+    "spl_last_error": (C.c_char_p, [_vp]),
+    "spl_invalid_reason": (_i, [_vp]),
+    "spl_launch_count": (_u64, [_vp]),
+    "spl_mat_from_coo": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _i, _pp]),
+    "spl_mat_from_coo_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _i, _pp]),
+    "spl_mat_from_compressed": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _u64, _vp, _u64, _vp, _pp]),
+    "spl_mat_from_compressed_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _pp]),
+    "spl_mat_eye": (_i, [_vp, _i, _i, _u64, _pp]),
+    "spl_mat_convert": (_i, [_vp, _vp, _i, _pp]),
+    "spl_mat_transpose": (_i, [_vp, _vp, _pp]),
+    "spl_mat_add": (_i, [_vp, _vp, _vp, _pp]),
+    "spl_mat_sub": (_i, [_vp, _vp, _vp, _pp]),
+    "spl_mat_mul": (_i, [_vp, _vp, _vp, _pp]),
+    "spl_mat_neg": (_i, [_vp, _vp, _pp]),
+    "spl_spmv": (_i, [_vp, _vp, _vp, _vp]),
+    "spl_spmv_ex": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "spl_spmv_host": (_i, [_vp, _vp, _vp, _vp]),
+    "spl_spmv_choice": (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_i)]),
+    "spl_mat_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_u64), C.POINTER(_u64),
+                          C.POINTER(_u64)]),
+    "spl_mat_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "spl_mat_device_ptrs": (_i, [_vp, _pp, _pp, _pp]),
+    "spl_mat_to_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "spl_mat_free": (_i, [_vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raises if it has not been built (python -m spalinalg_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built and there is no CPU "
+                "fallback.  Run `python -m spalinalg_b200.build`.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

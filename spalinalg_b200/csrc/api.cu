@@ -1,0 +1,472 @@
+// api.cu — the extern "C" boundary declared in include/spl.h.  Plain pointers and sizes in,
+// status codes out; nothing unwinds across it.  No CPU fallback: every entry point needs a
+// live CUDA context.
+#include <cstring>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace spl;
+
+#define API_BEGIN(ctx)                         \
+    if (!(ctx)) return SPL_ERR_ARG;            \
+    try {                                      \
+        SPL_CUDA(cudaSetDevice((ctx)->device));
+
+#define API_END(ctx)                                   \
+    }                                                  \
+    catch (const spl::Error &e) {                      \
+        (ctx)->last_error = e.msg;                     \
+        return e.status;                               \
+    }                                                  \
+    catch (const std::bad_alloc &) {                   \
+        (ctx)->last_error = "host allocation failed"; \
+        return SPL_ERR_OOM;                            \
+    }                                                  \
+    catch (...) {                                      \
+        (ctx)->last_error = "unknown failure";        \
+        return SPL_ERR_CUDA;                           \
+    }                                                  \
+    return SPL_OK;
+
+namespace {
+
+void check_enums(int format, int dtype) {
+    SPL_REQUIRE(format == SPL_CSR || format == SPL_CSC, SPL_ERR_ARG, "unknown format");
+    SPL_REQUIRE(dtype == SPL_F32 || dtype == SPL_F64, SPL_ERR_ARG,
+                "Scalar is implemented for f32 and f64 only (src/scalar.rs:55-57)");
+}
+
+void check_dims(spl_ctx *ctx, uint64_t nrows, uint64_t ncols) {
+    if (nrows == 0) {
+        ctx->invalid_reason = 1;
+        throw Error{SPL_ERR_INVALID, "nrows must be > 0 (src/csr.rs:144, src/coo.rs:105)"};
+    }
+    if (ncols == 0) {
+        ctx->invalid_reason = 2;
+        throw Error{SPL_ERR_INVALID, "ncols must be > 0 (src/csr.rs:145, src/coo.rs:106)"};
+    }
+    SPL_REQUIRE(nrows < (1ull << 32) && ncols < (1ull << 32), SPL_ERR_UNSUPPORTED,
+                "dimensions must be below 2^32 (device indices are 32 bit)");
+}
+
+[[noreturn]] void invalid(spl_ctx *ctx, int reason, const char *text) {
+    ctx->invalid_reason = reason;
+    throw Error{SPL_ERR_INVALID, text};
+}
+
+const char *kReasonText[10] = {
+    "",
+    "nrows must be > 0",
+    "ncols must be > 0",
+    "ptr.len() != n + 1",
+    "ptr[0] != 0",
+    "ind.len() != ptr[n]",
+    "values.len() != ptr[n]",
+    "ptr is not sorted",
+    "index out of range",
+    "indices not strictly increasing inside a row/column",
+};
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int spl_ctx_create(int device, void *stream, spl_ctx **out) {
+    if (!out) return SPL_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return SPL_ERR_CUDA;   // no device, no product path: there is no CPU fallback
+    }
+    spl_ctx *ctx = new (std::nothrow) spl_ctx();
+    if (!ctx) return SPL_ERR_OOM;
+    ctx->device = device;
+    try {
+        SPL_CUDA(cudaSetDevice(device));
+        if (stream) {
+            ctx->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            SPL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->owns_stream = true;
+        }
+        int sms = 0;
+        SPL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        ctx->num_sms = sms > 0 ? sms : kNumSmFallback;
+        // keep freed blocks in the pool: temporaries of the next call reuse them without a sync
+        cudaMemPool_t pool;
+        SPL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t threshold = UINT64_MAX;
+        SPL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        SPL_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint32_t)));
+        SPL_CUDA(cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)));
+    } catch (const spl::Error &) {
+        if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+        if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+        if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return SPL_ERR_CUDA;
+    }
+    *out = ctx;
+    return SPL_OK;
+}
+
+int spl_ctx_destroy(spl_ctx *ctx) {
+    if (!ctx) return SPL_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SPL_OK;
+}
+
+int spl_ctx_sync(spl_ctx *ctx) {
+    API_BEGIN(ctx)
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+const char *spl_last_error(const spl_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+int spl_invalid_reason(const spl_ctx *ctx) { return ctx ? ctx->invalid_reason : 0; }
+uint64_t spl_launch_count(const spl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                         uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                         const void *val_dev, int dedup, int dropzero, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev), SPL_ERR_ARG, "NULL COO array");
+    *out = assemble_from_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
+                                 row_dev, col_dev, val_dev, dedup, dropzero);
+    API_END(ctx)
+}
+
+int spl_mat_from_coo(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                     uint64_t len, const uint64_t *row, const uint64_t *col, const void *val,
+                     int dedup, int dropzero, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len == 0 || (row && col && val), SPL_ERR_ARG, "NULL COO array");
+    const size_t vs = dtype == SPL_F32 ? 4 : 8;
+    Tmp<uint32_t> r32(ctx, len), c32(ctx, len);
+    Tmp<unsigned char> v(ctx, len * vs);
+    if (len) {
+        Tmp<uint64_t> wide(ctx, len);
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(wide, row, len * 8, cudaMemcpyHostToDevice, ctx->stream));
+        narrow_u64(ctx, wide, r32, len, nrows, ctx->d_scratch);
+        SPL_CUDA(cudaMemcpyAsync(wide, col, len * 8, cudaMemcpyHostToDevice, ctx->stream));
+        narrow_u64(ctx, wide, c32, len, ncols, ctx->d_scratch);
+        SPL_CUDA(cudaMemcpyAsync(v, val, len * vs, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // bounds (CooMatrix::push, src/coo.rs:432-433) are re-checked on the narrowed arrays
+    *out = assemble_from_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
+                                 r32, c32, v, dedup, dropzero);
+    API_END(ctx)
+}
+
+int spl_mat_from_compressed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                                uint64_t nnz, const uint32_t *ptr_dev, const uint32_t *ind_dev,
+                                const void *val_dev, int validate, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(nnz < (1ull << 32), SPL_ERR_UNSUPPORTED, "nnz must be below 2^32");
+    SPL_REQUIRE(ptr_dev && (nnz == 0 || (ind_dev && val_dev)), SPL_ERR_ARG, "NULL array");
+    const uint32_t nmajor = (uint32_t)(format == SPL_CSR ? nrows : ncols);
+    const uint32_t nminor = (uint32_t)(format == SPL_CSR ? ncols : nrows);
+    if (validate) {
+        uint32_t first = 0, last = 0;
+        read_back(ctx, ptr_dev, &first, 1);
+        read_back(ctx, ptr_dev + nmajor, &last, 1);
+        if (first != 0) invalid(ctx, 4, kReasonText[4]);
+        if (last != nnz) invalid(ctx, 5, kReasonText[5]);
+        int why = validate_compressed(ctx, nmajor, nminor, (uint32_t)nnz, ptr_dev, ind_dev);
+        if (why) invalid(ctx, why, kReasonText[why]);
+    }
+    spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)nnz);
+    try {
+        SPL_CUDA(cudaMemcpyAsync(m->ptr, ptr_dev, ((size_t)nmajor + 1) * 4, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        if (nnz) {
+            SPL_CUDA(cudaMemcpyAsync(m->ind, ind_dev, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            SPL_CUDA(cudaMemcpyAsync(m->val, val_dev, nnz * m->vsize(), cudaMemcpyDeviceToDevice,
+                                     ctx->stream));
+        }
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    *out = m;
+    API_END(ctx)
+}
+
+int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t ptr_len, const uint64_t *ptr, uint64_t ind_len,
+                            const uint64_t *ind, uint64_t val_len, const void *val, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);                                     // assertions 1, 2
+    const uint64_t nmajor = format == SPL_CSR ? nrows : ncols;
+    const uint64_t nminor = format == SPL_CSR ? ncols : nrows;
+    if (ptr_len != nmajor + 1) invalid(ctx, 3, kReasonText[3]);
+    SPL_REQUIRE(ptr, SPL_ERR_ARG, "ptr is NULL");
+    if (ptr[0] != 0) invalid(ctx, 4, kReasonText[4]);
+    if (ind_len != ptr[nmajor]) invalid(ctx, 5, kReasonText[5]);
+    if (val_len != ptr[nmajor]) invalid(ctx, 6, kReasonText[6]);
+    const uint64_t nnz = ind_len;
+    SPL_REQUIRE(nnz < (1ull << 32), SPL_ERR_UNSUPPORTED, "nnz must be below 2^32");
+    SPL_REQUIRE(nnz == 0 || (ind && val), SPL_ERR_ARG, "NULL array");
+
+    spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)nnz);
+    try {
+        {
+            Tmp<uint64_t> wide(ctx, nmajor + 1 > nnz ? nmajor + 1 : nnz);
+            SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(uint32_t), ctx->stream));
+            SPL_CUDA(cudaMemcpyAsync(wide, ptr, (nmajor + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            narrow_u64(ctx, wide, m->ptr, nmajor + 1, nnz + 1, ctx->d_scratch);       // flag word 0
+            if (nnz) {
+                SPL_CUDA(cudaMemcpyAsync(wide, ind, nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+                narrow_u64(ctx, wide, m->ind, nnz, nminor, ctx->d_scratch + 1);       // flag word 1
+                SPL_CUDA(cudaMemcpyAsync(m->val, val, nnz * m->vsize(), cudaMemcpyHostToDevice,
+                                         ctx->stream));
+            }
+        }
+        uint32_t flags[2] = {0, 0};
+        read_back(ctx, ctx->d_scratch, flags, 2);
+        // a pointer above nnz cannot be part of a sorted array ending in nnz  -> assertion 7
+        if (flags[0]) invalid(ctx, 7, kReasonText[7]);
+        int why = validate_compressed(ctx, (uint32_t)nmajor, (uint32_t)nminor, (uint32_t)nnz, m->ptr,
+                                      m->ind);
+        if (why == 0 && flags[1]) why = 8;
+        if (why) invalid(ctx, why, kReasonText[why]);
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    *out = m;
+    API_END(ctx)
+}
+
+int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, size, size);   // assert!(size > 0), src/csr.rs:180
+    spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)size, (uint32_t)size, (uint32_t)size);
+    try {
+        fill_eye(ctx, dtype, (uint32_t)size, m->ptr, m->ind, m->val);
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    *out = m;
+    API_END(ctx)
+}
+
+static spl_mat *regroup(spl_ctx *ctx, const spl_mat *in, int out_format, uint32_t out_rows,
+                        uint32_t out_cols) {
+    // out's major axis is in's minor axis
+    spl_mat *m = new_mat(ctx, out_format, in->dtype, out_rows, out_cols, in->nnz);
+    try {
+        recompress(ctx, in->dtype, in->nmajor(), in->nminor(), in->nnz, in->ptr, in->ind, in->val,
+                   m->ptr, m->ind, m->val);
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    return m;
+}
+
+int spl_mat_convert(spl_ctx *ctx, const spl_mat *in, int format, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(in && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    check_enums(format, in->dtype);
+    if (format == in->format) {
+        spl_mat *m = new_mat(ctx, in->format, in->dtype, in->nrows, in->ncols, in->nnz);
+        SPL_CUDA(cudaMemcpyAsync(m->ptr, in->ptr, ((size_t)in->nmajor() + 1) * 4,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->ind, in->ind, (size_t)in->nnz * 4, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->val, in->val, (size_t)in->nnz * in->vsize(),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        *out = m;
+    } else {
+        *out = regroup(ctx, in, format, in->nrows, in->ncols);   // same matrix, other format
+    }
+    API_END(ctx)
+}
+
+int spl_mat_transpose(spl_ctx *ctx, const spl_mat *in, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(in && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    *out = regroup(ctx, in, in->format, in->ncols, in->nrows);   // same format, dims swapped
+    API_END(ctx)
+}
+
+int spl_mat_add(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    *out = addsub(ctx, a, b, 0);
+    API_END(ctx)
+}
+
+int spl_mat_sub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    *out = addsub(ctx, a, b, 1);
+    API_END(ctx)
+}
+
+int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    *out = spgemm(ctx, a, b);
+    API_END(ctx)
+}
+
+int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && out, SPL_ERR_ARG, "NULL handle");
+    *out = nullptr;
+    spl_mat *m = new_mat(ctx, a->format, a->dtype, a->nrows, a->ncols, a->nnz);
+    try {
+        SPL_CUDA(cudaMemcpyAsync(m->ptr, a->ptr, ((size_t)a->nmajor() + 1) * 4,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->ind, a->ind, (size_t)a->nnz * 4, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+        negate(ctx, a->dtype, a->nnz, a->val, m->val);
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    *out = m;
+    API_END(ctx)
+}
+
+int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && x_dev && y_dev, SPL_ERR_ARG, "NULL argument");
+    spmv(ctx, a, x_dev, y_dev, kernel & 0xff, (kernel >> 8) & 0xff);
+    API_END(ctx)
+}
+
+int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev) {
+    return spl_spmv_ex(ctx, a, x_dev, y_dev, SPL_SPMV_AUTO);
+}
+
+int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a && x_host && y_host, SPL_ERR_ARG, "NULL argument");
+    const size_t vs = a->vsize();
+    Tmp<unsigned char> x(ctx, (size_t)a->ncols * vs), y(ctx, (size_t)a->nrows * vs);
+    SPL_CUDA(cudaMemcpyAsync(x, x_host, (size_t)a->ncols * vs, cudaMemcpyHostToDevice, ctx->stream));
+    spmv(ctx, a, x, y, SPL_SPMV_AUTO, 0);
+    SPL_CUDA(cudaMemcpyAsync(y_host, y, (size_t)a->nrows * vs, cudaMemcpyDeviceToHost, ctx->stream));
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int spl_spmv_choice(spl_ctx *ctx, const spl_mat *a, int *kernel, int *lanes_per_row) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a, SPL_ERR_ARG, "NULL handle");
+    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
+    spmv_plan(ctx, const_cast<spl_mat *>(a));
+    if (kernel) *kernel = a->plan_kernel;
+    if (lanes_per_row) *lanes_per_row = a->plan_lanes;
+    API_END(ctx)
+}
+
+int spl_mat_info(const spl_mat *m, int *format, int *dtype, uint64_t *nrows, uint64_t *ncols,
+                 uint64_t *nnz) {
+    if (!m) return SPL_ERR_ARG;
+    if (format) *format = m->format;
+    if (dtype) *dtype = m->dtype;
+    if (nrows) *nrows = m->nrows;
+    if (ncols) *ncols = m->ncols;
+    if (nnz) *nnz = m->nnz;
+    return SPL_OK;
+}
+
+int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *ind, void *val) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
+    const size_t np = (size_t)m->nmajor() + 1;
+    Tmp<uint64_t> wide(ctx, np > m->nnz ? np : m->nnz);
+    if (ptr) {
+        widen_u32(ctx, m->ptr, wide, np);
+        SPL_CUDA(cudaMemcpyAsync(ptr, wide, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (ind && m->nnz) {
+        widen_u32(ctx, m->ind, wide, m->nnz);
+        SPL_CUDA(cudaMemcpyAsync(ind, wide, (size_t)m->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (val && m->nnz)
+        SPL_CUDA(cudaMemcpyAsync(val, m->val, (size_t)m->nnz * m->vsize(), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32_t **ind_dev,
+                        const void **val_dev) {
+    if (!m) return SPL_ERR_ARG;
+    if (ptr_dev) *ptr_dev = m->ptr;
+    if (ind_dev) *ind_dev = m->ind;
+    if (val_dev) *val_dev = m->val;
+    return SPL_OK;
+}
+
+int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
+    if (m->nnz) {
+        SPL_REQUIRE(row && col && val, SPL_ERR_ARG, "NULL array");
+        Tmp<uint32_t> major(ctx, m->nnz);
+        Tmp<uint64_t> wide(ctx, m->nnz);
+        expand_major(ctx, m->nmajor(), m->nnz, m->ptr, major);
+        uint64_t *major_out = m->format == SPL_CSR ? row : col;
+        uint64_t *minor_out = m->format == SPL_CSR ? col : row;
+        widen_u32(ctx, major, wide, m->nnz);
+        SPL_CUDA(cudaMemcpyAsync(major_out, wide, (size_t)m->nnz * 8, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        widen_u32(ctx, m->ind, wide, m->nnz);
+        SPL_CUDA(cudaMemcpyAsync(minor_out, wide, (size_t)m->nnz * 8, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(val, m->val, (size_t)m->nnz * m->vsize(), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int spl_mat_free(spl_ctx *ctx, spl_mat *m) {
+    API_BEGIN(ctx)
+    free_mat(ctx, m);
+    API_END(ctx)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

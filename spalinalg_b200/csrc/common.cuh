@@ -1,0 +1,180 @@
+// common.cuh — context, matrix handle, error plumbing and small device helpers
+// shared by every translation unit of libspalinalg_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <type_traits>
+
+#include "../../include/spl.h"
+
+namespace spl {
+
+struct Error {
+    int status;
+    std::string msg;
+};
+
+#define SPL_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            throw ::spl::Error{_e == cudaErrorMemoryAllocation ? SPL_ERR_OOM : SPL_ERR_CUDA, \
+                               std::string(#expr) + ": " + cudaGetErrorString(_e)};      \
+        }                                                                                \
+    } while (0)
+
+#define SPL_REQUIRE(cond, status, text)                      \
+    do {                                                     \
+        if (!(cond)) throw ::spl::Error{(status), (text)};   \
+    } while (0)
+
+constexpr int kNumSmFallback = 148;
+
+}  // namespace spl
+
+// Opaque handles of the C ABI.
+struct spl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = spl::kNumSmFallback;
+    std::string last_error;
+    int invalid_reason = 0;
+    uint64_t launches = 0;
+    uint32_t *h_scratch = nullptr;   // pinned, 64 words: small device->host read-backs
+    uint32_t *d_scratch = nullptr;   // device, 64 words
+};
+
+struct spl_mat {
+    int format = SPL_CSR;
+    int dtype = SPL_F64;
+    uint32_t nrows = 0, ncols = 0, nnz = 0;
+    uint32_t *ptr = nullptr;   // nmajor + 1
+    uint32_t *ind = nullptr;   // nnz
+    void *val = nullptr;       // nnz * sizeof(T)
+    // SpMV plan (filled lazily by the first spl_spmv on this matrix; read-only afterwards)
+    int plan_ready = 0;
+    int plan_kernel = 0;       // SPL_SPMV_VECTOR / SPL_SPMV_MERGE
+    int plan_lanes = 0;        // lanes per row of the vector kernel
+    uint32_t max_row_len = 0;
+
+    uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
+    uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }
+    size_t vsize() const { return dtype == SPL_F32 ? 4 : 8; }
+};
+
+namespace spl {
+
+// Stream-ordered device allocation (pool-backed: freed blocks are reused without a sync).
+template <typename T>
+inline T *dalloc(spl_ctx *ctx, size_t count) {
+    void *p = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    SPL_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
+    return static_cast<T *>(p);
+}
+inline void *dalloc_bytes(spl_ctx *ctx, size_t bytes) {
+    void *p = nullptr;
+    SPL_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream));
+    return p;
+}
+inline void dfree(spl_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// RAII temporary: freed (stream-ordered) when it goes out of scope, also on exceptions.
+template <typename T>
+struct Tmp {
+    spl_ctx *ctx;
+    T *p;
+    Tmp(spl_ctx *c, size_t count) : ctx(c), p(dalloc<T>(c, count)) {}
+    ~Tmp() { dfree(ctx, p); }
+    Tmp(const Tmp &) = delete;
+    Tmp &operator=(const Tmp &) = delete;
+    T *release() { T *q = p; p = nullptr; return q; }
+    operator T *() const { return p; }
+};
+
+inline void count_launch(spl_ctx *ctx, int n = 1) { ctx->launches += (uint64_t)n; }
+
+inline void check_launch(spl_ctx *ctx, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error{SPL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)};
+    count_launch(ctx);
+}
+
+// Reads `words` (<= 64) uint32 from device memory to the host, synchronising the stream.
+inline void read_back(spl_ctx *ctx, const uint32_t *d_src, uint32_t *dst, int words) {
+    SPL_CUDA(cudaMemcpyAsync(ctx->h_scratch, d_src, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < words; ++i) dst[i] = ctx->h_scratch[i];
+}
+
+inline int bits_for(uint64_t count) {   // bits needed to represent values in [0, count)
+    int b = 0;
+    while (b < 64 && (count - 1) >> b) ++b;
+    return count <= 1 ? 0 : b;
+}
+
+inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Inclusive warp scan (shuffle up).
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (unsigned)o) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one uint32 per thread.  `warp_sums` is shared memory with at
+// least blockDim.x/32 + 1 slots.  Returns the exclusive prefix; *total gets the block sum.
+// Contains two __syncthreads(); every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums,
+                                                         uint32_t *total) {
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    uint32_t incl = warp_inclusive_scan(v);
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < nwarps ? warp_sums[lane] : 0u;
+        uint32_t si = warp_inclusive_scan(s);
+        if (lane < nwarps) warp_sums[lane] = si - s;
+        if (lane == 31) warp_sums[nwarps] = si;
+    }
+    __syncthreads();
+    uint32_t res = warp_sums[warp] + incl - v;
+    if (total) *total = warp_sums[nwarps];
+    return res;
+}
+
+// first index in [lo, hi) with a[idx] > key  (a non-decreasing)
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *__restrict__ a, uint32_t lo,
+                                                    uint32_t hi, uint32_t key) {
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) <= key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+struct NoPayload {};
+
+}  // namespace spl

@@ -1,0 +1,55 @@
+// kernels.cuh — host-side entry points of each subsystem (one .cu file each); api.cu is the
+// only caller.  Everything runs on ctx->stream; functions throw spl::Error.
+#pragma once
+
+#include "common.cuh"
+
+namespace spl {
+
+// assemble.cu — COO -> CSR/CSC (a-2, a-3, a-11 of SURVEY.md section 8)
+spl_mat *assemble_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
+                               uint32_t len, const uint32_t *row, const uint32_t *col,
+                               const void *val, int dedup, int dropzero);
+// Shared tail of assembly and SpGEMM: sorted (key = major << minor_bits | minor, value) records
+// -> in-order segmented sum, optional zero drop, compaction, pointer array.  `vals` is updated
+// in place.  key64 selects uint64 keys, else uint32.
+spl_mat *finish_from_sorted(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
+                            uint32_t n, bool key64, const void *keys, void *vals, int minor_bits,
+                            int dedup, int dropzero);
+
+// recompress.cu — transpose / CSR<->CSC (a-4, a-5): same entries grouped by the other index.
+void recompress(spl_ctx *ctx, int dtype, uint32_t nmajor, uint32_t nminor, uint32_t nnz,
+                const uint32_t *ptr, const uint32_t *ind, const void *val, uint32_t *out_ptr,
+                uint32_t *out_ind, void *out_val);
+
+// spmv.cu — y = A x, CSR (a-6 restricted to B = n x 1, dense vectors)
+void spmv_plan(spl_ctx *ctx, spl_mat *a);
+void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes);
+
+// addsub.cu — C = A +/- B on compressed arrays of equal format (a-7)
+spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract);
+
+// spgemm.cu — C = A * B (a-6): expand products in ascending-k order, stable sort, in-order sum
+spl_mat *spgemm(spl_ctx *ctx, const spl_mat *a, const spl_mat *b);
+
+// misc.cu
+void negate(spl_ctx *ctx, int dtype, uint32_t nnz, const void *val, void *out);
+// 0 = valid, else the reference assertion ordinal (7, 8 or 9); ptr[0] and ptr[n] are checked by
+// the caller.
+int validate_compressed(spl_ctx *ctx, uint32_t nmajor, uint32_t nminor, uint32_t nnz,
+                        const uint32_t *ptr, const uint32_t *ind);
+// dst[i] = (uint32) src[i]; returns (through d_flag != 0) whether any src[i] >= limit.
+void narrow_u64(spl_ctx *ctx, const uint64_t *src, uint32_t *dst, size_t n, uint64_t limit,
+                uint32_t *d_flag);
+void widen_u32(spl_ctx *ctx, const uint32_t *src, uint64_t *dst, size_t n);
+void fill_eye(spl_ctx *ctx, int dtype, uint32_t size, uint32_t *ptr, uint32_t *ind, void *val);
+// major index of every stored entry (rowptr expansion, src/csr.rs:303-316)
+void expand_major(spl_ctx *ctx, uint32_t nmajor, uint32_t nnz, const uint32_t *ptr, uint32_t *out);
+// ptr[q] = first position p with sorted_major[p] >= q, for q in [0, nmajor]
+void fill_ptr(spl_ctx *ctx, const uint32_t *sorted_major, uint32_t nnz, uint32_t nmajor,
+              uint32_t *ptr);
+
+spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t nnz);
+void free_mat(spl_ctx *ctx, spl_mat *m);
+
+}  // namespace spl

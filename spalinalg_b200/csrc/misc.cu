@@ -1,0 +1,162 @@
+// misc.cu — streaming helpers around the hot path: negate (src/csr/ops/neg.rs:5-18),
+// CsrMatrix::new validation (src/csr.rs:144-156), index narrowing/widening between the host's
+// usize and the device's uint32, eye (src/csr.rs:179-188), rowptr expansion (src/csr.rs:303-316).
+#include "kernels.cuh"
+
+namespace spl {
+
+namespace {
+
+template <typename T>
+__global__ void negate_kernel(const T *__restrict__ in, T *__restrict__ out, uint32_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = -in[i];   // sign-bit flip: 0.0 -> -0.0, NaN payload kept
+}
+
+// assertion 7: ptr non-decreasing (src/csr.rs:150)
+__global__ void validate_ptr_kernel(const uint32_t *__restrict__ ptr, uint32_t nmajor,
+                                    uint32_t *fail) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < nmajor && ptr[m] > ptr[m + 1]) atomicMin(fail, 7u);
+}
+
+// assertion 8: index in range (:151); assertion 9: strictly increasing in a segment (:152-156).
+// One thread per stored entry; the segment boundary test uses the entry's own segment end.
+__global__ void validate_ind_kernel(const uint32_t *__restrict__ ptr,
+                                    const uint32_t *__restrict__ ind, uint32_t nmajor,
+                                    uint32_t nminor, uint32_t nnz, uint32_t *fail) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const uint32_t c = ind[p];
+    if (c >= nminor) atomicMin(fail, 8u);
+    if (p + 1 < nnz && ind[p + 1] <= c) {
+        // only a violation if p and p+1 lie in the same segment
+        const uint32_t seg = upper_bound_u32(ptr, 0u, nmajor + 1u, (uint32_t)p) - 1u;
+        if (p + 1 < ptr[seg + 1]) atomicMin(fail, 9u);
+    }
+}
+
+__global__ void narrow_kernel(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst, size_t n,
+                              uint64_t limit, uint32_t *flag) {
+    uint32_t bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t v = src[i];
+        bad |= v >= limit;
+        dst[i] = v > 0xffffffffull ? 0xffffffffu : (uint32_t)v;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flag, 1u);
+}
+
+__global__ void widen_kernel(const uint32_t *__restrict__ src, uint64_t *__restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+template <typename T>
+__global__ void eye_kernel(uint32_t size, uint32_t *ptr, uint32_t *ind, T *val) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= size) ptr[i] = (uint32_t)i;
+    if (i < size) {
+        ind[i] = (uint32_t)i;
+        val[i] = (T)1;
+    }
+}
+
+__global__ void expand_major_kernel(const uint32_t *__restrict__ ptr, uint32_t nmajor, uint32_t nnz,
+                                    uint32_t *__restrict__ out) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nnz) out[p] = upper_bound_u32(ptr, 0u, nmajor + 1u, (uint32_t)p) - 1u;
+}
+
+inline unsigned stream_grid(spl_ctx *ctx, size_t n) {
+    unsigned g = div_up(n ? n : 1, 256 * 4);
+    unsigned cap = (unsigned)ctx->num_sms * 16u;
+    return g < cap ? (g ? g : 1) : cap;
+}
+
+}  // namespace
+
+void negate(spl_ctx *ctx, int dtype, uint32_t nnz, const void *val, void *out) {
+    if (nnz == 0) return;
+    if (dtype == SPL_F32)
+        negate_kernel<float><<<stream_grid(ctx, nnz), 256, 0, ctx->stream>>>((const float *)val,
+                                                                            (float *)out, nnz);
+    else
+        negate_kernel<double><<<stream_grid(ctx, nnz), 256, 0, ctx->stream>>>((const double *)val,
+                                                                             (double *)out, nnz);
+    check_launch(ctx, "negate");
+}
+
+int validate_compressed(spl_ctx *ctx, uint32_t nmajor, uint32_t nminor, uint32_t nnz,
+                        const uint32_t *ptr, const uint32_t *ind) {
+    uint32_t fail = 0xffffffffu;
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0xff, sizeof(uint32_t), ctx->stream));
+    validate_ptr_kernel<<<div_up(nmajor, 256), 256, 0, ctx->stream>>>(ptr, nmajor, ctx->d_scratch);
+    check_launch(ctx, "validate_ptr");
+    read_back(ctx, ctx->d_scratch, &fail, 1);
+    if (fail != 0xffffffffu) return (int)fail;
+    if (nnz == 0) return 0;
+    // ptr is monotone with ptr[0]==0, ptr[n]==nnz (checked by the caller): every segment is inside ind
+    validate_ind_kernel<<<div_up(nnz, 256), 256, 0, ctx->stream>>>(ptr, ind, nmajor, nminor, nnz,
+                                                                  ctx->d_scratch);
+    check_launch(ctx, "validate_ind");
+    read_back(ctx, ctx->d_scratch, &fail, 1);
+    return fail == 0xffffffffu ? 0 : (int)fail;
+}
+
+void narrow_u64(spl_ctx *ctx, const uint64_t *src, uint32_t *dst, size_t n, uint64_t limit,
+                uint32_t *d_flag) {
+    if (n == 0) return;
+    narrow_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>(src, dst, n, limit, d_flag);
+    check_launch(ctx, "narrow");
+}
+
+void widen_u32(spl_ctx *ctx, const uint32_t *src, uint64_t *dst, size_t n) {
+    if (n == 0) return;
+    widen_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>(src, dst, n);
+    check_launch(ctx, "widen");
+}
+
+void fill_eye(spl_ctx *ctx, int dtype, uint32_t size, uint32_t *ptr, uint32_t *ind, void *val) {
+    const unsigned grid = div_up((uint64_t)size + 1, 256);
+    if (dtype == SPL_F32) eye_kernel<float><<<grid, 256, 0, ctx->stream>>>(size, ptr, ind, (float *)val);
+    else eye_kernel<double><<<grid, 256, 0, ctx->stream>>>(size, ptr, ind, (double *)val);
+    check_launch(ctx, "eye");
+}
+
+void expand_major(spl_ctx *ctx, uint32_t nmajor, uint32_t nnz, const uint32_t *ptr, uint32_t *out) {
+    if (nnz == 0) return;
+    expand_major_kernel<<<div_up(nnz, 256), 256, 0, ctx->stream>>>(ptr, nmajor, nnz, out);
+    check_launch(ctx, "expand_major");
+}
+
+spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t nnz) {
+    spl_mat *m = new spl_mat();
+    m->format = format;
+    m->dtype = dtype;
+    m->nrows = nrows;
+    m->ncols = ncols;
+    m->nnz = nnz;
+    try {
+        m->ptr = dalloc<uint32_t>(ctx, (size_t)m->nmajor() + 1);
+        m->ind = dalloc<uint32_t>(ctx, nnz);
+        m->val = dalloc_bytes(ctx, (size_t)nnz * m->vsize());
+    } catch (...) {
+        free_mat(ctx, m);
+        throw;
+    }
+    return m;
+}
+
+void free_mat(spl_ctx *ctx, spl_mat *m) {
+    if (!m) return;
+    dfree(ctx, m->ptr);
+    dfree(ctx, m->ind);
+    dfree(ctx, m->val);
+    delete m;
+}
+
+}  // namespace spl

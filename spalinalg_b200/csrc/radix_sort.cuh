@@ -1,0 +1,295 @@
+// radix_sort.cuh — stable LSD radix sort of (key, payload A[, payload B]) for sm_100a.
+//
+// Stability is what makes COO assembly bit-exact (duplicates must be summed in insertion
+// order, src/csr/conv/coo.rs:36-57) and what makes the CSR<->CSC scatter deterministic
+// (inner indices ascending, src/csr.rs:385-396).  Per digit pass:
+//   rs_hist     each block histograms its contiguous chunk of tiles        (reads keys)
+//   rs_scan     one block turns counts[digit][block] into global offsets   (tiny)
+//   rs_scatter  each block re-walks its chunk tile by tile: warp-striped coalesced loads,
+//               match.any ranking per warp, digit scan in shared memory, exchange through
+//               shared memory so runs of equal digits leave as contiguous coalesced stores.
+// Only the significant key bits are sorted (ceil(bits/8) passes, bits split evenly).
+// The grid is a multiple of the SM count; every block owns whole tiles.
+#pragma once
+
+#include "common.cuh"
+
+namespace spl {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BINS = 256;
+constexpr int RS_IPT = 12;                       // items per thread
+constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 3072 items per tile
+
+// ---- loaders: what pass 0 reads (later passes read the ping-pong buffers) ------------------
+template <typename V>
+struct LoadPlain {
+    const V *p;
+    __device__ __forceinline__ V operator()(uint32_t i) const { return p[i]; }
+};
+// key = hi[i] << lobits | lo[i]   ((row, col) for CSR assembly, (col, row) for CSC)
+template <typename K>
+struct LoadPack {
+    const uint32_t *hi;
+    const uint32_t *lo;
+    int lobits;
+    __device__ __forceinline__ K operator()(uint32_t i) const {
+        return (K)(((uint64_t)hi[i] << lobits) | (uint64_t)lo[i]);
+    }
+};
+// major index of compressed entry i: the segment of ptr[] that contains i
+struct LoadMajor {
+    const uint32_t *ptr;
+    uint32_t nmajor;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        return upper_bound_u32(ptr, 0u, nmajor + 1u, i) - 1u;
+    }
+};
+struct LoadNone {
+    __device__ __forceinline__ NoPayload operator()(uint32_t) const { return NoPayload{}; }
+};
+
+inline int rs_num_passes(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
+
+// ---- upsweep ---------------------------------------------------------------------------------
+template <typename K, typename LoadK>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(LoadK lk, uint32_t n, uint32_t tiles_per_block, int shift, uint32_t mask,
+               uint32_t *__restrict__ counts) {
+    __shared__ uint32_t hist[RS_WARPS][RS_BINS];
+    for (int j = threadIdx.x; j < RS_WARPS * RS_BINS; j += RS_THREADS) (&hist[0][0])[j] = 0;
+    __syncthreads();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_block * RS_TILE;
+    uint64_t end = begin + (uint64_t)tiles_per_block * RS_TILE;
+    if (end > n) end = n;
+    constexpr int U = 4;
+    for (uint64_t blk = begin; blk < end; blk += (uint64_t)RS_THREADS * U) {
+        uint32_t d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint64_t i = blk + (uint64_t)u * RS_THREADS + threadIdx.x;
+            d[u] = i < end ? ((uint32_t)(lk((uint32_t)i) >> shift) & mask) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            unsigned peers = __match_any_sync(0xffffffffu, d[u]);
+            if (d[u] != 0xffffffffu && lane == (unsigned)(__ffs(peers) - 1))
+                hist[warp][d[u]] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_BINS) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) c += hist[w][threadIdx.x];
+        counts[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = c;
+    }
+}
+
+// ---- spine: in-place exclusive scan over counts[digit][block], digit-major ----------------
+static __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *data, uint32_t m) {
+    __shared__ uint32_t ws[33];
+    const uint32_t per = (m + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, m), hi = min(lo + per, m);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; ++i) s += data[i];
+    uint32_t run = block_exclusive_scan(s, ws, nullptr);
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+// ---- downsweep -------------------------------------------------------------------------------
+template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_block, int shift,
+                  uint32_t mask, const uint32_t *__restrict__ offsets, K *__restrict__ out_k,
+                  A *__restrict__ out_a, B *__restrict__ out_b) {
+    constexpr bool kHasA = !std::is_same<A, NoPayload>::value;
+    constexpr bool kHasB = !std::is_same<B, NoPayload>::value;
+    __shared__ __align__(16) unsigned char exch_raw[RS_TILE * 8];
+    __shared__ uint32_t whist[RS_WARPS][RS_BINS];
+    __shared__ uint32_t glob[RS_BINS];      // global position of local position 0 of each digit
+    __shared__ uint32_t running[RS_BINS];   // next free global slot per digit for this block
+    __shared__ uint32_t ws[RS_WARPS + 1];
+
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x < RS_BINS)
+        running[threadIdx.x] = offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+
+    const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_block * RS_TILE;
+    for (uint32_t t = 0; t < tiles_per_block; ++t) {
+        const uint64_t tile_base = begin + (uint64_t)t * RS_TILE;
+        if (tile_base >= n) break;
+        const uint32_t tile_count = (uint32_t)(((uint64_t)n - tile_base) < RS_TILE
+                                                   ? ((uint64_t)n - tile_base) : RS_TILE);
+        const uint32_t my_base = warp * 32 * RS_IPT + lane;   // + i*32 : warp-striped
+
+        for (int j = threadIdx.x; j < RS_WARPS * RS_BINS; j += RS_THREADS) (&whist[0][0])[j] = 0;
+
+        K keys[RS_IPT];
+#pragma unroll
+        for (int i = 0; i < RS_IPT; ++i) {
+            uint32_t loc = my_base + i * 32;
+            keys[i] = loc < tile_count ? lk((uint32_t)(tile_base + loc)) : (K)0;
+        }
+        __syncthreads();
+
+        // rank inside the warp, digit by digit occurrence order (stable)
+        uint32_t rank[RS_IPT];
+#pragma unroll
+        for (int i = 0; i < RS_IPT; ++i) {
+            const bool valid = my_base + i * 32 < tile_count;
+            const uint32_t d = valid ? ((uint32_t)(keys[i] >> shift) & mask) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && (int)lane == leader) {
+                old = whist[warp][d];
+                whist[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[i] = old + __popc(peers & lanemask_lt());
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // per digit: exclusive prefix over warps, then over digits
+        uint32_t cnt = 0;
+        if (threadIdx.x < RS_BINS) {
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) {
+                uint32_t c = whist[w][threadIdx.x];
+                whist[w][threadIdx.x] = cnt;
+                cnt += c;
+            }
+        }
+        const uint32_t dbase = block_exclusive_scan(cnt, ws, nullptr);
+        if (threadIdx.x < RS_BINS) {
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) whist[w][threadIdx.x] += dbase;
+            glob[threadIdx.x] = running[threadIdx.x] - dbase;
+            running[threadIdx.x] += cnt;
+        }
+        __syncthreads();
+
+        // keys: to shared memory at their tile-local sorted position, then out coalesced
+        K *exk = reinterpret_cast<K *>(exch_raw);
+#pragma unroll
+        for (int i = 0; i < RS_IPT; ++i) {
+            if (my_base + i * 32 < tile_count) {
+                const uint32_t d = (uint32_t)(keys[i] >> shift) & mask;
+                rank[i] += whist[warp][d];
+                exk[rank[i]] = keys[i];
+            }
+        }
+        __syncthreads();
+        uint32_t gpos[RS_IPT];
+#pragma unroll
+        for (int j = 0; j < RS_IPT; ++j) {
+            const uint32_t p = j * RS_THREADS + threadIdx.x;
+            if (p < tile_count) {
+                const K k = exk[p];
+                gpos[j] = glob[(uint32_t)(k >> shift) & mask] + p;
+                out_k[gpos[j]] = k;
+            }
+        }
+        if constexpr (kHasA) {
+            __syncthreads();
+            A *exa = reinterpret_cast<A *>(exch_raw);
+#pragma unroll
+            for (int i = 0; i < RS_IPT; ++i) {
+                const uint32_t loc = my_base + i * 32;
+                if (loc < tile_count) exa[rank[i]] = la((uint32_t)(tile_base + loc));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RS_IPT; ++j) {
+                const uint32_t p = j * RS_THREADS + threadIdx.x;
+                if (p < tile_count) out_a[gpos[j]] = exa[p];
+            }
+        }
+        if constexpr (kHasB) {
+            __syncthreads();
+            B *exb = reinterpret_cast<B *>(exch_raw);
+#pragma unroll
+            for (int i = 0; i < RS_IPT; ++i) {
+                const uint32_t loc = my_base + i * 32;
+                if (loc < tile_count) exb[rank[i]] = lb((uint32_t)(tile_base + loc));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RS_IPT; ++j) {
+                const uint32_t p = j * RS_THREADS + threadIdx.x;
+                if (p < tile_count) out_b[gpos[j]] = exb[p];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- driver ----------------------------------------------------------------------------------
+// Sorts n records by the low `bits` bits of the key.  Pass 0 reads through the loaders and
+// writes buffer set 0; pass p writes set p&1.  Returns the index (0/1) of the set that holds
+// the sorted result, i.e. (passes-1)&1.  A/B = NoPayload (with LoadNone, null buffers) drops
+// that payload.
+template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
+int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB lb0, K *k_buf[2],
+               A *a_buf[2], B *b_buf[2]) {
+    const int passes = rs_num_passes(bits);
+    if (n == 0) return (passes - 1) & 1;
+    if (bits <= 0) bits = 1;
+    const uint32_t tiles = div_up(n, RS_TILE);
+    uint32_t grid = (uint32_t)ctx->num_sms * 3u;          // 3 resident CTAs per SM (registers)
+    if (grid > tiles) grid = tiles;
+    const uint32_t tiles_per_block = div_up(tiles, grid);
+    grid = div_up(tiles, tiles_per_block);
+    Tmp<uint32_t> counts(ctx, (size_t)RS_BINS * grid);
+
+    int shift = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int nb = (bits - shift + (passes - p) - 1) / (passes - p);   // even split
+        const uint32_t mask = (1u << nb) - 1u;
+        const uint32_t nbins = 1u << nb;
+        K *ok = k_buf[p & 1];
+        A *oa = a_buf[p & 1];
+        B *ob = b_buf[p & 1];
+        if (p == 0) {
+            rs_hist_kernel<K, LoadK><<<grid, RS_THREADS, 0, ctx->stream>>>(
+                lk0, n, tiles_per_block, shift, mask, counts);
+            check_launch(ctx, "rs_hist");
+            rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, nbins * grid);
+            check_launch(ctx, "rs_scan");
+            rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB><<<grid, RS_THREADS, 0, ctx->stream>>>(
+                lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, ok, oa, ob);
+            check_launch(ctx, "rs_scatter");
+        } else {
+            using PA = typename std::conditional<std::is_same<A, NoPayload>::value, LoadNone,
+                                                 LoadPlain<A>>::type;
+            using PB = typename std::conditional<std::is_same<B, NoPayload>::value, LoadNone,
+                                                 LoadPlain<B>>::type;
+            LoadPlain<K> lk{k_buf[(p - 1) & 1]};
+            PA la;
+            PB lb;
+            if constexpr (!std::is_same<A, NoPayload>::value) la.p = a_buf[(p - 1) & 1];
+            if constexpr (!std::is_same<B, NoPayload>::value) lb.p = b_buf[(p - 1) & 1];
+            rs_hist_kernel<K, LoadPlain<K>><<<grid, RS_THREADS, 0, ctx->stream>>>(
+                lk, n, tiles_per_block, shift, mask, counts);
+            check_launch(ctx, "rs_hist");
+            rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, nbins * grid);
+            check_launch(ctx, "rs_scan");
+            rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB><<<grid, RS_THREADS, 0, ctx->stream>>>(
+                lk, la, lb, n, tiles_per_block, shift, mask, counts, ok, oa, ob);
+            check_launch(ctx, "rs_scatter");
+        }
+        shift += nb;
+    }
+    return (passes - 1) & 1;
+}
+
+}  // namespace spl

@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the host mirror), against
+(1) the reference's own golden vectors and (2) the CPU oracle on seeded random inputs.
+Bar: bit-exact for structure, conversions, add/sub/mul/neg values; 1e-12 (f64) / 1e-5 (f32)
+relative for SpMV (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+import spalinalg_b200 as sp
+from spalinalg_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+SPMV_RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+def arrays(m):
+    if isinstance(m, sp.CsrMatrix):
+        return m.rowptr(), m.colind(), m.values()
+    return m.colptr(), m.rowind(), m.values()
+
+
+def same(got, want, what=""):
+    gp, gi, gv = got
+    wp, wi, wv = want
+    assert gp.dtype == np.uint64 and gi.dtype == np.uint64
+    assert np.array_equal(gp, np.asarray(wp, np.uint64)), f"{what}: ptr differs"
+    assert np.array_equal(gi, np.asarray(wi, np.uint64)), f"{what}: ind differs"
+    wv = np.asarray(wv, gv.dtype)
+    assert gv.tobytes() == wv.tobytes(), f"{what}: values differ (bitwise)"
+
+
+def G(m, dtype=np.float64):
+    return m[0], m[1], np.array(m[2], np.uint64), np.array(m[3], np.uint64), np.array(m[4], dtype)
+
+
+# ------------------------------------------------------------------ the reference's own tests
+def test_from_coo_golden(goldens):
+    """src/csr/conv/coo.rs:129-145, src/csc/conv/coo.rs:129-145."""
+    g = goldens["coo_pushes"]
+    coo = sp.CooMatrix.new(g["nrows"], g["ncols"])
+    for r, c, v in g["entries"]:
+        coo.push(int(r), int(c), v)
+    csr = sp.CsrMatrix.from_coo(coo)
+    assert csr.rowptr().tolist() == g["csr"][2] and csr.colind().tolist() == g["csr"][3]
+    assert csr.values().tolist() == g["csr"][4]
+    csc = sp.CscMatrix.from_coo(coo)
+    assert csc.colptr().tolist() == g["csc"][2] and csc.rowind().tolist() == g["csc"][3]
+    assert csc.values().tolist() == g["csc"][4]
+
+
+def test_from_dok_golden(goldens):
+    g = goldens["dok_inserts"]
+    dok = sp.DokMatrix.new(2, 3)
+    for r, c, v in g["entries"]:
+        dok.insert(int(r), int(c), v)
+    same(arrays(sp.CsrMatrix.from_dok(dok)), G(g["csr"])[2:])
+    same(arrays(sp.CscMatrix.from_dok(dok)), G(g["csc"])[2:])
+
+
+def test_conversions_golden(goldens):
+    g = goldens["csc_to_csr"]
+    csc = sp.CscMatrix.new(*G(g["csc"]))
+    same(arrays(sp.CsrMatrix.from_csc(csc)), G(g["csr"])[2:])
+    g = goldens["csr_to_csc"]
+    csr = sp.CsrMatrix.new(*G(g["csr"]))
+    same(arrays(sp.CscMatrix.from_csr(csr)), G(g["csc"])[2:])
+
+
+def test_transpose_golden(goldens):
+    t = sp.CsrMatrix.new(*G(goldens["csr_transpose"]["in"])).transpose()
+    same(arrays(t), G(goldens["csr_transpose"]["out"])[2:])
+    t = sp.CscMatrix.new(*G(goldens["csc_transpose"]["in"])).transpose()
+    same(arrays(t), G(goldens["csc_transpose"]["out"])[2:])
+
+
+@pytest.mark.parametrize("name", ["csr_add", "csr_sub", "csc_add", "csc_sub"])
+def test_add_sub_golden(goldens, name):
+    g = goldens[name]
+    cls = sp.CsrMatrix if name.startswith("csr") else sp.CscMatrix
+    lhs, rhs = cls.new(*G(g["lhs"])), cls.new(*G(g["rhs"]))
+    mat = lhs + rhs if name.endswith("add") else lhs - rhs
+    assert (mat.nrows(), mat.ncols()) == (4, 4)
+    same(arrays(mat), G(g["out"])[2:])
+    assert len(arrays(mat)[1]) == mat.nnz() and len(arrays(mat)[2]) == mat.nnz()   # exactly sized
+
+
+def test_mul_golden(goldens):
+    """src/csc/ops/mul.rs:68-95; CSR Mul pinned through it."""
+    g = goldens["csc_mul"]
+    lhs, rhs = sp.CscMatrix.new(*G(g["lhs"])), sp.CscMatrix.new(*G(g["rhs"]))
+    mat = lhs * rhs
+    assert (mat.nrows(), mat.ncols()) == (5, 4)
+    same(arrays(mat), G(g["out"])[2:])
+    mat_csr = lhs.to_csr() * rhs.to_csr()
+    same(arrays(mat_csr.to_csc()), G(g["out"])[2:])
+
+
+def test_neg_golden(goldens):
+    n = -sp.CsrMatrix.new(*G(goldens["csr_neg"]["in"]))
+    same(arrays(n), G(goldens["csr_neg"]["out"])[2:])
+    n = -sp.CscMatrix.new(*G(goldens["csc_neg"]["in"]))
+    same(arrays(n), G(goldens["csc_neg"]["out"])[2:])
+
+
+def test_new_panics(goldens):
+    """src/csr.rs:470-510, src/csc.rs:470-510: the 7+7 #[should_panic] constructions."""
+    for cls, key, major in ((sp.CsrMatrix, "csr_new_panics", "row"), (sp.CscMatrix, "csc_new_panics", "col")):
+        for name, (nr, nc, ptr, ind, val) in goldens[key]["cases"].items():
+            with pytest.raises(sp.Panic):
+                cls.new(nr, nc, ptr, ind, val)
+            want = orc.validate_compressed(nr, nc, ptr, ind, len(val), major)
+            assert sp.default_context().invalid_reason() == want, name
+    for m in goldens["valid_constructions"]["csr"]:
+        sp.CsrMatrix.new(*m)
+    for m in goldens["valid_constructions"]["csc"]:
+        sp.CscMatrix.new(*m)
+
+
+def test_eye_and_accessors():
+    e = sp.CsrMatrix.eye(5)
+    assert e.rowptr().tolist() == list(range(6)) and e.colind().tolist() == list(range(5))
+    assert e.values().tolist() == [1.0] * 5 and e.nnz() == 5 and e.shape() == (5, 5)
+    with pytest.raises(sp.Panic):
+        sp.CscMatrix.eye(0)
+    coo = e.to_coo()
+    assert list(coo.iter()) == [(i, i, 1.0) for i in range(5)]
+
+
+def test_shape_mismatch_panics():
+    a, b = sp.CsrMatrix.eye(3), sp.CsrMatrix.eye(4)
+    for op in (lambda: a + b, lambda: a - b, lambda: a * b):
+        with pytest.raises(sp.Panic):
+            op()
+
+
+# ------------------------------------------------------------------ differential vs the oracle
+def _oracle_assemble(nr, nc, r, c, v, major, dedup=True, dropzero=True):
+    return orc.compress_from_coo(nr, nc, orc.make_triplets(r, c, v), major, dedup, dropzero)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,n", [((1, 1), 5), ((7, 5), 0), ((7, 5), 200), ((300, 4000), 20000),
+                                     ((70000, 3), 50000), ((1, 90000), 40000), ((100000, 100000), 300000)])
+def test_assembly_random(dtype, shape, n):
+    rng = np.random.default_rng(hash((shape, n)) % 2**32)
+    nr, nc = shape
+    r, c, v = syn.random_coo(rng, nr, nc, n, dtype, dup_frac=0.3, cancel_frac=0.05)
+    # heavy duplication of a few cells: long in-order sums with cancellation
+    if n:
+        hot = rng.integers(0, len(v), 3)
+        extra = 500
+        r = np.concatenate([r, np.repeat(r[hot], extra)])
+        c = np.concatenate([c, np.repeat(c[hot], extra)])
+        v = np.concatenate([v, (rng.standard_normal(3 * extra) * 10.0 ** rng.integers(-8, 8, 3 * extra)).astype(dtype)])
+    coo = sp.CooMatrix.with_triplets(nr, nc, r, c, v)
+    same(arrays(sp.CsrMatrix.from_coo(coo)), _oracle_assemble(nr, nc, r, c, v, "row"), "csr")
+    same(arrays(sp.CscMatrix.from_coo(coo)), _oracle_assemble(nr, nc, r, c, v, "col"), "csc")
+
+
+def test_assembly_special_values():
+    ent = [(0, 0, -0.0), (0, 1, float("nan")), (1, 0, 1e-320), (1, 1, 1.0), (1, 1, -1.0),
+           (2, 2, 1e-310), (2, 2, 1e-310), (2, 0, 1e308), (2, 0, 1e308), (2, 1, 0.1), (2, 1, 0.2), (2, 1, -0.3)]
+    r = np.array([e[0] for e in ent], np.uint64)
+    c = np.array([e[1] for e in ent], np.uint64)
+    v = np.array([e[2] for e in ent], np.float64)
+    coo = sp.CooMatrix.with_triplets(3, 3, r, c, v)
+    same(arrays(sp.CsrMatrix.from_coo(coo)), _oracle_assemble(3, 3, r, c, v, "row"))
+    same(arrays(sp.CscMatrix.from_coo(coo)), _oracle_assemble(3, 3, r, c, v, "col"))
+
+
+def test_assembly_out_of_bounds_is_rejected():
+    import ctypes as C
+    ctx = sp.default_context()
+    r = np.array([0, 5], np.uint64); c = np.array([0, 0], np.uint64); v = np.array([1.0, 2.0])
+    h = C.c_void_p()
+    st = ctx._lib.spl_mat_from_coo(ctx._h, 0, 1, 3, 3, 2, r.ctypes.data, c.ctypes.data, v.ctypes.data, 1, 1, C.byref(h))
+    assert st == 6 and not h.value
+
+
+def _rand_csr(rng, n, m, density, dtype):
+    nnz_target = int(n * m * density)
+    r = rng.integers(0, n, nnz_target)
+    c = rng.integers(0, m, nnz_target)
+    key = np.unique(r.astype(np.int64) * m + c)
+    r, c = key // m, key % m
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=n))]).astype(np.uint64)
+    val = rng.standard_normal(len(key)).astype(dtype)
+    return ptr, c.astype(np.uint64), val
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,density", [(1, 1, 1.0), (5, 9, 0.4), (1000, 700, 0.01), (3, 50000, 0.2),
+                                         (50000, 3, 0.2), (20000, 20000, 0.0008)])
+def test_transpose_convert_random(dtype, n, m, density):
+    rng = np.random.default_rng(n * 31 + m)
+    a = _rand_csr(rng, n, m, density, dtype)
+    csr = sp.CsrMatrix.new(n, m, *a)
+    want = orc.recompress(n, m, *a)
+    t = csr.transpose()
+    assert t.shape() == (m, n)
+    same(arrays(t), want, "transpose")
+    csc = csr.to_csc()
+    assert csc.shape() == (n, m)
+    same(arrays(csc), want, "csr->csc")
+    same(arrays(csc.to_csr()), a, "csc->csr round trip")
+    same(arrays(t.transpose()), a, "transpose twice")
+    # CSC transpose: arrays regrouped by row
+    same(arrays(csc.transpose()), orc.recompress(m, n, *want), "csc transpose")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,density", [(4, 4, 0.5), (300, 300, 0.02), (200, 350, 0.03), (40000, 40000, 0.0002)])
+def test_add_sub_random(dtype, n, m, density):
+    rng = np.random.default_rng(n + m)
+    a = _rand_csr(rng, n, m, density, dtype)
+    b = _rand_csr(rng, n, m, density, dtype)
+    # make some overlapping entries cancel exactly: explicit zeros must be kept
+    A, B = sp.CsrMatrix.new(n, m, *a), sp.CsrMatrix.new(n, m, *b)
+    same(arrays(A + B), orc.addsub(0, n, m, a, b), "add")
+    same(arrays(A - B), orc.addsub(1, n, m, a, b), "sub")
+    z = A - A
+    assert z.nnz() == A.nnz() and not z.values().any()                   # a + (-a) stores 0.0
+    Ac, Bc = A.to_csc(), B.to_csc()
+    ac, bc = arrays(Ac), arrays(Bc)
+    same(arrays(Ac + Bc), orc.addsub(0, m, n, ac, bc), "csc add")
+    same(arrays(Ac - Bc), orc.addsub(1, m, n, ac, bc), "csc sub")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,k,m,density", [(5, 3, 4, 0.6), (60, 80, 50, 0.1), (2000, 1500, 1800, 0.004)])
+def test_mul_random(dtype, n, k, m, density):
+    rng = np.random.default_rng(n * k + m)
+    a = _rand_csr(rng, n, k, density, dtype)
+    b = _rand_csr(rng, k, m, density, dtype)
+    A, B = sp.CsrMatrix.new(n, k, *a), sp.CsrMatrix.new(k, m, *b)
+    same(arrays(A * B), orc.csr_mul(n, k, m, a, b), "csr mul")
+    Ac, Bc = A.to_csc(), B.to_csc()
+    same(arrays(Ac * Bc), orc.csr_mul(m, k, n, arrays(Bc), arrays(Ac)), "csc mul")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_neg_random(dtype):
+    rng = np.random.default_rng(11)
+    a = _rand_csr(rng, 500, 400, 0.05, dtype)
+    a[2][:3] = [0.0, -0.0, np.nan]
+    N = -sp.CsrMatrix.new(500, 400, *a)
+    got = arrays(N)
+    assert np.array_equal(got[0], a[0]) and np.array_equal(got[1], a[1])
+    assert got[2].tobytes() == orc.neg(a[2]).tobytes()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,density", [(1, 1, 1.0), (64, 64, 0.3), (5000, 4000, 0.004), (3000, 3000, 0.05),
+                                         (100000, 100000, 0.00005)])
+def test_spmv_random(dtype, n, m, density):
+    rng = np.random.default_rng(n ^ m)
+    a = _rand_csr(rng, n, m, density, dtype)
+    x = rng.standard_normal(m).astype(dtype)
+    A = sp.CsrMatrix.new(n, m, *a)
+    want = orc.csr_spmv(n, *a, x)
+    # |y - y_ref| <= rtol * sum |a||x| (componentwise backward-error bound; rows with cancellation)
+    scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x))
+    rtol = SPMV_RTOL[np.dtype(dtype)]
+    got = A.matvec(x)
+    assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), "auto"
+    assert np.all(got[np.diff(a[0].astype(np.int64)) == 0] == 0)          # empty rows give 0
+    import torch
+    xd = torch.from_numpy(x).cuda()
+    for lanes in (1, 2, 4, 8, 16, 32):
+        yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+        torch.cuda.synchronize()
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=1, lanes=lanes)
+        sp.default_context().sync()
+        got = yd.cpu().numpy()
+        assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), lanes
+
+
+def test_spmv_skewed_rows():
+    """Power-law-like rows (one row holding most entries) + many empty rows."""
+    rng = np.random.default_rng(5)
+    n = m = 20000
+    lens = np.zeros(n, np.int64)
+    lens[7] = 15000; lens[100:200] = 300; lens[1000::7] = 3
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ind = np.concatenate([np.sort(rng.choice(m, l, replace=False)) for l in lens if l]).astype(np.uint64)
+    val = rng.standard_normal(len(ind))
+    x = rng.standard_normal(m)
+    A = sp.CsrMatrix.new(n, m, ptr, ind, val)
+    want = orc.csr_spmv(n, ptr, ind, val, x)
+    scale = orc.csr_spmv(n, ptr, ind, np.abs(val), np.abs(x))
+    assert np.all(np.abs(A.matvec(x) - want) <= 1e-12 * np.maximum(scale, 1e-300))
+
+
+# ------------------------------------------------------------------ BASELINE shapes, properties
+def test_c1_laplacian_assembly_and_spmv():
+    """Config 1 at full size: shuffled COO -> CSR equals the generator's canonical CSR bit for
+    bit; A*1 equals the analytic row sums; CSR->CSC->CSR is the identity; A^T == A."""
+    g = 1024
+    r, c, v = syn.laplacian_2d(g)
+    n = g * g
+    want = syn.csr_from_sorted_triplets(n, r, c, v)          # emission order is not column-sorted:
+    order = np.lexsort((c, r))
+    want = (want[0], c[order], v[order])
+    perm = np.random.default_rng(42).permutation(len(v))
+    A = sp.CsrMatrix.from_coo(sp.CooMatrix.with_triplets(n, n, r[perm], c[perm], v[perm]))
+    same(arrays(A), want, "C1 assembly")
+    y = A.matvec(np.ones(n))
+    deg = np.diff(want[0].astype(np.int64))
+    assert np.array_equal(y, 4.0 - (deg - 1))               # exact in f64: small integers
+    same(arrays(A.to_csc().to_csr()), want, "round trip")
+    same(arrays(A.transpose()), want, "symmetric")
+
+
+def test_c2_stencil_transpose_properties():
+    """Config 2 structure at a reduced grid for the oracle (48^3) and full-size properties (128^3)."""
+    m = 48
+    r, c, v = syn.stencil_27(m)
+    n = m ** 3
+    a = syn.csr_from_sorted_triplets(n, r, c, v)
+    A = sp.CsrMatrix.new(n, n, *a)
+    same(arrays(A.to_csc()), orc.recompress(n, n, *a), "C2/48 csr->csc")
+    x = 1.0 / (1.0 + (np.arange(n) % 97))
+    want = orc.csr_spmv(n, *a, x)
+    assert np.all(np.abs(A.matvec(x) - want) <= 1e-12 * orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x)))
+
+
+def test_c2_full_size_round_trip():
+    m = 128
+    r, c, v = syn.stencil_27(m)
+    n = m ** 3
+    assert len(v) == 382 ** 3
+    a = syn.csr_from_sorted_triplets(n, r, c, v)
+    del r
+    A = sp.CsrMatrix.new(n, n, *a)
+    C_ = A.to_csc()
+    same(arrays(C_.to_csr()), a, "C2 csr->csc->csr")
+    same(arrays(A.transpose()), a, "C2 symmetric pattern and values")
+    y = A.matvec(np.ones(n))
+    deg = np.diff(a[0].astype(np.int64))
+    assert np.array_equal(y, 26.0 - (deg - 1))
