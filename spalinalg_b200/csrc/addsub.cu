@@ -46,14 +46,14 @@ union_fill_kernel(uint32_t nmajor, const uint32_t *__restrict__ aptr,
         if (ia < ib) {
             cind[pc] = ia; cval[pc] = aval[pa]; ++pa;
         } else if (ib < ia) {
-            cind[pc] = ib; cval[pc] = SUB ? -bval[pb] : bval[pb]; ++pb;
+            cind[pc] = ib; cval[pc] = SUB ? flip_sign(bval[pb]) : bval[pb]; ++pb;
         } else {
             cind[pc] = ia; cval[pc] = SUB ? aval[pa] - bval[pb] : aval[pa] + bval[pb]; ++pa; ++pb;
         }
         ++pc;
     }
     for (; pa < ea; ++pa, ++pc) { cind[pc] = aind[pa]; cval[pc] = aval[pa]; }
-    for (; pb < eb; ++pb, ++pc) { cind[pc] = bind[pb]; cval[pc] = SUB ? -bval[pb] : bval[pb]; }
+    for (; pb < eb; ++pb, ++pc) { cind[pc] = bind[pb]; cval[pc] = SUB ? flip_sign(bval[pb]) : bval[pb]; }
 }
 
 template <typename T>

@@ -177,4 +177,13 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *__restrict__
 
 struct NoPayload {};
 
+// Rust's unary minus on floats is a sign-bit flip for every input, NaN included (the GPU's FNEG
+// path may canonicalise NaN), so negate on the integer view.
+__device__ __forceinline__ float flip_sign(float v) {
+    return __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
+}
+__device__ __forceinline__ double flip_sign(double v) {
+    return __longlong_as_double(__double_as_longlong(v) ^ (long long)0x8000000000000000ull);
+}
+
 }  // namespace spl

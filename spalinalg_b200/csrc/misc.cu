@@ -11,7 +11,7 @@ template <typename T>
 __global__ void negate_kernel(const T *__restrict__ in, T *__restrict__ out, uint32_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x)
-        out[i] = -in[i];   // sign-bit flip: 0.0 -> -0.0, NaN payload kept
+        out[i] = flip_sign(in[i]);   // 0.0 -> -0.0, NaN payload kept
 }
 
 // assertion 7: ptr non-decreasing (src/csr.rs:150)
