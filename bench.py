@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of spalinalg on B200, BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one SpMV y = A x over the workload.  N = 1: config 2 of BASELINE.json (27-point stencil
+128^3, f64, 2.1 M rows, 55.7 M nnz; footprint 702 MB > L2, so no flush is needed).  N > 1: config
+5 (banded 9, n = 1e8, f64), row-sharded over the ranks, x exchanged over NCCL each step (halo
+slices when the column footprint allows, full all-gather otherwise) — fixed total work, strong
+scaling.  `value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V) of the whole job
+per second of the slowest rank, device-timed.  `e2e` = the same metric through the C ABI with
+host buffers: upload of A in the reference layout (usize indices) and x, SpMV, download of y.
+The line also carries the secondary metrics of the path (COO->CSR assembly on config 1,
+CSR->CSC on config 2), `roofline`, `cpu_baseline` (oracle port of the reference's only SpMV
+route, `&A * &X` with X n x 1, on a bounded sample) and `clocks`.
+
+--impl reference times that CPU route alone (the reference is Rust; no rustc here, so the
+oracle's line-by-line port stands in: cpu_baseline.kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+I_BYTES = 4   # device index width used for the algorithmic byte count
+
+
+def spmv_bytes(nnz, nrows, ncols, v):
+    return nnz * (I_BYTES + v) + (ncols + nrows) * v
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- CPU side
+def cpu_sample(kind="stencil", m=64):
+    """Bounded sample of the bench workload for the CPU legs: the same stencil at m^3."""
+    from spalinalg_b200 import synthetic as syn
+    r, c, v = syn.stencil_27(m)
+    n = m ** 3
+    ptr, ind, val = syn.csr_from_sorted_triplets(n, r, c, v)
+    x = 1.0 / (1.0 + (np.arange(n) % 97))
+    return n, ptr, ind, val, x
+
+
+def cpu_reference_step(n, ptr, ind, val, x):
+    """The reference's only SpMV route: &A * &X with X n x 1 (src/csr/ops/mul.rs:5-60)."""
+    import oracle as orc
+    xs = (np.arange(n + 1, dtype=np.uint64), np.zeros(n, np.uint64), x)
+    t0 = time.perf_counter()
+    orc.csr_mul(n, n, 1, (ptr, ind, val), xs, cap=n)      # n x 1 result: at most n entries
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m = 64
+    n, ptr, ind, val, x = cpu_sample(m=m)
+    nnz = len(val)
+    b = spmv_bytes(nnz, n, n, 8)
+    for _ in range(args.warmup):
+        cpu_reference_step(n, ptr, ind, val, x)
+    t = [cpu_reference_step(n, ptr, ind, val, x) for _ in range(args.steps)]
+    per = sum(t) / len(t)
+    value = b / per / 1e9
+    sample = f"27-point stencil {m}^3 (n={n}, nnz={nnz}), f64, X n x 1"
+    line = {
+        "impl": "reference", "metric": "spmv_algorithmic_bandwidth", "value": value, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.workload != "auto":
+        return args.workload
+    return "stencil27_128_f64" if args.gpus == 1 else "banded9_1e8_f64"
+
+
+# ------------------------------------------------------------------------------- device generators
+def stencil_device(torch, offsets_3d, m, diag, off, dtype):
+    """Row-major CSR of a stencil on an m^3 (or m^2) grid, built on the device."""
+    dev = "cuda"
+    dims = len(offsets_3d[0])
+    n = m ** dims
+    r = torch.arange(n, device=dev, dtype=torch.int64)
+    coords = []
+    rem = r
+    for d in range(dims):
+        coords.append(rem // (m ** (dims - 1 - d)))
+        rem = rem % (m ** (dims - 1 - d))
+    offs = sorted(offsets_3d, key=lambda o: sum(o[d] * m ** (dims - 1 - d) for d in range(dims)))
+    cols, masks, vals = [], [], []
+    for o in offs:
+        ok = torch.ones(n, device=dev, dtype=torch.bool)
+        lin = torch.zeros(n, device=dev, dtype=torch.int64)
+        for d in range(dims):
+            cd = coords[d] + o[d]
+            ok &= (cd >= 0) & (cd < m)
+            lin += cd * (m ** (dims - 1 - d))
+        cols.append(lin)
+        masks.append(ok)
+        vals.append(torch.full((n,), diag if all(x == 0 for x in o) else off, device=dev, dtype=dtype))
+    mask = torch.stack(masks, 1)
+    colind = torch.stack(cols, 1)[mask].to(torch.int32)
+    values = torch.stack(vals, 1)[mask]
+    rowptr = torch.zeros(n + 1, device=dev, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(mask.sum(1), 0)
+    return n, rowptr.to(torch.int32), colind, values
+
+
+def banded_device(torch, n, r0, r1, offsets, dtype, chunk=1 << 24):
+    """Rows [r0, r1) of the banded matrix of config 5, global column indices, on the device."""
+    dev = "cuda"
+    offs = sorted(offsets)
+    ptr_parts, col_parts, val_parts = [], [], []
+    base = 0
+    for s in range(r0, r1, chunk):
+        e = min(r1, s + chunk)
+        i = torch.arange(s, e, device=dev, dtype=torch.int64)
+        cols = torch.stack([i + d for d in offs], 1)
+        mask = (cols >= 0) & (cols < n)
+        vals = torch.stack([1.0 / (1 + abs(d)) + (i % 7).to(dtype) * 1e-3 for d in offs], 1)
+        cnt = torch.cumsum(mask.sum(1), 0)
+        ptr_parts.append(cnt + base)
+        base = int(ptr_parts[-1][-1].item())
+        col_parts.append(cols[mask].to(torch.int32))
+        val_parts.append(vals[mask].to(dtype))
+        del cols, mask, vals, i
+    rowptr = torch.cat([torch.zeros(1, device=dev, dtype=torch.int64)] + ptr_parts).to(torch.int32)
+    return rowptr, torch.cat(col_parts), torch.cat(val_parts)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "50", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for k, nme in enumerate(names):
+                    if r[4 + k].strip().lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        # "under load": drop samples taken while the GPU was idling (power well below the peak seen)
+        if power:
+            thr = 0.6 * max(power)
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+        else:
+            load = sm
+        return {"sm_mhz": statistics.median(load) if load else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "samples_under_load": len(load),
+                "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto",
+                    choices=["auto", "stencil27_128_f64", "laplace2d_1024_f64", "banded9_1e8_f64", "banded9_1e7_f64"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "allgather"])
+    ap.add_argument("--kernel", default="auto")       # auto | vectorN | merge
+    ap.add_argument("--no-extras", action="store_true", help="skip secondary metrics / cpu baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import spalinalg_b200 as sp
+    from spalinalg_b200 import _capi as capi, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    ngpu = world
+
+    stream = torch.cuda.current_stream()
+    ctx = sp.Context(local, stream.cuda_stream)
+    sp.set_default_context(ctx)
+    lib = ctx._lib
+    wl = workload_name(args)
+    f64 = torch.float64
+    V = 8
+
+    # ---- build the workload on the device -------------------------------------------------
+    halo = 0
+    if wl.startswith("stencil27"):
+        offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+        n, rowptr, colind, values = stencil_device(torch, offs, 128, 26.0, -1.0, f64)
+        r0, r1 = 0, n
+    elif wl.startswith("laplace2d"):
+        offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
+        n, rowptr, colind, values = stencil_device(torch, offs, 1024, 4.0, -1.0, f64)
+        r0, r1 = 0, n
+    else:
+        n = 10 ** 8 if "1e8" in wl else 10 ** 7
+        r0, r1 = sharding.row_partition(n, ngpu, rank)
+        rowptr, colind, values = banded_device(torch, n, r0, r1, range(-4, 5), f64)
+        halo = 4
+    nloc = r1 - r0
+    nnz_loc = int(colind.numel())
+    A = sp.CsrMatrix.from_device_arrays(nloc, n, nnz_loc, rowptr.data_ptr(), colind.data_ptr(),
+                                        values.data_ptr(), np.float64, validate=True, ctx=ctx)
+    nnz_t = torch.tensor([nnz_loc], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz_total = int(nnz_t.item())
+    bytes_total = spmv_bytes(nnz_total, n, n, V)
+    bytes_local = spmv_bytes(nnz_loc, nloc, n if ngpu == 1 else nloc + 2 * halo, V)
+
+    # x: global-length buffer on every rank (global column indices); each rank owns [r0, r1)
+    idx = torch.arange(n, device="cuda", dtype=torch.int64)
+    x_full = (1.0 / (1.0 + (idx % 97))).to(f64) if not wl.startswith("banded") else torch.sin(idx.to(f64) * 1e-3)
+    del idx
+    y = torch.zeros(nloc, device="cuda", dtype=f64)
+    exchange = "none"
+    if world > 1:
+        exchange = args.exchange if args.exchange != "auto" else ("halo" if halo else "allgather")
+
+    kern, lanes = capi.SPL_SPMV_AUTO, 0
+    if args.kernel.startswith("vector"):
+        kern, lanes = capi.SPL_SPMV_VECTOR, int(args.kernel[6:] or 0)
+    elif args.kernel == "merge":
+        kern = capi.SPL_SPMV_MERGE
+
+    def exchange_x():
+        if exchange == "allgather":
+            sharding.exchange_allgather(dist, x_full, r0, r1, world, n % world == 0)
+        elif exchange == "halo":
+            sharding.exchange_halo(dist, x_full, r0, r1, halo, rank, world)
+
+    def step():
+        if world > 1:
+            exchange_x()
+        A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness spot check before timing (not the oracle: analytic row sums) ------------
+    step()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    # ---- device-timed steps ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = bytes_total / (ms_step * 1e-3) / 1e9
+
+    # SpMV-kernel-only time on this rank (roofline of the dominant kernel)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+    peak, peak_src = peaks()
+    achieved = bytes_local / (kern_ms * 1e-3) / 1e9
+    choice = A.spmv_choice()
+
+    # ---- e2e through the C ABI with host buffers (rank-local share) ---------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    h_ptr = rowptr.to(torch.int64).cpu().pin_memory()
+    h_ind = colind.to(torch.int64).cpu().pin_memory()
+    h_val = values.cpu().pin_memory()
+    h_x = x_full.cpu().pin_memory()
+    h_y = torch.empty(nloc, dtype=f64).pin_memory()
+    h2d = (h_ptr.numel() + h_ind.numel()) * 8 + h_val.numel() * 8 + h_x.numel() * 8
+    d2h = h_y.numel() * 8
+
+    def e2e_step():
+        h = C.c_void_p()
+        ctx.check(lib.spl_mat_from_compressed(ctx._h, capi.SPL_CSR, capi.SPL_F64, nloc, n,
+                                              h_ptr.numel(), C.c_void_p(h_ptr.data_ptr()),
+                                              h_ind.numel(), C.c_void_p(h_ind.data_ptr()),
+                                              h_val.numel(), C.c_void_p(h_val.data_ptr()), C.byref(h)))
+        ctx.check(lib.spl_spmv_host(ctx._h, h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
+        ctx.check(lib.spl_mat_free(ctx._h, h))
+
+    e2e_step()
+    y_dev_host = y.cpu()
+    assert torch.equal(h_y, y_dev_host), "e2e result differs from the device-resident result"
+    barrier()
+    e2e_l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_launches = (ctx.launch_count() - e2e_l0) // e2e_steps
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = bytes_total / float(t.item()) / 1e9
+
+    # keep the device busy long enough for a few clock samples if the timed region was short
+    if rank == 0:
+        t_end = time.perf_counter() + max(0.0, 0.6 - ms_total * 2e-3)
+        while time.perf_counter() < t_end:
+            for _ in range(50):
+                A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+            torch.cuda.synchronize()
+        clk = clocks.stop()
+
+    # ---- secondary metrics of the path (rank 0, N = 1 only) ----------------------------------
+    extras = {}
+    cpu = None
+    if rank == 0 and ngpu == 1 and not args.no_extras:
+        extras = secondary_metrics(torch, sp, ctx, A, wl)
+        m = 64
+        sn, sptr, sind, sval, sx = cpu_sample(m=m)
+        sb = spmv_bytes(len(sval), sn, sn, 8)
+        cpu_reference_step(sn, sptr, sind, sval, sx)
+        ts = [cpu_reference_step(sn, sptr, sind, sval, sx) for _ in range(3)]
+        import oracle as orc
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orc.csr_spmv(sn, sptr, sind, sval, sx)
+        rowdot = (time.perf_counter() - t0) / 5
+        cpu = {"value": sb / statistics.median(ts) / 1e9, "unit": "GB/s", "cores": 1,
+               "kind": "port", "host_cores": os.cpu_count(),
+               "sample": f"27-point stencil {m}^3 (n={sn}, nnz={len(sval)}), f64; reference route "
+                         f"&A * &X (3 transposes + Gustavson), 3 reps median",
+               "rowdot_value": sb / rowdot / 1e9}
+
+    if rank == 0:
+        line = {
+            "metric": "spmv_algorithmic_bandwidth", "value": value, "unit": "GB/s", "n_gpus": ngpu,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if ngpu > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "nrows": n, "nnz": nnz_total, "algorithmic_bytes": bytes_total,
+                       "l2": "inputs larger than L2 (no flush)" if bytes_local > 2 * 126e6 else
+                             "footprint below 2x L2: L2-resident number",
+                       "exchange": exchange, "spmv_kernel": {1: "vector", 2: "merge"}.get(choice[0], "?"),
+                       "lanes_per_row": choice[1] if lanes == 0 else lanes,
+                       "pct_of_8TBps_nominal": 100.0 * achieved / 8000.0},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "launches_per_step": e2e_launches,
+                    "what": "spl_mat_from_compressed(host usize arrays, validating) + spl_spmv_host"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "spmv", "kernel_ms": kern_ms, "bytes_per_launch": bytes_local},
+            "clocks": clk,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary_metrics(torch, sp, ctx, A, wl):
+    """COO->CSR assembly on config 1 (shuffled and row-ordered) and CSR->CSC on the bench matrix."""
+    out = {}
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    # CSR -> CSC / transpose of the bench matrix
+    nnz = A.nnz()
+    ms = timed(lambda: A.to_csc())
+    b_tr = 2 * nnz * (4 + 8) + (A.nrows() + 1) * 4 + (A.ncols() + 1) * 4
+    out["csr_to_csc"] = {"workload": wl, "ms": ms, "mnnz_per_s": nnz / ms / 1e3, "gbps_algorithmic": b_tr / ms / 1e6}
+
+    # assembly: config 1, shuffled COO, device-resident SoA in -> device CSR out
+    offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
+    n, rowptr, colind, values = stencil_device(torch, offs, 1024, 4.0, -1.0, torch.float64)
+    rows = torch.repeat_interleave(torch.arange(n, device="cuda", dtype=torch.int32),
+                                   (rowptr[1:] - rowptr[:-1]).to(torch.int64))
+    g = torch.Generator(device="cuda"); g.manual_seed(42)
+    perm = torch.randperm(rows.numel(), device="cuda", generator=g)
+    for name, (r_, c_, v_) in {"shuffled": (rows[perm].contiguous(), colind[perm].contiguous(), values[perm].contiguous()),
+                               "row_ordered": (rows, colind, values)}.items():
+        ln = r_.numel()
+        ms = timed(lambda: sp.CsrMatrix.from_device_triplets(n, n, ln, r_.data_ptr(), c_.data_ptr(),
+                                                             v_.data_ptr(), np.float64, ctx=ctx))
+        b_asm = ln * (8 + 8) + ln * (4 + 8) + (n + 1) * 4
+        out[f"assembly_{name}"] = {"workload": "laplace2d_1024_f64 COO->CSR", "len": ln, "ms": ms,
+                                   "mnnz_per_s": ln / ms / 1e3, "gbps_algorithmic": b_asm / ms / 1e6}
+    return out
+
+
+if __name__ == "__main__":
+    main()

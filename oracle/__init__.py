@@ -123,18 +123,19 @@ def addsub(subtract, nmajor, nminor, a, b):
     return optr, oind[:nnz].copy(), oval[:nnz].copy()
 
 
-def csr_mul(an, ak, bn, a, b):
-    """CSR(A*B); for CSC operands call csr_mul(bn, ak, an, b, a) (see orc_impl.inc)."""
+def csr_mul(an, ak, bn, a, b, cap=None):
+    """CSR(A*B); for CSC operands call csr_mul(bn, ak, an, b, a) (see orc_impl.inc).
+    cap: known upper bound of nnz(C) -> one pass instead of size query + fill."""
     aptr, aind, aval = _u64(a[0]), _u64(a[1]), np.ascontiguousarray(a[2])
     bptr, bind, bval = _u64(b[0]), _u64(b[1]), np.ascontiguousarray(b[2], dtype=aval.dtype)
     suf = _suf(aval.dtype)
     fn = getattr(lib(), f"orc_csr_mul_{suf}")
     args = (_sz(an), _sz(ak), _sz(bn), _p(aptr), _p(aind), _p(aval), _p(bptr), _p(bind), _p(bval))
-    nnz = fn(*args, None, None, None)
+    nnz = cap if cap is not None else fn(*args, None, None, None)
     optr = np.zeros(an + 1, dtype=np.uint64)
     oind = np.zeros(max(nnz, 1), dtype=np.uint64)
     oval = np.zeros(max(nnz, 1), dtype=aval.dtype)
-    fn(*args, _p(optr), _p(oind), _p(oval))
+    nnz = fn(*args, _p(optr), _p(oind), _p(oval))
     return optr, oind[:nnz].copy(), oval[:nnz].copy()
 
 

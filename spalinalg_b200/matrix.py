@@ -428,6 +428,17 @@ class _Compressed:
                                                 C.byref(h)))
         return cls._wrap(ctx, h)
 
+    @classmethod
+    def from_device_arrays(cls, nrows, ncols, nnz, ptr_dev: int, ind_dev: int, val_dev: int, dtype,
+                           validate=True, ctx=None):
+        """CsrMatrix::new on device-resident uint32 ptr/ind and T values (copied)."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        ctx.check(ctx._lib.spl_mat_from_compressed_dev(
+            ctx._h, cls._FORMAT, _dtype_code(dtype), nrows, ncols, nnz, C.c_void_p(ptr_dev),
+            C.c_void_p(ind_dev), C.c_void_p(val_dev), int(validate), C.byref(h)))
+        return cls._wrap(ctx, h)
+
     def _convert(self, target_cls):
         h = C.c_void_p()
         self._ctx.check(self._ctx._lib.spl_mat_convert(self._ctx._h, self._h, target_cls._FORMAT,

@@ -1,0 +1,76 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the row partition and the x exchange
+(halo and all-gather), with the per-shard SpMV done by the oracle (checker only)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from spalinalg_b200 import sharding, synthetic as syn
+
+
+def test_row_partition_covers_rows():
+    for n, w in ((10, 3), (100000000, 8), (7, 8), (16, 2)):
+        parts = [sharding.row_partition(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+    assert sharding.column_halo(6, 23, 10, 20) == 4
+    assert sharding.column_halo(12, 18, 10, 20) == 0
+
+
+def _worker(rank, world, port, n, mode, out):
+    import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r, c, v = syn.banded(n, range(-4, 5))
+        ptr, ind, val = syn.csr_from_sorted_triplets(n, r, c, v)
+        x = np.sin(np.arange(n) * 1e-3)
+        r0, r1 = sharding.row_partition(n, world, rank)
+        lo, hi = int(ptr[r0]), int(ptr[r1])
+        lptr = (ptr[r0:r1 + 1] - ptr[r0]).astype(np.uint64)
+        lind, lval = ind[lo:hi], val[lo:hi]
+        halo = sharding.column_halo(int(lind.min()), int(lind.max()), r0, r1)
+        assert halo <= 4
+        x_full = torch.full((n,), float("nan"), dtype=torch.float64)
+        x_full[r0:r1] = torch.from_numpy(x[r0:r1])            # each rank only knows its own slice
+        if mode == "halo":
+            sharding.exchange_halo(dist, x_full, r0, r1, 4, rank, world)
+        else:
+            sharding.exchange_allgather(dist, x_full, r0, r1, world, n % world == 0)
+        y_loc = orc.csr_spmv(r1 - r0, lptr, lind, lval, x_full.numpy())
+        y_ref = orc.csr_spmv(n, ptr, ind, val, x)[r0:r1]
+        ok = bool(np.array_equal(y_loc, y_ref)) and not np.isnan(y_loc).any()
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put(int(flag.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("mode,n", [("halo", 1000), ("allgather", 1000), ("allgather", 1001)])
+def test_sharded_spmv_world2_gloo(mode, n):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, mode, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 1
