@@ -242,7 +242,10 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
     ngpu = world
 
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: our kernels, torch's generators, NCCL and the timing
+    # events (torch's default stream has handle 0, which the C ABI reads as "create your own")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = sp.Context(local, stream.cuda_stream)
     sp.set_default_context(ctx)
     lib = ctx._lib
