@@ -425,7 +425,7 @@ def main():
             "config": {"workload": wl, "nrows": n, "nnz": nnz_total, "algorithmic_bytes": bytes_total,
                        "l2": "inputs larger than L2 (no flush)" if bytes_local > 2 * 126e6 else
                              "footprint below 2x L2: L2-resident number",
-                       "exchange": exchange, "spmv_kernel": {1: "vector", 2: "merge"}.get(choice[0], "?"),
+                       "exchange": exchange, "spmv_kernel": {1: "vector", 2: "merge"}.get(kern or choice[0], "?"),
                        "lanes_per_row": choice[1] if lanes == 0 else lanes,
                        "pct_of_8TBps_nominal": 100.0 * achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

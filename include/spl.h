@@ -126,6 +126,8 @@ int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out);
  * 1e-12 (f64) / 1e-5 (f32) relative; rows without entries give 0).  A must be
  * CSR.  x has ncols elements, y nrows. */
 int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev);
+/* kernel: spl_spmv_kernel in bits 0-7; bits 8-15 optionally force the vector kernel's lanes per
+ * row (1, 2, 4, 8, 16 or 32; 0 = planned value). */
 int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel);
 /* Host-buffer form: uploads x, runs spl_spmv, downloads y, synchronises. */
 int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host);

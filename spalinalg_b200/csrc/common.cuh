@@ -61,6 +61,8 @@ struct spl_mat {
     int plan_kernel = 0;       // SPL_SPMV_VECTOR / SPL_SPMV_MERGE
     int plan_lanes = 0;        // lanes per row of the vector kernel
     uint32_t max_row_len = 0;
+    uint32_t *merge_rows = nullptr;   // merge-path tile start rows (merge_tiles + 1)
+    uint32_t merge_tiles = 0;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

@@ -22,18 +22,35 @@ __global__ void validate_ptr_kernel(const uint32_t *__restrict__ ptr, uint32_t n
 }
 
 // assertion 8: index in range (:151); assertion 9: strictly increasing in a segment (:152-156).
-// One thread per stored entry; the segment boundary test uses the entry's own segment end.
+// Streaming formulation without any search: count the descents ind[p] >= ind[p+1] over all
+// neighbouring entries (D) and the descents that sit exactly on the start of a non-empty
+// segment (R); every R is also a D, so the segments are strictly increasing iff D == R.
 __global__ void validate_ind_kernel(const uint32_t *__restrict__ ptr,
                                     const uint32_t *__restrict__ ind, uint32_t nmajor,
-                                    uint32_t nminor, uint32_t nnz, uint32_t *fail) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nnz) return;
-    const uint32_t c = ind[p];
-    if (c >= nminor) atomicMin(fail, 8u);
-    if (p + 1 < nnz && ind[p + 1] <= c) {
-        // only a violation if p and p+1 lie in the same segment
-        const uint32_t seg = upper_bound_u32(ptr, 0u, nmajor + 1u, (uint32_t)p) - 1u;
-        if (p + 1 < ptr[seg + 1]) atomicMin(fail, 9u);
+                                    uint32_t nminor, uint32_t nnz, uint32_t *fail,
+                                    unsigned long long *counters) {
+    unsigned long long d = 0, r = 0;
+    bool oob = false;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t p = tid; p < nnz; p += stride) {
+        const uint32_t c = ind[p];
+        oob |= c >= nminor;
+        if (p + 1 < nnz && ind[p + 1] <= c) ++d;
+    }
+    for (uint64_t m = tid; m < nmajor; m += stride) {
+        const uint32_t q = ptr[m];
+        if (q > 0 && q < nnz && ptr[m + 1] > q && ind[q] <= ind[q - 1]) ++r;
+    }
+    if (__any_sync(0xffffffffu, oob) && lane_id() == 0) atomicMin(fail, 8u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if (lane_id() == 0) {
+        if (d) atomicAdd(counters, d);
+        if (r) atomicAdd(counters + 1, r);
     }
 }
 
@@ -100,11 +117,16 @@ int validate_compressed(spl_ctx *ctx, uint32_t nmajor, uint32_t nminor, uint32_t
     if (fail != 0xffffffffu) return (int)fail;
     if (nnz == 0) return 0;
     // ptr is monotone with ptr[0]==0, ptr[n]==nnz (checked by the caller): every segment is inside ind
-    validate_ind_kernel<<<div_up(nnz, 256), 256, 0, ctx->stream>>>(ptr, ind, nmajor, nminor, nnz,
-                                                                  ctx->d_scratch);
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(ctx->d_scratch + 2);
+    SPL_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    validate_ind_kernel<<<stream_grid(ctx, nnz), 256, 0, ctx->stream>>>(ptr, ind, nmajor, nminor, nnz,
+                                                                       ctx->d_scratch, counters);
     check_launch(ctx, "validate_ind");
-    read_back(ctx, ctx->d_scratch, &fail, 1);
-    return fail == 0xffffffffu ? 0 : (int)fail;
+    uint32_t w[6];
+    read_back(ctx, ctx->d_scratch, w, 6);
+    if (w[0] != 0xffffffffu) return (int)w[0];
+    const bool increasing = w[2] == w[4] && w[3] == w[5];   // D == R
+    return increasing ? 0 : 9;
 }
 
 void narrow_u64(spl_ctx *ctx, const uint64_t *src, uint32_t *dst, size_t n, uint64_t limit,
@@ -142,8 +164,9 @@ spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
     m->nnz = nnz;
     try {
         m->ptr = dalloc<uint32_t>(ctx, (size_t)m->nmajor() + 1);
-        m->ind = dalloc<uint32_t>(ctx, nnz);
-        m->val = dalloc_bytes(ctx, (size_t)nnz * m->vsize());
+        // +16 entries of slack: the SpMV kernels read aligned groups of four entries
+        m->ind = dalloc<uint32_t>(ctx, (size_t)nnz + 16);
+        m->val = dalloc_bytes(ctx, ((size_t)nnz + 16) * m->vsize());
     } catch (...) {
         free_mat(ctx, m);
         throw;
@@ -156,6 +179,7 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->ptr);
     dfree(ctx, m->ind);
     dfree(ctx, m->val);
+    dfree(ctx, m->merge_rows);
     delete m;
 }
 

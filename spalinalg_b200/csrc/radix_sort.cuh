@@ -4,7 +4,7 @@
 // order, src/csr/conv/coo.rs:36-57) and what makes the CSR<->CSC scatter deterministic
 // (inner indices ascending, src/csr.rs:385-396).  Per digit pass:
 //   rs_hist     each block histograms its contiguous chunk of tiles        (reads keys)
-//   rs_scan     one block turns counts[digit][block] into global offsets   (tiny)
+//   rs_scan     one block per digit: exclusive prefix over the blocks + digit totals   (tiny)
 //   rs_scatter  each block re-walks its chunk tile by tile: warp-striped coalesced loads,
 //               match.any ranking per warp, digit scan in shared memory, exchange through
 //               shared memory so runs of equal digits leave as contiguous coalesced stores.
@@ -23,10 +23,11 @@ constexpr int RS_IPT = 12;                       // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 3072 items per tile
 
 // ---- loaders: what pass 0 reads (later passes read the ping-pong buffers) ------------------
+// Every loader takes a per-thread `state` word (0 at kernel start) it may use as a cursor.
 template <typename V>
 struct LoadPlain {
     const V *p;
-    __device__ __forceinline__ V operator()(uint32_t i) const { return p[i]; }
+    __device__ __forceinline__ V operator()(uint32_t i, uint32_t &) const { return p[i]; }
 };
 // key = hi[i] << lobits | lo[i]   ((row, col) for CSR assembly, (col, row) for CSC)
 template <typename K>
@@ -34,43 +35,63 @@ struct LoadPack {
     const uint32_t *hi;
     const uint32_t *lo;
     int lobits;
-    __device__ __forceinline__ K operator()(uint32_t i) const {
+    __device__ __forceinline__ K operator()(uint32_t i, uint32_t &) const {
         return (K)(((uint64_t)hi[i] << lobits) | (uint64_t)lo[i]);
     }
 };
-// major index of compressed entry i: the segment of ptr[] that contains i
+// major index of compressed entry i: the segment of ptr[] that contains i.  A thread asks for
+// ascending i, so the search gallops forward from the previous answer (state) instead of
+// bisecting the whole pointer array: 1-3 probes for neighbouring rows instead of log2(nmajor).
 struct LoadMajor {
     const uint32_t *ptr;
     uint32_t nmajor;
-    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-        return upper_bound_u32(ptr, 0u, nmajor + 1u, i) - 1u;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i, uint32_t &state) const {
+        uint32_t lo = state;                       // ptr[lo] <= i holds (ptr[0] == 0)
+        if (__ldg(ptr + lo) > i) lo = 0;           // not ascending after all: restart
+        uint32_t step = 1, hi = lo + 1;
+        while (hi <= nmajor && __ldg(ptr + hi) <= i) {   // gallop: ptr[hi] <= i
+            lo = hi;
+            step <<= 1;
+            hi = lo + step;
+        }
+        if (hi > nmajor + 1u) hi = nmajor + 1u;
+        // answer is the last index in [lo, hi) with ptr[idx] <= i
+        const uint32_t r = upper_bound_u32(ptr, lo + 1u, hi, i) - 1u;
+        state = r;
+        return r;
     }
 };
 struct LoadNone {
-    __device__ __forceinline__ NoPayload operator()(uint32_t) const { return NoPayload{}; }
+    __device__ __forceinline__ NoPayload operator()(uint32_t, uint32_t &) const { return NoPayload{}; }
 };
 
 inline int rs_num_passes(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
 
 // ---- upsweep ---------------------------------------------------------------------------------
+// Same block <-> chunk mapping as the downsweep, but 1024 threads and 8 keys in flight per thread:
+// the pass only reads keys, so it wants bytes in flight, not registers.
+constexpr int RH_THREADS = 1024;
+constexpr int RH_WARPS = RH_THREADS / 32;
+
 template <typename K, typename LoadK>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RH_THREADS)
 rs_hist_kernel(LoadK lk, uint32_t n, uint32_t tiles_per_block, int shift, uint32_t mask,
                uint32_t *__restrict__ counts) {
-    __shared__ uint32_t hist[RS_WARPS][RS_BINS];
-    for (int j = threadIdx.x; j < RS_WARPS * RS_BINS; j += RS_THREADS) (&hist[0][0])[j] = 0;
+    __shared__ uint32_t hist[RH_WARPS][RS_BINS];
+    for (int j = threadIdx.x; j < RH_WARPS * RS_BINS; j += RH_THREADS) (&hist[0][0])[j] = 0;
     __syncthreads();
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_block * RS_TILE;
     uint64_t end = begin + (uint64_t)tiles_per_block * RS_TILE;
     if (end > n) end = n;
-    constexpr int U = 4;
-    for (uint64_t blk = begin; blk < end; blk += (uint64_t)RS_THREADS * U) {
+    constexpr int U = 8;
+    uint32_t state = 0;
+    for (uint64_t blk = begin; blk < end; blk += (uint64_t)RH_THREADS * U) {
         uint32_t d[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            uint64_t i = blk + (uint64_t)u * RS_THREADS + threadIdx.x;
-            d[u] = i < end ? ((uint32_t)(lk((uint32_t)i) >> shift) & mask) : 0xffffffffu;
+            uint64_t i = blk + (uint64_t)u * RH_THREADS + threadIdx.x;
+            d[u] = i < end ? ((uint32_t)(lk((uint32_t)i, state) >> shift) & mask) : 0xffffffffu;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -84,32 +105,38 @@ rs_hist_kernel(LoadK lk, uint32_t n, uint32_t tiles_per_block, int shift, uint32
     if (threadIdx.x < RS_BINS) {
         uint32_t c = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) c += hist[w][threadIdx.x];
+        for (int w = 0; w < RH_WARPS; ++w) c += hist[w][threadIdx.x];
         counts[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = c;
     }
 }
 
-// ---- spine: in-place exclusive scan over counts[digit][block], digit-major ----------------
-static __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *data, uint32_t m) {
-    __shared__ uint32_t ws[33];
-    const uint32_t per = (m + blockDim.x - 1) / blockDim.x;
-    const uint32_t lo = min(threadIdx.x * per, m), hi = min(lo + per, m);
+// ---- spine: one block per digit turns counts[digit][0..grid) into exclusive prefixes over the
+// blocks and records the digit total; the downsweep scans the 256 totals itself ------------------
+static __global__ void __launch_bounds__(512) rs_scan_kernel(uint32_t *counts, uint32_t grid,
+                                                             uint32_t *__restrict__ totals) {
+    __shared__ uint32_t ws[17];
+    uint32_t *row = counts + (size_t)blockIdx.x * grid;
+    const uint32_t per = (grid + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, grid), hi = min(lo + per, grid);
     uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; ++i) s += data[i];
-    uint32_t run = block_exclusive_scan(s, ws, nullptr);
+    for (uint32_t i = lo; i < hi; ++i) s += row[i];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, ws, &total);
     for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t v = data[i];
-        data[i] = run;
+        uint32_t v = row[i];
+        row[i] = run;
         run += v;
     }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
 }
 
 // ---- downsweep -------------------------------------------------------------------------------
 template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_block, int shift,
-                  uint32_t mask, const uint32_t *__restrict__ offsets, K *__restrict__ out_k,
-                  A *__restrict__ out_a, B *__restrict__ out_b) {
+                  uint32_t mask, const uint32_t *__restrict__ offsets,
+                  const uint32_t *__restrict__ totals, K *__restrict__ out_k, A *__restrict__ out_a,
+                  B *__restrict__ out_b) {
     constexpr bool kHasA = !std::is_same<A, NoPayload>::value;
     constexpr bool kHasB = !std::is_same<B, NoPayload>::value;
     __shared__ __align__(16) unsigned char exch_raw[RS_TILE * 8];
@@ -119,8 +146,13 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
     __shared__ uint32_t ws[RS_WARPS + 1];
 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    if (threadIdx.x < RS_BINS)
-        running[threadIdx.x] = offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    {   // global start of this block's share of each digit = digits below + earlier blocks
+        const uint32_t tot = threadIdx.x < RS_BINS ? totals[threadIdx.x] : 0u;
+        const uint32_t below = block_exclusive_scan(tot, ws, nullptr);
+        if (threadIdx.x < RS_BINS)
+            running[threadIdx.x] = below + offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    }
+    uint32_t st_k = 0, st_a = 0, st_b = 0;
 
     const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_block * RS_TILE;
     for (uint32_t t = 0; t < tiles_per_block; ++t) {
@@ -136,7 +168,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
         for (int i = 0; i < RS_IPT; ++i) {
             uint32_t loc = my_base + i * 32;
-            keys[i] = loc < tile_count ? lk((uint32_t)(tile_base + loc)) : (K)0;
+            keys[i] = loc < tile_count ? lk((uint32_t)(tile_base + loc), st_k) : (K)0;
         }
         __syncthreads();
 
@@ -205,7 +237,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int i = 0; i < RS_IPT; ++i) {
                 const uint32_t loc = my_base + i * 32;
-                if (loc < tile_count) exa[rank[i]] = la((uint32_t)(tile_base + loc));
+                if (loc < tile_count) exa[rank[i]] = la((uint32_t)(tile_base + loc), st_a);
             }
             __syncthreads();
 #pragma unroll
@@ -220,7 +252,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int i = 0; i < RS_IPT; ++i) {
                 const uint32_t loc = my_base + i * 32;
-                if (loc < tile_count) exb[rank[i]] = lb((uint32_t)(tile_base + loc));
+                if (loc < tile_count) exb[rank[i]] = lb((uint32_t)(tile_base + loc), st_b);
             }
             __syncthreads();
 #pragma unroll
@@ -250,23 +282,23 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
     const uint32_t tiles_per_block = div_up(tiles, grid);
     grid = div_up(tiles, tiles_per_block);
     Tmp<uint32_t> counts(ctx, (size_t)RS_BINS * grid);
+    Tmp<uint32_t> totals(ctx, RS_BINS);
 
     int shift = 0;
     for (int p = 0; p < passes; ++p) {
         const int nb = (bits - shift + (passes - p) - 1) / (passes - p);   // even split
         const uint32_t mask = (1u << nb) - 1u;
-        const uint32_t nbins = 1u << nb;
         K *ok = k_buf[p & 1];
         A *oa = a_buf[p & 1];
         B *ob = b_buf[p & 1];
         if (p == 0) {
-            rs_hist_kernel<K, LoadK><<<grid, RS_THREADS, 0, ctx->stream>>>(
+            rs_hist_kernel<K, LoadK><<<grid, RH_THREADS, 0, ctx->stream>>>(
                 lk0, n, tiles_per_block, shift, mask, counts);
             check_launch(ctx, "rs_hist");
-            rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, nbins * grid);
+            rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
             check_launch(ctx, "rs_scan");
             rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB><<<grid, RS_THREADS, 0, ctx->stream>>>(
-                lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, ok, oa, ob);
+                lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
             check_launch(ctx, "rs_scatter");
         } else {
             using PA = typename std::conditional<std::is_same<A, NoPayload>::value, LoadNone,
@@ -278,13 +310,13 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
             PB lb;
             if constexpr (!std::is_same<A, NoPayload>::value) la.p = a_buf[(p - 1) & 1];
             if constexpr (!std::is_same<B, NoPayload>::value) lb.p = b_buf[(p - 1) & 1];
-            rs_hist_kernel<K, LoadPlain<K>><<<grid, RS_THREADS, 0, ctx->stream>>>(
+            rs_hist_kernel<K, LoadPlain<K>><<<grid, RH_THREADS, 0, ctx->stream>>>(
                 lk, n, tiles_per_block, shift, mask, counts);
             check_launch(ctx, "rs_hist");
-            rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>(counts, nbins * grid);
+            rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
             check_launch(ctx, "rs_scan");
             rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB><<<grid, RS_THREADS, 0, ctx->stream>>>(
-                lk, la, lb, n, tiles_per_block, shift, mask, counts, ok, oa, ob);
+                lk, la, lb, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
             check_launch(ctx, "rs_scatter");
         }
         shift += nb;

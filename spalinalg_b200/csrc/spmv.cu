@@ -4,12 +4,17 @@
 // (src/csr/ops/mul.rs:5-60): per row the column-ascending sum of round(a*x).  Parity bar
 // (BASELINE.json north_star): 1e-12 (f64) / 1e-5 (f32) relative, so the in-row reduction
 // order is free.  Two hand-written kernels:
-//   vector  LPR lanes per row (2..32), coalesced col/val loads inside the sub-warp, shuffle
-//           reduction; best when rows are long and regular.
+//   vector  LPR lanes per row (1..32) with 4 entries in flight per lane: consecutive lanes read
+//           consecutive entries (col/val loads coalesce, neighbouring columns share x-gather
+//           sectors), shuffle reduction.  Regular rows (stencils, bands, uniform random).
 //   merge   merge-path tiles over (row ends, nnz): every CTA takes the same number of
-//           (row + nnz) items, streams its nnz with coalesced 128-bit loads into shared memory
-//           as products, reduces rows from shared memory and hands partial rows to a fix-up.
-//           Balanced for skewed (power-law) rows and bandwidth-efficient for very short rows.
+//           (row + nnz) items; its contiguous col/val slice arrives in shared memory by TMA bulk
+//           copies (cp.async.bulk + mbarrier), products are formed in place, rows are reduced by
+//           a balanced per-thread path walk and a segmented shuffle scan; partial rows go to a
+//           deterministic fix-up.  Skewed (power-law) rows.
+// 128-bit per-lane loads of col/val were measured and rejected for the gather-bound patterns:
+// they put entries 4 apart on neighbouring lanes and triple the L1 wavefronts of the x gathers
+// ("SpMV").
 // Algorithmic bytes per launch: nnz*(4+V) + (ncols+nrows)*V  (SURVEY.md 8d); HBM-bound.
 #include "kernels.cuh"
 
@@ -23,22 +28,32 @@ __global__ void __launch_bounds__(256)
 spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
                    const uint32_t *__restrict__ ind, const T *__restrict__ val,
                    const T *__restrict__ x, T *__restrict__ y) {
+    constexpr int U = 4;   // entries in flight per lane: all col/val loads, then all x gathers
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t row = gtid / LPR;
     const uint32_t sub = (uint32_t)(gtid % LPR);
-    T acc0 = (T)0, acc1 = (T)0;
+    T acc = (T)0;
     if (row < nrows) {
         uint32_t p = __ldg(ptr + row) + sub;
         const uint32_t e = __ldg(ptr + row + 1);
-        for (; p + LPR < e; p += 2 * LPR) {
-            const uint32_t c0 = __ldg(ind + p), c1 = __ldg(ind + p + LPR);
-            const T v0 = __ldg(val + p), v1 = __ldg(val + p + LPR);
-            acc0 += v0 * __ldg(x + c0);
-            acc1 += v1 * __ldg(x + c1);
+        for (; p < e; p += U * LPR) {
+            uint32_t c[U];
+            T v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pu = p + u * LPR;
+                const bool ok = pu < e;
+                const uint32_t idx = ok ? pu : p;        // p itself is in range: safe dummy
+                c[u] = __ldg(ind + idx);
+                v[u] = ok ? __ldg(val + idx) : (T)0;
+            }
+            T xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += v[u] * xv[u];
         }
-        if (p < e) acc0 += __ldg(val + p) * __ldg(x + __ldg(ind + p));
     }
-    T acc = acc0 + acc1;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (sub == 0 && row < nrows) y[row] = acc;
@@ -66,6 +81,217 @@ void spmv_vector(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, int lanes) {
     }
 }
 
+
+// ------------------------------------------------------------------ merge-path kernel
+// Merge path over A = row end offsets ptr[1..nrows] and B = 0..nnz-1 (Merrill & Garland): the
+// path has nrows + nnz items; tile t owns items [t*ITEMS, (t+1)*ITEMS).  The tile start
+// coordinates depend on the matrix only and are cached in the plan (spl_mat::merge_rows).
+// Inside a tile: (1) the tile's nnz are streamed with 128-bit coalesced loads, multiplied by the
+// gathered x and parked in shared memory; (2) every thread walks IPT consecutive path items
+// from shared memory (balanced whatever the row lengths), writes the rows it finishes, and
+// (3) a segmented warp-shuffle scan hands the partial sum of a row that spans threads to the
+// thread that finishes it.  The row still open at the tile end goes to a per-tile carry that
+// spmv_merge_fixup_kernel adds in tile order (deterministic, no atomics).
+constexpr int MG_THREADS = 256;
+
+__global__ void merge_partition_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t nnz,
+                                       uint32_t items, uint32_t ntiles,
+                                       uint32_t *__restrict__ tile_rows) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const uint64_t total = (uint64_t)nrows + nnz;
+    uint64_t d = (uint64_t)t * items;
+    if (d > total) d = total;
+    uint64_t lo = d > nnz ? d - nnz : 0, hi = d < nrows ? d : nrows;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)__ldg(ptr + mid + 1) <= d - mid - 1) lo = mid + 1;
+        else hi = mid;
+    }
+    tile_rows[t] = (uint32_t)lo;
+}
+
+
+// ---- TMA (cp.async.bulk) + mbarrier: the contiguous col/val slice of a tile goes global ->
+// shared memory as two bulk copies issued by one thread; no registers, no per-lane loads.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <typename T, int IPT>
+__global__ void __launch_bounds__(MG_THREADS)
+spmv_merge_kernel(uint32_t nrows, uint32_t nnz, const uint32_t *__restrict__ ptr,
+                  const uint32_t *__restrict__ ind, const T *__restrict__ val,
+                  const T *__restrict__ x, T *__restrict__ y,
+                  const uint32_t *__restrict__ tile_rows, uint32_t *__restrict__ carry_row,
+                  T *__restrict__ carry_val) {
+    constexpr int ITEMS = MG_THREADS * IPT;
+    __shared__ __align__(16) T s_val[ITEMS + 8];           // values, then products, of the tile slice
+    __shared__ __align__(16) uint32_t s_ind[ITEMS + 8];
+    __shared__ uint32_t s_end[ITEMS + 1];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ T s_wval[MG_THREADS / 32];
+    __shared__ int s_wflag[MG_THREADS / 32];
+
+    const uint32_t tile = blockIdx.x;
+    const uint64_t total = (uint64_t)nrows + nnz;
+    const uint64_t d0 = (uint64_t)tile * ITEMS;
+    const uint64_t d1 = d0 + ITEMS < total ? d0 + ITEMS : total;
+    const uint32_t r0 = __ldg(tile_rows + tile), r1 = __ldg(tile_rows + tile + 1);
+    const uint32_t z0 = (uint32_t)(d0 - r0), z1 = (uint32_t)(d1 - r1);
+    const uint32_t t_rows = r1 - r0, t_nnz = z1 - z0, t_items = (uint32_t)(d1 - d0);
+
+    // (1a) TMA: the 16-byte aligned superset [za, zb) of the tile's slice, one bulk copy per array
+    const uint32_t za = z0 & ~3u, zb = (z1 + 3u) & ~3u;     // arrays carry 16 entries of slack
+    const uint32_t shift = z0 - za;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && zb > za) {
+        mbar_expect_tx(&s_bar, (zb - za) * (uint32_t)(sizeof(uint32_t) + sizeof(T)));
+        tma_bulk_g2s(s_ind, ind + za, (zb - za) * (uint32_t)sizeof(uint32_t), &s_bar);
+        tma_bulk_g2s(s_val, val + za, (zb - za) * (uint32_t)sizeof(T), &s_bar);
+    }
+    // (1b) row ends of the tile; the sentinel keeps the open row "unfinished"
+    for (uint32_t i = threadIdx.x; i < t_rows; i += MG_THREADS) s_end[i] = __ldg(ptr + r0 + 1 + i);
+    if (threadIdx.x == 0) s_end[t_rows] = 0xffffffffu;
+    // (1c) products in place: consecutive lanes take consecutive entries, so neighbouring columns
+    // share gather sectors; all IPT gathers of a thread are independent and in flight together
+    if (zb > za) mbar_wait(&s_bar, 0);
+    T *s_prod = s_val + shift;
+    {
+        T xv[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const uint32_t k = threadIdx.x + q * MG_THREADS;
+            xv[q] = k < t_nnz ? __ldg(x + s_ind[shift + k]) : (T)0;
+        }
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const uint32_t k = threadIdx.x + q * MG_THREADS;
+            if (k < t_nnz) s_prod[k] *= xv[q];
+        }
+    }
+    __syncthreads();
+
+    // (2) per-thread walk of IPT path items
+    uint32_t dt = threadIdx.x * IPT;
+    if (dt > t_items) dt = t_items;
+    uint32_t lo = dt > t_nnz ? dt - t_nnz : 0, hi = dt < t_rows ? dt : t_rows;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_end[mid] <= z0 + (dt - mid - 1)) lo = mid + 1;
+        else hi = mid;
+    }
+    uint32_t i = lo, j = dt - lo;
+    T sum = (T)0, first_sum = (T)0;
+    uint32_t first_row = 0;
+    int hit = 0;
+    uint32_t steps = t_items - dt < (uint32_t)IPT ? t_items - dt : (uint32_t)IPT;
+    uint32_t row_end = s_end[i];
+    for (uint32_t k = 0; k < steps; ++k) {
+        if (z0 + j < row_end) {
+            sum += s_prod[j];
+            ++j;
+        } else {
+            if (!hit) { first_sum = sum; first_row = i; hit = 1; }
+            else y[r0 + i] = sum;
+            sum = (T)0;
+            ++i;
+            row_end = s_end[i];
+        }
+    }
+
+    // (3) segmented scan of (hit, tail) across the block: c_t = partial of the row open at the
+    // start of thread t, contributed by the preceding threads
+    T v = sum;
+    int f = hit;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T pv = __shfl_up_sync(0xffffffffu, v, o);
+        const int pf = __shfl_up_sync(0xffffffffu, f, o);
+        if (lane >= (unsigned)o) {
+            if (!f) v += pv;
+            f |= pf;
+        }
+    }
+    if (lane == 31) { s_wval[warp] = v; s_wflag[warp] = f; }
+    T ev = __shfl_up_sync(0xffffffffu, v, 1);       // exclusive inside the warp
+    int ef = __shfl_up_sync(0xffffffffu, f, 1);
+    if (lane == 0) { ev = (T)0; ef = 0; }
+    __syncthreads();
+    T pv = (T)0;                                     // carry entering this warp
+    for (unsigned w = 0; w < warp; ++w) pv = s_wflag[w] ? s_wval[w] : pv + s_wval[w];
+    const T carry_in = ef ? ev : pv + ev;
+    if (hit) y[r0 + first_row] = first_sum + carry_in;
+    if (threadIdx.x == MG_THREADS - 1) {
+        carry_row[tile] = r1;                        // row still open at the tile end (== nrows: none)
+        carry_val[tile] = f ? v : pv + v;
+    }
+}
+
+template <typename T>
+__global__ void spmv_merge_fixup_kernel(uint32_t nrows, uint32_t ntiles,
+                                        const uint32_t *__restrict__ carry_row,
+                                        const T *__restrict__ carry_val, T *__restrict__ y) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t row = carry_row[t];
+    if (row >= nrows) return;
+    if (t > 0 && carry_row[t - 1] == row) return;    // the first tile of a run does the whole run
+    T acc = (T)0;
+    for (uint32_t u = t; u < ntiles && carry_row[u] == row; ++u) acc += carry_val[u];
+    y[row] += acc;
+}
+
+template <typename T>
+constexpr int merge_ipt() { return sizeof(T) == 8 ? 7 : 11; }   // odd: path walks stay off one bank
+
+template <typename T>
+void spmv_merge(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
+    constexpr int IPT = merge_ipt<T>();
+    const uint32_t ntiles = a->merge_tiles;
+    if (ntiles == 0) return;
+    Tmp<uint32_t> carry_row(ctx, ntiles);
+    Tmp<T> carry_val(ctx, ntiles);
+    spmv_merge_kernel<T, IPT><<<ntiles, MG_THREADS, 0, ctx->stream>>>(
+        a->nrows, a->nnz, a->ptr, a->ind, static_cast<const T *>(a->val), x, y, a->merge_rows,
+        carry_row, carry_val);
+    check_launch(ctx, "spmv_merge");
+    spmv_merge_fixup_kernel<T><<<div_up(ntiles, 256), 256, 0, ctx->stream>>>(a->nrows, ntiles, carry_row,
+                                                                            carry_val, y);
+    check_launch(ctx, "spmv_merge_fixup");
+}
+
 // ------------------------------------------------------------------ row statistics (plan)
 __global__ void max_row_len_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t *out) {
     uint32_t m = 0;
@@ -91,23 +317,47 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     }
     a->max_row_len = mx;
     const double mean = a->nrows ? (double)a->nnz / a->nrows : 0.0;
-    int lanes = 2;
-    while (lanes < 32 && lanes * 2 <= mean) lanes *= 2;   // largest power of two <= mean, >= 2
+    // each lane keeps 4 entries in flight, so one or two trips cover a row when lanes*8 >= mean
+    int lanes = 1;
+    while (lanes < 32 && lanes * 8 < mean) lanes *= 2;
+    if (lanes < 2 && mean > 3.0) lanes = 2;
     a->plan_lanes = lanes;
-    a->plan_kernel = SPL_SPMV_VECTOR;
+    // merge-path tile starts (matrix-only data, cached)
+    const int ipt = a->dtype == SPL_F64 ? merge_ipt<double>() : merge_ipt<float>();
+    const uint32_t items = MG_THREADS * ipt;
+    const uint64_t total = (uint64_t)a->nrows + a->nnz;
+    const uint32_t ntiles = div_up(total, items);
+    a->merge_rows = dalloc<uint32_t>(ctx, (size_t)ntiles + 1);
+    a->merge_tiles = ntiles;
+    merge_partition_kernel<<<div_up((uint64_t)ntiles + 1, 256), 256, 0, ctx->stream>>>(
+        a->ptr, a->nrows, a->nnz, items, ntiles, a->merge_rows);
+    check_launch(ctx, "merge_partition");
+    // skewed rows (power law) or very short rows -> merge path; long regular rows -> vector
+    const bool skewed = mean > 0 && (double)mx > 8.0 * mean + 64.0;
+    a->plan_kernel = skewed ? SPL_SPMV_MERGE : SPL_SPMV_VECTOR;
     a->plan_ready = 1;
 }
 
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes) {
     SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
-    if (kernel == SPL_SPMV_AUTO || lanes == 0) {
+    if (kernel == SPL_SPMV_AUTO) {
         spmv_plan(ctx, const_cast<spl_mat *>(a));
-        if (kernel == SPL_SPMV_AUTO) kernel = a->plan_kernel;
-        if (lanes == 0) lanes = a->plan_lanes;
+        kernel = a->plan_kernel;
+        lanes = 0;
+    }
+    if (kernel == SPL_SPMV_VECTOR && lanes == 0) {
+        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        lanes = a->plan_lanes;
     }
     if (kernel == SPL_SPMV_VECTOR) {
         if (a->dtype == SPL_F32) spmv_vector<float>(ctx, a, (const float *)x, (float *)y, lanes);
         else spmv_vector<double>(ctx, a, (const double *)x, (double *)y, lanes);
+        return;
+    }
+    if (kernel == SPL_SPMV_MERGE) {
+        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        if (a->dtype == SPL_F32) spmv_merge<float>(ctx, a, (const float *)x, (float *)y);
+        else spmv_merge<double>(ctx, a, (const double *)x, (double *)y);
         return;
     }
     throw Error{SPL_ERR_UNSUPPORTED, "unknown SpMV kernel"};

@@ -267,13 +267,13 @@ def test_spmv_random(dtype, n, m, density):
     assert np.all(got[np.diff(a[0].astype(np.int64)) == 0] == 0)          # empty rows give 0
     import torch
     xd = torch.from_numpy(x).cuda()
-    for lanes in (1, 2, 4, 8, 16, 32):
+    for kernel, lanes in [(1, l) for l in (1, 2, 4, 8, 16, 32)] + [(2, 0)]:   # vector x6, merge
         yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
         torch.cuda.synchronize()
-        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=1, lanes=lanes)
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
         sp.default_context().sync()
         got = yd.cpu().numpy()
-        assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), lanes
+        assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), (kernel, lanes)
 
 
 def test_spmv_skewed_rows():
@@ -290,6 +290,15 @@ def test_spmv_skewed_rows():
     want = orc.csr_spmv(n, ptr, ind, val, x)
     scale = orc.csr_spmv(n, ptr, ind, np.abs(val), np.abs(x))
     assert np.all(np.abs(A.matvec(x) - want) <= 1e-12 * np.maximum(scale, 1e-300))
+    assert A.spmv_choice()[0] == 2                       # skewed rows select the merge-path kernel
+    import torch
+    xd = torch.from_numpy(x).cuda()
+    for kernel, lanes in ((1, 32), (2, 0)):
+        yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+        torch.cuda.synchronize()
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
+        sp.default_context().sync()
+        assert np.all(np.abs(yd.cpu().numpy() - want) <= 1e-12 * np.maximum(scale, 1e-300)), kernel
 
 
 # ------------------------------------------------------------------ BASELINE shapes, properties
