@@ -82,10 +82,16 @@ __global__ void eye_kernel(uint32_t size, uint32_t *ptr, uint32_t *ind, T *val) 
     }
 }
 
-__global__ void expand_major_kernel(const uint32_t *__restrict__ ptr, uint32_t nmajor, uint32_t nnz,
-                                    uint32_t *__restrict__ out) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < nnz) out[p] = upper_bound_u32(ptr, 0u, nmajor + 1u, (uint32_t)p) - 1u;
+// LPR lanes per segment write the segment's index over its entries: consecutive lanes, consecutive
+// entries, so the stores coalesce (a search per entry was measured 6x slower).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+expand_major_kernel(const uint32_t *__restrict__ ptr, uint32_t nmajor, uint32_t *__restrict__ out) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t m = gtid / LPR;
+    if (m >= nmajor) return;
+    const uint32_t e = __ldg(ptr + m + 1);
+    for (uint32_t p = __ldg(ptr + m) + (uint32_t)(gtid % LPR); p < e; p += LPR) out[p] = (uint32_t)m;
 }
 
 inline unsigned stream_grid(spl_ctx *ctx, size_t n) {
@@ -151,7 +157,15 @@ void fill_eye(spl_ctx *ctx, int dtype, uint32_t size, uint32_t *ptr, uint32_t *i
 
 void expand_major(spl_ctx *ctx, uint32_t nmajor, uint32_t nnz, const uint32_t *ptr, uint32_t *out) {
     if (nnz == 0) return;
-    expand_major_kernel<<<div_up(nnz, 256), 256, 0, ctx->stream>>>(ptr, nmajor, nnz, out);
+    const double mean = (double)nnz / nmajor;
+    if (mean <= 2.0)
+        expand_major_kernel<1><<<div_up(nmajor, 256), 256, 0, ctx->stream>>>(ptr, nmajor, out);
+    else if (mean <= 12.0)
+        expand_major_kernel<4><<<div_up((uint64_t)nmajor * 4, 256), 256, 0, ctx->stream>>>(ptr, nmajor, out);
+    else if (mean <= 64.0)
+        expand_major_kernel<8><<<div_up((uint64_t)nmajor * 8, 256), 256, 0, ctx->stream>>>(ptr, nmajor, out);
+    else
+        expand_major_kernel<32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(ptr, nmajor, out);
     check_launch(ctx, "expand_major");
 }
 

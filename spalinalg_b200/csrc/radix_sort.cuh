@@ -68,9 +68,9 @@ struct LoadNone {
 inline int rs_num_passes(int bits) { return bits <= 0 ? 1 : (bits + 7) / 8; }
 
 // ---- upsweep ---------------------------------------------------------------------------------
-// Same block <-> chunk mapping as the downsweep, but 1024 threads and 8 keys in flight per thread:
+// Same block <-> chunk mapping as the downsweep, but 512 threads and 8 keys in flight per thread:
 // the pass only reads keys, so it wants bytes in flight, not registers.
-constexpr int RH_THREADS = 1024;
+constexpr int RH_THREADS = 512;
 constexpr int RH_WARPS = RH_THREADS / 32;
 
 template <typename K, typename LoadK>
@@ -277,7 +277,12 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
     if (n == 0) return (passes - 1) & 1;
     if (bits <= 0) bits = 1;
     const uint32_t tiles = div_up(n, RS_TILE);
-    uint32_t grid = (uint32_t)ctx->num_sms * 3u;          // 3 resident CTAs per SM (registers)
+    // one wave: grid = SMs x resident downsweep CTAs per SM (register-limited; asked, not guessed)
+    int occ = 0;
+    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &occ, rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>, RS_THREADS, 0));
+    if (occ < 1) occ = 1;
+    uint32_t grid = (uint32_t)ctx->num_sms * (uint32_t)occ;
     if (grid > tiles) grid = tiles;
     const uint32_t tiles_per_block = div_up(tiles, grid);
     grid = div_up(tiles, tiles_per_block);

@@ -33,8 +33,11 @@ void recompress_impl(spl_ctx *ctx, uint32_t nmajor, uint32_t nminor, uint32_t nn
     vb[last] = out_val;
     mb[last ^ 1] = m_tmp;
     vb[last ^ 1] = v_tmp;
+    // major index per entry: one coalesced expansion pass, then every radix pass reads plain arrays
+    Tmp<uint32_t> major(ctx, nnz);
+    expand_major(ctx, nmajor, nnz, ptr, major);
     LoadPlain<uint32_t> lk{ind};
-    LoadMajor lm{ptr, nmajor};
+    LoadPlain<uint32_t> lm{major};
     LoadPlain<VB> lv{val};
     const int r = radix_sort<uint32_t, uint32_t, VB>(ctx, nnz, bits, lk, lm, lv, kb, mb, vb);
     fill_ptr(ctx, kb[r], nnz, nminor, out_ptr);
