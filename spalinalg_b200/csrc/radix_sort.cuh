@@ -21,6 +21,9 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
 constexpr int RS_IPT = 12;                       // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 3072 items per tile
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 4                          // resident downsweep CTAs per SM the compiler must allow
+#endif
 
 // ---- loaders: what pass 0 reads (later passes read the ping-pong buffers) ------------------
 // Every loader takes a per-thread `state` word (0 at kernel start) it may use as a cursor.
@@ -132,7 +135,7 @@ static __global__ void __launch_bounds__(512) rs_scan_kernel(uint32_t *counts, u
 
 // ---- downsweep -------------------------------------------------------------------------------
 template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_block, int shift,
                   uint32_t mask, const uint32_t *__restrict__ offsets,
                   const uint32_t *__restrict__ totals, K *__restrict__ out_k, A *__restrict__ out_a,
@@ -279,6 +282,9 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
     const uint32_t tiles = div_up(n, RS_TILE);
     // one wave: grid = SMs x resident downsweep CTAs per SM (register-limited; asked, not guessed)
     int occ = 0;
+    SPL_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &occ, rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>, RS_THREADS, 0));
     if (occ < 1) occ = 1;
