@@ -102,60 +102,6 @@ def workload_name(args):
     return "stencil27_128_f64" if args.gpus == 1 else "banded9_1e8_f64"
 
 
-# ------------------------------------------------------------------------------- device generators
-def stencil_device(torch, offsets_3d, m, diag, off, dtype):
-    """Row-major CSR of a stencil on an m^3 (or m^2) grid, built on the device."""
-    dev = "cuda"
-    dims = len(offsets_3d[0])
-    n = m ** dims
-    r = torch.arange(n, device=dev, dtype=torch.int64)
-    coords = []
-    rem = r
-    for d in range(dims):
-        coords.append(rem // (m ** (dims - 1 - d)))
-        rem = rem % (m ** (dims - 1 - d))
-    offs = sorted(offsets_3d, key=lambda o: sum(o[d] * m ** (dims - 1 - d) for d in range(dims)))
-    cols, masks, vals = [], [], []
-    for o in offs:
-        ok = torch.ones(n, device=dev, dtype=torch.bool)
-        lin = torch.zeros(n, device=dev, dtype=torch.int64)
-        for d in range(dims):
-            cd = coords[d] + o[d]
-            ok &= (cd >= 0) & (cd < m)
-            lin += cd * (m ** (dims - 1 - d))
-        cols.append(lin)
-        masks.append(ok)
-        vals.append(torch.full((n,), diag if all(x == 0 for x in o) else off, device=dev, dtype=dtype))
-    mask = torch.stack(masks, 1)
-    colind = torch.stack(cols, 1)[mask].to(torch.int32)
-    values = torch.stack(vals, 1)[mask]
-    rowptr = torch.zeros(n + 1, device=dev, dtype=torch.int64)
-    rowptr[1:] = torch.cumsum(mask.sum(1), 0)
-    return n, rowptr.to(torch.int32), colind, values
-
-
-def banded_device(torch, n, r0, r1, offsets, dtype, chunk=1 << 24):
-    """Rows [r0, r1) of the banded matrix of config 5, global column indices, on the device."""
-    dev = "cuda"
-    offs = sorted(offsets)
-    ptr_parts, col_parts, val_parts = [], [], []
-    base = 0
-    for s in range(r0, r1, chunk):
-        e = min(r1, s + chunk)
-        i = torch.arange(s, e, device=dev, dtype=torch.int64)
-        cols = torch.stack([i + d for d in offs], 1)
-        mask = (cols >= 0) & (cols < n)
-        vals = torch.stack([1.0 / (1 + abs(d)) + (i % 7).to(dtype) * 1e-3 for d in offs], 1)
-        cnt = torch.cumsum(mask.sum(1), 0)
-        ptr_parts.append(cnt + base)
-        base = int(ptr_parts[-1][-1].item())
-        col_parts.append(cols[mask].to(torch.int32))
-        val_parts.append(vals[mask].to(dtype))
-        del cols, mask, vals, i
-    rowptr = torch.cat([torch.zeros(1, device=dev, dtype=torch.int64)] + ptr_parts).to(torch.int32)
-    return rowptr, torch.cat(col_parts), torch.cat(val_parts)
-
-
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -230,6 +176,7 @@ def main():
     import torch.distributed as dist
     import spalinalg_b200 as sp
     from spalinalg_b200 import _capi as capi, sharding
+    from spalinalg_b200.synthetic_device import banded_device, stencil_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -350,6 +297,14 @@ def main():
     peak, peak_src = peaks()
     achieved = bytes_local / (kern_ms * 1e-3) / 1e9
     choice = A.spmv_choice()
+    kname = {1: "vector", 2: "merge"}.get(kern or choice[0], "?")
+    traffic = None
+    try:                                   # per-launch DRAM bytes from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t_ = json.load(f)[wl]["spmv_" + kname]
+            traffic = t_["dram_read_bytes"] + t_["dram_write_bytes"]
+    except Exception:
+        pass
 
     # ---- e2e through the C ABI with host buffers (rank-local share) ---------------------------
     e2e_steps = max(3, min(args.steps, 10))
@@ -425,7 +380,7 @@ def main():
             "config": {"workload": wl, "nrows": n, "nnz": nnz_total, "algorithmic_bytes": bytes_total,
                        "l2": "inputs larger than L2 (no flush)" if bytes_local > 2 * 126e6 else
                              "footprint below 2x L2: L2-resident number",
-                       "exchange": exchange, "spmv_kernel": {1: "vector", 2: "merge"}.get(kern or choice[0], "?"),
+                       "exchange": exchange, "spmv_kernel": kname,
                        "lanes_per_row": choice[1] if lanes == 0 else lanes,
                        "pct_of_8TBps_nominal": 100.0 * achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -433,7 +388,7 @@ def main():
                     "what": "spl_mat_from_compressed(host usize arrays, validating) + spl_spmv_host"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "spmv", "kernel_ms": kern_ms, "bytes_per_launch": bytes_local},
             "clocks": clk,
         }
@@ -447,6 +402,7 @@ def main():
 
 
 def secondary_metrics(torch, sp, ctx, A, wl):
+    from spalinalg_b200.synthetic_device import stencil_device
     """COO->CSR assembly on config 1 (shuffled and row-ordered) and CSR->CSC on the bench matrix."""
     out = {}
 

@@ -4,6 +4,7 @@ Public surface mirrors the reference crate root (src/lib.rs:10-19): CooMatrix, C
 CsrMatrix, DokMatrix.  Device work goes through libspalinalg_b200.so (include/spl.h); build it
 with `python -m spalinalg_b200.build`.  No CPU fallback.
 """
+from . import matrix
 from .matrix import (Context, CooMatrix, CscMatrix, CsrMatrix, DeviceError, DokMatrix, Panic,
                      default_context, set_default_context)
 

@@ -1,0 +1,199 @@
+"""BASELINE.json configs 3, 4, 5 on the GPU: bit-exact parity against the oracle at sizes the oracle
+finishes in seconds, and size-independent properties at the full sizes (validity of the output,
+idempotence of assembly, linearity against a direct COO evaluation, agreement of the two SpMV
+kernels, (A+B)x = Ax + Bx)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+import spalinalg_b200 as sp
+from spalinalg_b200 import _capi as capi
+from spalinalg_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(autouse=True, scope="module")
+def one_stream():
+    """torch (generators, checks) and the library share one explicit stream, so no cross-stream
+    synchronisation is needed between a torch op and the API call that consumes its output."""
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    old = getattr(sp.matrix._tls, "ctx", None)
+    sp.set_default_context(sp.Context(0, stream.cuda_stream))
+    yield
+    torch.cuda.synchronize()
+    sp.set_default_context(old)
+    torch.cuda.set_stream(torch.cuda.default_stream())
+
+
+def gen():
+    from spalinalg_b200 import synthetic_device as sd
+    return sd
+
+
+def dev_arrays(A):
+    sd = gen()
+    p, i, v = A.device_ptrs()
+    nmajor = A.nrows() if isinstance(A, sp.CsrMatrix) else A.ncols()
+    tdt = torch.float32 if A.dtype == np.float32 else torch.float64
+    return (sd.device_view(torch, p, nmajor + 1, torch.int32), sd.device_view(torch, i, max(A.nnz(), 1), torch.int32)[:A.nnz()],
+            sd.device_view(torch, v, max(A.nnz(), 1), tdt)[:A.nnz()])
+
+
+def spmv(A, x, kernel=capi.SPL_SPMV_AUTO, lanes=0):
+    y = torch.empty(A.nrows(), device="cuda", dtype=x.dtype)
+    torch.cuda.synchronize()
+    A.spmv_device(x.data_ptr(), y.data_ptr(), kernel, lanes)
+    sp.default_context().sync()
+    return y
+
+
+def coo_matvec_f64(n, r, c, v, x):
+    """Direct COO evaluation in f64 (order-free reference for the linearity property)."""
+    y = torch.zeros(n, device="cuda", dtype=torch.float64)
+    y.index_add_(0, r.long(), v.double() * x.double()[c.long()])
+    return y
+
+
+def same_host(A, want):
+    assert np.array_equal(A.rowptr(), want[0]) and np.array_equal(A.colind(), want[1])
+    assert A.values().tobytes() == want[2].tobytes()
+
+
+# ------------------------------------------------------------------ config 3
+def test_c3_reduced_bit_exact_vs_oracle():
+    sd = gen()
+    n = 1_000_000
+    r, c, v = sd.random_uniform_coo_device(torch, n, 16, 800_000, torch.float32, seed=1)
+    A = sp.CsrMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    rh, ch, vh = r.cpu().numpy().astype(np.uint64), c.cpu().numpy().astype(np.uint64), v.cpu().numpy()
+    want = orc.compress_from_coo(n, n, orc.make_triplets(rh, ch, vh), "row")
+    same_host(A, want)
+    C = sp.CscMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    wantc = orc.compress_from_coo(n, n, orc.make_triplets(rh, ch, vh), "col")
+    assert np.array_equal(C.colptr(), wantc[0]) and np.array_equal(C.rowind(), wantc[1])
+    assert C.values().tobytes() == wantc[2].tobytes()
+
+
+def test_c3_full_size_properties():
+    sd = gen()
+    n, per_row, extra = 10_000_000, 16, 8_000_000
+    r, c, v = sd.random_uniform_coo_device(torch, n, per_row, extra, torch.float32, seed=1)
+    ln = r.numel()
+    assert ln == 168_000_000
+    A = sp.CsrMatrix.from_device_triplets(n, n, ln, r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    ptr, ind, val = dev_arrays(A)
+    # (1) the output is a valid CsrMatrix (sorted pointers, strictly increasing columns, in range)
+    sp.CsrMatrix.from_device_arrays(n, n, A.nnz(), ptr.data_ptr(), ind.data_ptr(), val.data_ptr(), np.float32, validate=True)
+    # (2) nnz = distinct cells minus cells whose in-order sum is exactly zero (at most the negations)
+    key = r.long() * n + c.long()
+    uniq = int(torch.unique(key).numel())
+    del key
+    assert uniq - extra // 100 - 1 <= A.nnz() <= uniq
+    assert not bool((val == 0).any())                                       # zero sums were dropped
+    # (3) linearity: A x equals the direct COO evaluation (f32 sums, order differs)
+    x = torch.rand(n, device="cuda", dtype=torch.float32) - 0.5
+    y = spmv(A, x).double()
+    yref = coo_matvec_f64(n, r, c, v, x)
+    scale = coo_matvec_f64(n, r, c, v.abs(), x.abs())
+    assert bool(((y - yref).abs() <= 1e-5 * scale + 1e-30).all())
+    # (4) idempotence: assembling the assembled matrix's own entries returns it bit for bit
+    rows2 = torch.repeat_interleave(torch.arange(n, device="cuda", dtype=torch.int32),
+                                    (ptr[1:] - ptr[:-1]).long())
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    perm = torch.randperm(A.nnz(), device="cuda", generator=g)
+    r2, c2, v2 = rows2[perm].contiguous(), ind[perm].contiguous(), val[perm].contiguous()
+    B = sp.CsrMatrix.from_device_triplets(n, n, A.nnz(), r2.data_ptr(), c2.data_ptr(), v2.data_ptr(), np.float32)
+    bp, bi, bv = dev_arrays(B)
+    assert B.nnz() == A.nnz() and torch.equal(bp, ptr) and torch.equal(bi, ind)
+    assert torch.equal(bv.view(torch.int32), val.view(torch.int32))
+
+
+# ------------------------------------------------------------------ config 4
+def test_c4_reduced_bit_exact_and_merge_path():
+    sd = gen()
+    scale = 18
+    n = 1 << scale
+    r, c, v = sd.rmat_coo_device(torch, scale, 32, torch.float32, seed=3)
+    A = sp.CsrMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    rh, ch, vh = r.cpu().numpy().astype(np.uint64), c.cpu().numpy().astype(np.uint64), v.cpu().numpy()
+    want = orc.compress_from_coo(n, n, orc.make_triplets(rh, ch, vh), "row")
+    same_host(A, want)
+    assert A.spmv_choice()[0] == capi.SPL_SPMV_MERGE                       # skewed rows
+    x = torch.rand(n, device="cuda", dtype=torch.float32) - 0.5
+    xh = x.cpu().numpy()
+    yw = orc.csr_spmv(n, *want, xh)
+    sc = orc.csr_spmv(n, want[0], want[1], np.abs(want[2]), np.abs(xh))
+    for kern, lanes in ((capi.SPL_SPMV_MERGE, 0), (capi.SPL_SPMV_VECTOR, 32), (capi.SPL_SPMV_AUTO, 0)):
+        y = spmv(A, x, kern, lanes).cpu().numpy()
+        assert np.all(np.abs(y - yw) <= 1e-5 * np.maximum(sc, 1e-30)), kern
+    # transpose of a skewed matrix, bit-exact
+    T = A.transpose()
+    wt = orc.recompress(n, n, *want)
+    same_host(T, wt)
+
+
+def test_c4_full_size_properties():
+    sd = gen()
+    scale = 24
+    n = 1 << scale
+    r, c, v = sd.rmat_coo_device(torch, scale, 32, torch.float32, seed=3)
+    assert r.numel() == 1 << 29
+    A = sp.CsrMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    ptr, ind, val = dev_arrays(A)
+    sp.CsrMatrix.from_device_arrays(n, n, A.nnz(), ptr.data_ptr(), ind.data_ptr(), val.data_ptr(), np.float32, validate=True)
+    assert A.nnz() < r.numel()                                               # duplicates merged
+    x = torch.rand(n, device="cuda", dtype=torch.float32) - 0.5
+    yref = coo_matvec_f64(n, r, c, v, x)
+    sc = coo_matvec_f64(n, r, c, v.abs(), x.abs())
+    del r, c, v
+    ym = spmv(A, x, capi.SPL_SPMV_MERGE).double()
+    yv = spmv(A, x, capi.SPL_SPMV_VECTOR, 32).double()
+    # duplicates are summed in f32 during assembly as well: allow two roundings per addend
+    assert bool(((ym - yref).abs() <= 4e-5 * sc + 1e-30).all())
+    assert bool(((yv - ym).abs() <= 1e-5 * sc + 1e-30).all())
+
+
+# ------------------------------------------------------------------ config 5
+def _banded(n, offsets, r0=0, r1=None):
+    sd = gen()
+    r1 = n if r1 is None else r1
+    ptr, col, val = sd.banded_device(torch, n, r0, r1, offsets, torch.float64)
+    A = sp.CsrMatrix.from_device_arrays(r1 - r0, n, col.numel(), ptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                        np.float64, validate=True)
+    return A, (ptr, col, val)
+
+
+def test_c5_reduced_add_sub_bit_exact():
+    n = 200_000
+    A, (ap, ac, av) = _banded(n, range(-4, 5))
+    B, (bp, bc, bv) = _banded(n, (-8, -2, 0, 2, 8))
+    a = (ap.cpu().numpy().astype(np.uint64), ac.cpu().numpy().astype(np.uint64), av.cpu().numpy())
+    b = (bp.cpu().numpy().astype(np.uint64), bc.cpu().numpy().astype(np.uint64), bv.cpu().numpy())
+    same_host(A + B, orc.addsub(0, n, n, a, b))
+    same_host(A - B, orc.addsub(1, n, n, a, b))
+
+
+def test_c5_full_size_spmv_and_add():
+    n = 100_000_000
+    A, _ = _banded(n, range(-4, 5))
+    assert A.nnz() == 899_999_980
+    B, _ = _banded(n, (-8, -2, 0, 2, 8))
+    x = torch.sin(torch.arange(n, device="cuda", dtype=torch.float64) * 1e-3)
+    ya, yb = spmv(A, x), spmv(B, x)
+    # analytic check of A x on a slice: y_i = sum_d (1/(1+|d|) + (i mod 7) 1e-3) x_{i+d}
+    i = torch.arange(10, 1_000_010, device="cuda", dtype=torch.int64)
+    want = torch.zeros(i.numel(), device="cuda", dtype=torch.float64)
+    for d in range(-4, 5):
+        want += (1.0 / (1 + abs(d)) + (i % 7).double() * 1e-3) * x[i + d]
+    assert bool(((ya[i] - want).abs() <= 1e-12 * 10).all())
+    C = A + B
+    assert C.nnz() == 9 * n - 20 + 2 * (n - 8)                               # union adds offsets +-8
+    yc = spmv(C, x)
+    assert bool(((yc - (ya + yb)).abs() <= 1e-12 * 20).all())
+    D = C - B                                                                # pattern of C, values of A (+0.0 on +-8)
+    yd = spmv(D, x)
+    assert bool(((yd - ya).abs() <= 1e-12 * 20).all())
