@@ -18,6 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "--fmad=false", "--ftz=false", "--prec-div=true", "--prec-sqrt=true",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
+FLAGS += os.environ.get("SPL_EXTRA_NVCC_FLAGS", "").split()      # tuning experiments (-DRS_IPT_VALUE=8 ...)
 
 
 def _sources():

@@ -19,10 +19,13 @@ namespace spl {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
-constexpr int RS_IPT = 12;                       // items per thread
+#ifndef RS_IPT_VALUE
+#define RS_IPT_VALUE 16
+#endif
+constexpr int RS_IPT = RS_IPT_VALUE;             // items per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;     // 3072 items per tile
 #ifndef RS_MIN_BLOCKS
-#define RS_MIN_BLOCKS 4                          // resident downsweep CTAs per SM the compiler must allow
+#define RS_MIN_BLOCKS 2                          // resident downsweep CTAs per SM the compiler must allow
 #endif
 
 // ---- loaders: what pass 0 reads (later passes read the ping-pong buffers) ------------------
@@ -173,6 +176,15 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
             uint32_t loc = my_base + i * 32;
             keys[i] = loc < tile_count ? lk((uint32_t)(tile_base + loc), st_k) : (K)0;
         }
+        // payload A is requested now so that its DRAM latency hides behind the ranking
+        A pa[kHasA ? RS_IPT : 1];
+        if constexpr (kHasA) {
+#pragma unroll
+            for (int i = 0; i < RS_IPT; ++i) {
+                const uint32_t loc = my_base + i * 32;
+                if (loc < tile_count) pa[i] = la((uint32_t)(tile_base + loc), st_a);
+            }
+        }
         __syncthreads();
 
         // rank inside the warp, digit by digit occurrence order (stable)
@@ -223,6 +235,15 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
                 exk[rank[i]] = keys[i];
             }
         }
+        // payload B is requested before the keys leave: its latency hides behind the two exchanges
+        B pb[kHasB ? RS_IPT : 1];
+        if constexpr (kHasB) {
+#pragma unroll
+            for (int i = 0; i < RS_IPT; ++i) {
+                const uint32_t loc = my_base + i * 32;
+                if (loc < tile_count) pb[i] = lb((uint32_t)(tile_base + loc), st_b);
+            }
+        }
         __syncthreads();
         uint32_t gpos[RS_IPT];
 #pragma unroll
@@ -240,7 +261,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int i = 0; i < RS_IPT; ++i) {
                 const uint32_t loc = my_base + i * 32;
-                if (loc < tile_count) exa[rank[i]] = la((uint32_t)(tile_base + loc), st_a);
+                if (loc < tile_count) exa[rank[i]] = pa[i];
             }
             __syncthreads();
 #pragma unroll
@@ -255,7 +276,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int i = 0; i < RS_IPT; ++i) {
                 const uint32_t loc = my_base + i * 32;
-                if (loc < tile_count) exb[rank[i]] = lb((uint32_t)(tile_base + loc), st_b);
+                if (loc < tile_count) exb[rank[i]] = pb[i];
             }
             __syncthreads();
 #pragma unroll
