@@ -5,14 +5,21 @@
 
 A step is one SpMV y = A x over the workload.  N = 1: config 2 of BASELINE.json (27-point stencil
 128^3, f64, 2.1 M rows, 55.7 M nnz; footprint 702 MB > L2, so no flush is needed).  N > 1: config
-5 (banded 9, n = 1e8, f64), row-sharded over the ranks, x exchanged over NCCL each step (halo
-slices when the column footprint allows, full all-gather otherwise) — fixed total work, strong
-scaling.  `value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V) of the whole job
-per second of the slowest rank, device-timed.  `e2e` = the same metric through the C ABI with
-host buffers: upload of A in the reference layout (usize indices) and x, SpMV, download of y.
-The line also carries the secondary metrics of the path (COO->CSR assembly on config 1,
-CSR->CSC on config 2), `roofline`, `cpu_baseline` (oracle port of the reference's only SpMV
-route, `&A * &X` with X n x 1, on a bounded sample) and `clocks`.
+5 (banded 9, n = 1e8, f64), row-sharded over the ranks — fixed total work, strong scaling.  The
+exchange of x is part of every step: `peer` (default for banded/stencil shards) leaves x in its
+owners' peer-visible memory and gathers it inside the SpMV kernel over NVLink, ordered by a
+device-side flag barrier; `halo` sends boundary slices with NCCL send/recv; `allgather` is the
+NCCL all-gather general matrices need.  `value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V,
+SURVEY.md 8d) of the whole job per second of the slowest rank, device-timed.  `e2e` = the same
+metric through the reference-facing call `&A * &x` with HOST vectors: A is a constructed
+CsrMatrix (device resident, as the reference's is host resident), every step copies x from pinned
+host memory to the device, runs the SpMV and copies y back (spl_spmv_host at N = 1; upload into
+the peer slice + barrier + spl_spmv_peer + download at N > 1).  `e2e_cold` adds the construction
+of A from the reference-layout host arrays (usize indices, validating CsrMatrix::new) to every
+step.  The line also carries the secondary metrics of the path (COO->CSR assembly on config 1,
+CSR->CSC on config 2, config 5 on one GPU as the strong-scaling base; sharded add and sharded
+assembly at N > 1), `roofline`, `cpu_baseline` (oracle port of the reference's only SpMV route,
+`&A * &X` with X n x 1, on a bounded sample) and `clocks`.
 
 --impl reference times that CPU route alone (the reference is Rust; no rustc here, so the
 oracle's line-by-line port stands in: cpu_baseline.kind = "port").
@@ -162,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto",
                     choices=["auto", "stencil27_128_f64", "laplace2d_1024_f64", "banded9_1e8_f64", "banded9_1e7_f64"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "allgather"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "halo", "allgather"])
     ap.add_argument("--kernel", default="auto")       # auto | vectorN | merge
     ap.add_argument("--no-extras", action="store_true", help="skip secondary metrics / cpu baseline")
     args = ap.parse_args()
@@ -176,6 +183,7 @@ def main():
     import torch.distributed as dist
     import spalinalg_b200 as sp
     from spalinalg_b200 import _capi as capi, sharding
+    from spalinalg_b200 import synthetic_device
     from spalinalg_b200.synthetic_device import banded_device, stencil_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,14 +234,31 @@ def main():
     bytes_total = spmv_bytes(nnz_total, n, n, V)
     bytes_local = spmv_bytes(nnz_loc, nloc, n if ngpu == 1 else nloc + 2 * halo, V)
 
-    # x: global-length buffer on every rank (global column indices); each rank owns [r0, r1)
-    idx = torch.arange(n, device="cuda", dtype=torch.int64)
-    x_full = (1.0 / (1.0 + (idx % 97))).to(f64) if not wl.startswith("banded") else torch.sin(idx.to(f64) * 1e-3)
-    del idx
-    y = torch.zeros(nloc, device="cuda", dtype=f64)
+    # x: `peer` keeps only the owned slice (peer-visible memory, mapped by every rank); the NCCL
+    # exchanges use a global-length buffer per rank of which the rank owns [r0, r1)
+    from spalinalg_b200 import dist as spd
     exchange = "none"
     if world > 1:
-        exchange = args.exchange if args.exchange != "auto" else ("halo" if halo else "allgather")
+        exchange = args.exchange if args.exchange != "auto" else ("peer" if halo else "allgather")
+
+    def x_values(lo, hi):
+        idx = torch.arange(lo, hi, device="cuda", dtype=torch.int64)
+        if wl.startswith("banded"):
+            return torch.sin(idx.to(f64) * 1e-3)
+        return (1.0 / (1.0 + (idx % 97))).to(f64)
+
+    xv = None
+    if exchange == "peer":
+        starts = spd.partition_starts(n, world)
+        xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+        x_loc = synthetic_device.device_view(torch, xv.local_ptr, nloc, f64)
+        x_loc.copy_(x_values(r0, r1))
+        x_full = None
+        dA = spd.DistCsrMatrix(A, starts, rank, n, n)
+    else:
+        x_full = x_values(0, n)
+        x_loc = x_full[r0:r1]
+    y = torch.zeros(nloc, device="cuda", dtype=f64)
 
     kern, lanes = capi.SPL_SPMV_AUTO, 0
     if args.kernel.startswith("vector"):
@@ -241,25 +266,40 @@ def main():
     elif args.kernel == "merge":
         kern = capi.SPL_SPMV_MERGE
 
-    def exchange_x():
-        if exchange == "allgather":
+    def local_spmv():
+        if exchange == "peer":
+            dA.spmv_peer(xv, y.data_ptr())
+        else:
+            A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+
+    def step():
+        if exchange == "peer":
+            xv.barrier()                      # device-side: peers' slices are final before the gathers
+        elif exchange == "allgather":
             sharding.exchange_allgather(dist, x_full, r0, r1, world, n % world == 0)
         elif exchange == "halo":
             sharding.exchange_halo(dist, x_full, r0, r1, halo, rank, world)
-
-    def step():
-        if world > 1:
-            exchange_x()
-        A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+        local_spmv()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness spot check before timing (not the oracle: analytic row sums) ------------
+    # ---- correctness spot check before timing: analytic row sums are checked by the tests; here
+    # the sharded result must equal the single-buffer kernel's on the same rows ----------------
     step()
     torch.cuda.synchronize()
+    if exchange == "peer":
+        xv.check()
+        lo, hi = max(0, r0 - halo), min(n, r1 + halo)
+        x_chk = torch.zeros(n if n <= 2 * 10 ** 8 else 1, device="cuda", dtype=f64)
+        x_chk[lo:hi] = x_values(lo, hi)
+        y_chk = torch.empty_like(y)
+        A.spmv_device(x_chk.data_ptr(), y_chk.data_ptr(), kern, lanes)
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_chk), "peer-gather SpMV differs from the single-buffer kernel"
+        del x_chk, y_chk
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -284,20 +324,22 @@ def main():
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = bytes_total / (ms_step * 1e-3) / 1e9
+    if xv is not None:
+        xv.check()
 
     # SpMV-kernel-only time on this rank (roofline of the dominant kernel)
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(args.steps):
-        A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+        local_spmv()
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / args.steps
     peak, peak_src = peaks()
     achieved = bytes_local / (kern_ms * 1e-3) / 1e9
     choice = A.spmv_choice()
-    kname = {1: "vector", 2: "merge"}.get(kern or choice[0], "?")
+    kname = "vector" if exchange == "peer" else {1: "vector", 2: "merge"}.get(kern or choice[0], "?")
     traffic = None
     try:                                   # per-launch DRAM bytes from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
@@ -306,28 +348,26 @@ def main():
     except Exception:
         pass
 
-    # ---- e2e through the C ABI with host buffers (rank-local share) ---------------------------
-    e2e_steps = max(3, min(args.steps, 10))
-    h_ptr = rowptr.to(torch.int64).cpu().pin_memory()
-    h_ind = colind.to(torch.int64).cpu().pin_memory()
-    h_val = values.cpu().pin_memory()
-    h_x = x_full.cpu().pin_memory()
+    # ---- e2e through the reference-facing call with HOST vectors ------------------------------
+    # A is a constructed CsrMatrix (device resident; the reference's lives in host memory); a step
+    # is `&A * &x`: x from pinned host memory, SpMV, y back to pinned host memory.
+    e2e_steps = max(3, min(args.steps, 20))
+    h_x = x_loc.cpu().pin_memory() if world > 1 else x_full.cpu().pin_memory()
     h_y = torch.empty(nloc, dtype=f64).pin_memory()
-    h2d = (h_ptr.numel() + h_ind.numel()) * 8 + h_val.numel() * 8 + h_x.numel() * 8
+    h2d = h_x.numel() * 8
     d2h = h_y.numel() * 8
 
     def e2e_step():
-        h = C.c_void_p()
-        ctx.check(lib.spl_mat_from_compressed(ctx._h, capi.SPL_CSR, capi.SPL_F64, nloc, n,
-                                              h_ptr.numel(), C.c_void_p(h_ptr.data_ptr()),
-                                              h_ind.numel(), C.c_void_p(h_ind.data_ptr()),
-                                              h_val.numel(), C.c_void_p(h_val.data_ptr()), C.byref(h)))
-        ctx.check(lib.spl_spmv_host(ctx._h, h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
-        ctx.check(lib.spl_mat_free(ctx._h, h))
+        if world == 1:
+            ctx.check(lib.spl_spmv_host(ctx._h, A._h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
+            return
+        x_loc.copy_(h_x, non_blocking=True)           # this rank's slice of the new x
+        step()                                        # exchange + SpMV
+        h_y.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     e2e_step()
-    y_dev_host = y.cpu()
-    assert torch.equal(h_y, y_dev_host), "e2e result differs from the device-resident result"
+    assert torch.equal(h_y, y.cpu()), "e2e result differs from the device-resident result"
     barrier()
     e2e_l0 = ctx.launch_count()
     t0 = time.perf_counter()
@@ -341,18 +381,47 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = bytes_total / float(t.item()) / 1e9
 
+    # cold variant: construction of A from the reference-layout host arrays inside every step
+    cold = None
+    if world == 1 and not args.no_extras:
+        h_ptr = rowptr.to(torch.int64).cpu().pin_memory()
+        h_ind = colind.to(torch.int64).cpu().pin_memory()
+        h_val = values.cpu().pin_memory()
+
+        def cold_step():
+            h = C.c_void_p()
+            ctx.check(lib.spl_mat_from_compressed(ctx._h, capi.SPL_CSR, capi.SPL_F64, nloc, n,
+                                                  h_ptr.numel(), C.c_void_p(h_ptr.data_ptr()),
+                                                  h_ind.numel(), C.c_void_p(h_ind.data_ptr()),
+                                                  h_val.numel(), C.c_void_p(h_val.data_ptr()), C.byref(h)))
+            ctx.check(lib.spl_spmv_host(ctx._h, h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
+            ctx.check(lib.spl_mat_free(ctx._h, h))
+
+        cold_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cold_step()
+        torch.cuda.synchronize()
+        cs = (time.perf_counter() - t0) / 3
+        cold = {"value": bytes_total / cs / 1e9, "unit": "GB/s", "ms_per_step": cs * 1e3,
+                "h2d_bytes_per_step": (h_ptr.numel() + h_ind.numel() + h_val.numel()) * 8 + h2d,
+                "what": "CsrMatrix::new from host usize arrays (validating) + &A * &x, every step"}
+        del h_ptr, h_ind, h_val
+
     # keep the device busy long enough for a few clock samples if the timed region was short
     if rank == 0:
         t_end = time.perf_counter() + max(0.0, 0.6 - ms_total * 2e-3)
         while time.perf_counter() < t_end:
             for _ in range(50):
-                A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
+                local_spmv()
             torch.cuda.synchronize()
         clk = clocks.stop()
 
-    # ---- secondary metrics of the path (rank 0, N = 1 only) ----------------------------------
+    # ---- secondary metrics of the path ------------------------------------------------------
     extras = {}
     cpu = None
+    if ngpu > 1 and not args.no_extras:
+        extras = sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world)
     if rank == 0 and ngpu == 1 and not args.no_extras:
         extras = secondary_metrics(torch, sp, ctx, A, wl)
         m = 64
@@ -383,15 +452,18 @@ def main():
                        "exchange": exchange, "spmv_kernel": kname,
                        "lanes_per_row": choice[1] if lanes == 0 else lanes,
                        "pct_of_8TBps_nominal": 100.0 * achieved / 8000.0},
-            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d * ngpu, "d2h_bytes_per_step": d2h * ngpu,
                     "steps": e2e_steps, "launches_per_step": e2e_launches,
-                    "what": "spl_mat_from_compressed(host usize arrays, validating) + spl_spmv_host"},
+                    "what": "&A * &x on a constructed (device-resident) CsrMatrix with pinned host x, y: "
+                            + ("spl_spmv_host" if ngpu == 1 else f"slice upload + {exchange} exchange + SpMV + download, all ranks")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "spmv", "kernel_ms": kern_ms, "bytes_per_launch": bytes_local},
             "clocks": clk,
         }
+        if cold:
+            line["e2e_cold"] = cold
         if cpu:
             line["cpu_baseline"] = cpu
         line.update(extras)
@@ -401,9 +473,70 @@ def main():
         dist.destroy_process_group()
 
 
+def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
+    """Row-sharded add (config 5: A + B, B = offsets {-8,-2,0,2,8}; no exchange) and row-sharded
+    COO->CSR assembly (config-3 style random triplets, block-distributed by entry index, routed by
+    one all-to-all).  Times are the slowest rank's; rates are whole-job."""
+    from spalinalg_b200.synthetic_device import banded_device, random_uniform_coo_device
+    out = {}
+
+    def timed_all(fn, reps=3, warm=1):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            dist.barrier(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return statistics.median(ts)
+
+    def total(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    bp, bc, bv = banded_device(torch, n, r0, r1, (-8, -2, 0, 2, 8), torch.float64)
+    B = sp.CsrMatrix.from_device_arrays(r1 - r0, n, bc.numel(), bp.data_ptr(), bc.data_ptr(), bv.data_ptr(),
+                                        np.float64, validate=False, ctx=ctx)
+    del bp, bc, bv
+    keep = {}
+
+    def add():
+        keep["C"] = A + B
+    ms = timed_all(add)
+    na, nb, nc = total(A.nnz()), total(B.nnz()), total(keep["C"].nnz())
+    b_add = (na + nb + nc) * 12 + 3 * (n + world) * 4
+    out["sharded_add"] = {"workload": "banded9 + banded{-8,-2,0,2,8}, n=1e8, f64, rows sharded, no exchange",
+                          "ms": ms, "nnz_out": nc, "mnnz_per_s": (na + nb) / ms / 1e3,
+                          "gbps_algorithmic": b_add / ms / 1e6}
+    del keep["C"], B
+
+    nr = 10_000_000
+    per = nr // world                      # each rank emits the triplets of `per` rows' worth of entries
+    r_, c_, v_ = random_uniform_coo_device(torch, per, 16, per * 16 // 20, torch.float32, seed=100 + rank)
+    # spread the rows over the whole matrix so that ~ (world-1)/world of the entries change rank
+    r_ = ((r_.to(torch.int64) * world + rank) % nr).to(torch.int32)
+    c_ = ((c_.to(torch.int64) * world + (rank * 7) % world) % nr).to(torch.int32)
+
+    def asm():
+        keep["D"] = spd.DistCsrMatrix.from_device_triplets(dist, torch, nr, nr, r_, c_, v_, ctx=ctx)
+    ms = timed_all(asm)
+    ln = total(int(v_.numel()))
+    out["sharded_assembly"] = {"workload": "random 1e7 x 1e7, 16/row + 5% duplicates, f32, triplets block-"
+                                           "distributed by entry index, one all-to-all",
+                               "len": ln, "nnz_out": total(keep["D"].local.nnz()), "ms": ms,
+                               "mnnz_per_s": ln / ms / 1e3}
+    return out if rank == 0 else {}
+
+
 def secondary_metrics(torch, sp, ctx, A, wl):
-    from spalinalg_b200.synthetic_device import stencil_device
-    """COO->CSR assembly on config 1 (shuffled and row-ordered) and CSR->CSC on the bench matrix."""
+    """COO->CSR assembly on config 1 (shuffled and row-ordered), CSR->CSC on the bench matrix, and
+    SpMV on config 5 (one GPU: the base of the N > 1 strong-scaling runs) and config 1."""
+    from spalinalg_b200.synthetic_device import banded_device, stencil_device
     out = {}
 
     def timed(fn, reps=5, warm=2):
@@ -439,6 +572,47 @@ def secondary_metrics(torch, sp, ctx, A, wl):
         b_asm = ln * (8 + 8) + ln * (4 + 8) + (n + 1) * 4
         out[f"assembly_{name}"] = {"workload": "laplace2d_1024_f64 COO->CSR", "len": ln, "ms": ms,
                                    "mnnz_per_s": ln / ms / 1e3, "gbps_algorithmic": b_asm / ms / 1e6}
+
+    def spmv_rate(M, x, y, copies=1, reps=100):
+        """Back-to-back launches; `copies` > 1 rotates over independent (A, x, y) sets whose total
+        footprint exceeds L2, so every launch reads from HBM."""
+        for i in range(5):
+            M[i % copies].spmv_device(x[i % copies].data_ptr(), y[i % copies].data_ptr())
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(reps):
+            M[i % copies].spmv_device(x[i % copies].data_ptr(), y[i % copies].data_ptr())
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peak, _ = peaks()
+    # config 1 SpMV, 4 rotating copies (4 x 80 MB > L2)
+    A1 = [sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(),
+                                          values.data_ptr(), np.float64, validate=False, ctx=ctx) for _ in range(4)]
+    x1 = [torch.rand(n, device="cuda", dtype=torch.float64) for _ in range(4)]
+    y1 = [torch.empty(n, device="cuda", dtype=torch.float64) for _ in range(4)]
+    b1 = spmv_bytes(int(colind.numel()), n, n, 8)
+    ms = spmv_rate(A1, x1, y1, copies=4, reps=200)
+    out["spmv_laplace2d_1024_f64"] = {"ms": ms, "gbps": b1 / ms / 1e6, "frac_measured_peak": b1 / ms / 1e6 / peak,
+                                      "l2": "4 rotating copies of (A, x, y), 320 MB > L2"}
+    ms = spmv_rate(A1[:1], x1[:1], y1[:1], reps=200)
+    out["spmv_laplace2d_1024_f64_l2_resident"] = {"ms": ms, "gbps": b1 / ms / 1e6}
+    del A1, x1, y1, rows, perm
+    # config 5 on one GPU
+    n5 = 10 ** 8
+    p5, c5, v5 = banded_device(torch, n5, 0, n5, range(-4, 5), torch.float64)
+    A5 = sp.CsrMatrix.from_device_arrays(n5, n5, c5.numel(), p5.data_ptr(), c5.data_ptr(), v5.data_ptr(),
+                                         np.float64, validate=False, ctx=ctx)
+    nnz5 = int(c5.numel())
+    del p5, c5, v5
+    x5 = torch.rand(n5, device="cuda", dtype=torch.float64)
+    y5 = torch.empty(n5, device="cuda", dtype=torch.float64)
+    b5 = spmv_bytes(nnz5, n5, n5, 8)
+    ms = spmv_rate([A5], [x5], [y5], reps=20)
+    out["spmv_banded9_1e8_f64_1gpu"] = {"ms": ms, "gbps": b5 / ms / 1e6, "frac_measured_peak": b5 / ms / 1e6 / peak,
+                                        "note": "same workload as the N > 1 runs: base of their strong scaling"}
     return out
 
 

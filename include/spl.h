@@ -47,6 +47,10 @@ typedef enum {
 typedef enum { SPL_CSR = 0, SPL_CSC = 1 } spl_format;
 typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:55-57 */
 
+/* Row sharding across the GPUs of one box: at most this many ranks. */
+#define SPL_MAX_PEERS 8
+#define SPL_IPC_HANDLE_BYTES 64
+
 /* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics. */
 typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2 } spl_spmv_kernel;
 
@@ -149,6 +153,56 @@ int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32
  * host triplets in storage order.  Arrays need nnz slots.  Synchronises. */
 int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val);
 int spl_mat_free(spl_ctx *ctx, spl_mat *m);
+
+/* ---- row sharding across GPUs (one process per GPU) ----------------
+ * The reference is single-process; these entry points are the sharded forms of the
+ * same reference items.  Rank g owns the contiguous block [starts[g], starts[g+1]) of
+ * the major axis (rows for CSR).  Collectives that move bulk data (the all-to-all of
+ * routed triplets, the all-gather of x for general matrices) stay with the caller's
+ * communicator (NCCL through torch.distributed); what is declared here is the device
+ * work either side of them and the peer-memory path that needs no collective. */
+
+/* Sending side of sharded From<&CooMatrix> (src/csr/conv/coo.rs:3-116,
+ * src/csc/conv/coo.rs:3-116): stable partition of this rank's triplets by owning
+ * rank.  keys_out_dev[i] = (major - starts[owner]) << bits(nminor) | minor, bits(n) =
+ * ceil(log2 n); vals_out_dev carries the values; both have len slots and hold the
+ * share of rank 0 first, then rank 1, ...; counts_host[g] = entries for rank g.
+ * Inside a share the insertion order is kept, so concatenating the received shares in
+ * source-rank order keeps the global insertion order among duplicates. */
+int spl_coo_route_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                      uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                      const void *val_dev, int world, const uint64_t *major_starts,
+                      uint64_t *keys_out_dev, void *vals_out_dev, uint64_t *counts_host);
+/* Receiving side: assembly of one shard (nrows x ncols are the SHARD's dimensions)
+ * from packed keys as produced by spl_coo_route_dev.  Same semantics and bit-exactness
+ * as spl_mat_from_coo_dev. */
+int spl_mat_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t len, const uint64_t *keys_dev, const void *vals_dev,
+                            int dedup, int dropzero, spl_mat **out);
+
+/* Peer-visible device memory (CUDA IPC over NVLink/NVSwitch).  alloc returns a zeroed
+ * cudaMalloc block plus the handle to send to the other ranks; open maps a peer's block
+ * into this process (peer access is enabled on demand). */
+int spl_peer_alloc(spl_ctx *ctx, uint64_t bytes, void **dev_ptr, unsigned char *handle_out);
+int spl_peer_open(spl_ctx *ctx, const unsigned char *handle, void **peer_ptr);
+int spl_peer_close(spl_ctx *ctx, void *peer_ptr);
+int spl_peer_free(spl_ctx *ctx, void *dev_ptr);
+/* Device-side barrier over peer memory: flag_ptrs[g] is rank g's uint32[SPL_MAX_PEERS]
+ * flag block (own block included, all zero-initialised); epoch must grow by one per
+ * call on every rank.  Everything this rank's stream wrote before the barrier is
+ * visible to peers' kernels launched after it.  Bounded spin: SPL_ERR_CUDA after
+ * timeout_ms if a peer never arrives (reported at the next synchronising call through
+ * spl_peer_barrier_status). */
+int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
+                     uint32_t timeout_ms);
+int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out);
+/* Row-sharded y_local = A_local * x with x left where it lives: x_slices[g] is rank
+ * g's slice of x (columns [col_starts[g], col_starts[g+1]), own slice included), mapped
+ * with spl_peer_open.  One kernel: every gather goes to the slice that owns the column,
+ * local HBM or a peer's over NVLink; no staging copy, no collective (the sharded form
+ * of `&A * &X`, src/csr/ops/mul.rs:5-60).  A_local is CSR with global column indices. */
+int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
+                  const uint64_t *col_starts, const void *const *x_slices, void *y_dev);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ SPL_OK, SPL_ERR_SHAPE, SPL_ERR_INVALID, SPL_ERR_CUDA, SPL_ERR_UNSUPPORTED, SPL_E
 SPL_CSR, SPL_CSC = 0, 1
 SPL_F32, SPL_F64 = 0, 1
 SPL_SPMV_AUTO, SPL_SPMV_VECTOR, SPL_SPMV_MERGE = 0, 1, 2
+SPL_MAX_PEERS, SPL_IPC_HANDLE_BYTES = 8, 64
 
 STATUS_NAMES = {0: "SPL_OK", 1: "SPL_ERR_SHAPE", 2: "SPL_ERR_INVALID", 3: "SPL_ERR_CUDA",
                 4: "SPL_ERR_UNSUPPORTED", 5: "SPL_ERR_OOM", 6: "SPL_ERR_ARG"}
@@ -49,6 +50,15 @@ SIGNATURES = {
     "spl_mat_device_ptrs": (_i, [_vp, _pp, _pp, _pp]),
     "spl_mat_to_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "spl_mat_free": (_i, [_vp, _vp]),
+    "spl_coo_route_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "spl_mat_from_packed_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _i, _i, _pp]),
+    "spl_peer_alloc": (_i, [_vp, _u64, _pp, _vp]),
+    "spl_peer_open": (_i, [_vp, _vp, _pp]),
+    "spl_peer_close": (_i, [_vp, _vp]),
+    "spl_peer_free": (_i, [_vp, _vp]),
+    "spl_peer_barrier": (_i, [_vp, _i, _i, _vp, C.c_uint32, C.c_uint32]),
+    "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
+    "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -102,6 +102,7 @@ int spl_ctx_create(int device, void *stream, spl_ctx **out) {
         SPL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
         SPL_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint32_t)));
         SPL_CUDA(cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)));
+        SPL_CUDA(cudaMemset(ctx->d_scratch, 0, 64 * sizeof(uint32_t)));
     } catch (const spl::Error &) {
         if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
         if (ctx->d_scratch) cudaFree(ctx->d_scratch);
@@ -465,6 +466,124 @@ int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col,
 int spl_mat_free(spl_ctx *ctx, spl_mat *m) {
     API_BEGIN(ctx)
     free_mat(ctx, m);
+    API_END(ctx)
+}
+
+// ---- row sharding across GPUs ------------------------------------------------
+
+int spl_coo_route_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                      uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                      const void *val_dev, int world, const uint64_t *major_starts,
+                      uint64_t *keys_out_dev, void *vals_out_dev, uint64_t *counts_host) {
+    API_BEGIN(ctx)
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(major_starts && counts_host, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev && keys_out_dev && vals_out_dev),
+                SPL_ERR_ARG, "NULL COO array");
+    route_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len, row_dev, col_dev,
+                  val_dev, world, major_starts, keys_out_dev, vals_out_dev, counts_host);
+    API_END(ctx)
+}
+
+int spl_mat_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t len, const uint64_t *keys_dev, const void *vals_dev, int dedup,
+                            int dropzero, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len == 0 || (keys_dev && vals_dev), SPL_ERR_ARG, "NULL COO array");
+    *out = assemble_from_packed_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
+                                    keys_dev, vals_dev, dedup, dropzero);
+    API_END(ctx)
+}
+
+int spl_peer_alloc(spl_ctx *ctx, uint64_t bytes, void **dev_ptr, unsigned char *handle_out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(dev_ptr && handle_out, SPL_ERR_ARG, "NULL argument");
+    *dev_ptr = nullptr;
+    void *p = nullptr;
+    SPL_CUDA(cudaMalloc(&p, bytes ? bytes : 1));        // plain cudaMalloc: IPC-exportable
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == SPL_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    cudaError_t e = cudaMemset(p, 0, bytes ? bytes : 1);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        throw Error{SPL_ERR_CUDA, std::string("spl_peer_alloc: ") + cudaGetErrorString(e)};
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    API_END(ctx)
+}
+
+int spl_peer_open(spl_ctx *ctx, const unsigned char *handle, void **peer_ptr) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(handle && peer_ptr, SPL_ERR_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    SPL_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    API_END(ctx)
+}
+
+int spl_peer_close(spl_ctx *ctx, void *peer_ptr) {
+    API_BEGIN(ctx)
+    if (peer_ptr) {
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SPL_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    }
+    API_END(ctx)
+}
+
+int spl_peer_free(spl_ctx *ctx, void *dev_ptr) {
+    API_BEGIN(ctx)
+    if (dev_ptr) {
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SPL_CUDA(cudaFree(dev_ptr));
+    }
+    API_END(ctx)
+}
+
+int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
+                     uint32_t timeout_ms) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(flag_ptrs, SPL_ERR_ARG, "NULL argument");
+    peer_barrier(ctx, world, rank, flag_ptrs, epoch, timeout_ms);
+    API_END(ctx)
+}
+
+int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out) {
+    API_BEGIN(ctx)
+    uint32_t w = 0;
+    read_back(ctx, ctx->d_scratch + 32, &w, 1);
+    if (timed_out) *timed_out = (int)w;
+    if (w) SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 32, 0, sizeof(uint32_t), ctx->stream));   // report once
+    SPL_REQUIRE(w == 0, SPL_ERR_CUDA, "spl_peer_barrier timed out waiting for a peer");
+    API_END(ctx)
+}
+
+int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
+                  const uint64_t *col_starts, const void *const *x_slices, void *y_dev) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a_local && col_starts && x_slices && y_dev, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
+                "world must be 1..8 and rank inside it");
+    SPL_REQUIRE(col_starts[0] == 0 && col_starts[world] == a_local->ncols, SPL_ERR_SHAPE,
+                "col_starts must run from 0 to A.ncols()");
+    PeerX px{};
+    px.world = world;
+    px.rank = rank;
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) px.start[g] = (uint32_t)col_starts[g < world ? g : world];
+    for (int g = 0; g < world; ++g) {
+        SPL_REQUIRE(col_starts[g] <= col_starts[g + 1], SPL_ERR_ARG, "col_starts must be non-decreasing");
+        SPL_REQUIRE(x_slices[g] || col_starts[g] == col_starts[g + 1], SPL_ERR_ARG, "NULL x slice");
+        px.slice[g] = x_slices[g];
+    }
+    spmv_peer(ctx, a_local, px, y_dev);
     API_END(ctx)
 }
 

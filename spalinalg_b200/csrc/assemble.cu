@@ -151,16 +151,15 @@ spl_mat *finish_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32
     return m;
 }
 
-template <typename K, typename VB>
+template <typename K, typename VB, typename LoadK>
 spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
-                       uint32_t len, const uint32_t *major_idx, const uint32_t *minor_idx,
-                       const VB *val, int minor_bits, int bits, int dedup, int dropzero) {
+                       uint32_t len, LoadK lk, const VB *val, int minor_bits, int bits, int dedup,
+                       int dropzero) {
     Tmp<K> k0(ctx, len), k1(ctx, len);
     Tmp<VB> v0(ctx, len), v1(ctx, len);
     K *kb[2] = {k0, k1};
     VB *vb[2] = {v0, v1};
     NoPayload *nb[2] = {nullptr, nullptr};
-    LoadPack<K> lk{major_idx, minor_idx, minor_bits};
     LoadPlain<VB> lv{val};
     const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, lk, lv, LoadNone{}, kb, vb, nb);
     if (dtype == SPL_F32)
@@ -168,6 +167,90 @@ spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint
                                      reinterpret_cast<float *>(vb[r]), minor_bits, dedup, dropzero);
     return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, kb[r],
                                   reinterpret_cast<double *>(vb[r]), minor_bits, dedup, dropzero);
+}
+
+// ---- row-sharded assembly: routing of triplets to their owners ----------------
+// owner of a major index: the block [starts[g], starts[g+1]) that contains it (world <= 8)
+struct Owners {
+    uint32_t start[SPL_MAX_PEERS + 1];
+    int world;
+    __device__ __forceinline__ uint32_t of(uint32_t major) const {
+        uint32_t g = 0;
+#pragma unroll
+        for (int q = 1; q < SPL_MAX_PEERS; ++q) g += (q < world && major >= start[q]) ? 1u : 0u;
+        return g;
+    }
+};
+struct LoadOwner {
+    const uint32_t *major;
+    Owners own;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i, uint32_t &) const {
+        return own.of(major[i]);
+    }
+};
+// key the owner will sort: (major - owner's first major) << minor_bits | minor
+struct LoadPackLocal {
+    const uint32_t *major;
+    const uint32_t *minor;
+    Owners own;
+    int minor_bits;
+    __device__ __forceinline__ uint64_t operator()(uint32_t i, uint32_t &) const {
+        const uint32_t m = major[i];
+        return ((uint64_t)(m - own.start[own.of(m)]) << minor_bits) | (uint64_t)minor[i];
+    }
+};
+template <typename K>
+struct LoadNarrow {   // packed 64-bit keys that fit K
+    const uint64_t *p;
+    __device__ __forceinline__ K operator()(uint32_t i, uint32_t &) const { return (K)p[i]; }
+};
+
+__global__ void owner_count_kernel(const uint32_t *__restrict__ major, uint32_t n, Owners own,
+                                   uint32_t *__restrict__ counts) {
+    __shared__ uint32_t s[SPL_MAX_PEERS];
+    if (threadIdx.x < SPL_MAX_PEERS) s[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t c[SPL_MAX_PEERS] = {};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = own.of(major[i]);
+#pragma unroll
+        for (int q = 0; q < SPL_MAX_PEERS; ++q) c[q] += g == (uint32_t)q;
+    }
+#pragma unroll
+    for (int q = 0; q < SPL_MAX_PEERS; ++q) {
+        uint32_t v = c[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane_id() == 0 && v) atomicAdd(&s[q], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < SPL_MAX_PEERS && s[threadIdx.x]) atomicAdd(counts + threadIdx.x, s[threadIdx.x]);
+}
+
+__global__ void packed_bounds_kernel(const uint64_t *__restrict__ keys, uint32_t n, int minor_bits,
+                                     uint32_t nmajor, uint32_t nminor, uint32_t *flag) {
+    uint32_t bad = 0;
+    const uint64_t mask = minor_bits >= 64 ? ~0ull : ((1ull << minor_bits) - 1ull);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        bad |= ((k >> minor_bits) >= nmajor) | ((k & mask) >= nminor);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flag, 1u);
+}
+
+void check_coo_bounds(spl_ctx *ctx, uint32_t len, const uint32_t *row, const uint32_t *col,
+                      uint32_t nrows, uint32_t ncols) {
+    if (len == 0) return;
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+    unsigned grid = div_up(len, 256 * 8);
+    coo_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(row, col, len, nrows, ncols, ctx->d_scratch);
+    check_launch(ctx, "coo_bounds");
+    uint32_t bad = 0;
+    read_back(ctx, ctx->d_scratch, &bad, 1);
+    SPL_REQUIRE(bad == 0, SPL_ERR_ARG,
+                "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
 }
 
 }  // namespace
@@ -202,37 +285,122 @@ spl_mat *finish_from_sorted(spl_ctx *ctx, int format, int dtype, uint32_t nrows,
 spl_mat *assemble_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
                                uint32_t len, const uint32_t *row, const uint32_t *col,
                                const void *val, int dedup, int dropzero) {
-    if (len > 0) {
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
-        unsigned grid = div_up(len, 256 * 8);
-        coo_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(row, col, len, nrows, ncols, ctx->d_scratch);
-        check_launch(ctx, "coo_bounds");
-        uint32_t bad = 0;
-        read_back(ctx, ctx->d_scratch, &bad, 1);
-        SPL_REQUIRE(bad == 0, SPL_ERR_ARG,
-                    "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
-    }
+    check_coo_bounds(ctx, len, row, col, nrows, ncols);
     const uint32_t *major_idx = format == SPL_CSR ? row : col;
     const uint32_t *minor_idx = format == SPL_CSR ? col : row;
     const int major_bits = bits_for(format == SPL_CSR ? nrows : ncols);
     const int minor_bits = bits_for(format == SPL_CSR ? ncols : nrows);
     const int bits = major_bits + minor_bits;
     if (bits <= 32) {
+        LoadPack<uint32_t> lk{major_idx, minor_idx, minor_bits};
         if (dtype == SPL_F32)
-            return assemble_impl<uint32_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, major_idx,
-                                                     minor_idx, (const uint32_t *)val, minor_bits,
-                                                     bits, dedup, dropzero);
-        return assemble_impl<uint32_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, major_idx,
-                                                 minor_idx, (const uint64_t *)val, minor_bits, bits,
-                                                 dedup, dropzero);
+            return assemble_impl<uint32_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                     (const uint32_t *)val, minor_bits, bits, dedup,
+                                                     dropzero);
+        return assemble_impl<uint32_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                 (const uint64_t *)val, minor_bits, bits, dedup,
+                                                 dropzero);
     }
+    LoadPack<uint64_t> lk{major_idx, minor_idx, minor_bits};
     if (dtype == SPL_F32)
-        return assemble_impl<uint64_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, major_idx,
-                                                 minor_idx, (const uint32_t *)val, minor_bits, bits,
-                                                 dedup, dropzero);
-    return assemble_impl<uint64_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, major_idx,
-                                             minor_idx, (const uint64_t *)val, minor_bits, bits, dedup,
-                                             dropzero);
+        return assemble_impl<uint64_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                 (const uint32_t *)val, minor_bits, bits, dedup,
+                                                 dropzero);
+    return assemble_impl<uint64_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                             (const uint64_t *)val, minor_bits, bits, dedup, dropzero);
+}
+
+// Packed keys as produced by route_coo_dev on the sending ranks (and concatenated in source-rank
+// order by the all-to-all, which keeps the global insertion order among duplicates).
+spl_mat *assemble_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
+                                  uint32_t len, const uint64_t *keys, const void *val, int dedup,
+                                  int dropzero) {
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols;
+    const uint32_t nminor = format == SPL_CSR ? ncols : nrows;
+    const int minor_bits = bits_for(nminor);
+    const int bits = bits_for(nmajor) + minor_bits;
+    if (len) {
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        packed_bounds_kernel<<<div_up(len, 256 * 8), 256, 0, ctx->stream>>>(keys, len, minor_bits, nmajor,
+                                                                          nminor, ctx->d_scratch);
+        check_launch(ctx, "packed_bounds");
+        uint32_t bad = 0;
+        read_back(ctx, ctx->d_scratch, &bad, 1);
+        SPL_REQUIRE(bad == 0, SPL_ERR_ARG, "packed COO key out of bounds for this shard");
+    }
+    if (bits <= 32) {
+        LoadNarrow<uint32_t> lk{keys};
+        if (dtype == SPL_F32)
+            return assemble_impl<uint32_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                     (const uint32_t *)val, minor_bits, bits, dedup,
+                                                     dropzero);
+        return assemble_impl<uint32_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                 (const uint64_t *)val, minor_bits, bits, dedup,
+                                                 dropzero);
+    }
+    LoadPlain<uint64_t> lk{keys};
+    if (dtype == SPL_F32)
+        return assemble_impl<uint64_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                                 (const uint32_t *)val, minor_bits, bits, dedup,
+                                                 dropzero);
+    return assemble_impl<uint64_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
+                                             (const uint64_t *)val, minor_bits, bits, dedup, dropzero);
+}
+
+// Stable partition of this rank's triplets by the rank that owns their major index: one radix
+// pass over the owner id carrying (packed local key, value).  Stability keeps every owner's
+// share in insertion order.  counts[g] = entries routed to rank g.
+template <typename VB>
+static void route_impl(spl_ctx *ctx, uint32_t len, const uint32_t *major, const uint32_t *minor,
+                       const VB *val, const Owners &own, int minor_bits, uint64_t *out_keys,
+                       VB *out_val) {
+    Tmp<uint32_t> okeys(ctx, len);
+    uint32_t *kb[2] = {okeys, nullptr};
+    uint64_t *ab[2] = {out_keys, nullptr};
+    VB *vb[2] = {out_val, nullptr};
+    LoadOwner lo{major, own};
+    LoadPackLocal lp{major, minor, own, minor_bits};
+    LoadPlain<VB> lv{val};
+    radix_sort<uint32_t, uint64_t, VB>(ctx, len, bits_for((uint64_t)own.world), lo, lp, lv, kb, ab, vb);
+}
+
+void route_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                   const uint32_t *row, const uint32_t *col, const void *val, int world,
+                   const uint64_t *major_starts, uint64_t *out_keys, void *out_val,
+                   uint64_t *counts_host) {
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS, SPL_ERR_ARG, "world must be 1..8");
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols;
+    SPL_REQUIRE(major_starts[0] == 0 && major_starts[world] == nmajor, SPL_ERR_ARG,
+                "major_starts must run from 0 to the number of rows (CSR) / columns (CSC)");
+    Owners own;
+    own.world = world;
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) {
+        const uint64_t v = major_starts[g < world ? g : world];
+        SPL_REQUIRE(g == 0 || g > world || v >= major_starts[g - 1], SPL_ERR_ARG,
+                    "major_starts must be non-decreasing");
+        own.start[g] = (uint32_t)v;
+    }
+    for (int g = 0; g < world; ++g) counts_host[g] = 0;
+    if (len == 0) return;
+    check_coo_bounds(ctx, len, row, col, nrows, ncols);
+    const uint32_t *major = format == SPL_CSR ? row : col;
+    const uint32_t *minor = format == SPL_CSR ? col : row;
+    const int minor_bits = bits_for(format == SPL_CSR ? ncols : nrows);
+    uint32_t *cnt = ctx->d_scratch + 8;
+    SPL_CUDA(cudaMemsetAsync(cnt, 0, SPL_MAX_PEERS * sizeof(uint32_t), ctx->stream));
+    unsigned grid = div_up(len, 256 * 8);
+    if (grid > (unsigned)ctx->num_sms * 8u) grid = (unsigned)ctx->num_sms * 8u;
+    owner_count_kernel<<<grid, 256, 0, ctx->stream>>>(major, len, own, cnt);
+    check_launch(ctx, "owner_count");
+    if (dtype == SPL_F32)
+        route_impl<uint32_t>(ctx, len, major, minor, (const uint32_t *)val, own, minor_bits, out_keys,
+                             (uint32_t *)out_val);
+    else
+        route_impl<uint64_t>(ctx, len, major, minor, (const uint64_t *)val, own, minor_bits, out_keys,
+                             (uint64_t *)out_val);
+    uint32_t c[SPL_MAX_PEERS];
+    read_back(ctx, cnt, c, SPL_MAX_PEERS);
+    for (int g = 0; g < world; ++g) counts_host[g] = c[g];
 }
 
 }  // namespace spl

@@ -17,6 +17,15 @@ spl_mat *finish_from_sorted(spl_ctx *ctx, int format, int dtype, uint32_t nrows,
                             uint32_t n, bool key64, const void *keys, void *vals, int minor_bits,
                             int dedup, int dropzero);
 
+// row-sharded assembly (8e): sender-side stable partition by owner, receiver-side assembly
+void route_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                   const uint32_t *row, const uint32_t *col, const void *val, int world,
+                   const uint64_t *major_starts, uint64_t *out_keys, void *out_val,
+                   uint64_t *counts_host);
+spl_mat *assemble_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
+                                  uint32_t len, const uint64_t *keys, const void *val, int dedup,
+                                  int dropzero);
+
 // recompress.cu — transpose / CSR<->CSC (a-4, a-5): same entries grouped by the other index.
 void recompress(spl_ctx *ctx, int dtype, uint32_t nmajor, uint32_t nminor, uint32_t nnz,
                 const uint32_t *ptr, const uint32_t *ind, const void *val, uint32_t *out_ptr,
@@ -25,6 +34,19 @@ void recompress(spl_ctx *ctx, int dtype, uint32_t nmajor, uint32_t nminor, uint3
 // spmv.cu — y = A x, CSR (a-6 restricted to B = n x 1, dense vectors)
 void spmv_plan(spl_ctx *ctx, spl_mat *a);
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes);
+
+// x gathered from the slice that owns the column (local HBM or a peer's over NVLink)
+struct PeerX {
+    const void *slice[SPL_MAX_PEERS];
+    uint32_t start[SPL_MAX_PEERS + 1];
+    int world;
+    int rank;
+};
+void spmv_peer(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *y);
+
+// peer.cu — CUDA IPC buffers and the flag barrier over peer memory
+void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
+                  uint32_t timeout_ms);
 
 // addsub.cu — C = A +/- B on compressed arrays of equal format (a-7)
 spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract);

@@ -23,11 +23,38 @@ namespace spl {
 namespace {
 
 // ------------------------------------------------------------------ vector kernel
-template <typename T, int LPR>
+// Where x[c] comes from.  XLocal: one device array.  XPeer: the slice of the rank that owns
+// column c — this GPU's HBM for the own block, a peer's HBM over NVLink (CUDA IPC mapping)
+// otherwise; the exchange of x is the gather itself, there is no staging copy and no collective.
+template <typename T>
+struct XLocal {
+    const T *x;
+    __device__ __forceinline__ T operator()(uint32_t c) const { return __ldg(x + c); }
+};
+template <typename T>
+struct XPeer {
+    const T *mine;
+    uint32_t my_start, my_len;
+    const T *slice[SPL_MAX_PEERS];
+    uint32_t start[SPL_MAX_PEERS + 1];
+    int world;
+    __device__ __forceinline__ T operator()(uint32_t c) const {
+        const uint32_t o = c - my_start;
+        if (o < my_len) return __ldg(mine + o);
+        const T *p = mine;                       // never dereferenced at index o: c is in some block
+        uint32_t off = 0;
+#pragma unroll
+        for (int g = 0; g < SPL_MAX_PEERS; ++g)
+            if (g < world && c >= start[g] && c < start[g + 1]) { p = slice[g]; off = c - start[g]; }
+        return __ldcg(p + off);                  // peer HBM: L2-coherent load, not kept in L1
+    }
+};
+
+template <typename T, int LPR, typename XG>
 __global__ void __launch_bounds__(256)
 spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
-                   const uint32_t *__restrict__ ind, const T *__restrict__ val,
-                   const T *__restrict__ x, T *__restrict__ y) {
+                   const uint32_t *__restrict__ ind, const T *__restrict__ val, const XG xg,
+                   T *__restrict__ y) {
     constexpr int U = 4;   // entries in flight per lane: all col/val loads, then all x gathers
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t row = gtid / LPR;
@@ -49,7 +76,7 @@ spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
             }
             T xv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = __ldg(x + c[u]);
+            for (int u = 0; u < U; ++u) xv[u] = xg(c[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u) acc += v[u] * xv[u];
         }
@@ -59,26 +86,38 @@ spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
     if (sub == 0 && row < nrows) y[row] = acc;
 }
 
-template <typename T, int LPR>
-void launch_vector(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
+template <typename T, int LPR, typename XG>
+void launch_vector(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y) {
     const uint64_t threads = (uint64_t)a->nrows * LPR;
     const unsigned grid = div_up(threads, 256);
-    spmv_vector_kernel<T, LPR><<<grid, 256, 0, ctx->stream>>>(a->nrows, a->ptr, a->ind,
-                                                              static_cast<const T *>(a->val), x, y);
+    spmv_vector_kernel<T, LPR, XG><<<grid, 256, 0, ctx->stream>>>(a->nrows, a->ptr, a->ind,
+                                                                  static_cast<const T *>(a->val), xg, y);
     check_launch(ctx, "spmv_vector");
 }
 
-template <typename T>
-void spmv_vector(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, int lanes) {
+template <typename T, typename XG>
+void spmv_vector(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, int lanes) {
     switch (lanes) {
-        case 1: launch_vector<T, 1>(ctx, a, x, y); break;
-        case 2: launch_vector<T, 2>(ctx, a, x, y); break;
-        case 4: launch_vector<T, 4>(ctx, a, x, y); break;
-        case 8: launch_vector<T, 8>(ctx, a, x, y); break;
-        case 16: launch_vector<T, 16>(ctx, a, x, y); break;
-        case 32: launch_vector<T, 32>(ctx, a, x, y); break;
+        case 1: launch_vector<T, 1>(ctx, a, xg, y); break;
+        case 2: launch_vector<T, 2>(ctx, a, xg, y); break;
+        case 4: launch_vector<T, 4>(ctx, a, xg, y); break;
+        case 8: launch_vector<T, 8>(ctx, a, xg, y); break;
+        case 16: launch_vector<T, 16>(ctx, a, xg, y); break;
+        case 32: launch_vector<T, 32>(ctx, a, xg, y); break;
         default: throw Error{SPL_ERR_ARG, "lanes per row must be 1, 2, 4, 8, 16 or 32"};
     }
+}
+
+template <typename T>
+void spmv_peer_t(spl_ctx *ctx, const spl_mat *a, const PeerX &px, T *y, int lanes) {
+    XPeer<T> xg;
+    xg.world = px.world;
+    for (int g = 0; g < SPL_MAX_PEERS; ++g) xg.slice[g] = static_cast<const T *>(px.slice[g]);
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) xg.start[g] = px.start[g];
+    xg.mine = xg.slice[px.rank];
+    xg.my_start = px.start[px.rank];
+    xg.my_len = px.start[px.rank + 1] - px.start[px.rank];
+    spmv_vector<T>(ctx, a, xg, y, lanes);
 }
 
 
@@ -350,8 +389,8 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         lanes = a->plan_lanes;
     }
     if (kernel == SPL_SPMV_VECTOR) {
-        if (a->dtype == SPL_F32) spmv_vector<float>(ctx, a, (const float *)x, (float *)y, lanes);
-        else spmv_vector<double>(ctx, a, (const double *)x, (double *)y, lanes);
+        if (a->dtype == SPL_F32) spmv_vector<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y, lanes);
+        else spmv_vector<double>(ctx, a, XLocal<double>{(const double *)x}, (double *)y, lanes);
         return;
     }
     if (kernel == SPL_SPMV_MERGE) {
@@ -361,6 +400,15 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         return;
     }
     throw Error{SPL_ERR_UNSUPPORTED, "unknown SpMV kernel"};
+}
+
+// Row-sharded SpMV with x left in its owners' memory: the vector kernel with the
+// peer gather.  Skewed shards should all-gather x and use the merge kernel instead.
+void spmv_peer(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *y) {
+    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv_peer needs a CSR matrix");
+    spmv_plan(ctx, const_cast<spl_mat *>(a));
+    if (a->dtype == SPL_F32) spmv_peer_t<float>(ctx, a, px, (float *)y, a->plan_lanes);
+    else spmv_peer_t<double>(ctx, a, px, (double *)y, a->plan_lanes);
 }
 
 }  // namespace spl

@@ -1,0 +1,236 @@
+"""Row-sharded forms of the hot path across the GPUs of one box.
+
+One process per GPU.  Rank g owns the contiguous row block [starts[g], starts[g+1]); its CSR block
+keeps GLOBAL column indices.  What moves between ranks, and how:
+
+  assembly   COO triplets start block-distributed by entry index.  Each rank partitions its
+             triplets by owning rank on the device (spl_coo_route_dev: one stable radix pass, keys
+             already packed for the receiver), one all-to-all (NCCL) moves them, the receiver
+             concatenates the shares in source-rank order — which keeps the global insertion order
+             among duplicates — and runs the single-GPU assembly (spl_mat_from_packed_dev).
+             Bit-exact against the reference's From<&CooMatrix> on the whole matrix.
+  SpMV       x stays where it lives.  Every rank keeps its slice of x in peer-visible memory
+             (CUDA IPC over NVLink/NVSwitch); spl_spmv_peer gathers each x[c] from the slice that
+             owns column c inside the SpMV kernel itself: no staging copy, no collective, and for a
+             banded or stencil matrix only the few halo columns ever cross NVLink.  Ordering between
+             iterations is a device-side flag barrier over the same peer memory (spl_peer_barrier).
+             General (random / power-law) matrices all-gather x with NCCL instead (sharding.py).
+  add/sub/neg  no exchange when the operands share the partition.
+
+torch.distributed is the plumbing (rendezvous, the all-to-all, object exchange of IPC handles);
+the device work goes through the C ABI.  The CPU tests (gloo, world size 2) drive the same host
+logic with a numpy stand-in for the two device calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+from .matrix import Context, CsrMatrix, Panic, _dtype_code, default_context
+from .sharding import row_partition
+
+
+def partition_starts(n: int, world: int) -> List[int]:
+    """starts[g] = first row of rank g (equal-row blocks), starts[world] = n."""
+    return [row_partition(n, world, g)[0] for g in range(world)] + [n]
+
+
+def bits_for(count: int) -> int:
+    """Bits needed for values in [0, count) — the packing rule of spl_coo_route_dev."""
+    return 0 if count <= 1 else int(count - 1).bit_length()
+
+
+# ------------------------------------------------------------------------- sharded assembly
+def exchange_routed(dist, torch, keys, vals, counts: Sequence[int], group=None):
+    """All-to-all of routed triplets.  `keys`/`vals` hold this rank's shares for rank 0, 1, ...
+    back to back (`counts[g]` entries each).  Returns (recv_keys, recv_vals, recv_counts) with the
+    received shares concatenated in SOURCE-RANK order (insertion order among duplicates)."""
+    world = dist.get_world_size(group)
+    send = torch.tensor(list(counts), dtype=torch.int64, device=keys.device)
+    recv = torch.empty(world, dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_counts = [int(v) for v in recv.tolist()]
+    total = sum(recv_counts)
+    rk = torch.empty(total, dtype=keys.dtype, device=keys.device)
+    rv = torch.empty(total, dtype=vals.dtype, device=vals.device)
+    dist.all_to_all_single(rk, keys, recv_counts, list(counts), group=group)
+    dist.all_to_all_single(rv, vals, recv_counts, list(counts), group=group)
+    return rk, rv, recv_counts
+
+
+def route_device(ctx: Context, torch, fmt: int, nrows: int, ncols: int, row, col, val, starts):
+    """Device stable partition by owner (spl_coo_route_dev) of uint32 row/col (int32 tensors) and
+    f32/f64 values.  Returns (keys int64 tensor, vals tensor, counts list)."""
+    n = int(val.numel())
+    world = len(starts) - 1
+    keys = torch.empty(n, dtype=torch.int64, device=val.device)
+    vals = torch.empty_like(val)
+    st = (C.c_uint64 * (world + 1))(*starts)
+    cnt = (C.c_uint64 * world)()
+    ctx.check(ctx._lib.spl_coo_route_dev(
+        ctx._h, fmt, _dtype_code(np.float32 if val.dtype == torch.float32 else np.float64), nrows, ncols, n,
+        C.c_void_p(row.data_ptr()), C.c_void_p(col.data_ptr()), C.c_void_p(val.data_ptr()), world,
+        C.cast(st, C.c_void_p), C.c_void_p(keys.data_ptr()), C.c_void_p(vals.data_ptr()),
+        C.cast(cnt, C.c_void_p)))
+    return keys, vals, [int(c) for c in cnt]
+
+
+class DistCsrMatrix:
+    """Row block of a CSR matrix on this rank plus the partition it belongs to."""
+
+    def __init__(self, local: CsrMatrix, starts: Sequence[int], rank: int, nrows: int, ncols: int):
+        self.local, self.starts, self.rank = local, list(starts), int(rank)
+        self.world = len(starts) - 1
+        self._nrows, self._ncols = int(nrows), int(ncols)
+
+    def nrows(self): return self._nrows
+    def ncols(self): return self._ncols
+    def local_rows(self): return self.starts[self.rank], self.starts[self.rank + 1]
+
+    @classmethod
+    def from_device_triplets(cls, dist, torch, nrows: int, ncols: int, row, col, val,
+                             ctx: Optional[Context] = None, dedup=True, dropzero=True, group=None):
+        """Sharded From<&CooMatrix<T>> for CsrMatrix<T> (src/csr/conv/coo.rs:3-116).  row/col are
+        this rank's int32 (uint32 bit pattern) device tensors, val f32/f64; entries are
+        block-distributed by entry index (rank 0 holds the first entries of the COO list)."""
+        ctx = ctx or default_context()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        starts = partition_starts(nrows, world)
+        keys, vals, counts = route_device(ctx, torch, capi.SPL_CSR, nrows, ncols, row, col, val, starts)
+        rk, rv, _ = exchange_routed(dist, torch, keys, vals, counts, group)   # route ended with a stream sync
+        torch.cuda.current_stream().synchronize()     # NCCL ran on torch's stream, assembly runs on ctx's
+        nloc = starts[rank + 1] - starts[rank]
+        h = C.c_void_p()
+        dtype = np.float32 if val.dtype == torch.float32 else np.float64
+        ctx.check(ctx._lib.spl_mat_from_packed_dev(
+            ctx._h, capi.SPL_CSR, _dtype_code(dtype), max(nloc, 1), ncols, int(rk.numel()),
+            C.c_void_p(rk.data_ptr()), C.c_void_p(rv.data_ptr()), int(dedup), int(dropzero), C.byref(h)))
+        return cls(CsrMatrix._wrap(ctx, h), starts, rank, nrows, ncols)
+
+    # add / sub / neg: rank-local on a shared partition ("sharded add/sub")
+    def _same_partition(self, rhs):
+        if (self._nrows, self._ncols) != (rhs._nrows, rhs._ncols):
+            raise Panic("assertion `left == right` failed: shapes differ")
+        if self.starts != rhs.starts or self.rank != rhs.rank:
+            raise Panic("operands of a sharded add/sub must share the row partition")
+
+    def __add__(self, rhs):
+        self._same_partition(rhs)
+        return DistCsrMatrix(self.local + rhs.local, self.starts, self.rank, self._nrows, self._ncols)
+
+    def __sub__(self, rhs):
+        self._same_partition(rhs)
+        return DistCsrMatrix(self.local - rhs.local, self.starts, self.rank, self._nrows, self._ncols)
+
+    def __neg__(self):
+        return DistCsrMatrix(-self.local, self.starts, self.rank, self._nrows, self._ncols)
+
+    def nnz_global(self, dist, torch, group=None):
+        t = torch.tensor([self.local.nnz()], dtype=torch.int64,
+                         device="cuda" if torch.cuda.is_available() else "cpu")
+        dist.all_reduce(t, group=group)
+        return int(t.item())
+
+    def spmv_peer(self, x: "PeerVector", y_dev: int):
+        """y_local = A_local x with x gathered from its owners' slices (spl_spmv_peer)."""
+        ctx = self.local._ctx
+        st = (C.c_uint64 * (self.world + 1))(*x.starts)
+        sl = (C.c_void_p * self.world)(*x.ptrs)
+        ctx.check(ctx._lib.spl_spmv_peer(ctx._h, self.local._h, self.world, self.rank,
+                                         C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(y_dev)))
+
+
+# ------------------------------------------------------------------------- peer memory
+class PeerBuffer:
+    """`nbytes` of zeroed device memory on every rank, each mapped into every other rank
+    (CUDA IPC; handles travel through torch.distributed's object all-gather)."""
+
+    def __init__(self, ctx: Context, dist, nbytes: int, group=None):
+        self.ctx = ctx
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        p = C.c_void_p()
+        handle = (C.c_ubyte * capi.SPL_IPC_HANDLE_BYTES)()
+        ctx.check(ctx._lib.spl_peer_alloc(ctx._h, int(nbytes), C.byref(p), C.cast(handle, C.c_void_p)))
+        self.local = p.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs: List[int] = []
+        self._opened: List[int] = []
+        for g, hb in enumerate(handles):
+            if g == self.rank:
+                self.ptrs.append(self.local)
+                continue
+            q = C.c_void_p()
+            buf = (C.c_ubyte * capi.SPL_IPC_HANDLE_BYTES).from_buffer_copy(hb)
+            ctx.check(ctx._lib.spl_peer_open(ctx._h, C.cast(buf, C.c_void_p), C.byref(q)))
+            self.ptrs.append(q.value)
+            self._opened.append(q.value)
+
+    def close(self, dist=None, group=None):
+        for q in self._opened:
+            self.ctx._lib.spl_peer_close(self.ctx._h, C.c_void_p(q))
+        self._opened = []
+        if dist is not None:
+            dist.barrier(group=group)          # nobody frees a block a peer still has mapped
+        if self.local:
+            self.ctx._lib.spl_peer_free(self.ctx._h, C.c_void_p(self.local))
+            self.local = None
+
+
+class PeerVector:
+    """x sharded conformally with the columns: rank g's slice holds x[starts[g]:starts[g+1]] in
+    peer-visible memory; `barrier()` orders one iteration's writes before the next one's reads."""
+
+    def __init__(self, ctx: Context, dist, n: int, dtype, starts: Optional[Sequence[int]] = None, group=None):
+        self.ctx, self.dtype = ctx, np.dtype(dtype)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.starts = list(starts) if starts is not None else partition_starts(n, self.world)
+        self.n = int(n)
+        longest = max(self.starts[g + 1] - self.starts[g] for g in range(self.world))
+        self._data = PeerBuffer(ctx, dist, max(longest, 1) * self.dtype.itemsize, group)
+        self._flags = PeerBuffer(ctx, dist, 4 * capi.SPL_MAX_PEERS, group)
+        self.ptrs = self._data.ptrs
+        self.local_ptr = self._data.local
+        self.local_len = self.starts[self.rank + 1] - self.starts[self.rank]
+        self._epoch = 0
+        dist.barrier(group=group)              # every flag block exists (and is zero) before first use
+
+    def barrier(self, timeout_ms: int = 2000):
+        """Device-side barrier on the context's stream (no host synchronisation)."""
+        self._epoch += 1
+        fl = (C.c_void_p * self.world)(*self._flags.ptrs)
+        self.ctx.check(self.ctx._lib.spl_peer_barrier(self.ctx._h, self.world, self.rank,
+                                                      C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms)))
+
+    def check(self):
+        """Raises if a barrier timed out (synchronises the stream)."""
+        t = C.c_int()
+        self.ctx.check(self.ctx._lib.spl_peer_barrier_status(self.ctx._h, C.byref(t)))
+
+    def close(self, dist=None, group=None):
+        self._data.close(dist, group)
+        self._flags.close(dist, group)
+
+
+# ------------------------------------------------------------------------- numpy stand-ins (tests)
+def route_numpy(nrows: int, ncols: int, row, col, val, starts):
+    """What spl_coo_route_dev computes, in numpy (CSR): used by the CPU gloo tests to drive the
+    host logic, and by the GPU tests as the checker of the device routing."""
+    row = np.asarray(row, np.uint64)
+    col = np.asarray(col, np.uint64)
+    b = np.asarray(starts[1:-1], np.uint64)
+    owner = np.searchsorted(b, row, side="right")
+    order = np.argsort(owner, kind="stable")
+    base = np.asarray(starts, np.uint64)[owner]
+    keys = ((row - base) << np.uint64(bits_for(ncols))) | col
+    counts = np.bincount(owner, minlength=len(starts) - 1).tolist()
+    return keys[order].astype(np.uint64), np.asarray(val)[order], counts
+
+
+def unpack_keys(keys, ncols: int):
+    mb = np.uint64(bits_for(ncols))
+    keys = np.asarray(keys, np.uint64)
+    return keys >> mb, keys & ((np.uint64(1) << mb) - np.uint64(1))
