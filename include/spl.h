@@ -52,7 +52,7 @@ typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:
 #define SPL_IPC_HANDLE_BYTES 64
 
 /* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics. */
-typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2 } spl_spmv_kernel;
+typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3 } spl_spmv_kernel;
 
 /* ---- context ------------------------------------------------------------ */
 

@@ -41,7 +41,7 @@ else:
     tdt = torch.float64
 x = torch.rand(n, device="cuda", dtype=tdt) - 0.5
 y = torch.empty(n, device="cuda", dtype=tdt)
-k, l = (2, 0) if kern == "merge" else (1, int(kern[6:]))
+k, l = (2, 0) if kern == "merge" else (3, 0) if kern == "split" else (1, int(kern[6:]))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 A.spmv_device(x.data_ptr(), y.data_ptr(), k, l)
 e0.record()

@@ -63,6 +63,8 @@ struct spl_mat {
     uint32_t max_row_len = 0;
     uint32_t *merge_rows = nullptr;   // merge-path tile start rows (merge_tiles + 1)
     uint32_t merge_tiles = 0;
+    uint32_t *split_rows = nullptr;   // nnz-split kernel: row holding the first entry of each chunk
+    uint32_t split_chunks = 0;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

@@ -194,6 +194,7 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->ind);
     dfree(ctx, m->val);
     dfree(ctx, m->merge_rows);
+    dfree(ctx, m->split_rows);
     delete m;
 }
 

@@ -72,13 +72,13 @@ spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
                 const bool ok = pu < e;
                 const uint32_t idx = ok ? pu : p;        // p itself is in range: safe dummy
                 c[u] = __ldg(ind + idx);
-                v[u] = ok ? __ldg(val + idx) : (T)0;
+                v[u] = __ldg(val + idx);
             }
             T xv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) xv[u] = xg(c[u]);
 #pragma unroll
-            for (int u = 0; u < U; ++u) acc += v[u] * xv[u];
+            for (int u = 0; u < U; ++u) acc += p + u * LPR < e ? v[u] * xv[u] : (T)0;   // 0, never 0 * inf
         }
     }
 #pragma unroll
@@ -331,6 +331,214 @@ void spmv_merge(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
     check_launch(ctx, "spmv_merge_fixup");
 }
 
+// ------------------------------------------------------------------ nnz-split kernel
+// Merge-path's balance at warp granularity, without a block barrier: every warp owns a fixed chunk
+// of K = 32*IPL consecutive stored entries, whatever the rows look like (a 700 000-entry row of a
+// power-law matrix is just 2 700 chunks).  Lane l holds entries l, l+32, ... of the chunk: IPL
+// coalesced col/val loads and then IPL independent x gathers are in flight per lane.  Rows are
+// found from a per-chunk start row computed once per matrix (split_rows): rows [R0, R1) end inside
+// the chunk (or are empty) and are written here, row R1 is still open at the chunk end and goes to
+// the carry arrays, which a fix-up adds in chunk order (no atomics: run-to-run identical).
+//   chunk inside one row  -> shuffle reduction straight from registers (the heavy-row fast path)
+//   otherwise             -> products parked in the warp's 1 KB of shared memory, one lane per
+//                            row; rows longer than 32 entries are summed by the whole warp.
+// Only 8 KB of shared memory per CTA, so L1 keeps caching the hot columns of x.
+constexpr int SP_THREADS = 256;
+constexpr int SP_WARPS = SP_THREADS / 32;
+template <typename T>
+constexpr int split_ipl() { return sizeof(T) == 8 ? 4 : 8; }
+constexpr int SP_FIX_SEQ = 32;        // carries one thread adds itself before handing the run to a CTA
+
+__global__ void split_partition_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t nnz,
+                                       uint32_t chunk, uint32_t nchunks,
+                                       uint32_t *__restrict__ chunk_row) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nchunks) return;
+    // the row r with ptr[r] <= pos < ptr[r+1]  (pos < nnz, so it exists and is not empty)
+    const uint32_t pos = w * chunk;
+    chunk_row[w] = w == 0 ? 0u : upper_bound_u32(ptr, 0u, nrows + 1u, pos) - 1u;
+}
+
+template <typename T, int IPL>
+__global__ void __launch_bounds__(SP_THREADS)
+spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
+                  const uint32_t *__restrict__ ind, const T *__restrict__ val,
+                  const T *__restrict__ x, T *__restrict__ y, const uint32_t *__restrict__ chunk_row,
+                  uint32_t *__restrict__ carry_row, T *__restrict__ carry_val) {
+    constexpr uint32_t K = 32 * IPL;
+    __shared__ T s_prod[SP_WARPS][K];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * SP_WARPS + warp;
+    if (w >= nchunks) return;
+    const uint32_t base = w * K;
+    const uint32_t count = nnz - base < K ? nnz - base : K;
+    const bool last = w + 1 == nchunks;
+    const uint32_t R0 = __ldg(chunk_row + w);
+    const uint32_t R1 = last ? nrows : __ldg(chunk_row + w + 1);
+
+    uint32_t c[IPL];
+    T v[IPL];
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) {
+        const uint32_t j = lane + 32 * u;
+        const uint32_t p = base + (j < count ? j : 0u);     // entry `base` exists: safe dummy
+        c[u] = __ldg(ind + p);
+        v[u] = __ldg(val + p);
+    }
+    T prod[IPL];
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) prod[u] = __ldg(x + c[u]);
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) prod[u] = lane + 32 * u < count ? v[u] * prod[u] : (T)0;
+
+    if (R0 == R1) {          // the whole chunk lies inside the open row
+        T s = prod[0];
+#pragma unroll
+        for (int u = 1; u < IPL; ++u) s += prod[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            carry_row[w] = R1;
+            carry_val[w] = s;
+        }
+        return;
+    }
+
+    T *sp = s_prod[warp];
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) sp[lane + 32 * u] = prod[u];
+    __syncwarp();
+    for (uint32_t rb = R0; rb < R1; rb += 32) {
+        const uint32_t r = rb + lane;
+        const bool valid = r < R1;
+        uint32_t lo = 0, hi = 0;
+        if (valid) {
+            lo = __ldg(ptr + r);
+            hi = __ldg(ptr + r + 1) - base;          // ends inside the chunk: hi <= count
+            lo = lo > base ? lo - base : 0u;         // the first row may have started earlier
+        }
+        const bool wide = hi - lo > 32u;
+        if (valid && !wide) {
+            T s = (T)0;
+            for (uint32_t j = lo; j < hi; ++j) s += sp[j];
+            y[r] = s;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, valid && wide);
+        while (todo) {                               // rows of more than 32 entries: the whole warp adds
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t l2 = __shfl_sync(0xffffffffu, lo, src), h2 = __shfl_sync(0xffffffffu, hi, src);
+            T s = (T)0;
+            for (uint32_t j = l2 + lane; j < h2; j += 32) s += sp[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((int)lane == src) y[r] = s;
+        }
+    }
+    // the row still open at the chunk end (none for the last chunk: every row ends by nnz)
+    T s = (T)0;
+    if (!last) {
+        const uint32_t p1 = __ldg(ptr + R1);
+        for (uint32_t j = (p1 > base ? p1 - base : 0u) + lane; j < count; j += 32) s += sp[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) {
+        carry_row[w] = R1;                           // == nrows for the last chunk: no carry
+        carry_val[w] = s;
+    }
+}
+
+// Carries of one row sit in consecutive chunks.  The first chunk of a run adds the run in chunk
+// order; runs longer than SP_FIX_SEQ are queued for a CTA each (fixed summation tree: deterministic).
+template <typename T>
+__global__ void spmv_split_fixup_kernel(uint32_t nrows, uint32_t nchunks,
+                                        const uint32_t *__restrict__ carry_row,
+                                        const T *__restrict__ carry_val, T *__restrict__ y,
+                                        uint32_t *__restrict__ long_runs, uint32_t *__restrict__ n_long,
+                                        uint32_t long_cap) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchunks) return;
+    const uint32_t row = carry_row[t];
+    if (row >= nrows) return;
+    if (t > 0 && carry_row[t - 1] == row) return;
+    T acc = (T)0;
+    uint32_t u = t;
+    for (; u < nchunks && u < t + SP_FIX_SEQ && carry_row[u] == row; ++u) acc += carry_val[u];
+    if (u < nchunks && u == t + SP_FIX_SEQ && carry_row[u] == row) {
+        const uint32_t slot = atomicAdd(n_long, 1u);
+        if (slot < long_cap) { long_runs[slot] = t; return; }
+        for (; u < nchunks && carry_row[u] == row; ++u) acc += carry_val[u];     // queue full: finish here
+    }
+    y[row] += acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmv_split_fixup_long_kernel(uint32_t nchunks, const uint32_t *__restrict__ carry_row,
+                             const T *__restrict__ carry_val, T *__restrict__ y,
+                             const uint32_t *__restrict__ long_runs, const uint32_t *__restrict__ n_long,
+                             uint32_t long_cap) {
+    __shared__ T s_part[8];
+    __shared__ int s_more;
+    const uint32_t n = min(*n_long, long_cap);
+    for (uint32_t q = blockIdx.x; q < n; q += gridDim.x) {
+        const uint32_t t = long_runs[q];
+        const uint32_t row = carry_row[t];
+        T acc = (T)0;
+        for (uint32_t b = t;; b += 256) {            // 256 carries per trip until the run ends
+            const uint32_t u = b + threadIdx.x;
+            const bool in = u < nchunks && carry_row[u] == row;
+            if (in) acc += carry_val[u];
+            if (threadIdx.x == 0) s_more = 0;
+            __syncthreads();
+            if (threadIdx.x == 255 && in) s_more = 1;          // the run reaches past this trip
+            __syncthreads();
+            const int more = s_more;
+            __syncthreads();
+            if (!more) break;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane_id() == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T s = s_part[0];
+            for (int k = 1; k < 8; ++k) s += s_part[k];
+            y[row] += s;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+void spmv_split(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
+    constexpr int IPL = split_ipl<T>();
+    const uint32_t nchunks = a->split_chunks;
+    if (nchunks == 0) {                              // no stored entry: y = 0
+        SPL_CUDA(cudaMemsetAsync(y, 0, sizeof(T) * (size_t)a->nrows, ctx->stream));
+        return;
+    }
+    constexpr uint32_t kLongCap = 1u << 16;
+    Tmp<uint32_t> carry_row(ctx, nchunks);
+    Tmp<T> carry_val(ctx, nchunks);
+    Tmp<uint32_t> long_runs(ctx, kLongCap + 1);
+    uint32_t *n_long = long_runs.p + kLongCap;
+    SPL_CUDA(cudaMemsetAsync(n_long, 0, sizeof(uint32_t), ctx->stream));
+    spmv_split_kernel<T, IPL><<<div_up(nchunks, SP_WARPS), SP_THREADS, 0, ctx->stream>>>(
+        a->nrows, a->nnz, nchunks, a->ptr, a->ind, static_cast<const T *>(a->val), x, y, a->split_rows,
+        carry_row, carry_val);
+    check_launch(ctx, "spmv_split");
+    spmv_split_fixup_kernel<T><<<div_up(nchunks, 256), 256, 0, ctx->stream>>>(
+        a->nrows, nchunks, carry_row, carry_val, y, long_runs, n_long, kLongCap);
+    check_launch(ctx, "spmv_split_fixup");
+    if (a->max_row_len > (uint32_t)(SP_FIX_SEQ * 32 * IPL)) {     // only then can a run exceed SP_FIX_SEQ
+        spmv_split_fixup_long_kernel<T><<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(
+            nchunks, carry_row, carry_val, y, long_runs, n_long, kLongCap);
+        check_launch(ctx, "spmv_split_fixup_long");
+    }
+}
+
 // ------------------------------------------------------------------ row statistics (plan)
 __global__ void max_row_len_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t *out) {
     uint32_t m = 0;
@@ -356,10 +564,13 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     }
     a->max_row_len = mx;
     const double mean = a->nrows ? (double)a->nnz / a->nrows : 0.0;
-    // each lane keeps 4 entries in flight, so one or two trips cover a row when lanes*8 >= mean
+    // lanes per row, from the measured sweeps (profiles/r1_spmv_notes.md): one lane up to ~12
+    // entries per row (5- and 9-entry rows: 0.46 / 0.88-0.93 of peak against 0.42 / 0.75-0.85 with
+    // two lanes), four lanes for 16..40 (random 16/row and the 27-point stencil), then one or two
+    // trips of 4 in-flight entries per lane
     int lanes = 1;
-    while (lanes < 32 && lanes * 8 < mean) lanes *= 2;
-    if (lanes < 2 && mean > 3.0) lanes = 2;
+    if (mean > 12.0) lanes = 4;
+    while (lanes < 32 && lanes * 10 < mean) lanes *= 2;
     a->plan_lanes = lanes;
     // merge-path tile starts (matrix-only data, cached)
     const int ipt = a->dtype == SPL_F64 ? merge_ipt<double>() : merge_ipt<float>();
@@ -371,9 +582,18 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     merge_partition_kernel<<<div_up((uint64_t)ntiles + 1, 256), 256, 0, ctx->stream>>>(
         a->ptr, a->nrows, a->nnz, items, ntiles, a->merge_rows);
     check_launch(ctx, "merge_partition");
-    // skewed rows (power law) or very short rows -> merge path; long regular rows -> vector
+    // nnz-split chunk start rows (matrix-only data, cached)
+    const uint32_t chunk = 32u * (a->dtype == SPL_F64 ? split_ipl<double>() : split_ipl<float>());
+    a->split_chunks = div_up(a->nnz, chunk);
+    a->split_rows = dalloc<uint32_t>(ctx, (size_t)a->split_chunks + 1);
+    if (a->split_chunks) {
+        split_partition_kernel<<<div_up(a->split_chunks, 256), 256, 0, ctx->stream>>>(
+            a->ptr, a->nrows, a->nnz, chunk, a->split_chunks, a->split_rows);
+        check_launch(ctx, "split_partition");
+    }
+    // skewed rows (power law) -> balanced nnz-split kernel; regular rows -> vector
     const bool skewed = mean > 0 && (double)mx > 8.0 * mean + 64.0;
-    a->plan_kernel = skewed ? SPL_SPMV_MERGE : SPL_SPMV_VECTOR;
+    a->plan_kernel = skewed ? SPL_SPMV_SPLIT : SPL_SPMV_VECTOR;
     a->plan_ready = 1;
 }
 
@@ -397,6 +617,12 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         spmv_plan(ctx, const_cast<spl_mat *>(a));
         if (a->dtype == SPL_F32) spmv_merge<float>(ctx, a, (const float *)x, (float *)y);
         else spmv_merge<double>(ctx, a, (const double *)x, (double *)y);
+        return;
+    }
+    if (kernel == SPL_SPMV_SPLIT) {
+        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        if (a->dtype == SPL_F32) spmv_split<float>(ctx, a, (const float *)x, (float *)y);
+        else spmv_split<double>(ctx, a, (const double *)x, (double *)y);
         return;
     }
     throw Error{SPL_ERR_UNSUPPORTED, "unknown SpMV kernel"};

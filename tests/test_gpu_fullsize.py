@@ -122,12 +122,12 @@ def test_c4_reduced_bit_exact_and_merge_path():
     rh, ch, vh = r.cpu().numpy().astype(np.uint64), c.cpu().numpy().astype(np.uint64), v.cpu().numpy()
     want = orc.compress_from_coo(n, n, orc.make_triplets(rh, ch, vh), "row")
     same_host(A, want)
-    assert A.spmv_choice()[0] == capi.SPL_SPMV_MERGE                       # skewed rows
+    assert A.spmv_choice()[0] == capi.SPL_SPMV_SPLIT                       # skewed rows
     x = torch.rand(n, device="cuda", dtype=torch.float32) - 0.5
     xh = x.cpu().numpy()
     yw = orc.csr_spmv(n, *want, xh)
     sc = orc.csr_spmv(n, want[0], want[1], np.abs(want[2]), np.abs(xh))
-    for kern, lanes in ((capi.SPL_SPMV_MERGE, 0), (capi.SPL_SPMV_VECTOR, 32), (capi.SPL_SPMV_AUTO, 0)):
+    for kern, lanes in ((capi.SPL_SPMV_MERGE, 0), (capi.SPL_SPMV_SPLIT, 0), (capi.SPL_SPMV_VECTOR, 32), (capi.SPL_SPMV_AUTO, 0)):
         y = spmv(A, x, kern, lanes).cpu().numpy()
         assert np.all(np.abs(y - yw) <= 1e-5 * np.maximum(sc, 1e-30)), kern
     # transpose of a skewed matrix, bit-exact
@@ -155,6 +155,9 @@ def test_c4_full_size_properties():
     # duplicates are summed in f32 during assembly as well: allow two roundings per addend
     assert bool(((ym - yref).abs() <= 4e-5 * sc + 1e-30).all())
     assert bool(((yv - ym).abs() <= 1e-5 * sc + 1e-30).all())
+    ys = spmv(A, x, capi.SPL_SPMV_SPLIT).double()
+    assert bool(((ys - ym).abs() <= 1e-5 * sc + 1e-30).all())
+    assert torch.equal(ys, spmv(A, x, capi.SPL_SPMV_SPLIT).double())         # run-to-run identical
 
 
 # ------------------------------------------------------------------ config 5

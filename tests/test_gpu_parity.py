@@ -267,7 +267,7 @@ def test_spmv_random(dtype, n, m, density):
     assert np.all(got[np.diff(a[0].astype(np.int64)) == 0] == 0)          # empty rows give 0
     import torch
     xd = torch.from_numpy(x).cuda()
-    for kernel, lanes in [(1, l) for l in (1, 2, 4, 8, 16, 32)] + [(2, 0)]:   # vector x6, merge
+    for kernel, lanes in [(1, l) for l in (1, 2, 4, 8, 16, 32)] + [(2, 0), (3, 0)]:   # vector x6, merge, split
         yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
         torch.cuda.synchronize()
         A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
@@ -290,15 +290,56 @@ def test_spmv_skewed_rows():
     want = orc.csr_spmv(n, ptr, ind, val, x)
     scale = orc.csr_spmv(n, ptr, ind, np.abs(val), np.abs(x))
     assert np.all(np.abs(A.matvec(x) - want) <= 1e-12 * np.maximum(scale, 1e-300))
-    assert A.spmv_choice()[0] == 2                       # skewed rows select the merge-path kernel
+    assert A.spmv_choice()[0] == 3                       # skewed rows select the balanced nnz-split kernel
     import torch
     xd = torch.from_numpy(x).cuda()
-    for kernel, lanes in ((1, 32), (2, 0)):
+    for kernel, lanes in ((1, 32), (2, 0), (3, 0)):
         yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
         torch.cuda.synchronize()
         A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
         sp.default_context().sync()
         assert np.all(np.abs(yd.cpu().numpy() - want) <= 1e-12 * np.maximum(scale, 1e-300)), kernel
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spmv_split_long_runs_and_edges(dtype):
+    """nnz-split kernel: a row spanning > 32 chunks (CTA fix-up), a row ending exactly on a chunk
+    boundary, leading/trailing empty rows, rows of 33..200 entries (whole-warp sums), inf in x."""
+    import torch
+    rng = np.random.default_rng(9)
+    n = m = 30000
+    K = 128 if dtype == np.float64 else 256
+    lens = np.zeros(n, np.int64)
+    lens[5] = K - 3; lens[6] = 3; lens[7] = 40 * K + 17; lens[8] = 2 * K; lens[50:80] = rng.integers(33, 200, 30)
+    lens[300:20000:3] = rng.integers(0, 9, len(lens[300:20000:3]))
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    ind = np.concatenate([np.sort(rng.choice(m, l, replace=False)) for l in lens if l]).astype(np.uint64)
+    val = rng.standard_normal(len(ind)).astype(dtype)
+    x = rng.standard_normal(m).astype(dtype)
+    A = sp.CsrMatrix.new(n, m, ptr, ind, val)
+    want = orc.csr_spmv(n, ptr, ind, val, x)
+    scale = orc.csr_spmv(n, ptr, ind, np.abs(val), np.abs(x))
+    rtol = SPMV_RTOL[np.dtype(dtype)]
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+    torch.cuda.synchronize()
+    A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=3)
+    sp.default_context().sync()
+    got = yd.cpu().numpy()
+    assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny))
+    assert np.all(got[lens == 0] == 0)
+    # a column holding +inf must give inf (never 0 * inf = nan from a masked slot) in the rows using it
+    col = int(ind[int(ptr[7]) + 3])
+    x2 = x.copy(); x2[col] = np.inf
+    for kernel, lanes in ((3, 0), (1, 4), (1, 32)):
+        yd.fill_(7.0)
+        xd2 = torch.from_numpy(x2).cuda()
+        torch.cuda.synchronize()
+        A.spmv_device(xd2.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
+        sp.default_context().sync()
+        got = yd.cpu().numpy()
+        w2 = orc.csr_spmv(n, ptr, ind, val, x2)
+        assert np.array_equal(np.isnan(got), np.isnan(w2)) and np.array_equal(np.isinf(got), np.isinf(w2)), kernel
 
 
 # ------------------------------------------------------------------ BASELINE shapes, properties
