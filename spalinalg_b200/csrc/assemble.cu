@@ -28,79 +28,125 @@ __global__ void coo_bounds_kernel(const uint32_t *__restrict__ row, const uint32
     if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flag, 1u);
 }
 
-// One thread per record; the thread on a run head walks its run and adds in order.
-// flags[i] = 1 iff record i is a head whose (summed) value survives.  vals updated in place
-// at heads only (non-heads are never written, so concurrent readers see the inputs).
-template <typename K, typename T>
-__global__ void __launch_bounds__(256)
-seg_reduce_kernel(const K *__restrict__ keys, T *vals, uint32_t n, int dedup, int dropzero,
-                  uint8_t *__restrict__ flags) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const K k = keys[i];
-    bool head = true;
-    if (dedup && i > 0) head = keys[i - 1] != k;
-    uint8_t keep = 0;
-    if (head) {
-        T s = vals[i];
-        if (dedup) {
-            uint64_t j = i + 1;
-            bool grew = false;
-            while (j < n && keys[j] == k) {
-                s = s + vals[j];          // one rounding per addend, insertion order
-                ++j;
-                grew = true;
-            }
-            if (grew) vals[i] = s;
-        }
-        keep = dropzero ? (s != (T)0) : 1;   // -0.0 and +0.0 dropped, NaN kept
-    }
-    flags[i] = keep;
-}
+// Tile = CP_THREADS x CP_IPT consecutive records, warp-striped: in step i thread t looks at record
+// tile_base + i*CP_THREADS + t, so every load and store below is coalesced, and all of a thread's
+// loads are issued before the first dependent instruction (in-order issue would otherwise expose
+// one memory latency per record).
 
+// Pass 1 of the tail.  A record whose key differs from its predecessor's heads a run of equal keys
+// (one matrix cell); the head adds the run left to right, one rounding per addend, in insertion
+// order (src/csr/conv/coo.rs:43-52) and stores the sum in place.  flags[i] = 1 iff record i is a
+// head whose sum survives the zero test (:60-73: -0.0 and +0.0 dropped, NaN kept).  tile_sums[b] =
+// survivors of tile b.
+template <typename K, typename T>
 __global__ void __launch_bounds__(CP_THREADS)
-flag_count_kernel(const uint8_t *__restrict__ flags, uint32_t n, uint32_t *__restrict__ tile_sums) {
+seg_reduce_kernel(const K *__restrict__ keys, T *vals, uint32_t n, int dedup, int dropzero,
+                  uint8_t *__restrict__ flags, uint32_t *__restrict__ tile_sums) {
     __shared__ uint32_t ws[CP_THREADS / 32 + 1];
-    const uint64_t base = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)threadIdx.x * CP_IPT;
-    uint32_t c = 0;
-    if (base + CP_IPT <= n) {
-        uint4 v = __ldg(reinterpret_cast<const uint4 *>(flags + base));
-        c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-    } else {
-        for (int i = 0; i < CP_IPT; ++i)
-            if (base + i < n) c += flags[base + i];
+    const uint64_t tile_base = (uint64_t)blockIdx.x * CP_TILE;
+    const unsigned lane = lane_id();
+    K k[CP_IPT], kn[CP_IPT], kp[CP_IPT];
+    T s[CP_IPT];
+#pragma unroll
+    for (int i = 0; i < CP_IPT; ++i) {
+        const uint64_t idx = tile_base + (uint64_t)i * CP_THREADS + threadIdx.x;
+        const bool ok = idx < n;
+        k[i] = ok ? keys[idx] : (K)0;
+        s[i] = ok ? vals[idx] : (T)0;
+        // neighbours that live in another warp's (or tile's) registers come from memory
+        kp[i] = (lane == 0 && ok && idx > 0) ? keys[idx - 1] : (K)0;
+        kn[i] = (lane == 31 && idx + 1 < n) ? keys[idx + 1] : (K)0;
+    }
+    uint32_t kept = 0;
+#pragma unroll
+    for (int i = 0; i < CP_IPT; ++i) {
+        const uint64_t idx = tile_base + (uint64_t)i * CP_THREADS + threadIdx.x;
+        const bool ok = idx < n;
+        const K up = __shfl_up_sync(0xffffffffu, k[i], 1), dn = __shfl_down_sync(0xffffffffu, k[i], 1);
+        const K prev = lane == 0 ? kp[i] : up, next = lane == 31 ? kn[i] : dn;
+        const bool head = ok && (!dedup || idx == 0 || prev != k[i]);
+        if (head && dedup && idx + 1 < n && next == k[i]) {          // duplicates: rare, walk the run
+            T acc = s[i];
+            for (uint64_t j = idx + 1; j < n && keys[j] == k[i]; ++j) acc = acc + vals[j];
+            s[i] = acc;
+            vals[idx] = acc;        // only heads are written; non-heads keep their input value
+        }
+        const bool keep = head && (!dropzero || s[i] != (T)0);
+        if (ok) flags[idx] = keep ? 1 : 0;
+        kept += keep;
     }
     uint32_t total;
-    block_exclusive_scan(c, ws, &total);
+    block_exclusive_scan(kept, ws, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// Survivors to their final slots: minor index, value, and (temporarily) the major index.
+// Pass 2 of the tail: survivors to their final slots (minor index, value) and the pointer array.
+// Position of record idx = tile offset + survivors before it in the tile, from 16 ballots per warp
+// and one scan of the (step, warp) counts.  ptr[q] = first final position whose major is >= q: the
+// first record of every major (survivor or not) writes the entries for the majors it skips.
 template <typename K, typename T>
 __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t *__restrict__ flags, const K *__restrict__ keys,
                const T *__restrict__ vals, uint32_t n, const uint32_t *__restrict__ tile_offsets,
-               int minor_bits, uint32_t *__restrict__ out_ind, T *__restrict__ out_val,
-               uint32_t *__restrict__ out_major) {
-    __shared__ uint32_t ws[CP_THREADS / 32 + 1];
-    const uint64_t base = (uint64_t)blockIdx.x * CP_TILE + (uint64_t)threadIdx.x * CP_IPT;
-    uint8_t f[CP_IPT];
-    uint32_t c = 0;
+               int minor_bits, uint32_t nmajor, uint32_t *__restrict__ out_ind, T *__restrict__ out_val,
+               uint32_t *__restrict__ ptr) {
+    constexpr int W = CP_THREADS / 32;
+    __shared__ uint32_t s_cnt[CP_IPT * W + 1];
+    const uint64_t tile_base = (uint64_t)blockIdx.x * CP_TILE;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const bool wide = minor_bits >= (int)(8 * sizeof(K));
+    const K minor_mask = wide ? ~(K)0 : (((K)1 << minor_bits) - 1);
+    K k[CP_IPT], kp[CP_IPT];
+    T v[CP_IPT];
+    uint32_t below[CP_IPT];
+    uint32_t fbits = 0;
 #pragma unroll
     for (int i = 0; i < CP_IPT; ++i) {
-        f[i] = (base + i < n) ? flags[base + i] : 0;
-        c += f[i];
+        const uint64_t idx = tile_base + (uint64_t)i * CP_THREADS + threadIdx.x;
+        const bool ok = idx < n;
+        const bool f = ok && flags[idx];
+        fbits |= (uint32_t)f << i;
+        k[i] = ok ? keys[idx] : (K)0;
+        v[i] = f ? vals[idx] : (T)0;
+        kp[i] = (lane == 0 && ok && idx > 0) ? keys[idx - 1] : (K)0;
     }
-    uint32_t pos = block_exclusive_scan(c, ws, nullptr) + tile_offsets[blockIdx.x];
-    const K minor_mask = (minor_bits >= (int)(8 * sizeof(K))) ? ~(K)0 : (((K)1 << minor_bits) - 1);
 #pragma unroll
     for (int i = 0; i < CP_IPT; ++i) {
-        if (f[i]) {
-            const K k = keys[base + i];
-            out_ind[pos] = (uint32_t)(k & minor_mask);
-            out_major[pos] = minor_bits >= (int)(8 * sizeof(K)) ? 0u : (uint32_t)(k >> minor_bits);
-            out_val[pos] = vals[base + i];
-            ++pos;
+        const unsigned bal = __ballot_sync(0xffffffffu, (fbits >> i) & 1u);
+        below[i] = __popc(bal & lanemask_lt());
+        if (lane == 0) s_cnt[i * W + warp] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp == 0) {                       // exclusive scan of the CP_IPT*W (= 128) counts: 4 per lane
+        constexpr int PER = CP_IPT * W / 32;
+        uint32_t c[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { c[q] = s_cnt[lane * PER + q]; sum += c[q]; }
+        uint32_t run = warp_inclusive_scan(sum) - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { s_cnt[lane * PER + q] = run; run += c[q]; }
+    }
+    __syncthreads();
+    const uint32_t off = tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < CP_IPT; ++i) {
+        const uint64_t idx = tile_base + (uint64_t)i * CP_THREADS + threadIdx.x;
+        const K up = __shfl_up_sync(0xffffffffu, k[i], 1);
+        if (idx >= n) continue;
+        const uint32_t pos = off + s_cnt[i * W + warp] + below[i];      // survivors before record idx
+        if ((fbits >> i) & 1u) {
+            out_ind[pos] = (uint32_t)(k[i] & minor_mask);
+            out_val[pos] = v[i];
+        }
+        const K prev = lane == 0 ? kp[i] : up;
+        const uint32_t mj = wide ? 0u : (uint32_t)(k[i] >> minor_bits);
+        const uint32_t mp = wide ? 0u : (uint32_t)(prev >> minor_bits);
+        // majors (mp, mj] start at pos; record 0 also writes major 0 .. mj = 0
+        if (idx == 0) for (uint32_t q = 0; q <= mj; ++q) ptr[q] = 0;
+        else for (uint32_t q = mp + 1; q <= mj; ++q) ptr[q] = pos;
+        if (idx == (uint64_t)n - 1) {
+            const uint32_t end = pos + ((fbits >> i) & 1u);
+            for (uint32_t q = mj + 1; q <= nmajor; ++q) ptr[q] = end;
         }
     }
 }
@@ -125,13 +171,11 @@ spl_mat *finish_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32
         return e;
     }
     Tmp<uint8_t> flags(ctx, (size_t)n + CP_IPT);
-    seg_reduce_kernel<K, T><<<div_up(n, 256), 256, 0, ctx->stream>>>(keys, vals, n, dedup, dropzero,
-                                                                     flags);
-    check_launch(ctx, "seg_reduce");
     const unsigned tiles = div_up(n, CP_TILE);
     Tmp<uint32_t> sums(ctx, tiles + 1);
-    flag_count_kernel<<<tiles, CP_THREADS, 0, ctx->stream>>>(flags, n, sums);
-    check_launch(ctx, "flag_count");
+    seg_reduce_kernel<K, T><<<tiles, CP_THREADS, 0, ctx->stream>>>(keys, vals, n, dedup, dropzero, flags,
+                                                                   sums);
+    check_launch(ctx, "seg_reduce");
     scan_spine_kernel<<<1, 1024, 0, ctx->stream>>>(sums, tiles);
     check_launch(ctx, "scan_spine");
     uint32_t nnz = 0;
@@ -139,11 +183,9 @@ spl_mat *finish_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32
 
     spl_mat *m = new_mat(ctx, format, dtype, nrows, ncols, nnz);
     try {
-        Tmp<uint32_t> major(ctx, nnz);
         compact_kernel<K, T><<<tiles, CP_THREADS, 0, ctx->stream>>>(
-            flags, keys, vals, n, sums, minor_bits, m->ind, static_cast<T *>(m->val), major);
+            flags, keys, vals, n, sums, minor_bits, nmajor, m->ind, static_cast<T *>(m->val), m->ptr);
         check_launch(ctx, "compact");
-        fill_ptr(ctx, major, nnz, nmajor, m->ptr);
     } catch (...) {
         free_mat(ctx, m);
         throw;

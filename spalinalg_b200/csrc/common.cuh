@@ -179,6 +179,27 @@ __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *__restrict__
     return lo;
 }
 
+// Streaming load (SASS LDG.E.NA, L1::no_allocate) for data a kernel reads exactly once with fully
+// coalesced warps — the col/val stream of the nnz-split and merge SpMV kernels — so that it does
+// not push the reusable x out of L1.  Measured on B200 (profiles/r1_spmv_notes.md): +6 % on the
+// R-MAT matrix; NOT for the vector kernel, whose few-lanes-per-row loads re-read their sectors
+// from L1 (0.88 -> 0.41 of peak on 9-entry rows when its stream bypassed L1).
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 struct NoPayload {};
 
 // Rust's unary minus on floats is a sign-bit flip for every input, NaN included (the GPU's FNEG

@@ -71,8 +71,8 @@ spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
                 const uint32_t pu = p + u * LPR;
                 const bool ok = pu < e;
                 const uint32_t idx = ok ? pu : p;        // p itself is in range: safe dummy
-                c[u] = __ldg(ind + idx);
-                v[u] = __ldg(val + idx);
+                c[u] = __ldg(ind + idx);     // L1-allocating on purpose: with few lanes per row a warp
+                v[u] = __ldg(val + idx);     // touches 32 rows' sectors and re-reads them from L1
             }
             T xv[U];
 #pragma unroll
@@ -382,8 +382,8 @@ spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t
     for (int u = 0; u < IPL; ++u) {
         const uint32_t j = lane + 32 * u;
         const uint32_t p = base + (j < count ? j : 0u);     // entry `base` exists: safe dummy
-        c[u] = __ldg(ind + p);
-        v[u] = __ldg(val + p);
+        c[u] = ld_stream(ind + p);
+        v[u] = ld_stream(val + p);
     }
     T prod[IPL];
 #pragma unroll
