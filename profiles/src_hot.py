@@ -9,7 +9,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
 tot = sum(int(r[col["# Samples"]] or 0) for r in data)
 print("kernel:", rows[0][1][:100], "| total samples", tot)
 stalls = [h for h in hdr if h.startswith("stall_")]
