@@ -434,7 +434,19 @@ def main():
         for _ in range(5):
             orc.csr_spmv(sn, sptr, sind, sval, sx)
         rowdot = (time.perf_counter() - t0) / 5
+        # COO->CSR on the CPU: the oracle port of From<&CooMatrix> (src/csr/conv/coo.rs:3-116) on a
+        # 512^2 Laplacian with the triplets shuffled like the device run's
+        from spalinalg_b200 import synthetic as syn
+        ar, ac, av = syn.laplacian_2d(512)
+        perm = np.random.default_rng(42).permutation(len(av))
+        trip = orc.make_triplets(ar[perm], ac[perm], av[perm])
+        t0 = time.perf_counter()
+        for _ in range(3):
+            orc.compress_from_coo(512 * 512, 512 * 512, trip, "row")
+        asm_s = (time.perf_counter() - t0) / 3
         cpu = {"value": sb / statistics.median(ts) / 1e9, "unit": "GB/s", "cores": 1,
+               "assembly": {"value": len(av) / asm_s / 1e6, "unit": "Mnnz/s", "cores": 1,
+                            "sample": f"2-D Laplacian 512^2, {len(av)} shuffled triplets, f64, COO->CSR"},
                "kind": "port", "host_cores": os.cpu_count(),
                "sample": f"27-point stencil {m}^3 (n={sn}, nnz={len(sval)}), f64; reference route "
                          f"&A * &X (3 transposes + Gustavson), 3 reps median",
@@ -526,10 +538,28 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         keep["D"] = spd.DistCsrMatrix.from_device_triplets(dist, torch, nr, nr, r_, c_, v_, ctx=ctx)
     ms = timed_all(asm)
     ln = total(int(v_.numel()))
+    D = keep["D"]
+    nnz_d = total(D.local.nnz())
     out["sharded_assembly"] = {"workload": "random 1e7 x 1e7, 16/row + 5% duplicates, f32, triplets block-"
                                            "distributed by entry index, one all-to-all",
-                               "len": ln, "nnz_out": total(keep["D"].local.nnz()), "ms": ms,
-                               "mnnz_per_s": ln / ms / 1e3}
+                               "len": ln, "nnz_out": nnz_d, "ms": ms, "mnnz_per_s": ln / ms / 1e3}
+    del r_, c_, v_
+
+    # general (random-column) matrix: x exchanged by NCCL all-gather, then the local SpMV
+    d0, d1 = D.local_rows()
+    xg = torch.rand(nr, device="cuda", dtype=torch.float32) - 0.5
+    yg = torch.empty(d1 - d0, device="cuda", dtype=torch.float32)
+    even = nr % world == 0
+
+    def spmv_ag():
+        from spalinalg_b200 import sharding
+        sharding.exchange_allgather(dist, xg, d0, d1, world, even)
+        D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
+    ms = timed_all(spmv_ag, reps=7, warm=3)
+    b_ag = nnz_d * 8 + 2 * nr * 4
+    out["sharded_spmv_allgather"] = {"workload": "the matrix assembled above (random 16/row, f32), x all-gathered "
+                                                 "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
+                                     "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
     return out if rank == 0 else {}
 
 
@@ -564,7 +594,8 @@ def secondary_metrics(torch, sp, ctx, A, wl):
                                    (rowptr[1:] - rowptr[:-1]).to(torch.int64))
     g = torch.Generator(device="cuda"); g.manual_seed(42)
     perm = torch.randperm(rows.numel(), device="cuda", generator=g)
-    for name, (r_, c_, v_) in {"shuffled": (rows[perm].contiguous(), colind[perm].contiguous(), values[perm].contiguous()),
+    out_host_triplets = (rows[perm].contiguous(), colind[perm].contiguous(), values[perm].contiguous())
+    for name, (r_, c_, v_) in {"shuffled": out_host_triplets,
                                "row_ordered": (rows, colind, values)}.items():
         ln = r_.numel()
         ms = timed(lambda: sp.CsrMatrix.from_device_triplets(n, n, ln, r_.data_ptr(), c_.data_ptr(),
@@ -572,6 +603,33 @@ def secondary_metrics(torch, sp, ctx, A, wl):
         b_asm = ln * (8 + 8) + ln * (4 + 8) + (n + 1) * 4
         out[f"assembly_{name}"] = {"workload": "laplace2d_1024_f64 COO->CSR", "len": ln, "ms": ms,
                                    "mnnz_per_s": ln / ms / 1e3, "gbps_algorithmic": b_asm / ms / 1e6}
+
+    # the same assembly through the reference-facing call: host usize (u64) row/col + f64 values in
+    # pinned memory -> spl_mat_from_coo (upload, narrow, sort, sum) -> CsrMatrix
+    sr, sc_, sv = out_host_triplets
+    coo_h = [t.cpu().pin_memory() for t in (sr.to(torch.int64), sc_.to(torch.int64), sv)]
+    lib = ctx._lib
+    import ctypes as C
+    from spalinalg_b200 import _capi as capi
+
+    def asm_host():
+        h = C.c_void_p()
+        ctx.check(lib.spl_mat_from_coo(ctx._h, capi.SPL_CSR, capi.SPL_F64, n, n, coo_h[2].numel(),
+                                       C.c_void_p(coo_h[0].data_ptr()), C.c_void_p(coo_h[1].data_ptr()),
+                                       C.c_void_p(coo_h[2].data_ptr()), 1, 1, C.byref(h)))
+        ctx.check(lib.spl_mat_free(ctx._h, h))
+    asm_host(); asm_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        asm_host()
+    torch.cuda.synchronize()
+    hs = (time.perf_counter() - t0) / 5
+    out["assembly_shuffled_e2e"] = {"workload": "laplace2d_1024_f64 COO->CSR from pinned host usize triplets",
+                                    "len": int(coo_h[2].numel()), "ms": hs * 1e3,
+                                    "mnnz_per_s": coo_h[2].numel() / hs / 1e6,
+                                    "h2d_bytes": int(coo_h[2].numel()) * 24}
+    del coo_h
 
     def spmv_rate(M, x, y, copies=1, reps=100):
         """Back-to-back launches; `copies` > 1 rotates over independent (A, x, y) sets whose total
@@ -599,7 +657,7 @@ def secondary_metrics(torch, sp, ctx, A, wl):
                                       "l2": "4 rotating copies of (A, x, y), 320 MB > L2"}
     ms = spmv_rate(A1[:1], x1[:1], y1[:1], reps=200)
     out["spmv_laplace2d_1024_f64_l2_resident"] = {"ms": ms, "gbps": b1 / ms / 1e6}
-    del A1, x1, y1, rows, perm
+    del A1, x1, y1, rows, perm, out_host_triplets
     # config 5 on one GPU
     n5 = 10 ** 8
     p5, c5, v5 = banded_device(torch, n5, 0, n5, range(-4, 5), torch.float64)
