@@ -75,14 +75,18 @@ spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
     }
     const int minor_bits = bits_for(bn);
     const int bits = bits_for(an) + minor_bits;
-    Tmp<K> k0(ctx, total), k1(ctx, total), k2(ctx, total);
-    Tmp<VB> v0(ctx, total), v1(ctx, total), v2(ctx, total);
+    const size_t sort_n = minor_bits == 0 ? 0 : total;      // no sort buffers on the n x 1 fast path
+    Tmp<K> k0(ctx, sort_n), k1(ctx, sort_n), k2(ctx, total);
+    Tmp<VB> v0(ctx, sort_n), v1(ctx, sort_n), v2(ctx, total);
     if (total) {
         expand_kernel<K, T><<<div_up(annz, 256), 256, 0, ctx->stream>>>(
             an, annz, a->ptr, a->ind, (const T *)a->val, b->ptr, b->ind, (const T *)b->val, off,
             minor_bits, k2, reinterpret_cast<T *>(v2.p));
         check_launch(ctx, "expand");
     }
+    if (minor_bits == 0)     // B is n x 1 (the reference's SpMV route): the key is the row of A and the
+        return finish_from_sorted(ctx, format, dtype, out_rows, out_cols, total, sizeof(K) == 8, k2.p,
+                                  v2.p, minor_bits, /*dedup=*/1, /*dropzero=*/0);   // products are in row order
     K *kb[2] = {k0, k1};
     VB *vb[2] = {v0, v1};
     NoPayload *nb[2] = {nullptr, nullptr};

@@ -325,6 +325,46 @@ class DokMatrix:
         return DokMatrix.with_entries(self._ncols, self._nrows, ((c, r, v) for (r, c, v) in self.iter()),
                                       self._dtype)
 
+    # conversions into DOK and DOK arithmetic: host-side shells (src/dok.rs:640-775)
+    @classmethod
+    def from_coo(cls, coo: "CooMatrix"):
+        """From<&CooMatrix> (src/dok.rs:640-668): `*entry.or_default() += value`, i.e. every cell is
+        summed from T::default() = 0.0 in insertion order (a lone -0.0 becomes +0.0); no zero drop."""
+        m = cls(coo.nrows(), coo.ncols(), coo.dtype)
+        zero = m._dtype.type(0)
+        for (r, c, v) in coo.iter():
+            m._map[(r, c)] = m._dtype.type(m._map.get((r, c), zero) + m._dtype.type(v))
+        return m
+
+    @classmethod
+    def from_csr(cls, csr: "CsrMatrix"):
+        """From<&CsrMatrix> (src/dok.rs:707-720): storage-order collect of the stored entries."""
+        m = cls(csr.nrows(), csr.ncols(), csr.dtype)
+        m._map = {(int(r), int(c)): m._dtype.type(v) for (r, c, v) in csr.iter()}
+        return m
+
+    @classmethod
+    def from_csc(cls, csc: "CscMatrix"):
+        """From<&CscMatrix> (src/dok.rs:676-693)."""
+        return cls.from_csr(csc)
+
+    def _merge(self, rhs: "DokMatrix", sign):
+        out = DokMatrix(self._nrows, self._ncols, self._dtype)       # dims of self, like the reference
+        out._map = dict(self._map)
+        zero = self._dtype.type(0)
+        for key, v in rhs._map.items():                               # or_default() then += / -=
+            base = out._map.get(key, zero)
+            out._map[key] = self._dtype.type(base + v) if sign > 0 else self._dtype.type(base - v)
+        return out
+
+    def __add__(self, rhs: "DokMatrix"): return self._merge(rhs, +1)       # src/dok.rs:722-736
+    def __sub__(self, rhs: "DokMatrix"): return self._merge(rhs, -1)       # src/dok.rs:738-752
+
+    def __neg__(self):                                                     # src/dok.rs:754-769
+        out = DokMatrix(self._nrows, self._ncols, self._dtype)
+        out._map = {k: self._dtype.type(-v) for k, v in self._map.items()}
+        return out
+
     def triplets(self):
         n = len(self._map)
         r = np.fromiter((k[0] for k in self._map), np.uint64, n)

@@ -93,6 +93,22 @@ def test_dok_shell():
         dok.insert(2, 0, 1.0)
 
 
+def test_dok_arithmetic_and_from_coo():
+    """src/dok.rs:1081-1111 (add, sub, neg goldens) and From<&CooMatrix> (src/dok.rs:640-668)."""
+    lhs = sp.DokMatrix.with_entries(1, 1, [(0, 0, 1.0)])
+    rhs = sp.DokMatrix.with_entries(1, 1, [(0, 0, 2.0)])
+    assert list((lhs + rhs).iter()) == [(0, 0, 3.0)]
+    assert list((lhs - rhs).iter()) == [(0, 0, -1.0)]
+    assert list((-lhs).iter()) == [(0, 0, -1.0)]
+    only_rhs = sp.DokMatrix.with_entries(2, 2, [(1, 1, 5.0)])
+    assert (sp.DokMatrix.new(2, 2) - only_rhs).get(1, 1) == -5.0           # 0.0 - v
+    coo = sp.CooMatrix.with_entries(2, 3, [(0, 0, 1.0), (1, 1, 2.0), (0, 0, 0.5), (1, 2, -0.0)])
+    dok = sp.DokMatrix.from_coo(coo)
+    assert dok.length() == 3 and dok.get(0, 0) == 1.5 and dok.get(1, 1) == 2.0
+    import numpy as np
+    assert not np.signbit(dok.get(1, 2))                                    # 0.0 + -0.0 = +0.0, entry kept
+
+
 def test_synthetic_generators():
     from spalinalg_b200 import synthetic as syn
     r, c, v = syn.laplacian_2d(8)

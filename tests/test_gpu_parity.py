@@ -240,6 +240,43 @@ def test_mul_random(dtype, n, k, m, density):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_mul_by_n_by_1_is_the_reference_spmv(dtype, fmt):
+    """`&A * &X` with X n x 1 — the reference's only SpMV route (src/csr/ops/mul.rs:5-60): rows of A
+    without a stored entry are absent from the result, values are the sequential ascending-k sums,
+    bit for bit (the device skips the sort here: products are already in row order)."""
+    rng = np.random.default_rng(77)
+    n, k = 3000, 2500
+    a = _rand_csr(rng, n, k, 0.004, dtype)
+    xs = rng.standard_normal(k).astype(dtype)
+    present = rng.random(k) < 0.9                                  # some rows of X are empty
+    xptr = np.concatenate([[0], np.cumsum(present)]).astype(np.uint64)
+    x = (xptr, np.zeros(int(present.sum()), np.uint64), xs[present])
+    want = orc.csr_mul(n, k, 1, a, x)
+    A, X = sp.CsrMatrix.new(n, k, *a), sp.CsrMatrix.new(k, 1, *x)
+    if fmt == "csr":
+        same(arrays(A * X), want, "csr A * X")
+    else:
+        got = A.to_csc() * X.to_csc()
+        same(arrays(got.to_csr()), want, "csc A * X")
+
+
+def test_dok_round_trip_through_device():
+    """From<&DokMatrix> for CsrMatrix / CscMatrix (src/csr/conv/dok.rs:3-76) and back
+    (src/dok.rs:676-720): explicit zeros survive both ways, nothing is summed or dropped."""
+    rng = np.random.default_rng(4)
+    dok = sp.DokMatrix.new(40, 30)
+    for _ in range(300):
+        dok.insert(int(rng.integers(40)), int(rng.integers(30)), float(rng.standard_normal()))
+    dok.insert(3, 3, 0.0)
+    for cls, back in ((sp.CsrMatrix, sp.DokMatrix.from_csr), (sp.CscMatrix, sp.DokMatrix.from_csc)):
+        m = cls.from_dok(dok)
+        assert m.nnz() == dok.length()
+        d2 = back(m)
+        assert d2.shape() == dok.shape() and d2._map == dok._map
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_neg_random(dtype):
     rng = np.random.default_rng(11)
     a = _rand_csr(rng, 500, 400, 0.05, dtype)
