@@ -4,8 +4,10 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <type_traits>
 
@@ -56,8 +58,11 @@ struct spl_mat {
     uint32_t *ptr = nullptr;   // nmajor + 1
     uint32_t *ind = nullptr;   // nnz
     void *val = nullptr;       // nnz * sizeof(T)
-    // SpMV plan (filled lazily by the first spl_spmv on this matrix; read-only afterwards)
-    int plan_ready = 0;
+    // SpMV plan (filled lazily by the first spl_spmv on this matrix; read-only afterwards).
+    // A matrix may be shared read-only by several host threads / contexts (spl.h): the first
+    // caller plans under plan_mu, everybody else sees plan_ready (acquire) and only reads.
+    std::mutex plan_mu;
+    std::atomic<int> plan_ready{0};
     int plan_kernel = 0;       // SPL_SPMV_VECTOR / SPL_SPMV_MERGE
     int plan_lanes = 0;        // lanes per row of the vector kernel
     uint32_t max_row_len = 0;

@@ -553,7 +553,9 @@ __global__ void max_row_len_kernel(const uint32_t *__restrict__ ptr, uint32_t nr
 }  // namespace
 
 void spmv_plan(spl_ctx *ctx, spl_mat *a) {
-    if (a->plan_ready) return;
+    if (a->plan_ready.load(std::memory_order_acquire)) return;
+    std::lock_guard<std::mutex> lock(a->plan_mu);
+    if (a->plan_ready.load(std::memory_order_relaxed)) return;
     uint32_t mx = 0;
     if (a->nnz) {
         SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
@@ -594,7 +596,9 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     // skewed rows (power law) -> balanced nnz-split kernel; regular rows -> vector
     const bool skewed = mean > 0 && (double)mx > 8.0 * mean + 64.0;
     a->plan_kernel = skewed ? SPL_SPMV_SPLIT : SPL_SPMV_VECTOR;
-    a->plan_ready = 1;
+    // the plan arrays were written on this context's stream: make them visible to any other stream
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    a->plan_ready.store(1, std::memory_order_release);
 }
 
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes) {
