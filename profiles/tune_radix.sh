@@ -1,9 +1,10 @@
 #!/bin/bash
 # Rebuilds the library on the GPU box with different radix tile shapes and times config 2
-# (CSR->CSC, shuffled assembly) and config 3 assembly.  Usage: bash profiles/tune_radix.sh "IPT,MINBLOCKS ..."
+# (CSR->CSC, shuffled assembly) and config 3 (assembly, CSR->CSC).
+# Usage: bash profiles/tune_radix.sh "IPT,MINBLOCKS[,THREADS] ..."
 for v in $1; do
-  ipt=${v%,*}; mb=${v#*,}
-  SPL_EXTRA_NVCC_FLAGS="-DRS_IPT_VALUE=$ipt -DRS_MIN_BLOCKS=$mb" python -m spalinalg_b200.build --force > /tmp/build.log 2>&1 || { echo "build failed $v"; tail -5 /tmp/build.log; continue; }
+  IFS=, read ipt mb thr <<< "$v"; thr=${thr:-256}
+  SPL_EXTRA_NVCC_FLAGS="-DRS_IPT_VALUE=$ipt -DRS_MIN_BLOCKS=$mb -DRS_THREADS_VALUE=$thr" python -m spalinalg_b200.build --force > /tmp/build.log 2>&1 || { echo "build failed $v"; tail -5 /tmp/build.log; continue; }
   python profiles/run_configs.py c2 c3 > /tmp/run.log 2>&1
   python - "$v" <<'PY'
 import json, sys

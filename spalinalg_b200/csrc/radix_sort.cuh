@@ -16,7 +16,10 @@
 
 namespace spl {
 
-constexpr int RS_THREADS = 256;
+#ifndef RS_THREADS_VALUE
+#define RS_THREADS_VALUE 256
+#endif
+constexpr int RS_THREADS = RS_THREADS_VALUE;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BINS = 256;
 #ifndef RS_IPT_VALUE
@@ -143,7 +146,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
                   B *__restrict__ out_b) {
     constexpr bool kHasA = !std::is_same<A, NoPayload>::value;
     constexpr bool kHasB = !std::is_same<B, NoPayload>::value;
-    __shared__ __align__(16) unsigned char exch_raw[RS_TILE * 8];
+    extern __shared__ __align__(16) unsigned char exch_raw[];   // RS_TILE * 8 bytes (dynamic: > 48 KB total)
     __shared__ uint32_t whist[RS_WARPS][RS_BINS];
     __shared__ uint32_t glob[RS_BINS];      // global position of local position 0 of each digit
     __shared__ uint32_t running[RS_BINS];   // next free global slot per digit for this block
@@ -312,8 +315,11 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
     SPL_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
+    constexpr size_t kExch = (size_t)RS_TILE * 8;
+    SPL_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExch));
     SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occ, rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>, RS_THREADS, 0));
+        &occ, rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB>, RS_THREADS, kExch));
     if (occ < 1) occ = 1;
     uint32_t grid = (uint32_t)ctx->num_sms * (uint32_t)occ;
     if (grid > tiles) grid = tiles;
@@ -335,7 +341,7 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
             check_launch(ctx, "rs_hist");
             rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
             check_launch(ctx, "rs_scan");
-            rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB><<<grid, RS_THREADS, 0, ctx->stream>>>(
+            rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB><<<grid, RS_THREADS, kExch, ctx->stream>>>(
                 lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
             check_launch(ctx, "rs_scatter");
         } else {
@@ -353,7 +359,12 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
             check_launch(ctx, "rs_hist");
             rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
             check_launch(ctx, "rs_scan");
-            rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB><<<grid, RS_THREADS, 0, ctx->stream>>>(
+            SPL_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExch));
+            SPL_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB>,
+                                          cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+            rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB><<<grid, RS_THREADS, kExch, ctx->stream>>>(
                 lk, la, lb, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
             check_launch(ctx, "rs_scatter");
         }
