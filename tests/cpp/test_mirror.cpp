@@ -1,0 +1,114 @@
+// The reference's own hot-path unit tests, restated against the C++ host mirror
+// (include/spalinalg.hpp) — same inputs, same expected arrays, exact comparison.
+// Each check names the reference test it restates (file:line under /root/reference).
+// Exit code 0 = all passed.  Needs a CUDA device (no CPU fallback).
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "spalinalg.hpp"
+
+using namespace spalinalg;
+using V = std::vector<std::size_t>;
+using D = std::vector<double>;
+
+static int failures = 0;
+#define CHECK(cond)                                                           \
+    do {                                                                      \
+        if (!(cond)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); ++failures; } \
+    } while (0)
+
+template <typename F>
+static bool panics(F &&f) {
+    try { f(); } catch (const Panic &) { return true; }
+    return false;
+}
+
+static int run();
+
+int main() {
+    try {
+        return run();
+    } catch (const DeviceError &e) {
+        std::printf("no CUDA device / device failure: %s\n", e.what());
+        return 2;
+    }
+}
+
+static int run() {
+    {   // src/csr/conv/coo.rs:129-145 and src/csc/conv/coo.rs:129-145
+        CooMatrix<double> coo(2, 3);
+        coo.push(1, 2, 5.0); coo.push(0, 2, 4.0); coo.push(0, 1, 3.0); coo.push(0, 0, 1.0);
+        coo.push(0, 0, 2.0); coo.push(1, 0, 0.0); coo.push(1, 1, 1.0); coo.push(1, 1, -1.0);
+        auto csr = CsrMatrix<double>::from(coo);
+        CHECK(csr.rowptr() == (V{0, 3, 4}) && csr.colind() == (V{0, 1, 2, 2}) && csr.values() == (D{3, 3, 4, 5}));
+        auto csc = CscMatrix<double>::from(coo);
+        CHECK(csc.colptr() == (V{0, 1, 2, 4}) && csc.rowind() == (V{0, 0, 0, 1}) && csc.values() == (D{3, 3, 4, 5}));
+        CHECK(csr.values().capacity() >= csr.values().size() && csr.nnz() == 4);
+    }
+    {   // src/csr.rs:352-356 (transpose doctest), src/csc.rs:352-356
+        CsrMatrix<double> m(2, 2, V{0, 2, 3}, V{0, 1, 1}, D{1, 2, 3});
+        auto t = m.transpose();
+        CHECK(t.rowptr() == (V{0, 1, 3}) && t.colind() == (V{0, 0, 1}) && t.values() == (D{1, 2, 3}));
+        CscMatrix<double> c(2, 2, V{0, 2, 3}, V{0, 1, 1}, D{1, 2, 3});
+        auto tc = c.transpose();
+        CHECK(tc.colptr() == (V{0, 1, 3}) && tc.rowind() == (V{0, 0, 1}) && tc.values() == (D{1, 2, 3}));
+        // CSR -> CSC -> CSR round trip (src/csc/conv/csr.rs:3-53, src/csr/conv/csc.rs:3-53)
+        auto back = CsrMatrix<double>::from(CscMatrix<double>::from(m));
+        CHECK(back.rowptr() == m.rowptr() && back.colind() == m.colind() && back.values() == m.values());
+    }
+    {   // src/csr/ops/add.rs:82-105 and src/csr/ops/sub.rs:82-108
+        CsrMatrix<double> lhs(4, 4, V{0, 1, 3, 4, 7}, V{0, 0, 2, 1, 1, 2, 3}, D{1, 2, 3, 4, 5, 6, 7});
+        CsrMatrix<double> rhs(4, 4, V{0, 2, 3, 4, 5}, V{0, 2, 2, 3, 1}, D{2, 4, 8, 10, 6});
+        auto add = lhs + rhs;
+        CHECK(add.rowptr() == (V{0, 2, 4, 6, 9}) && add.colind() == (V{0, 2, 0, 2, 1, 3, 1, 2, 3}) &&
+              add.values() == (D{3, 4, 2, 11, 4, 10, 11, 6, 7}));
+        auto sub = lhs - rhs;
+        CHECK(sub.rowptr() == (V{0, 2, 4, 6, 9}) && sub.colind() == (V{0, 2, 0, 2, 1, 3, 1, 2, 3}) &&
+              sub.values() == (D{-1, -4, 2, -5, 4, -10, -1, 6, 7}));
+        CHECK(panics([&] { CsrMatrix<double> other(3, 4, V{0, 0, 0, 0}, V{}, D{}); (void)(lhs + other); }));   // add.rs:9-10
+        auto neg = -lhs;                                                        // src/csr/ops/neg.rs:25-36
+        CHECK(neg.rowptr() == lhs.rowptr() && neg.colind() == lhs.colind() && neg.values() == (D{-1, -2, -3, -4, -5, -6, -7}));
+    }
+    {   // src/csc/ops/mul.rs:68-95 (5x3 * 3x4); CSR Mul pinned through CSC(M) arrays == CSR(M^T) arrays
+        CscMatrix<double> lhs(5, 3, V{0, 3, 4, 6}, V{0, 1, 4, 3, 1, 2}, D{1, -5, 4, 3, 7, 2});
+        CscMatrix<double> rhs(3, 4, V{0, 3, 4, 5, 6}, V{0, 1, 2, 2, 0, 1}, D{1, -5, 7, 3, -2, 4});
+        auto mul = lhs * rhs;
+        CHECK(mul.nrows() == 5 && mul.ncols() == 4);
+        CHECK(mul.colptr() == (V{0, 5, 7, 10, 11}) && mul.rowind() == (V{0, 1, 2, 3, 4, 1, 2, 0, 1, 4, 3}) &&
+              mul.values() == (D{1, 44, 14, -15, 4, 21, 6, -2, 10, -8, 12}));
+        auto mul_csr = CsrMatrix<double>::from(lhs) * CsrMatrix<double>::from(rhs);
+        auto again = CscMatrix<double>::from(mul_csr);
+        CHECK(again.colptr() == mul.colptr() && again.rowind() == mul.rowind() && again.values() == mul.values());
+    }
+    {   // src/csr.rs:470-510: the seven CsrMatrix::new panics
+        CHECK(panics([] { CsrMatrix<double>(0, 1, V{0}, V{}, D{}); }));                        // nrows > 0
+        CHECK(panics([] { CsrMatrix<double>(1, 0, V{0, 0}, V{}, D{}); }));                     // ncols > 0
+        CHECK(panics([] { CsrMatrix<double>(1, 1, V{0}, V{}, D{}); }));                        // rowptr.len() == nrows + 1
+        CHECK(panics([] { CsrMatrix<double>(1, 1, V{1, 1}, V{0}, D{1}); }));                   // rowptr[0] == 0
+        CHECK(panics([] { CsrMatrix<double>(1, 1, V{0, 1}, V{}, D{}); }));                     // colind.len() == nz
+        CHECK(panics([] { CsrMatrix<double>(2, 2, V{0, 2, 1}, V{0}, D{1}); }));                // rowptr sorted
+        CHECK(panics([] { CsrMatrix<double>(1, 2, V{0, 2}, V{1, 0}, D{1, 2}); }));             // colind increasing
+        CHECK(panics([] { CsrMatrix<double>(1, 2, V{0, 1}, V{2}, D{1}); }));                   // col < ncols
+        CHECK(!panics([] { CsrMatrix<double>(1, 2, V{0, 2}, V{0, 1}, D{1, 2}); }));
+    }
+    {   // eye (src/csr.rs:179-188), DOK conversion keeps explicit zeros (src/csr/conv/dok.rs:89-99)
+        auto e = CscMatrix<float>::eye(3);
+        CHECK(e.colptr() == (V{0, 1, 2, 3}) && e.rowind() == (V{0, 1, 2}) && e.values() == (std::vector<float>{1, 1, 1}));
+        DokMatrix<double> dok(2, 3);
+        dok.insert(1, 2, 5.0); dok.insert(0, 0, 0.0); dok.insert(0, 1, 3.0);
+        auto m = CsrMatrix<double>::from(dok);
+        CHECK(m.rowptr() == (V{0, 2, 3}) && m.colind() == (V{0, 1, 2}) && m.values() == (D{0, 3, 5}));
+        CHECK(CooMatrix<double>::from(m).length() == 3);
+    }
+    {   // `&A * &X` with X n x 1 is the reference's SpMV (src/csr/ops/mul.rs:5-60); matvec is its dense form
+        CsrMatrix<double> a(3, 3, V{0, 2, 2, 4}, V{0, 2, 1, 2}, D{1, 2, 3, 4});
+        CsrMatrix<double> x(3, 1, V{0, 1, 2, 3}, V{0, 0, 0}, D{10, 20, 30});
+        auto ax = a * x;
+        CHECK(ax.rowptr() == (V{0, 1, 1, 2}) && ax.colind() == (V{0, 0}) && ax.values() == (D{70, 180}));
+        CHECK(a.matvec(D{10, 20, 30}) == (D{70, 0, 180}));
+        CHECK(panics([&] { (void)(x * a); }));                                             // mul.rs:9
+    }
+    if (failures == 0) std::printf("cpp mirror: all reference tests passed\n");
+    return failures == 0 ? 0 : 1;
+}
