@@ -134,6 +134,43 @@ class DistCsrMatrix:
         dist.all_reduce(t, group=group)
         return int(t.item())
 
+    def to_csc(self, dist, torch, group=None) -> "DistCscMatrix":
+        """Sharded From<&CsrMatrix> for CscMatrix (src/csc/conv/csr.rs:3-53): row-sharded CSR in,
+        column-sharded CSC out (rank g gets columns [cstarts[g], cstarts[g+1]), global row indices).
+        The stored entries are routed to the owner of their column with the same device partition as
+        sharded assembly (spl_coo_route_dev, format CSC), one all-to-all, and a (column, row) sort on
+        the receiver with no duplicate sum and no zero drop: bit-exact columns of the whole matrix's
+        CSC form."""
+        from .synthetic_device import device_view
+        ctx = self.local._ctx
+        world, rank = self.world, self.rank
+        cstarts = partition_starts(self._ncols, world)
+        r0, r1 = self.local_rows()
+        nnz = self.local.nnz()
+        tdt = torch.float32 if self.local.dtype == np.float32 else torch.float64
+        p_ptr, p_ind, p_val = self.local.device_ptrs()
+        ptr = device_view(torch, p_ptr, r1 - r0 + 1, torch.int32)
+        if nnz:
+            col = device_view(torch, p_ind, nnz, torch.int32)
+            val = device_view(torch, p_val, nnz, tdt)
+            counts = (ptr[1:] - ptr[:-1]).to(torch.int64)
+            row = torch.repeat_interleave(torch.arange(r0, r1, device=ptr.device, dtype=torch.int32), counts)
+        else:
+            col = torch.empty(0, dtype=torch.int32, device=ptr.device)
+            val = torch.empty(0, dtype=tdt, device=ptr.device)
+            row = torch.empty(0, dtype=torch.int32, device=ptr.device)
+        torch.cuda.current_stream().synchronize()
+        keys, vals, cnts = route_device(ctx, torch, capi.SPL_CSC, self._nrows, self._ncols, row, col, val, cstarts)
+        rk, rv, _ = exchange_routed(dist, torch, keys, vals, cnts, group)
+        torch.cuda.current_stream().synchronize()
+        h = C.c_void_p()
+        from .matrix import CscMatrix
+        ncl = cstarts[rank + 1] - cstarts[rank]
+        ctx.check(ctx._lib.spl_mat_from_packed_dev(
+            ctx._h, capi.SPL_CSC, _dtype_code(self.local.dtype), self._nrows, max(ncl, 1), int(rk.numel()),
+            C.c_void_p(rk.data_ptr()), C.c_void_p(rv.data_ptr()), 0, 0, C.byref(h)))
+        return DistCscMatrix(CscMatrix._wrap(ctx, h), cstarts, rank, self._nrows, self._ncols)
+
     def spmv_peer(self, x: "PeerVector", y_dev: int):
         """y_local = A_local x with x gathered from its owners' slices (spl_spmv_peer)."""
         ctx = self.local._ctx
@@ -141,6 +178,19 @@ class DistCsrMatrix:
         sl = (C.c_void_p * self.world)(*x.ptrs)
         ctx.check(ctx._lib.spl_spmv_peer(ctx._h, self.local._h, self.world, self.rank,
                                          C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(y_dev)))
+
+
+class DistCscMatrix:
+    """Column block of a CSC matrix on this rank (global row indices) plus its column partition."""
+
+    def __init__(self, local, starts: Sequence[int], rank: int, nrows: int, ncols: int):
+        self.local, self.starts, self.rank = local, list(starts), int(rank)
+        self.world = len(starts) - 1
+        self._nrows, self._ncols = int(nrows), int(ncols)
+
+    def nrows(self): return self._nrows
+    def ncols(self): return self._ncols
+    def local_cols(self): return self.starts[self.rank], self.starts[self.rank + 1]
 
 
 # ------------------------------------------------------------------------- peer memory

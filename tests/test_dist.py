@@ -214,3 +214,46 @@ def test_peer_barrier_arrival_and_timeout():
     with pytest.raises(sp.DeviceError):
         ctx.check(ctx._lib.spl_peer_barrier_status(ctx._h, C.byref(t)))
     assert t.value == 1
+
+
+@pytest.mark.gpu
+def test_sharded_front_end_world1_nccl():
+    """The DistCsrMatrix / PeerVector front end with a one-rank NCCL group on this GPU: the same
+    host code as the multi-GPU runs (tests/test_multi_gpu.py needs two GPUs), checked against the
+    oracle: assembly, peer SpMV with barrier epochs, add, CSR -> CSC."""
+    import spalinalg_b200 as sp
+    from spalinalg_b200.synthetic_device import device_view
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        ctx = sp.default_context()
+        n = 3001
+        r, c, v = make_coo(n, n, 50000, 8)
+        full = orc.compress_from_coo(n, n, orc.make_triplets(r, c, v), "row")
+        D = spd.DistCsrMatrix.from_device_triplets(dist, torch, n, n, _t(r, np.int32), _t(c, np.int32),
+                                                   _t(v, np.float64), ctx=ctx)
+        assert np.array_equal(D.local.rowptr(), full[0]) and np.array_equal(D.local.colind(), full[1])
+        assert D.local.values().tobytes() == full[2].tobytes()
+        x = np.random.default_rng(1).standard_normal(n)
+        xv = spd.PeerVector(ctx, dist, n, np.float64)
+        device_view(torch, xv.local_ptr, n, torch.float64).copy_(torch.from_numpy(x))
+        y = torch.zeros(n, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(2):
+            xv.barrier()
+            D.spmv_peer(xv, y.data_ptr())
+        ctx.sync()
+        xv.check()
+        yw = orc.csr_spmv(n, *full, x)
+        sc = orc.csr_spmv(n, full[0], full[1], np.abs(full[2]), np.abs(x))
+        assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
+        S = D + D
+        w = orc.addsub(0, n, n, full, full)
+        assert np.array_equal(S.local.colind(), w[1]) and S.local.values().tobytes() == w[2].tobytes()
+        T = D.to_csc(dist, torch)
+        wc = orc.recompress(n, n, *full)
+        assert np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
+        assert T.local.values().tobytes() == wc[2].tobytes()
+        xv.close(dist)
+    finally:
+        dist.destroy_process_group()

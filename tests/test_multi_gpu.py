@@ -4,7 +4,8 @@ shard against the CPU oracle's result on the WHOLE problem:
   * sharded COO->CSR assembly (device routing, NCCL all-to-all, packed assembly): bit-exact shard;
   * peer-memory SpMV (CUDA IPC slices, device-side barrier, gather in the kernel) and the NCCL
     all-gather variant: within 1e-12 relative (f64);
-  * sharded add / sub / neg on the shared partition: bit-exact."""
+  * sharded add / sub / neg on the shared partition: bit-exact;
+  * row-sharded CSR -> column-sharded CSC (all-to-all by column owner): bit-exact."""
 import os
 import socket
 
@@ -82,6 +83,13 @@ def _worker(rank, world, port, out):
             ok &= bool(np.array_equal(M.local.rowptr(), w[0]) and np.array_equal(M.local.colind(), w[1])
                        and M.local.values().tobytes() == w[2].tobytes())
         ok &= (-D).local.values().tobytes() == orc.neg(want[2]).tobytes()
+
+        # row-sharded CSR -> column-sharded CSC: the columns of the whole matrix's CSC form
+        T = D.to_csc(dist, torch)
+        wc = shard_of(orc.recompress(n, n, *full), T.starts, rank)
+        ok &= bool(np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
+                   and T.local.values().tobytes() == wc[2].tobytes())
+        assert ok, "sharded CSR -> CSC differs from the oracle"
         xv.close(dist)
     finally:
         flag = torch.tensor([1 if ok else 0], device="cuda")
