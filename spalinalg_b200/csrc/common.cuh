@@ -70,6 +70,14 @@ struct spl_mat {
     uint32_t merge_tiles = 0;
     uint32_t *split_rows = nullptr;   // nnz-split kernel: row holding the first entry of each chunk
     uint32_t split_chunks = 0;
+    // hot-column cache (skewed matrices whose few hottest columns carry much of the matrix):
+    // col_order[j] = the j-th most frequent column (hot_count of them); ind_rank = the matrix's
+    // column indices with every hot column replaced by (flag | its slot j)
+    uint32_t *ind_rank = nullptr;
+    uint32_t *col_order = nullptr;
+    uint32_t hot_count = 0;
+    std::atomic<int> hot_state{0};    // 0 not tried, 1 one split product done, 2 decided (ind_rank set or not)
+    double hot_coverage = 0.0;        // share of the stored entries that fall in the hot columns
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

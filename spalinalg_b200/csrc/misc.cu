@@ -195,6 +195,8 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->val);
     dfree(ctx, m->merge_rows);
     dfree(ctx, m->split_rows);
+    dfree(ctx, m->ind_rank);
+    dfree(ctx, m->col_order);
     delete m;
 }
 

@@ -16,7 +16,10 @@
 // they put entries 4 apart on neighbouring lanes and triple the L1 wavefronts of the x gathers
 // ("SpMV").
 // Algorithmic bytes per launch: nnz*(4+V) + (ncols+nrows)*V  (SURVEY.md 8d); HBM-bound.
+#include <cstdlib>
+
 #include "kernels.cuh"
+#include "radix_sort.cuh"
 
 namespace spl {
 
@@ -359,17 +362,19 @@ __global__ void split_partition_kernel(const uint32_t *__restrict__ ptr, uint32_
     chunk_row[w] = w == 0 ? 0u : upper_bound_u32(ptr, 0u, nrows + 1u, pos) - 1u;
 }
 
-template <typename T, int IPL>
-__global__ void __launch_bounds__(SP_THREADS)
-spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
-                  const uint32_t *__restrict__ ind, const T *__restrict__ val,
-                  const T *__restrict__ x, T *__restrict__ y, const uint32_t *__restrict__ chunk_row,
-                  uint32_t *__restrict__ carry_row, T *__restrict__ carry_val) {
+constexpr uint32_t kHotFlag = 0x80000000u;   // column index = slot in the hot-column cache
+constexpr uint32_t kHotBytes = 128 * 1024;    // shared memory given to the hot x values per CTA
+
+// One warp, one chunk.  HOT: indices carrying kHotFlag name a slot of the CTA's shared-memory copy of
+// the hottest x values instead of a column.
+template <typename T, int IPL, bool HOT>
+__device__ __forceinline__ void
+split_chunk(uint32_t w, uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
+            const uint32_t *__restrict__ ind, const T *__restrict__ val, const T *__restrict__ x,
+            T *__restrict__ y, const uint32_t *__restrict__ chunk_row, uint32_t *__restrict__ carry_row,
+            T *__restrict__ carry_val, T *sp, const T *s_hot) {
     constexpr uint32_t K = 32 * IPL;
-    __shared__ T s_prod[SP_WARPS][K];
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t w = blockIdx.x * SP_WARPS + warp;
-    if (w >= nchunks) return;
+    const unsigned lane = lane_id();
     const uint32_t base = w * K;
     const uint32_t count = nnz - base < K ? nnz - base : K;
     const bool last = w + 1 == nchunks;
@@ -387,7 +392,8 @@ spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t
     }
     T prod[IPL];
 #pragma unroll
-    for (int u = 0; u < IPL; ++u) prod[u] = __ldg(x + c[u]);
+    for (int u = 0; u < IPL; ++u)
+        prod[u] = (HOT && (c[u] & kHotFlag)) ? s_hot[c[u] & ~kHotFlag] : __ldg(x + c[u]);
 #pragma unroll
     for (int u = 0; u < IPL; ++u) prod[u] = lane + 32 * u < count ? v[u] * prod[u] : (T)0;
 
@@ -404,7 +410,6 @@ spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t
         return;
     }
 
-    T *sp = s_prod[warp];
 #pragma unroll
     for (int u = 0; u < IPL; ++u) sp[lane + 32 * u] = prod[u];
     __syncwarp();
@@ -446,6 +451,43 @@ spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t
     if (lane == 0) {
         carry_row[w] = R1;                           // == nrows for the last chunk: no carry
         carry_val[w] = s;
+    }
+}
+
+template <typename T, int IPL>
+__global__ void __launch_bounds__(SP_THREADS)
+spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
+                  const uint32_t *__restrict__ ind, const T *__restrict__ val,
+                  const T *__restrict__ x, T *__restrict__ y, const uint32_t *__restrict__ chunk_row,
+                  uint32_t *__restrict__ carry_row, T *__restrict__ carry_val) {
+    __shared__ T s_prod[SP_WARPS][32 * IPL];
+    const uint32_t w = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
+    if (w >= nchunks) return;
+    split_chunk<T, IPL, false>(w, nrows, nnz, nchunks, ptr, ind, val, x, y, chunk_row, carry_row, carry_val,
+                               s_prod[threadIdx.x >> 5], nullptr);
+}
+
+// Hot-column variant: one persistent CTA of 1 024 threads per SM keeps the x values of the `nhot`
+// hottest columns in shared memory (loaded once per launch through the hot-column list) and its 32
+// warps walk the chunks with a grid stride.  Gathers of hot columns never leave the SM.
+constexpr int SPH_THREADS = 1024;
+template <typename T, int IPL>
+__global__ void __launch_bounds__(SPH_THREADS, 1)
+spmv_split_hot_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
+                      const uint32_t *__restrict__ ind_hot, const T *__restrict__ val,
+                      const T *__restrict__ x, T *__restrict__ y, const uint32_t *__restrict__ chunk_row,
+                      uint32_t *__restrict__ carry_row, T *__restrict__ carry_val,
+                      const uint32_t *__restrict__ hot_cols, uint32_t nhot) {
+    extern __shared__ __align__(16) unsigned char sph_raw[];
+    T *s_hot = reinterpret_cast<T *>(sph_raw);
+    T *s_prod = s_hot + nhot;
+    for (uint32_t j = threadIdx.x; j < nhot; j += SPH_THREADS) s_hot[j] = __ldg(x + __ldg(hot_cols + j));
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, warps = SPH_THREADS / 32;
+    for (uint32_t w = blockIdx.x * warps + warp; w < nchunks; w += gridDim.x * warps) {
+        split_chunk<T, IPL, true>(w, nrows, nnz, nchunks, ptr, ind_hot, val, x, y, chunk_row, carry_row, carry_val,
+                                  s_prod + warp * (32 * IPL), s_hot);
+        __syncwarp();          // the product buffer is reused by the warp's next chunk
     }
 }
 
@@ -525,10 +567,21 @@ void spmv_split(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
     Tmp<uint32_t> long_runs(ctx, kLongCap + 1);
     uint32_t *n_long = long_runs.p + kLongCap;
     SPL_CUDA(cudaMemsetAsync(n_long, 0, sizeof(uint32_t), ctx->stream));
-    spmv_split_kernel<T, IPL><<<div_up(nchunks, SP_WARPS), SP_THREADS, 0, ctx->stream>>>(
-        a->nrows, a->nnz, nchunks, a->ptr, a->ind, static_cast<const T *>(a->val), x, y, a->split_rows,
-        carry_row, carry_val);
-    check_launch(ctx, "spmv_split");
+    if (a->hot_state.load(std::memory_order_acquire) == 2 && a->ind_rank) {   // hot columns: persistent CTAs, hottest x values in shared memory
+        const uint32_t nhot = a->hot_count;
+        const size_t smem = (size_t)nhot * sizeof(T) + (size_t)(SPH_THREADS / 32) * 32 * IPL * sizeof(T);
+        auto k = spmv_split_hot_kernel<T, IPL>;
+        SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<ctx->num_sms, SPH_THREADS, smem, ctx->stream>>>(
+            a->nrows, a->nnz, nchunks, a->ptr, a->ind_rank, static_cast<const T *>(a->val), x, y,
+            a->split_rows, carry_row, carry_val, a->col_order, nhot);
+        check_launch(ctx, "spmv_split_hot");
+    } else {
+        spmv_split_kernel<T, IPL><<<div_up(nchunks, SP_WARPS), SP_THREADS, 0, ctx->stream>>>(
+            a->nrows, a->nnz, nchunks, a->ptr, a->ind, static_cast<const T *>(a->val), x, y, a->split_rows,
+            carry_row, carry_val);
+        check_launch(ctx, "spmv_split");
+    }
     spmv_split_fixup_kernel<T><<<div_up(nchunks, 256), 256, 0, ctx->stream>>>(
         a->nrows, nchunks, carry_row, carry_val, y, long_runs, n_long, kLongCap);
     check_launch(ctx, "spmv_split_fixup");
@@ -537,6 +590,93 @@ void spmv_split(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
             nchunks, carry_row, carry_val, y, long_runs, n_long, kLongCap);
         check_launch(ctx, "spmv_split_fixup_long");
     }
+}
+
+// ------------------------------------------------------------------ hot-column renumbering
+// A power-law matrix sends a large share of its gathers to a few thousand columns, but those sit
+// one per 128-byte line of x, and L1 has tags for ~1 500 lines: ncu showed a 5 % L1 hit rate on the
+// R-MAT matrix.  Renumbering the columns by how often they occur packs the hot part of x into a
+// few hundred contiguous lines that L1 can hold.  Once per matrix: column histogram, stable sort by
+// descending count, rank of every column, and a copy of the column indices in the new numbering.
+// Per product: x is gathered into the new order (one pass over x), and the nnz-split kernel runs
+// on (ind_rank, permuted x).  Rows are untouched, so y needs no fix-up.
+
+__global__ void col_hist_kernel(const uint32_t *__restrict__ ind, uint32_t nnz, uint32_t *__restrict__ counts) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+         p += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(counts + ind[p], 1u);
+}
+// sort key: descending count = ascending (nrows - count); a column occurs at most once per row
+struct LoadCountKey {
+    const uint32_t *counts;
+    uint32_t nrows;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i, uint32_t &) const { return nrows - counts[i]; }
+};
+struct LoadIota {
+    __device__ __forceinline__ uint32_t operator()(uint32_t i, uint32_t &) const { return i; }
+};
+__global__ void hot_sum_kernel(const uint32_t *__restrict__ sorted_keys, uint32_t n, uint32_t nrows,
+                               unsigned long long *__restrict__ out) {
+    unsigned long long s = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        s += nrows - sorted_keys[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane_id() == 0 && s) atomicAdd(out, s);
+}
+// code[order[j]] = flag | j for the nhot hottest columns (j < nhot), the column itself otherwise
+__global__ void hot_code_kernel(const uint32_t *__restrict__ order, uint32_t n, uint32_t nhot,
+                                uint32_t *__restrict__ code) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        const uint32_t c = order[j];
+        code[c] = j < nhot ? (kHotFlag | j) : c;
+    }
+}
+__global__ void renumber_kernel(const uint32_t *__restrict__ ind, uint32_t nnz, const uint32_t *__restrict__ rank,
+                                uint32_t *__restrict__ out) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz;
+         p += (uint64_t)gridDim.x * blockDim.x)
+        out[p] = __ldg(rank + ind[p]);
+}
+void plan_hot_columns(spl_ctx *ctx, spl_mat *a) {
+    const uint32_t ncols = a->ncols, nnz = a->nnz;
+    const uint32_t kHotColumns = kHotBytes / (uint32_t)a->vsize();      // 32 768 (f32) / 16 384 (f64)
+    if (ncols < 4 * kHotColumns || nnz == 0) return;       // small x: nothing to gain
+    Tmp<uint32_t> counts(ctx, ncols);
+    SPL_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)ncols, ctx->stream));
+    const unsigned sgrid = (unsigned)ctx->num_sms * 16u;
+    col_hist_kernel<<<sgrid, 256, 0, ctx->stream>>>(a->ind, nnz, counts);
+    check_launch(ctx, "col_hist");
+    Tmp<uint32_t> k0(ctx, ncols), k1(ctx, ncols), o0(ctx, ncols), o1(ctx, ncols);
+    uint32_t *kb[2] = {k0, k1};
+    uint32_t *ob[2] = {o0, o1};
+    NoPayload *nb[2] = {nullptr, nullptr};
+    const int r = radix_sort<uint32_t, uint32_t, NoPayload>(ctx, ncols, bits_for((uint64_t)a->nrows + 1),
+                                                            LoadCountKey{counts, a->nrows}, LoadIota{},
+                                                            LoadNone{}, kb, ob, nb);
+    unsigned long long *sum = reinterpret_cast<unsigned long long *>(ctx->d_scratch + 2);
+    SPL_CUDA(cudaMemsetAsync(sum, 0, sizeof(unsigned long long), ctx->stream));
+    hot_sum_kernel<<<32, 256, 0, ctx->stream>>>(kb[r], kHotColumns, a->nrows, sum);
+    check_launch(ctx, "hot_sum");
+    uint32_t w[2];
+    read_back(ctx, ctx->d_scratch + 2, w, 2);
+    const double hot = (double)(((uint64_t)w[1] << 32) | w[0]);
+    a->hot_coverage = hot / (double)nnz;
+    if (std::getenv("SPL_DEBUG"))
+        std::fprintf(stderr, "[spl] hot-column coverage of the %u hottest columns: %.3f\n", kHotColumns,
+                     a->hot_coverage);
+    if (a->hot_coverage < 0.2 || ncols >= kHotFlag) return;  // uniform columns: keep the plain indices
+    a->hot_count = kHotColumns;
+    a->col_order = dalloc<uint32_t>(ctx, kHotColumns);      // the hot columns, hottest first
+    SPL_CUDA(cudaMemcpyAsync(a->col_order, ob[r], sizeof(uint32_t) * (size_t)kHotColumns,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    uint32_t *code = ob[r ^ 1];                             // scratch: code[c] = c, or flag | slot if hot
+    hot_code_kernel<<<div_up(ncols, 256), 256, 0, ctx->stream>>>(ob[r], ncols, kHotColumns, code);
+    check_launch(ctx, "hot_code");
+    a->ind_rank = dalloc<uint32_t>(ctx, (size_t)nnz + 16);
+    renumber_kernel<<<sgrid, 256, 0, ctx->stream>>>(a->ind, nnz, code, a->ind_rank);
+    check_launch(ctx, "renumber");
 }
 
 // ------------------------------------------------------------------ row statistics (plan)
@@ -624,7 +764,22 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         return;
     }
     if (kernel == SPL_SPMV_SPLIT) {
-        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        spl_mat *m = const_cast<spl_mat *>(a);
+        spmv_plan(ctx, m);
+        // The hot-column cache costs a histogram, a sort of the columns and a second index array
+        // (~5 products' worth on the R-MAT matrix): it is built when a matrix comes back for its
+        // second product, not for a one-off.
+        if (m->hot_state.load(std::memory_order_acquire) != 2) {
+            std::lock_guard<std::mutex> lock(m->plan_mu);
+            const int st = m->hot_state.load(std::memory_order_relaxed);
+            if (st == 0) {
+                m->hot_state.store(1, std::memory_order_release);
+            } else if (st == 1) {
+                plan_hot_columns(ctx, m);
+                SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+                m->hot_state.store(2, std::memory_order_release);
+            }
+        }
         if (a->dtype == SPL_F32) spmv_split<float>(ctx, a, (const float *)x, (float *)y);
         else spmv_split<double>(ctx, a, (const double *)x, (double *)y);
         return;
