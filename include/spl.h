@@ -18,8 +18,8 @@
  *  - One spl_ctx per host thread (it owns a stream and the last-error text).
  *    spl_mat objects are immutable after creation and may be shared read-only.
  *  - There is no CPU fallback: without a CUDA device spl_ctx_create fails.
- *  - Limits: dims and nnz below 2^32 (device indices are 32 bit), else
- *    SPL_ERR_UNSUPPORTED.
+ *  - Limits: dims below 2^32, nnz / COO length / intermediate products below
+ *    2^32 - 65536 (device indices and positions are 32 bit), else SPL_ERR_UNSUPPORTED.
  */
 #ifndef SPL_H
 #define SPL_H

@@ -14,7 +14,7 @@ def load(path):
         unit = row["Metric Unit"]
         v = v / 1000 if unit in ("ns", "nsecond") else (v * 1000 if unit in ("ms", "msecond") else v)
         name = row["Kernel Name"]
-        short = re.sub(r"^void ", "", name)
+        short = re.sub(r"^void ", "", name).replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
         short = re.sub(r"\(.*", "", short)
         out.append((short, v, row.get("Grid Size", ""), row.get("Block Size", "")))
     return out

@@ -217,8 +217,8 @@ spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract) 
                 "add/sub: shapes differ (assert_eq!, src/csr/ops/add.rs:9-10)");
     SPL_REQUIRE(a->format == b->format && a->dtype == b->dtype, SPL_ERR_ARG,
                 "add/sub: operands must share format and scalar type");
-    SPL_REQUIRE((uint64_t)a->nnz + b->nnz < (1ull << 32), SPL_ERR_UNSUPPORTED,
-                "add/sub: nnz(A)+nnz(B) must stay below 2^32");
+    SPL_REQUIRE((uint64_t)a->nnz + b->nnz < kMaxEntries, SPL_ERR_UNSUPPORTED,
+                "add/sub: nnz(A)+nnz(B) must stay below 2^32 - 65536");
     const uint32_t nmajor = a->nmajor();
     Tmp<uint32_t> cnt(ctx, nmajor);
     Tmp<uint32_t> cptr(ctx, (size_t)nmajor + 1);

@@ -143,7 +143,7 @@ int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, ui
     *out = nullptr;
     check_enums(format, dtype);
     check_dims(ctx, nrows, ncols);
-    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
     SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev), SPL_ERR_ARG, "NULL COO array");
     *out = assemble_from_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
                                  row_dev, col_dev, val_dev, dedup, dropzero);
@@ -158,7 +158,7 @@ int spl_mat_from_coo(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64
     *out = nullptr;
     check_enums(format, dtype);
     check_dims(ctx, nrows, ncols);
-    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
     SPL_REQUIRE(len == 0 || (row && col && val), SPL_ERR_ARG, "NULL COO array");
     const size_t vs = dtype == SPL_F32 ? 4 : 8;
     Tmp<uint32_t> r32(ctx, len), c32(ctx, len);
@@ -186,7 +186,7 @@ int spl_mat_from_compressed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nr
     *out = nullptr;
     check_enums(format, dtype);
     check_dims(ctx, nrows, ncols);
-    SPL_REQUIRE(nnz < (1ull << 32), SPL_ERR_UNSUPPORTED, "nnz must be below 2^32");
+    SPL_REQUIRE(nnz < kMaxEntries, SPL_ERR_UNSUPPORTED, "nnz must be below 2^32 - 65536");
     SPL_REQUIRE(ptr_dev && (nnz == 0 || (ind_dev && val_dev)), SPL_ERR_ARG, "NULL array");
     const uint32_t nmajor = (uint32_t)(format == SPL_CSR ? nrows : ncols);
     const uint32_t nminor = (uint32_t)(format == SPL_CSR ? ncols : nrows);
@@ -232,7 +232,7 @@ int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
     if (ind_len != ptr[nmajor]) invalid(ctx, 5, kReasonText[5]);
     if (val_len != ptr[nmajor]) invalid(ctx, 6, kReasonText[6]);
     const uint64_t nnz = ind_len;
-    SPL_REQUIRE(nnz < (1ull << 32), SPL_ERR_UNSUPPORTED, "nnz must be below 2^32");
+    SPL_REQUIRE(nnz < kMaxEntries, SPL_ERR_UNSUPPORTED, "nnz must be below 2^32 - 65536");
     SPL_REQUIRE(nnz == 0 || (ind && val), SPL_ERR_ARG, "NULL array");
 
     spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)nnz);
@@ -478,7 +478,7 @@ int spl_coo_route_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint6
     API_BEGIN(ctx)
     check_enums(format, dtype);
     check_dims(ctx, nrows, ncols);
-    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
     SPL_REQUIRE(major_starts && counts_host, SPL_ERR_ARG, "NULL argument");
     SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev && keys_out_dev && vals_out_dev),
                 SPL_ERR_ARG, "NULL COO array");
@@ -495,7 +495,7 @@ int spl_mat_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
     *out = nullptr;
     check_enums(format, dtype);
     check_dims(ctx, nrows, ncols);
-    SPL_REQUIRE(len < (1ull << 32), SPL_ERR_UNSUPPORTED, "COO length must be below 2^32");
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
     SPL_REQUIRE(len == 0 || (keys_dev && vals_dev), SPL_ERR_ARG, "NULL COO array");
     *out = assemble_from_packed_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
                                     keys_dev, vals_dev, dedup, dropzero);

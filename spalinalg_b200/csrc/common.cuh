@@ -35,6 +35,9 @@ struct Error {
     } while (0)
 
 constexpr int kNumSmFallback = 148;
+// 32-bit positions: kernels step a position by up to a tile (<= 65536 entries) past the last entry
+// before testing it, so entry counts stay that far below 2^32.
+constexpr uint64_t kMaxEntries = (1ull << 32) - 65536;
 
 }  // namespace spl
 

@@ -68,7 +68,7 @@ spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
         check_launch(ctx, "product_count");
         uint32_t t64[2];
         read_back(ctx, ctx->d_scratch + 2, t64, 2);
-        SPL_REQUIRE(t64[1] == 0, SPL_ERR_UNSUPPORTED,
+        SPL_REQUIRE(t64[1] == 0 && t64[0] < kMaxEntries, SPL_ERR_UNSUPPORTED,
                     "mul: more than 2^32 intermediate products (expand-sort-compress limit)");
         total = t64[0];
         exclusive_scan_u32(ctx, cnt, annz, off);
