@@ -3,8 +3,9 @@
 // Reference semantics (src/csr/conv/coo.rs:3-116, src/csc/conv/coo.rs:3-116): entries ordered
 // by (major, minor); duplicates of one cell added left to right in insertion order, the first
 // value copied (:43-52); cells whose sum == 0 removed (:60-73); exactly sized outputs.
-// Device formulation: stable LSD radix sort of key = major << minor_bits | minor carrying the
-// value, then one sequential in-order sum per run of equal keys (a tree reduction would change
+// Device formulation: one pass checks bounds, packs key = major << minor_bits | minor and detects
+// already sorted input (no sort then); otherwise a stable LSD radix sort of the key carrying the
+// value; then one sequential in-order sum per run of equal keys (a tree reduction would change
 // the rounding and, through the zero drop, the structure), flag, compact, build the pointers.
 #include "kernels.cuh"
 #include "radix_sort.cuh"
@@ -211,6 +212,70 @@ spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint
                                   reinterpret_cast<double *>(vb[r]), minor_bits, dedup, dropzero);
 }
 
+// First pass over the caller's triplets: the bounds of CooMatrix::push (src/coo.rs:432-433), the
+// packed sort key major << minor_bits | minor, a private copy of the values (the tail sums in place
+// and the input must stay untouched) and whether the keys are already non-decreasing.  A sorted
+// list — triplets emitted row by row, column by column, as element loops and stencil generators do
+// — needs no sort at all: a stable sort would leave it where it is.
+template <typename K, typename VB>
+__global__ void __launch_bounds__(256)
+prepare_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor,
+               const VB *__restrict__ val, uint32_t n, uint32_t nmajor, uint32_t nminor, int minor_bits,
+               K *__restrict__ keys, VB *__restrict__ vals, uint32_t *__restrict__ flags) {
+    uint32_t bad = 0, unsorted = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t mj = major[i], mn = minor[i];
+        bad |= (mj >= nmajor) | (mn >= nminor);
+        const K k = (K)(((uint64_t)mj << minor_bits) | (uint64_t)mn);
+        keys[i] = k;
+        vals[i] = val[i];
+        if (i + 1 < n) {
+            const K kn = (K)(((uint64_t)major[i + 1] << minor_bits) | (uint64_t)minor[i + 1]);
+            unsorted |= kn < k;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flags, 1u);
+    if (__any_sync(0xffffffffu, unsorted) && lane_id() == 0) atomicOr(flags + 1, 1u);
+}
+
+template <typename K, typename VB>
+spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                      const uint32_t *major_idx, const uint32_t *minor_idx, const VB *val, int minor_bits,
+                      int bits, int dedup, int dropzero) {
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols, nminor = format == SPL_CSR ? ncols : nrows;
+    Tmp<K> k0(ctx, len), k1(ctx, len);
+    Tmp<VB> v0(ctx, len), v1(ctx, len);
+    uint32_t flags[2] = {0, 0};
+    if (len) {
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(uint32_t), ctx->stream));
+        unsigned grid = div_up(len, 256 * 4);
+        if (grid > (unsigned)ctx->num_sms * 16u) grid = (unsigned)ctx->num_sms * 16u;
+        prepare_kernel<K, VB><<<grid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len, nmajor, nminor,
+                                                             minor_bits, k0, v0, ctx->d_scratch);
+        check_launch(ctx, "prepare");
+        read_back(ctx, ctx->d_scratch, flags, 2);
+        SPL_REQUIRE(flags[0] == 0, SPL_ERR_ARG,
+                    "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
+    }
+    K *keys = k0;
+    VB *vals = v0;
+    if (flags[1]) {       // pass 0 reads (k0, v0) and writes (k1, v1); later passes ping-pong
+        K *kb[2] = {k1, k0};
+        VB *vb[2] = {v1, v0};
+        NoPayload *nb[2] = {nullptr, nullptr};
+        const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, LoadPlain<K>{k0}, LoadPlain<VB>{v0},
+                                                   LoadNone{}, kb, vb, nb);
+        keys = kb[r];
+        vals = vb[r];
+    }
+    if (dtype == SPL_F32)
+        return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, keys,
+                                     reinterpret_cast<float *>(vals), minor_bits, dedup, dropzero);
+    return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, keys,
+                                  reinterpret_cast<double *>(vals), minor_bits, dedup, dropzero);
+}
+
 // ---- row-sharded assembly: routing of triplets to their owners ----------------
 // owner of a major index: the block [starts[g], starts[g+1]) that contains it (world <= 8)
 struct Owners {
@@ -327,29 +392,23 @@ spl_mat *finish_from_sorted(spl_ctx *ctx, int format, int dtype, uint32_t nrows,
 spl_mat *assemble_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
                                uint32_t len, const uint32_t *row, const uint32_t *col,
                                const void *val, int dedup, int dropzero) {
-    check_coo_bounds(ctx, len, row, col, nrows, ncols);
     const uint32_t *major_idx = format == SPL_CSR ? row : col;
     const uint32_t *minor_idx = format == SPL_CSR ? col : row;
     const int major_bits = bits_for(format == SPL_CSR ? nrows : ncols);
     const int minor_bits = bits_for(format == SPL_CSR ? ncols : nrows);
     const int bits = major_bits + minor_bits;
     if (bits <= 32) {
-        LoadPack<uint32_t> lk{major_idx, minor_idx, minor_bits};
         if (dtype == SPL_F32)
-            return assemble_impl<uint32_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
-                                                     (const uint32_t *)val, minor_bits, bits, dedup,
-                                                     dropzero);
-        return assemble_impl<uint32_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
-                                                 (const uint64_t *)val, minor_bits, bits, dedup,
-                                                 dropzero);
+            return assemble_coo<uint32_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, major_idx, minor_idx,
+                                                    (const uint32_t *)val, minor_bits, bits, dedup, dropzero);
+        return assemble_coo<uint32_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, major_idx, minor_idx,
+                                                (const uint64_t *)val, minor_bits, bits, dedup, dropzero);
     }
-    LoadPack<uint64_t> lk{major_idx, minor_idx, minor_bits};
     if (dtype == SPL_F32)
-        return assemble_impl<uint64_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, lk,
-                                                 (const uint32_t *)val, minor_bits, bits, dedup,
-                                                 dropzero);
-    return assemble_impl<uint64_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, lk,
-                                             (const uint64_t *)val, minor_bits, bits, dedup, dropzero);
+        return assemble_coo<uint64_t, uint32_t>(ctx, format, dtype, nrows, ncols, len, major_idx, minor_idx,
+                                                (const uint32_t *)val, minor_bits, bits, dedup, dropzero);
+    return assemble_coo<uint64_t, uint64_t>(ctx, format, dtype, nrows, ncols, len, major_idx, minor_idx,
+                                            (const uint64_t *)val, minor_bits, bits, dedup, dropzero);
 }
 
 // Packed keys as produced by route_coo_dev on the sending ranks (and concatenated in source-rank

@@ -261,6 +261,32 @@ def test_mul_by_n_by_1_is_the_reference_spmv(dtype, fmt):
         same(arrays(got.to_csr()), want, "csc A * X")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fmt", ["row", "col"])
+def test_assembly_of_sorted_triplets_skips_the_sort(dtype, fmt):
+    """Triplets already ordered by (major, minor) — duplicates adjacent, in insertion order — take
+    the no-sort path; one element out of place takes the sort.  Both must equal the oracle bit for
+    bit (in-order duplicate sums, cancellations dropped)."""
+    rng = np.random.default_rng(12)
+    n, m, length = 700, 900, 30000
+    r = rng.integers(0, n, length).astype(np.uint64)
+    c = rng.integers(0, m, length).astype(np.uint64)
+    v = rng.standard_normal(length).astype(dtype)
+    r = np.concatenate([r, r[:3000], r[:1000]]); c = np.concatenate([c, c[:3000], c[:1000]])
+    v = np.concatenate([v, rng.standard_normal(3000).astype(dtype), -v[:1000]])
+    order = np.lexsort((c, r), ) if fmt == "row" else np.lexsort((r, c))     # stable: duplicates keep their order
+    r, c, v = r[order], c[order], v[order]
+    cls = sp.CsrMatrix if fmt == "row" else sp.CscMatrix
+    for variant in ("sorted", "one_swap"):
+        if variant == "one_swap":
+            r, c, v = r.copy(), c.copy(), v.copy()
+            for a in (r, c, v):
+                a[[10, 20000]] = a[[20000, 10]]
+        got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+        want = orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), fmt)
+        same(arrays(got), want, f"{fmt} {variant}")
+
+
 def test_dok_round_trip_through_device():
     """From<&DokMatrix> for CsrMatrix / CscMatrix (src/csr/conv/dok.rs:3-76) and back
     (src/dok.rs:676-720): explicit zeros survive both ways, nothing is summed or dropped."""
