@@ -76,6 +76,24 @@ def cpu_reference_step(n, ptr, ind, val, x):
     return time.perf_counter() - t0
 
 
+def cpu_assembly_baseline():
+    """COO->CSR on the CPU: the oracle port of From<&CooMatrix> (src/csr/conv/coo.rs:3-116) on a 512^2
+    Laplacian with the triplets shuffled like the device run's.  One core: the reference is
+    single-threaded."""
+    import oracle as orc
+    from spalinalg_b200 import synthetic as syn
+    ar, ac, av = syn.laplacian_2d(512)
+    perm = np.random.default_rng(42).permutation(len(av))
+    trip = orc.make_triplets(ar[perm], ac[perm], av[perm])
+    orc.compress_from_coo(512 * 512, 512 * 512, trip, "row")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        orc.compress_from_coo(512 * 512, 512 * 512, trip, "row")
+    asm_s = (time.perf_counter() - t0) / 3
+    return {"value": len(av) / asm_s / 1e6, "unit": "Mnnz/s", "cores": 1,
+            "sample": f"2-D Laplacian 512^2, {len(av)} shuffled triplets, f64, COO->CSR"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -90,6 +108,7 @@ def run_reference_arm(args):
     per = sum(t) / len(t)
     value = b / per / 1e9
     sample = f"27-point stencil {m}^3 (n={n}, nnz={nnz}), f64, X n x 1"
+    asm = cpu_assembly_baseline()
     line = {
         "impl": "reference", "metric": "spmv_algorithmic_bandwidth", "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
@@ -97,7 +116,7 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
+                         "host_cores": os.cpu_count(), "assembly": asm},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -434,19 +453,8 @@ def main():
         for _ in range(5):
             orc.csr_spmv(sn, sptr, sind, sval, sx)
         rowdot = (time.perf_counter() - t0) / 5
-        # COO->CSR on the CPU: the oracle port of From<&CooMatrix> (src/csr/conv/coo.rs:3-116) on a
-        # 512^2 Laplacian with the triplets shuffled like the device run's
-        from spalinalg_b200 import synthetic as syn
-        ar, ac, av = syn.laplacian_2d(512)
-        perm = np.random.default_rng(42).permutation(len(av))
-        trip = orc.make_triplets(ar[perm], ac[perm], av[perm])
-        t0 = time.perf_counter()
-        for _ in range(3):
-            orc.compress_from_coo(512 * 512, 512 * 512, trip, "row")
-        asm_s = (time.perf_counter() - t0) / 3
         cpu = {"value": sb / statistics.median(ts) / 1e9, "unit": "GB/s", "cores": 1,
-               "assembly": {"value": len(av) / asm_s / 1e6, "unit": "Mnnz/s", "cores": 1,
-                            "sample": f"2-D Laplacian 512^2, {len(av)} shuffled triplets, f64, COO->CSR"},
+               "assembly": cpu_assembly_baseline(),
                "kind": "port", "host_cores": os.cpu_count(),
                "sample": f"27-point stencil {m}^3 (n={sn}, nnz={len(sval)}), f64; reference route "
                          f"&A * &X (3 transposes + Gustavson), 3 reps median",
