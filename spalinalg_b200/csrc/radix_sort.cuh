@@ -148,6 +148,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
     constexpr bool kHasB = !std::is_same<B, NoPayload>::value;
     extern __shared__ __align__(16) unsigned char exch_raw[];   // RS_TILE * 8 bytes (dynamic: > 48 KB total)
     __shared__ uint32_t whist[RS_WARPS][RS_BINS];
+    __shared__ uint32_t wmask[RS_WARPS][RS_BINS];   // lanes per digit of the item being ranked (zero between items)
     __shared__ uint32_t glob[RS_BINS];      // global position of local position 0 of each digit
     __shared__ uint32_t running[RS_BINS];   // next free global slot per digit for this block
     __shared__ uint32_t ws[RS_WARPS + 1];
@@ -159,6 +160,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
         if (threadIdx.x < RS_BINS)
             running[threadIdx.x] = below + offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
     }
+    for (int j = threadIdx.x; j < RS_WARPS * RS_BINS; j += RS_THREADS) (&wmask[0][0])[j] = 0;
     uint32_t st_k = 0, st_a = 0, st_b = 0;
 
     const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_block * RS_TILE;
@@ -194,18 +196,31 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
         for (int i = 0; i < RS_IPT; ++i) {
             const bool valid = my_base + i * 32 < tile_count;
             const uint32_t d = valid ? ((uint32_t)(keys[i] >> shift) & mask) : 0u;
-            // lanes holding the same digit: one ballot per digit bit (287 Gkeys/s on B200 against
-            // 149 Gkeys/s for the match.any instruction, profiles/micro/match_bench.cu)
-            unsigned peers = __ballot_sync(0xffffffffu, valid);
+            // lanes holding the same digit: every lane ORs its bit into the digit's word of a per-warp
+            // shared-memory table, then reads the word back (measured on B200, profiles/micro/
+            // match_bench.cu: 507 Gkeys/s, against 288 for eight ballots over the digit bits and 149 for
+            // the match.any instruction; OR is commutative, so the mask — and with it the stable rank —
+            // does not depend on the order the hardware applies the atomics in).  A/B on one box: CSR->CSC
+            // -5.5 % (config 2) / -7 % (config 3); 64-bit-key assembly +2 %, so those keep the ballots.
+            unsigned peers;
+            if constexpr (sizeof(K) == 4) {
+                if (valid) atomicOr(&wmask[warp][d], 1u << lane);
+                __syncwarp();
+                peers = valid ? wmask[warp][d] : 0u;
+                __syncwarp();
+            } else {        // 64-bit keys sit at the register cap: the ballot form measured 2 % faster there
+                peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? bal : ~bal;
+                for (int b = 0; b < 8; ++b) {
+                    const bool bit = (d >> b) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
             }
             const int leader = valid ? __ffs(peers) - 1 : (int)lane;
             uint32_t old = 0;
             if (valid && (int)lane == leader) {
+                if constexpr (sizeof(K) == 4) wmask[warp][d] = 0;     // ready for the next item
                 old = whist[warp][d];
                 whist[warp][d] = old + __popc(peers);
             }
