@@ -51,7 +51,9 @@ typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:
 #define SPL_MAX_PEERS 8
 #define SPL_IPC_HANDLE_BYTES 64
 
-/* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics. */
+/* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics — VECTOR (1..32 lanes per
+ * row) for regular rows, SPLIT (fixed chunks of stored entries per warp, the merge-path balance at
+ * warp granularity) for skewed rows; MERGE is the block-level merge-path kernel, selectable. */
 typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3 } spl_spmv_kernel;
 
 /* ---- context ------------------------------------------------------------ */
@@ -135,7 +137,8 @@ int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev);
 int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel);
 /* Host-buffer form: uploads x, runs spl_spmv, downloads y, synchronises. */
 int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host);
-/* Which kernel AUTO resolves to for this matrix (SPL_SPMV_VECTOR / _MERGE). */
+/* Which kernel AUTO resolves to for this matrix (SPL_SPMV_VECTOR / _SPLIT) and the vector kernel's
+ * lanes per row. */
 int spl_spmv_choice(spl_ctx *ctx, const spl_mat *a, int *kernel, int *lanes_per_row);
 
 /* ---- access --------------------------------------------------------------- */
