@@ -546,6 +546,19 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         keep["D"] = spd.DistCsrMatrix.from_device_triplets(dist, torch, nr, nr, r_, c_, v_, ctx=ctx)
     ms = timed_all(asm)
     ln = total(int(v_.numel()))
+    ex = spd.PeerExchange(ctx, dist)
+
+    def asm_peer():
+        keep["P"] = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, nr, nr, r_, c_, v_, ex)
+    ms_p = timed_all(asm_peer)
+    ex.check()
+    assert keep["P"].local.nnz() == keep["D"].local.nnz()
+    del keep["P"]
+    ex.close()
+    out["sharded_assembly_peer"] = {"workload": "same triplets; routing and exchange fused: the partition pass writes "
+                                                "into the owners' buffers over NVLink (peer memory), no all-to-all",
+                                    "len": total(int(v_.numel())), "ms": ms_p,
+                                    "mnnz_per_s": total(int(v_.numel())) / ms_p / 1e3}
     D = keep["D"]
     nnz_d = total(D.local.nnz())
     out["sharded_assembly"] = {"workload": "random 1e7 x 1e7, 16/row + 5% duplicates, f32, triplets block-"

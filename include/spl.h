@@ -176,6 +176,21 @@ int spl_coo_route_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint6
                       uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
                       const void *val_dev, int world, const uint64_t *major_starts,
                       uint64_t *keys_out_dev, void *vals_out_dev, uint64_t *counts_host);
+/* The same routing fused with the exchange, over peer memory (no staging buffer, no all-to-all):
+ * spl_coo_route_count_dev checks the bounds and counts this rank's triplets per owning rank; the
+ * caller shares the counts, sizes the receive buffers (spl_peer_alloc / spl_peer_open) and gives
+ * every sender its slot: dst_offsets[g] = entries that ranks before this one send to rank g.
+ * spl_coo_route_peers_dev then runs the stable partition and writes each record straight into its
+ * owner's buffers key_bufs[g] (uint64 packed keys) / val_bufs[g] over NVLink.  Bracket it with
+ * spl_peer_barrier: before (the owners are done with the previous contents) and after (every
+ * record has landed). */
+int spl_coo_route_count_dev(spl_ctx *ctx, int format, uint64_t nrows, uint64_t ncols, uint64_t len,
+                            const uint32_t *row_dev, const uint32_t *col_dev, int world,
+                            const uint64_t *major_starts, uint64_t *counts_host);
+int spl_coo_route_peers_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                            const void *val_dev, int world, const uint64_t *major_starts,
+                            void *const *key_bufs, void *const *val_bufs, const uint64_t *dst_offsets);
 /* Receiving side: assembly of one shard (nrows x ncols are the SHARD's dimensions)
  * from packed keys as produced by spl_coo_route_dev.  Same semantics and bit-exactness
  * as spl_mat_from_coo_dev. */

@@ -51,6 +51,8 @@ SIGNATURES = {
     "spl_mat_to_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "spl_mat_free": (_i, [_vp, _vp]),
     "spl_coo_route_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "spl_coo_route_count_dev": (_i, [_vp, _i, _u64, _u64, _u64, _vp, _vp, _i, _vp, _vp]),
+    "spl_coo_route_peers_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "spl_mat_from_packed_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _i, _i, _pp]),
     "spl_peer_alloc": (_i, [_vp, _u64, _pp, _vp]),
     "spl_peer_open": (_i, [_vp, _vp, _pp]),

@@ -487,6 +487,34 @@ int spl_coo_route_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint6
     API_END(ctx)
 }
 
+int spl_coo_route_count_dev(spl_ctx *ctx, int format, uint64_t nrows, uint64_t ncols, uint64_t len,
+                            const uint32_t *row_dev, const uint32_t *col_dev, int world,
+                            const uint64_t *major_starts, uint64_t *counts_host) {
+    API_BEGIN(ctx)
+    check_enums(format, SPL_F64);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
+    SPL_REQUIRE(major_starts && counts_host && (len == 0 || (row_dev && col_dev)), SPL_ERR_ARG, "NULL argument");
+    route_count_dev(ctx, format, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len, row_dev, col_dev, world,
+                    major_starts, counts_host);
+    API_END(ctx)
+}
+
+int spl_coo_route_peers_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                            uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
+                            const void *val_dev, int world, const uint64_t *major_starts,
+                            void *const *key_bufs, void *const *val_bufs, const uint64_t *dst_offsets) {
+    API_BEGIN(ctx)
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(len < kMaxEntries, SPL_ERR_UNSUPPORTED, "COO length must be below 2^32 - 65536");
+    SPL_REQUIRE(major_starts && key_bufs && val_bufs && dst_offsets, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev), SPL_ERR_ARG, "NULL COO array");
+    route_coo_peers_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len, row_dev, col_dev,
+                        val_dev, world, major_starts, key_bufs, val_bufs, dst_offsets);
+    API_END(ctx)
+}
+
 int spl_mat_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
                             uint64_t len, const uint64_t *keys_dev, const void *vals_dev, int dedup,
                             int dropzero, spl_mat **out) {

@@ -504,4 +504,75 @@ void route_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t
     for (int g = 0; g < world; ++g) counts_host[g] = c[g];
 }
 
+// ---- fused routing + exchange over peer memory -----------------------------------------------
+// route_count_dev: bounds and how many of this rank's triplets each rank owns (host needs them to
+// lay out the receive buffers).  route_coo_peers_dev: the same stable partition as route_coo_dev,
+// but the pass writes every record straight into its owner's receive buffer (CUDA IPC mapping, NVLink)
+// at the slot the caller computed from everybody's counts: no staging buffer, no all-to-all.
+static Owners make_owners(int format, uint32_t nrows, uint32_t ncols, int world, const uint64_t *major_starts) {
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS, SPL_ERR_ARG, "world must be 1..8");
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols;
+    SPL_REQUIRE(major_starts[0] == 0 && major_starts[world] == nmajor, SPL_ERR_ARG,
+                "major_starts must run from 0 to the number of rows (CSR) / columns (CSC)");
+    Owners own;
+    own.world = world;
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) {
+        const uint64_t v = major_starts[g < world ? g : world];
+        SPL_REQUIRE(g == 0 || g > world || v >= major_starts[g - 1], SPL_ERR_ARG,
+                    "major_starts must be non-decreasing");
+        own.start[g] = (uint32_t)v;
+    }
+    return own;
+}
+
+void route_count_dev(spl_ctx *ctx, int format, uint32_t nrows, uint32_t ncols, uint32_t len,
+                     const uint32_t *row, const uint32_t *col, int world, const uint64_t *major_starts,
+                     uint64_t *counts_host) {
+    const Owners own = make_owners(format, nrows, ncols, world, major_starts);
+    for (int g = 0; g < world; ++g) counts_host[g] = 0;
+    if (len == 0) return;
+    uint32_t *cnt = ctx->d_scratch + 8;
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+    SPL_CUDA(cudaMemsetAsync(cnt, 0, SPL_MAX_PEERS * sizeof(uint32_t), ctx->stream));
+    unsigned grid = div_up(len, 256 * 8);
+    if (grid > (unsigned)ctx->num_sms * 8u) grid = (unsigned)ctx->num_sms * 8u;
+    coo_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(row, col, len, nrows, ncols, ctx->d_scratch);
+    check_launch(ctx, "coo_bounds");
+    owner_count_kernel<<<grid, 256, 0, ctx->stream>>>(format == SPL_CSR ? row : col, len, own, cnt);
+    check_launch(ctx, "owner_count");
+    uint32_t w[16];
+    read_back(ctx, ctx->d_scratch, w, 16);
+    SPL_REQUIRE(w[0] == 0, SPL_ERR_ARG,
+                "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
+    for (int g = 0; g < world; ++g) counts_host[g] = w[8 + g];
+}
+
+void route_coo_peers_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                         const uint32_t *row, const uint32_t *col, const void *val, int world,
+                         const uint64_t *major_starts, void *const *key_bufs, void *const *val_bufs,
+                         const uint64_t *dst_offsets) {
+    const Owners own = make_owners(format, nrows, ncols, world, major_starts);
+    if (len == 0) return;
+    const uint32_t *major = format == SPL_CSR ? row : col;
+    const uint32_t *minor = format == SPL_CSR ? col : row;
+    const int minor_bits = bits_for(format == SPL_CSR ? ncols : nrows);
+    LoadOwner lo{major, own};
+    LoadPackLocal lp{major, minor, own, minor_bits};
+    auto run = [&](auto tag) {
+        using VB = decltype(tag);
+        DestPeers<uint64_t, VB> dest{};
+        for (int g = 0; g < world; ++g) {
+            SPL_REQUIRE(key_bufs[g] && val_bufs[g], SPL_ERR_ARG, "NULL receive buffer");
+            SPL_REQUIRE(dst_offsets[g] < kMaxEntries, SPL_ERR_UNSUPPORTED, "receive offset beyond 2^32");
+            dest.a[g] = static_cast<uint64_t *>(key_bufs[g]);
+            dest.b[g] = static_cast<VB *>(val_bufs[g]);
+            dest.off[g] = (uint32_t)dst_offsets[g];
+        }
+        radix_pass_to_peers<uint64_t, VB>(ctx, len, bits_for((uint64_t)world), lo, lp,
+                                          LoadPlain<VB>{static_cast<const VB *>(val)}, dest);
+    };
+    if (dtype == SPL_F32) run(uint32_t{});
+    else run(uint64_t{});
+}
+
 }  // namespace spl

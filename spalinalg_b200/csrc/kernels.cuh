@@ -22,6 +22,13 @@ void route_coo_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t
                    const uint32_t *row, const uint32_t *col, const void *val, int world,
                    const uint64_t *major_starts, uint64_t *out_keys, void *out_val,
                    uint64_t *counts_host);
+void route_count_dev(spl_ctx *ctx, int format, uint32_t nrows, uint32_t ncols, uint32_t len,
+                     const uint32_t *row, const uint32_t *col, int world, const uint64_t *major_starts,
+                     uint64_t *counts_host);
+void route_coo_peers_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                         const uint32_t *row, const uint32_t *col, const void *val, int world,
+                         const uint64_t *major_starts, void *const *key_bufs, void *const *val_bufs,
+                         const uint64_t *dst_offsets);
 spl_mat *assemble_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
                                   uint32_t len, const uint64_t *keys, const void *val, int dedup,
                                   int dropzero);

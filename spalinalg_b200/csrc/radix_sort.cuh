@@ -137,13 +137,37 @@ static __global__ void __launch_bounds__(512) rs_scan_kernel(uint32_t *counts, u
     if (threadIdx.x == 0) totals[blockIdx.x] = total;
 }
 
+// ---- where a pass writes ---------------------------------------------------------------------
+// DestSingle: the usual ping-pong buffers, digits laid out one after the other.
+// DestPeers:  the digit is the rank that owns the record (row-sharded assembly): digit d
+//             goes to rank d's receive buffers — peer memory mapped over NVLink — starting at off[d],
+//             the slot this rank's share begins at there.  The keys (owner ids) are not written.
+template <typename K, typename A, typename B>
+struct DestSingle {
+    K *k;
+    A *a;
+    B *b;
+    static constexpr bool kSingle = true;
+    __device__ __forceinline__ uint32_t base(uint32_t, uint32_t below) const { return below; }
+};
+template <typename A, typename B>
+struct DestPeers {
+    A *a[SPL_MAX_PEERS];
+    B *b[SPL_MAX_PEERS];
+    uint32_t off[SPL_MAX_PEERS];
+    static constexpr bool kSingle = false;
+    __device__ __forceinline__ uint32_t base(uint32_t d, uint32_t) const {
+        return d < (uint32_t)SPL_MAX_PEERS ? off[d] : 0u;
+    }
+};
+
 // ---- downsweep -------------------------------------------------------------------------------
-template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
+template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB,
+          typename Dest = DestSingle<K, A, B>>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_block, int shift,
                   uint32_t mask, const uint32_t *__restrict__ offsets,
-                  const uint32_t *__restrict__ totals, K *__restrict__ out_k, A *__restrict__ out_a,
-                  B *__restrict__ out_b) {
+                  const uint32_t *__restrict__ totals, const Dest dest) {
     constexpr bool kHasA = !std::is_same<A, NoPayload>::value;
     constexpr bool kHasB = !std::is_same<B, NoPayload>::value;
     extern __shared__ __align__(16) unsigned char exch_raw[];   // RS_TILE * 8 bytes (dynamic: > 48 KB total)
@@ -158,7 +182,7 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
         const uint32_t tot = threadIdx.x < RS_BINS ? totals[threadIdx.x] : 0u;
         const uint32_t below = block_exclusive_scan(tot, ws, nullptr);
         if (threadIdx.x < RS_BINS)
-            running[threadIdx.x] = below + offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+            running[threadIdx.x] = dest.base(threadIdx.x, below) + offsets[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
     }
     for (int j = threadIdx.x; j < RS_WARPS * RS_BINS; j += RS_THREADS) (&wmask[0][0])[j] = 0;
     uint32_t st_k = 0, st_a = 0, st_b = 0;
@@ -270,13 +294,16 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
         }
         __syncthreads();
         uint32_t gpos[RS_IPT];
+        uint32_t dgt[Dest::kSingle ? 1 : RS_IPT];      // DestPeers: which rank's buffers slot j goes to
 #pragma unroll
         for (int j = 0; j < RS_IPT; ++j) {
             const uint32_t p = j * RS_THREADS + threadIdx.x;
             if (p < tile_count) {
                 const K k = exk[p];
-                gpos[j] = glob[(uint32_t)(k >> shift) & mask] + p;
-                out_k[gpos[j]] = k;
+                const uint32_t dg = (uint32_t)(k >> shift) & mask;
+                gpos[j] = glob[dg] + p;
+                if constexpr (Dest::kSingle) dest.k[gpos[j]] = k;
+                else dgt[j] = dg;
             }
         }
         if constexpr (kHasA) {
@@ -291,7 +318,10 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int j = 0; j < RS_IPT; ++j) {
                 const uint32_t p = j * RS_THREADS + threadIdx.x;
-                if (p < tile_count) out_a[gpos[j]] = exa[p];
+                if (p < tile_count) {
+                    if constexpr (Dest::kSingle) dest.a[gpos[j]] = exa[p];
+                    else dest.a[dgt[j]][gpos[j]] = exa[p];
+                }
             }
         }
         if constexpr (kHasB) {
@@ -306,7 +336,10 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 #pragma unroll
             for (int j = 0; j < RS_IPT; ++j) {
                 const uint32_t p = j * RS_THREADS + threadIdx.x;
-                if (p < tile_count) out_b[gpos[j]] = exb[p];
+                if (p < tile_count) {
+                    if constexpr (Dest::kSingle) dest.b[gpos[j]] = exb[p];
+                    else dest.b[dgt[j]][gpos[j]] = exb[p];
+                }
             }
         }
         __syncthreads();
@@ -357,7 +390,7 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
             rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
             check_launch(ctx, "rs_scan");
             rs_scatter_kernel<K, A, B, LoadK, LoadA, LoadB><<<grid, RS_THREADS, kExch, ctx->stream>>>(
-                lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
+                lk0, la0, lb0, n, tiles_per_block, shift, mask, counts, totals, DestSingle<K, A, B>{ok, oa, ob});
             check_launch(ctx, "rs_scatter");
         } else {
             using PA = typename std::conditional<std::is_same<A, NoPayload>::value, LoadNone,
@@ -380,12 +413,43 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
                                           cudaFuncAttributePreferredSharedMemoryCarveout,
                                           cudaSharedmemCarveoutMaxShared));
             rs_scatter_kernel<K, A, B, LoadPlain<K>, PA, PB><<<grid, RS_THREADS, kExch, ctx->stream>>>(
-                lk, la, lb, n, tiles_per_block, shift, mask, counts, totals, ok, oa, ob);
+                lk, la, lb, n, tiles_per_block, shift, mask, counts, totals, DestSingle<K, A, B>{ok, oa, ob});
             check_launch(ctx, "rs_scatter");
         }
         shift += nb;
     }
     return (passes - 1) & 1;
+}
+
+// One stable pass over a digit of at most 3 bits (the owning rank) whose output goes straight to the
+// owners' receive buffers.  `bits` = bits of the owner id.
+template <typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
+void radix_pass_to_peers(spl_ctx *ctx, uint32_t n, int bits, LoadK lk, LoadA la, LoadB lb,
+                         const DestPeers<A, B> &dest) {
+    if (n == 0) return;
+    if (bits <= 0) bits = 1;
+    using Kern = DestPeers<A, B>;
+    auto kern = rs_scatter_kernel<uint32_t, A, B, LoadK, LoadA, LoadB, Kern>;
+    constexpr size_t kExch = (size_t)RS_TILE * 8;
+    const uint32_t tiles = div_up(n, RS_TILE);
+    int occ = 0;
+    SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExch));
+    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RS_THREADS, kExch));
+    if (occ < 1) occ = 1;
+    uint32_t grid = (uint32_t)ctx->num_sms * (uint32_t)occ;
+    if (grid > tiles) grid = tiles;
+    const uint32_t tiles_per_block = div_up(tiles, grid);
+    grid = div_up(tiles, tiles_per_block);
+    Tmp<uint32_t> counts(ctx, (size_t)RS_BINS * grid);
+    Tmp<uint32_t> totals(ctx, RS_BINS);
+    const uint32_t mask = (1u << bits) - 1u;
+    rs_hist_kernel<uint32_t, LoadK><<<grid, RH_THREADS, 0, ctx->stream>>>(lk, n, tiles_per_block, 0, mask, counts);
+    check_launch(ctx, "rs_hist");
+    rs_scan_kernel<<<RS_BINS, 512, 0, ctx->stream>>>(counts, grid, totals);
+    check_launch(ctx, "rs_scan");
+    kern<<<grid, RS_THREADS, kExch, ctx->stream>>>(lk, la, lb, n, tiles_per_block, 0, mask, counts, totals, dest);
+    check_launch(ctx, "rs_scatter_to_peers");
 }
 
 }  // namespace spl

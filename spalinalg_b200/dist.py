@@ -91,23 +91,76 @@ class DistCsrMatrix:
     def local_rows(self): return self.starts[self.rank], self.starts[self.rank + 1]
 
     @classmethod
+    def from_device_triplets_peer(cls, dist, torch, nrows: int, ncols: int, row, col, val, exchange: "PeerExchange",
+                                  dedup=True, dropzero=True):
+        """Sharded From<&CooMatrix<T>> for CsrMatrix<T> with routing and exchange fused: the partition
+        pass writes every triplet straight into its owner's receive buffer over NVLink (peer memory),
+        bracketed by two device-side barriers; the only collective is the all-gather of world*world
+        counts that lays the buffers out.  Same result, bit for bit, as from_device_triplets."""
+        ctx, group = exchange.ctx, exchange.group
+        world, rank = exchange.world, exchange.rank
+        starts = partition_starts(nrows, world)
+        n = int(val.numel())
+        dtype = np.float32 if val.dtype == torch.float32 else np.float64
+        st = (C.c_uint64 * (world + 1))(*starts)
+        cnt = (C.c_uint64 * world)()
+        ctx.check(ctx._lib.spl_coo_route_count_dev(ctx._h, capi.SPL_CSR, nrows, ncols, n, C.c_void_p(row.data_ptr()),
+                                                   C.c_void_p(col.data_ptr()), world, C.cast(st, C.c_void_p),
+                                                   C.cast(cnt, C.c_void_p)))
+        mine = torch.tensor([int(c) for c in cnt], dtype=torch.int64, device=val.device)
+        allc = torch.empty(world * world, dtype=torch.int64, device=val.device)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        M = allc.view(world, world).tolist()                     # M[src][dst]
+        recv_total = [sum(M[s][d] for s in range(world)) for d in range(world)]
+        offs = [sum(M[s][d] for s in range(rank)) for d in range(world)]      # source-rank order
+        exchange.ensure(max(recv_total), np.dtype(dtype).itemsize)
+        kb = (C.c_void_p * world)(*exchange._keys.ptrs)
+        vb = (C.c_void_p * world)(*exchange._vals.ptrs)
+        off = (C.c_uint64 * world)(*offs)
+        exchange.barrier()                                        # owners are done with the old contents
+        ctx.check(ctx._lib.spl_coo_route_peers_dev(
+            ctx._h, capi.SPL_CSR, _dtype_code(dtype), nrows, ncols, n, C.c_void_p(row.data_ptr()),
+            C.c_void_p(col.data_ptr()), C.c_void_p(val.data_ptr()), world, C.cast(st, C.c_void_p),
+            C.cast(kb, C.c_void_p), C.cast(vb, C.c_void_p), C.cast(off, C.c_void_p)))
+        exchange.barrier()                                        # every record has landed
+        nloc = starts[rank + 1] - starts[rank]
+        h = C.c_void_p()
+        ctx.check(ctx._lib.spl_mat_from_packed_dev(
+            ctx._h, capi.SPL_CSR, _dtype_code(dtype), max(nloc, 1), ncols, recv_total[rank],
+            C.c_void_p(exchange._keys.local), C.c_void_p(exchange._vals.local), int(dedup), int(dropzero),
+            C.byref(h)))
+        return cls(CsrMatrix._wrap(ctx, h), starts, rank, nrows, ncols)
+
+    @classmethod
     def from_device_triplets(cls, dist, torch, nrows: int, ncols: int, row, col, val,
                              ctx: Optional[Context] = None, dedup=True, dropzero=True, group=None):
         """Sharded From<&CooMatrix<T>> for CsrMatrix<T> (src/csr/conv/coo.rs:3-116).  row/col are
         this rank's int32 (uint32 bit pattern) device tensors, val f32/f64; entries are
         block-distributed by entry index (rank 0 holds the first entries of the COO list)."""
+        import os
+        import time
         ctx = ctx or default_context()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         starts = partition_starts(nrows, world)
+        timing = os.environ.get("SPL_DIST_TIMING") and rank == 0
+        t0 = time.perf_counter()
         keys, vals, counts = route_device(ctx, torch, capi.SPL_CSR, nrows, ncols, row, col, val, starts)
+        t1 = time.perf_counter()
         rk, rv, _ = exchange_routed(dist, torch, keys, vals, counts, group)   # route ended with a stream sync
         torch.cuda.current_stream().synchronize()     # NCCL ran on torch's stream, assembly runs on ctx's
+        t2 = time.perf_counter()
         nloc = starts[rank + 1] - starts[rank]
         h = C.c_void_p()
         dtype = np.float32 if val.dtype == torch.float32 else np.float64
         ctx.check(ctx._lib.spl_mat_from_packed_dev(
             ctx._h, capi.SPL_CSR, _dtype_code(dtype), max(nloc, 1), ncols, int(rk.numel()),
             C.c_void_p(rk.data_ptr()), C.c_void_p(rv.data_ptr()), int(dedup), int(dropzero), C.byref(h)))
+        if timing:
+            ctx.sync()
+            t3 = time.perf_counter()
+            print(f"[spl dist] sharded assembly on rank 0: route {1e3 * (t1 - t0):.2f} ms, all-to-all "
+                  f"{1e3 * (t2 - t1):.2f} ms, shard assembly {1e3 * (t3 - t2):.2f} ms "
+                  f"({int(val.numel())} triplets in, {int(rk.numel())} received)", flush=True)
         return cls(CsrMatrix._wrap(ctx, h), starts, rank, nrows, ncols)
 
     # add / sub / neg: rank-local on a shared partition (SURVEY.md 8e, "sharded add/sub")
@@ -228,6 +281,53 @@ class PeerBuffer:
         if self.local:
             self.ctx._lib.spl_peer_free(self.ctx._h, C.c_void_p(self.local))
             self.local = None
+
+
+class PeerExchange:
+    """Receive buffers for the fused routing + exchange of sharded assembly: every rank owns a key
+    buffer (uint64) and a value buffer in peer-visible memory that all ranks can write, plus the flag
+    block of the device-side barrier.  Buffers grow collectively (every rank sees the same counts) and
+    are reused from call to call."""
+
+    def __init__(self, ctx: Context, dist, group=None):
+        self.ctx, self.dist, self.group = ctx, dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cap = 0
+        self.vsize = 0
+        self._keys = self._vals = None
+        self._flags = PeerBuffer(ctx, dist, 4 * capi.SPL_MAX_PEERS, group)
+        self._epoch = 0
+        dist.barrier(group=group)
+
+    def ensure(self, capacity: int, vsize: int):
+        """Collective: every rank calls it with the same arguments."""
+        if capacity <= self.cap and vsize <= self.vsize:
+            return
+        self.ctx.sync()
+        for b in (self._keys, self._vals):
+            if b is not None:
+                b.close(self.dist, self.group)
+        cap = max(int(capacity * 1.25) + 1024, 1 << 16)
+        self._keys = PeerBuffer(self.ctx, self.dist, 8 * cap, self.group)
+        self._vals = PeerBuffer(self.ctx, self.dist, max(vsize, self.vsize) * cap, self.group)
+        self.cap, self.vsize = cap, max(vsize, self.vsize)
+        self.dist.barrier(group=self.group)
+
+    def barrier(self, timeout_ms: int = 5000):
+        self._epoch += 1
+        fl = (C.c_void_p * self.world)(*self._flags.ptrs)
+        self.ctx.check(self.ctx._lib.spl_peer_barrier(self.ctx._h, self.world, self.rank,
+                                                      C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms)))
+
+    def check(self):
+        t = C.c_int()
+        self.ctx.check(self.ctx._lib.spl_peer_barrier_status(self.ctx._h, C.byref(t)))
+
+    def close(self):
+        for b in (self._keys, self._vals, self._flags):
+            if b is not None:
+                b.close(self.dist, self.group)
+        self._keys = self._vals = self._flags = None
 
 
 class PeerVector:

@@ -234,6 +234,14 @@ def test_sharded_front_end_world1_nccl():
                                                    _t(v, np.float64), ctx=ctx)
         assert np.array_equal(D.local.rowptr(), full[0]) and np.array_equal(D.local.colind(), full[1])
         assert D.local.values().tobytes() == full[2].tobytes()
+        ex = spd.PeerExchange(ctx, dist)
+        for _ in range(2):                                    # second call reuses the receive buffers
+            P = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, n, n, _t(r, np.int32), _t(c, np.int32),
+                                                            _t(v, np.float64), ex)
+            assert np.array_equal(P.local.rowptr(), full[0]) and np.array_equal(P.local.colind(), full[1])
+            assert P.local.values().tobytes() == full[2].tobytes()
+        ex.check()
+        ex.close()
         x = np.random.default_rng(1).standard_normal(n)
         xv = spd.PeerVector(ctx, dist, n, np.float64)
         device_view(torch, xv.local_ptr, n, torch.float64).copy_(torch.from_numpy(x))

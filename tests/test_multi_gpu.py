@@ -46,6 +46,19 @@ def _worker(rank, world, port, out):
         ok &= bool(np.array_equal(L.rowptr(), want[0]) and np.array_equal(L.colind(), want[1])
                    and L.values().tobytes() == want[2].tobytes())
         assert ok, "sharded assembly differs from the oracle"
+        # the same with routing and exchange fused over peer memory (two calls: buffer reuse, f32 after f64)
+        ex = spd.PeerExchange(ctx, dist)
+        for dt in (np.float64, np.float32, np.float64):
+            vv = v.astype(dt)
+            fullp = orc.compress_from_coo(n, n, orc.make_triplets(r, c, vv), "row")
+            P = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, n, n, dev(r[a:b], np.int32),
+                                                            dev(c[a:b], np.int32), dev(vv[a:b], dt), ex)
+            wp = shard_of(fullp, P.starts, rank)
+            ok &= bool(np.array_equal(P.local.rowptr(), wp[0]) and np.array_equal(P.local.colind(), wp[1])
+                       and P.local.values().tobytes() == wp[2].tobytes())
+        ex.check()
+        assert ok, "peer-memory sharded assembly differs from the oracle"
+        ex.close()
 
         # SpMV: x sharded like the columns, left in its owners' memory
         x = np.random.default_rng(9).standard_normal(n)
