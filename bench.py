@@ -578,6 +578,24 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
     ms = timed_all(spmv_ag, reps=7, warm=3)
     b_ag = nnz_d * 8 + 2 * nr * 4
+    # the same exchange done by pulling the peers' slices over NVLink (peer memory) instead of NCCL
+    from spalinalg_b200.synthetic_device import device_view
+    xs = spd.PeerVector(ctx, dist, nr, np.float32, D.starts)
+    device_view(torch, xs.local_ptr, d1 - d0, torch.float32).copy_(xg[d0:d1])
+    torch.cuda.synchronize()
+
+    def spmv_pull():
+        xs.barrier()
+        xs.pull(xg.data_ptr())
+        D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
+    y_ag = yg.clone()
+    ms_pull = timed_all(spmv_pull, reps=7, warm=3)
+    xs.check()
+    assert torch.equal(y_ag, yg), "pulled all-gather gives a different y"
+    out["sharded_spmv_peer_pull"] = {"workload": "same matrix; x all-gathered by one pull kernel over peer memory "
+                                                 "(device barrier + 128-bit NVLink reads), then the local SpMV",
+                                     "ms": ms_pull, "gbps_algorithmic": b_ag / ms_pull / 1e6}
+    xs.close(dist)
     out["sharded_spmv_allgather"] = {"workload": "the matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}

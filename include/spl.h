@@ -214,6 +214,13 @@ int spl_peer_free(spl_ctx *ctx, void *dev_ptr);
 int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
                      uint32_t timeout_ms);
 int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out);
+/* All-gather of x by pulling over peer memory, for general (random / power-law) shards whose
+ * gathers would be 4-byte NVLink transactions: one kernel copies every peer's slice
+ * (slices[g] = x[starts[g] .. starts[g+1]), mapped with spl_peer_open) into the local full-length
+ * vector x_full_dev with 128-bit coalesced loads; the own slice is not touched (keep it in place
+ * or copy it yourself).  Order it with spl_peer_barrier like spl_spmv_peer. */
+int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *starts,
+                  const void *const *slices, void *x_full_dev);
 /* Row-sharded y_local = A_local * x with x left where it lives: x_slices[g] is rank
  * g's slice of x (columns [col_starts[g], col_starts[g+1]), own slice included), mapped
  * with spl_peer_open.  One kernel: every gather goes to the slice that owns the column,

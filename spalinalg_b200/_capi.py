@@ -59,6 +59,7 @@ SIGNATURES = {
     "spl_peer_close": (_i, [_vp, _vp]),
     "spl_peer_free": (_i, [_vp, _vp]),
     "spl_peer_barrier": (_i, [_vp, _i, _i, _vp, C.c_uint32, C.c_uint32]),
+    "spl_peer_pull": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
     "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
 }

@@ -584,6 +584,15 @@ int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, 
     API_END(ctx)
 }
 
+int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *starts,
+                  const void *const *slices, void *x_full_dev) {
+    API_BEGIN(ctx)
+    check_enums(SPL_CSR, dtype);
+    SPL_REQUIRE(starts && slices && x_full_dev, SPL_ERR_ARG, "NULL argument");
+    peer_pull(ctx, world, rank, dtype == SPL_F32 ? 4 : 8, starts, slices, x_full_dev);
+    API_END(ctx)
+}
+
 int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out) {
     API_BEGIN(ctx)
     uint32_t w = 0;

@@ -54,6 +54,8 @@ void spmv_peer(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *y);
 // peer.cu — CUDA IPC buffers and the flag barrier over peer memory
 void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
                   uint32_t timeout_ms);
+void peer_pull(spl_ctx *ctx, int world, int rank, size_t vsize, const uint64_t *starts,
+               const void *const *slices, void *x_full);
 
 // addsub.cu — C = A +/- B on compressed arrays of equal format (a-7)
 spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract);

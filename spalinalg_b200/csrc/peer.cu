@@ -44,7 +44,59 @@ __global__ void peer_barrier_kernel(FlagBlocks f, int world, int rank, uint32_t 
     }
 }
 
+// All-gather of x by pulling: every rank copies its peers' slices (peer memory, NVLink reads) into
+// its own full-length vector with 128-bit coalesced loads.  One launch moves all slices; the grid
+// is split among the source ranks in proportion to their slice lengths.
+struct PullSlices {
+    const unsigned char *src[SPL_MAX_PEERS];
+    unsigned long long dst_off[SPL_MAX_PEERS];     // byte offset of slice g in the full vector
+    unsigned long long bytes[SPL_MAX_PEERS];
+    int world, rank;
+};
+
+__global__ void __launch_bounds__(256) peer_pull_kernel(PullSlices ps, unsigned char *__restrict__ dst) {
+    // blockIdx.y = source rank; blocks of a row stride over that slice
+    const int g = blockIdx.y;
+    if (g >= ps.world || g == ps.rank) return;
+    const unsigned char *src = ps.src[g];
+    unsigned char *out = dst + ps.dst_off[g];
+    const unsigned long long n = ps.bytes[g];
+    const unsigned long long n16 = (((unsigned long long)(uintptr_t)src | (unsigned long long)(uintptr_t)out) & 15ull) ? 0ull : n / 16;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(out);
+    for (; i + 3 * stride < n16; i += 4 * stride) {          // four 16-byte loads in flight per thread
+        const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + stride), c = __ldcg(s4 + i + 2 * stride),
+                    d = __ldcg(s4 + i + 3 * stride);
+        d4[i] = a; d4[i + stride] = b; d4[i + 2 * stride] = c; d4[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) d4[i] = __ldcg(s4 + i);
+    for (unsigned long long b = n16 * 16 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
+        out[b] = src[b];
+}
+
 }  // namespace
+
+void peer_pull(spl_ctx *ctx, int world, int rank, size_t vsize, const uint64_t *starts,
+               const void *const *slices, void *x_full) {
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
+                "world must be 1..8 and rank inside it");
+    if (world == 1) return;
+    PullSlices ps{};
+    ps.world = world;
+    ps.rank = rank;
+    for (int g = 0; g < world; ++g) {
+        SPL_REQUIRE(starts[g] <= starts[g + 1], SPL_ERR_ARG, "starts must be non-decreasing");
+        SPL_REQUIRE(slices[g] || starts[g] == starts[g + 1], SPL_ERR_ARG, "NULL slice");
+        ps.src[g] = static_cast<const unsigned char *>(slices[g]);
+        ps.dst_off[g] = starts[g] * vsize;
+        ps.bytes[g] = (starts[g + 1] - starts[g]) * vsize;
+    }
+    dim3 grid((unsigned)ctx->num_sms * 2u, (unsigned)world);
+    peer_pull_kernel<<<grid, 256, 0, ctx->stream>>>(ps, static_cast<unsigned char *>(x_full));
+    check_launch(ctx, "peer_pull");
+}
 
 void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
                   uint32_t timeout_ms) {

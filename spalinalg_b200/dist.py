@@ -355,6 +355,15 @@ class PeerVector:
         self.ctx.check(self.ctx._lib.spl_peer_barrier(self.ctx._h, self.world, self.rank,
                                                       C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms)))
 
+    def pull(self, x_full_dev: int):
+        """All-gather by pulling: copies every peer's slice into the local full-length vector at
+        `x_full_dev` (device address, n elements).  The own slice is left to the caller."""
+        st = (C.c_uint64 * (self.world + 1))(*self.starts)
+        sl = (C.c_void_p * self.world)(*self.ptrs)
+        self.ctx.check(self.ctx._lib.spl_peer_pull(self.ctx._h, _dtype_code(self.dtype), self.world, self.rank,
+                                                   C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p),
+                                                   C.c_void_p(x_full_dev)))
+
     def check(self):
         """Raises if a barrier timed out (synchronises the stream)."""
         t = C.c_int()

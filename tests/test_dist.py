@@ -196,6 +196,31 @@ def test_spmv_peer_gathers_from_owning_slice(dtype, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,world,n", [(np.float64, 2, 1001), (np.float32, 3, 100003), (np.float64, 8, 70001)])
+def test_peer_pull_gathers_every_slice(dtype, world, n):
+    """spl_peer_pull with the slices in separate buffers of one process: every rank's full vector
+    must end up with all the other slices (odd lengths: unaligned slices take the byte path)."""
+    import spalinalg_b200 as sp
+    from spalinalg_b200 import _capi as capi
+    ctx = sp.default_context()
+    x = np.random.default_rng(2).standard_normal(n).astype(dtype)
+    starts = spd.partition_starts(n, world)
+    slices = [_t(x[starts[g]:starts[g + 1]], dtype) for g in range(world)]
+    st = (C.c_uint64 * (world + 1))(*starts)
+    sl = (C.c_void_p * world)(*[s.data_ptr() for s in slices])
+    for g in range(world):
+        full = torch.full((n,), 7.0, dtype=slices[0].dtype, device="cuda")
+        torch.cuda.synchronize()
+        ctx.check(ctx._lib.spl_peer_pull(ctx._h, capi.SPL_F32 if dtype == np.float32 else capi.SPL_F64, world, g,
+                                         C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(full.data_ptr())))
+        ctx.sync()
+        got = full.cpu().numpy()
+        want = x.copy()
+        want[starts[g]:starts[g + 1]] = 7.0                      # the own slice is not touched
+        assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
 def test_peer_barrier_arrival_and_timeout():
     """One rank of a 2-rank barrier on this GPU: the peer's arrival is a flag value written ahead of
     time; without it the bounded spin must give up and report, never hang."""

@@ -84,6 +84,18 @@ def _worker(rank, world, port, out):
         torch.cuda.synchronize()
         ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
         assert ok, "all-gather SpMV differs from the oracle"
+        # the all-gather done by pulling the peers' slices over NVLink (spl_peer_pull)
+        x_full.fill_(float("nan"))
+        x_full[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
+        torch.cuda.synchronize()
+        xv.barrier()
+        xv.pull(x_full.data_ptr())
+        y.zero_()
+        L.spmv_device(x_full.data_ptr(), y.data_ptr())
+        torch.cuda.synchronize()
+        xv.check()
+        ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
+        assert ok, "pulled all-gather SpMV differs from the oracle"
 
         # add / sub / neg on the shared partition
         r2, c2, v2 = make_coo(n, n, 300000, 321)
