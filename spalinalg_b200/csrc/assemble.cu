@@ -29,6 +29,58 @@ __global__ void coo_bounds_kernel(const uint32_t *__restrict__ row, const uint32
     if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flag, 1u);
 }
 
+// Pointer entries are written by the record that starts a major: ptr[lo..hi] = position.  A run of
+// empty rows/columns can be arbitrarily long (one stored entry in a 10^8-row matrix), and one thread
+// must not write millions of entries: ranges of 64 or more go to a queue that fill_gaps_kernel
+// empties with a CTA per range.
+struct GapQueue {
+    uint32_t *count;     // number of queued ranges (may exceed cap: the excess was written inline)
+    uint4 *items;        // (lo, hi, value, -)
+    uint32_t cap;
+};
+constexpr uint32_t kGapCap = 16384;
+
+__device__ __forceinline__ void emit_ptr(uint32_t *__restrict__ ptr, uint64_t lo, uint64_t hi, uint32_t value,
+                                         const GapQueue &gq) {
+    if (hi < lo) return;
+    if (hi - lo >= 64 && gq.items) {
+        const uint32_t slot = atomicAdd(gq.count, 1u);
+        if (slot < gq.cap) {
+            gq.items[slot] = make_uint4((uint32_t)lo, (uint32_t)hi, value, 0u);
+            return;
+        }
+    }
+    for (uint64_t q = lo; q <= hi; ++q) ptr[q] = value;
+}
+
+__global__ void __launch_bounds__(256) fill_gaps_kernel(uint32_t *__restrict__ ptr, GapQueue gq) {
+    const uint32_t n = min(*gq.count, gq.cap);
+    for (uint32_t g = blockIdx.x; g < n; g += gridDim.x) {
+        const uint4 it = gq.items[g];
+        for (uint64_t q = (uint64_t)it.x + threadIdx.x; q <= (uint64_t)it.y; q += blockDim.x) ptr[q] = it.z;
+    }
+}
+
+// Owns the queue's temporary storage for one pointer build.
+struct GapQueueOwner {
+    Tmp<uint32_t> mem;
+    GapQueue q;
+    GapQueueOwner(spl_ctx *ctx) : mem(ctx, 4 + 4 * (size_t)kGapCap) {
+        q.count = mem.p;
+#ifdef SPL_NO_GAPQ
+        q.items = nullptr;
+#else
+        q.items = reinterpret_cast<uint4 *>(mem.p + 4);
+#endif
+        q.cap = kGapCap;
+        cudaMemsetAsync(mem.p, 0, sizeof(uint32_t), ctx->stream);
+    }
+    void drain(spl_ctx *ctx, uint32_t *ptr) {
+        fill_gaps_kernel<<<(unsigned)ctx->num_sms * 2u, 256, 0, ctx->stream>>>(ptr, q);
+        check_launch(ctx, "fill_gaps");
+    }
+};
+
 // Tile = CP_THREADS x CP_IPT consecutive records, warp-striped: in step i thread t looks at record
 // tile_base + i*CP_THREADS + t, so every load and store below is coalesced, and all of a thread's
 // loads are issued before the first dependent instruction (in-order issue would otherwise expose
@@ -90,7 +142,7 @@ __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t *__restrict__ flags, const K *__restrict__ keys,
                const T *__restrict__ vals, uint32_t n, const uint32_t *__restrict__ tile_offsets,
                int minor_bits, uint32_t nmajor, uint32_t *__restrict__ out_ind, T *__restrict__ out_val,
-               uint32_t *__restrict__ ptr) {
+               uint32_t *__restrict__ ptr, GapQueue gq) {
     constexpr int W = CP_THREADS / 32;
     __shared__ uint32_t s_cnt[CP_IPT * W + 1];
     const uint64_t tile_base = (uint64_t)blockIdx.x * CP_TILE;
@@ -143,23 +195,20 @@ compact_kernel(const uint8_t *__restrict__ flags, const K *__restrict__ keys,
         const uint32_t mj = wide ? 0u : (uint32_t)(k[i] >> minor_bits);
         const uint32_t mp = wide ? 0u : (uint32_t)(prev >> minor_bits);
         // majors (mp, mj] start at pos; record 0 also writes major 0 .. mj = 0
-        if (idx == 0) for (uint32_t q = 0; q <= mj; ++q) ptr[q] = 0;
-        else for (uint32_t q = mp + 1; q <= mj; ++q) ptr[q] = pos;
-        if (idx == (uint64_t)n - 1) {
-            const uint32_t end = pos + ((fbits >> i) & 1u);
-            for (uint32_t q = mj + 1; q <= nmajor; ++q) ptr[q] = end;
-        }
+        if (idx == 0) emit_ptr(ptr, 0, mj, 0u, gq);
+        else emit_ptr(ptr, (uint64_t)mp + 1, mj, pos, gq);
+        if (idx == (uint64_t)n - 1) emit_ptr(ptr, (uint64_t)mj + 1, nmajor, pos + ((fbits >> i) & 1u), gq);
     }
 }
 
 __global__ void fill_ptr_kernel(const uint32_t *__restrict__ sorted_major, uint32_t nnz,
-                                uint32_t nmajor, uint32_t *__restrict__ ptr) {
+                                uint32_t nmajor, uint32_t *__restrict__ ptr, GapQueue gq) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p > nnz) return;
     // entries p-1 and p bracket the majors whose segment starts at p
-    const int64_t lo = p == 0 ? 0 : (int64_t)sorted_major[p - 1] + 1;
-    const int64_t hi = p == nnz ? (int64_t)nmajor : (int64_t)sorted_major[p];
-    for (int64_t q = lo; q <= hi; ++q) ptr[q] = (uint32_t)p;
+    const uint64_t lo = p == 0 ? 0 : (uint64_t)sorted_major[p - 1] + 1;
+    const uint64_t hi = p == nnz ? (uint64_t)nmajor : (uint64_t)sorted_major[p];
+    emit_ptr(ptr, lo, hi, (uint32_t)p, gq);
 }
 
 template <typename K, typename T>
@@ -184,9 +233,11 @@ spl_mat *finish_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32
 
     spl_mat *m = new_mat(ctx, format, dtype, nrows, ncols, nnz);
     try {
+        GapQueueOwner gaps(ctx);
         compact_kernel<K, T><<<tiles, CP_THREADS, 0, ctx->stream>>>(
-            flags, keys, vals, n, sums, minor_bits, nmajor, m->ind, static_cast<T *>(m->val), m->ptr);
+            flags, keys, vals, n, sums, minor_bits, nmajor, m->ind, static_cast<T *>(m->val), m->ptr, gaps.q);
         check_launch(ctx, "compact");
+        gaps.drain(ctx, m->ptr);
     } catch (...) {
         free_mat(ctx, m);
         throw;
@@ -364,9 +415,11 @@ void check_coo_bounds(spl_ctx *ctx, uint32_t len, const uint32_t *row, const uin
 
 void fill_ptr(spl_ctx *ctx, const uint32_t *sorted_major, uint32_t nnz, uint32_t nmajor,
               uint32_t *ptr) {
+    GapQueueOwner gaps(ctx);
     fill_ptr_kernel<<<div_up((uint64_t)nnz + 1, 256), 256, 0, ctx->stream>>>(sorted_major, nnz,
-                                                                            nmajor, ptr);
+                                                                            nmajor, ptr, gaps.q);
     check_launch(ctx, "fill_ptr");
+    gaps.drain(ctx, ptr);
 }
 
 spl_mat *finish_from_sorted(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,

@@ -287,6 +287,24 @@ def test_assembly_of_sorted_triplets_skips_the_sort(dtype, fmt):
         same(arrays(got), want, f"{fmt} {variant}")
 
 
+def test_long_runs_of_empty_rows_and_columns():
+    """A handful of entries in a 5e6 x 3e6 matrix: the pointer arrays are almost entirely runs of
+    empty rows / columns (written by the queued gap filler, not by one thread)."""
+    n, m = 5_000_000, 3_000_000
+    r = np.array([7, 7, 2_500_000, n - 1, n - 1], np.uint64)
+    c = np.array([5, 2_999_999, 0, 123, 123], np.uint64)
+    v = np.array([1.0, 2.0, 3.0, 4.0, 0.5])
+    coo = sp.CooMatrix.with_triplets(n, m, r, c, v)
+    trip = orc.make_triplets(r, c, v)
+    A = sp.CsrMatrix.from_coo(coo)
+    want = orc.compress_from_coo(n, m, trip, "row")
+    same(arrays(A), want, "csr")
+    same(arrays(sp.CscMatrix.from_coo(coo)), orc.compress_from_coo(n, m, trip, "col"), "csc")
+    same(arrays(A.transpose()), orc.recompress(n, m, *want), "transpose")
+    same(arrays(A.to_csc()), orc.recompress(n, m, *want), "to_csc")
+    same(arrays(A + A), orc.addsub(0, n, m, want, want), "add")
+
+
 def test_dok_round_trip_through_device():
     """From<&DokMatrix> for CsrMatrix / CscMatrix (src/csr/conv/dok.rs:3-76) and back
     (src/dok.rs:676-720): explicit zeros survive both ways, nothing is summed or dropped."""
