@@ -78,6 +78,46 @@ def route_device(ctx: Context, torch, fmt: int, nrows: int, ncols: int, row, col
     return keys, vals, [int(c) for c in cnt]
 
 
+def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col, val, exchange, dedup, dropzero):
+    """Route this rank's triplets to the owners of their major index (rows for CSR, columns for CSC)
+    through peer memory and assemble the own shard.  Returns (spl_mat handle, major partition)."""
+    ctx, group = exchange.ctx, exchange.group
+    world, rank = exchange.world, exchange.rank
+    nmajor = nrows if fmt == capi.SPL_CSR else ncols
+    starts = partition_starts(nmajor, world)
+    n = int(val.numel())
+    dtype = np.float32 if val.dtype == torch.float32 else np.float64
+    st = (C.c_uint64 * (world + 1))(*starts)
+    cnt = (C.c_uint64 * world)()
+    ctx.check(ctx._lib.spl_coo_route_count_dev(ctx._h, fmt, nrows, ncols, n, C.c_void_p(row.data_ptr()),
+                                               C.c_void_p(col.data_ptr()), world, C.cast(st, C.c_void_p),
+                                               C.cast(cnt, C.c_void_p)))
+    mine = torch.tensor([int(c) for c in cnt], dtype=torch.int64, device=val.device)
+    allc = torch.empty(world * world, dtype=torch.int64, device=val.device)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    M = allc.view(world, world).tolist()                     # M[src][dst]
+    recv_total = [sum(M[s][d] for s in range(world)) for d in range(world)]
+    offs = [sum(M[s][d] for s in range(rank)) for d in range(world)]      # source-rank order
+    exchange.ensure(max(recv_total), np.dtype(dtype).itemsize)
+    kb = (C.c_void_p * world)(*exchange._keys.ptrs)
+    vb = (C.c_void_p * world)(*exchange._vals.ptrs)
+    off = (C.c_uint64 * world)(*offs)
+    exchange.barrier()                                        # owners are done with the old contents
+    ctx.check(ctx._lib.spl_coo_route_peers_dev(
+        ctx._h, fmt, _dtype_code(dtype), nrows, ncols, n, C.c_void_p(row.data_ptr()),
+        C.c_void_p(col.data_ptr()), C.c_void_p(val.data_ptr()), world, C.cast(st, C.c_void_p),
+        C.cast(kb, C.c_void_p), C.cast(vb, C.c_void_p), C.cast(off, C.c_void_p)))
+    exchange.barrier()                                        # every record has landed
+    nloc = max(starts[rank + 1] - starts[rank], 1)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.spl_mat_from_packed_dev(
+        ctx._h, fmt, _dtype_code(dtype), nloc if fmt == capi.SPL_CSR else nrows,
+        ncols if fmt == capi.SPL_CSR else nloc, recv_total[rank],
+        C.c_void_p(exchange._keys.local), C.c_void_p(exchange._vals.local), int(dedup), int(dropzero),
+        C.byref(h)))
+    return h, starts
+
+
 class DistCsrMatrix:
     """Row block of a CSR matrix on this rank plus the partition it belongs to."""
 
@@ -97,39 +137,9 @@ class DistCsrMatrix:
         pass writes every triplet straight into its owner's receive buffer over NVLink (peer memory),
         bracketed by two device-side barriers; the only collective is the all-gather of world*world
         counts that lays the buffers out.  Same result, bit for bit, as from_device_triplets."""
-        ctx, group = exchange.ctx, exchange.group
-        world, rank = exchange.world, exchange.rank
-        starts = partition_starts(nrows, world)
-        n = int(val.numel())
-        dtype = np.float32 if val.dtype == torch.float32 else np.float64
-        st = (C.c_uint64 * (world + 1))(*starts)
-        cnt = (C.c_uint64 * world)()
-        ctx.check(ctx._lib.spl_coo_route_count_dev(ctx._h, capi.SPL_CSR, nrows, ncols, n, C.c_void_p(row.data_ptr()),
-                                                   C.c_void_p(col.data_ptr()), world, C.cast(st, C.c_void_p),
-                                                   C.cast(cnt, C.c_void_p)))
-        mine = torch.tensor([int(c) for c in cnt], dtype=torch.int64, device=val.device)
-        allc = torch.empty(world * world, dtype=torch.int64, device=val.device)
-        dist.all_gather_into_tensor(allc, mine, group=group)
-        M = allc.view(world, world).tolist()                     # M[src][dst]
-        recv_total = [sum(M[s][d] for s in range(world)) for d in range(world)]
-        offs = [sum(M[s][d] for s in range(rank)) for d in range(world)]      # source-rank order
-        exchange.ensure(max(recv_total), np.dtype(dtype).itemsize)
-        kb = (C.c_void_p * world)(*exchange._keys.ptrs)
-        vb = (C.c_void_p * world)(*exchange._vals.ptrs)
-        off = (C.c_uint64 * world)(*offs)
-        exchange.barrier()                                        # owners are done with the old contents
-        ctx.check(ctx._lib.spl_coo_route_peers_dev(
-            ctx._h, capi.SPL_CSR, _dtype_code(dtype), nrows, ncols, n, C.c_void_p(row.data_ptr()),
-            C.c_void_p(col.data_ptr()), C.c_void_p(val.data_ptr()), world, C.cast(st, C.c_void_p),
-            C.cast(kb, C.c_void_p), C.cast(vb, C.c_void_p), C.cast(off, C.c_void_p)))
-        exchange.barrier()                                        # every record has landed
-        nloc = starts[rank + 1] - starts[rank]
-        h = C.c_void_p()
-        ctx.check(ctx._lib.spl_mat_from_packed_dev(
-            ctx._h, capi.SPL_CSR, _dtype_code(dtype), max(nloc, 1), ncols, recv_total[rank],
-            C.c_void_p(exchange._keys.local), C.c_void_p(exchange._vals.local), int(dedup), int(dropzero),
-            C.byref(h)))
-        return cls(CsrMatrix._wrap(ctx, h), starts, rank, nrows, ncols)
+        h, starts = _assemble_over_peers(dist, torch, capi.SPL_CSR, nrows, ncols, row, col, val, exchange,
+                                         dedup, dropzero)
+        return cls(CsrMatrix._wrap(exchange.ctx, h), starts, exchange.rank, nrows, ncols)
 
     @classmethod
     def from_device_triplets(cls, dist, torch, nrows: int, ncols: int, row, col, val,
@@ -187,7 +197,7 @@ class DistCsrMatrix:
         dist.all_reduce(t, group=group)
         return int(t.item())
 
-    def to_csc(self, dist, torch, group=None) -> "DistCscMatrix":
+    def to_csc(self, dist, torch, group=None, exchange: Optional["PeerExchange"] = None) -> "DistCscMatrix":
         """Sharded From<&CsrMatrix> for CscMatrix (src/csc/conv/csr.rs:3-53): row-sharded CSR in,
         column-sharded CSC out (rank g gets columns [cstarts[g], cstarts[g+1]), global row indices).
         The stored entries are routed to the owner of their column with the same device partition as
@@ -213,6 +223,11 @@ class DistCsrMatrix:
             val = torch.empty(0, dtype=tdt, device=ptr.device)
             row = torch.empty(0, dtype=torch.int32, device=ptr.device)
         torch.cuda.current_stream().synchronize()
+        from .matrix import CscMatrix
+        if exchange is not None:                  # routing and exchange fused over peer memory
+            h, cstarts = _assemble_over_peers(dist, torch, capi.SPL_CSC, self._nrows, self._ncols, row, col, val,
+                                              exchange, False, False)
+            return DistCscMatrix(CscMatrix._wrap(ctx, h), cstarts, rank, self._nrows, self._ncols)
         keys, vals, cnts = route_device(ctx, torch, capi.SPL_CSC, self._nrows, self._ncols, row, col, val, cstarts)
         rk, rv, _ = exchange_routed(dist, torch, keys, vals, cnts, group)
         torch.cuda.current_stream().synchronize()

@@ -283,10 +283,12 @@ def test_sharded_front_end_world1_nccl():
         S = D + D
         w = orc.addsub(0, n, n, full, full)
         assert np.array_equal(S.local.colind(), w[1]) and S.local.values().tobytes() == w[2].tobytes()
-        T = D.to_csc(dist, torch)
         wc = orc.recompress(n, n, *full)
-        assert np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
-        assert T.local.values().tobytes() == wc[2].tobytes()
+        ex2 = spd.PeerExchange(ctx, dist)
+        for T in (D.to_csc(dist, torch), D.to_csc(dist, torch, exchange=ex2)):
+            assert np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
+            assert T.local.values().tobytes() == wc[2].tobytes()
+        ex2.close()
         xv.close(dist)
     finally:
         dist.destroy_process_group()

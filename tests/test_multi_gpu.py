@@ -115,6 +115,13 @@ def _worker(rank, world, port, out):
         ok &= bool(np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
                    and T.local.values().tobytes() == wc[2].tobytes())
         assert ok, "sharded CSR -> CSC differs from the oracle"
+        ex2 = spd.PeerExchange(ctx, dist)
+        T2 = D.to_csc(dist, torch, exchange=ex2)               # the same through peer memory
+        ok &= bool(np.array_equal(T2.local.colptr(), wc[0]) and np.array_equal(T2.local.rowind(), wc[1])
+                   and T2.local.values().tobytes() == wc[2].tobytes())
+        ex2.check()
+        ex2.close()
+        assert ok, "peer-memory sharded CSR -> CSC differs from the oracle"
         xv.close(dist)
     finally:
         flag = torch.tensor([1 if ok else 0], device="cuda")
