@@ -208,6 +208,15 @@ public:
     std::size_t nnz() const { return nnz_; }                                              // csr.rs:287-289
     const std::vector<T> &values() const { download(); return host_->val; }
     spl_mat *raw() const { return dev_.get(); }
+    // values_mut() (src/csr.rs:270-272): hand f a writable copy of the values, then store it back
+    template <typename F>
+    void values_mut(F &&f) {
+        std::vector<T> v = values();
+        f(v);
+        if (v.size() != nnz_) throw Panic("values_mut: the number of values must not change");
+        ctx().check(spl_mat_set_values(ctx().raw(), raw(), v.data()));
+        if (host_) host_->val = v;
+    }
     CooMatrix<T> to_coo() const {                                                         // coo.rs:629-705
         std::vector<std::uint64_t> r(nnz_), c(nnz_);
         std::vector<T> v(nnz_);

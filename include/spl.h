@@ -149,6 +149,10 @@ int spl_mat_info(const spl_mat *m, int *format, int *dtype, uint64_t *nrows, uin
 /* rowptr()/colind()/values() (src/csr.rs:228-258) as host copies, indices widened
  * to usize.  ptr needs nmajor+1 slots, ind and val nnz.  Synchronises. */
 int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *ind, void *val);
+/* values_mut() (src/csr.rs:270-272, src/csc.rs:270-272): overwrite the stored values, structure
+ * kept.  val points to nnz host values of the matrix's scalar type.  Needs exclusive access to the
+ * matrix, as `&mut self` does in the reference. */
+int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val);
 /* Borrow the device arrays (uint32 ptr[nmajor+1], uint32 ind[nnz], T val[nnz]). */
 int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32_t **ind_dev,
                         const void **val_dev);

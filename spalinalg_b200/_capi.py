@@ -47,6 +47,7 @@ SIGNATURES = {
     "spl_mat_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_u64), C.POINTER(_u64),
                           C.POINTER(_u64)]),
     "spl_mat_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "spl_mat_set_values": (_i, [_vp, _vp, _vp]),
     "spl_mat_device_ptrs": (_i, [_vp, _pp, _pp, _pp]),
     "spl_mat_to_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "spl_mat_free": (_i, [_vp, _vp]),

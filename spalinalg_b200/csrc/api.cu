@@ -431,6 +431,16 @@ int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *in
     API_END(ctx)
 }
 
+int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(m && (val || m->nnz == 0), SPL_ERR_ARG, "NULL argument");
+    if (m->nnz) {
+        SPL_CUDA(cudaMemcpyAsync(m->val, val, (size_t)m->nnz * m->vsize(), cudaMemcpyHostToDevice, ctx->stream));
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));      // the caller may reuse its buffer at once
+    }
+    API_END(ctx)
+}
+
 int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32_t **ind_dev,
                         const void **val_dev) {
     if (!m) return SPL_ERR_ARG;

@@ -506,6 +506,32 @@ class _Compressed:
 
     def values(self): return self._download()[2]
 
+    def set_values(self, values):
+        """Overwrite the stored values, structure kept (what a caller does through values_mut(),
+        src/csr.rs:270-272 / src/csc.rs:270-272)."""
+        v = np.ascontiguousarray(values, dtype=self._dtype)
+        if len(v) != self._nnz:
+            raise Panic("assertion `left == right` failed: values.len() == self.nnz()")
+        self._ctx.check(self._ctx._lib.spl_mat_set_values(self._ctx._h, self._h, _ptr(v)))
+        if self._host is not None:
+            self._host = (self._host[0], self._host[1], v.copy())
+
+    def values_mut(self):
+        """`with m.values_mut() as v: v[...] = ...` — a writable host copy of the values that is
+        written back to the device on exit (src/csr.rs:270-272)."""
+        mat = self
+
+        class _Mut:
+            def __enter__(self_inner):
+                self_inner.v = mat.values().copy()
+                return self_inner.v
+
+            def __exit__(self_inner, exc_type, exc, tb):
+                if exc_type is None:
+                    mat.set_values(self_inner.v)
+                return False
+        return _Mut()
+
     def device_ptrs(self):
         p, i, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ctx._lib.spl_mat_device_ptrs(self._h, C.byref(p), C.byref(i), C.byref(v))

@@ -107,6 +107,8 @@ static int run() {
         auto ax = a * x;
         CHECK(ax.rowptr() == (V{0, 1, 1, 2}) && ax.colind() == (V{0, 0}) && ax.values() == (D{70, 180}));
         CHECK(a.matvec(D{10, 20, 30}) == (D{70, 0, 180}));
+        a.values_mut([](D &v) { for (auto &e : v) e *= 2; });                            // src/csr.rs:270-272
+        CHECK(a.values() == (D{2, 4, 6, 8}) && a.matvec(D{10, 20, 30}) == (D{140, 0, 360}));
         CHECK(panics([&] { (void)(x * a); }));                                             // mul.rs:9
     }
     if (failures == 0) std::printf("cpp mirror: all reference tests passed\n");

@@ -287,6 +287,17 @@ def test_assembly_of_sorted_triplets_skips_the_sort(dtype, fmt):
         same(arrays(got), want, f"{fmt} {variant}")
 
 
+def test_values_mut_round_trip():
+    """values_mut() (src/csr.rs:270-272): new values, same structure, seen by the next operation."""
+    A = sp.CsrMatrix.new(2, 3, np.array([0, 2, 3], np.uint64), np.array([0, 2, 1], np.uint64), np.array([1.0, 2.0, 3.0]))
+    with A.values_mut() as v:
+        v *= 10.0
+    assert A.values().tolist() == [10.0, 20.0, 30.0] and A.colind().tolist() == [0, 2, 1]
+    assert A.matvec(np.array([1.0, 1.0, 1.0])).tolist() == [30.0, 30.0]
+    with pytest.raises(sp.Panic):
+        A.set_values(np.zeros(2))
+
+
 def test_long_runs_of_empty_rows_and_columns():
     """A handful of entries in a 5e6 x 3e6 matrix: the pointer arrays are almost entirely runs of
     empty rows / columns (written by the queued gap filler, not by one thread)."""
