@@ -58,16 +58,42 @@ scan_downsweep_kernel(const uint32_t *__restrict__ in, uint32_t n,
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
     uint32_t s = 0;
+    // whole 64-byte group of 16-byte aligned arrays: 128-bit loads and stores
+    const bool full = base + SCAN_IPT <= n && ((((uintptr_t)in) | ((uintptr_t)out)) & 15u) == 0;
+    if (full) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(in + base);
 #pragma unroll
-    for (int i = 0; i < SCAN_IPT; ++i) {
-        v[i] = (base + i < n) ? in[base + i] : 0u;
-        s += v[i];
+        for (int i = 0; i < SCAN_IPT / 4; ++i) {
+            const uint4 q = __ldg(p + i);
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < SCAN_IPT; ++i) s += v[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_IPT; ++i) {
+            v[i] = (base + i < n) ? in[base + i] : 0u;
+            s += v[i];
+        }
     }
     uint32_t run = block_exclusive_scan(s, ws, nullptr) + tile_offsets[blockIdx.x];
+    if (full) {
+        uint4 *o = reinterpret_cast<uint4 *>(out + base);
 #pragma unroll
-    for (int i = 0; i < SCAN_IPT; ++i) {
-        if (base + i < n) out[base + i] = run;
-        run += v[i];
+        for (int i = 0; i < SCAN_IPT / 4; ++i) {
+            uint4 q;
+            q.x = run; run += v[4 * i];
+            q.y = run; run += v[4 * i + 1];
+            q.z = run; run += v[4 * i + 2];
+            q.w = run; run += v[4 * i + 3];
+            o[i] = q;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_IPT; ++i) {
+            if (base + i < n) out[base + i] = run;
+            run += v[i];
+        }
     }
     // the thread owning element n-1 also writes the grand total
     if (n > 0 && base <= (uint64_t)n - 1 && (uint64_t)n - 1 < base + SCAN_IPT) out[n] = run;
