@@ -481,3 +481,38 @@ def test_c2_full_size_round_trip():
     y = A.matvec(np.ones(n))
     deg = np.diff(a[0].astype(np.int64))
     assert np.array_equal(y, 26.0 - (deg - 1))
+
+
+# ------------------------------------------------------------------ boundary sizes
+@pytest.mark.parametrize("length", [1, 2, 31, 32, 33, 255, 256, 257, 4095, 4096, 4097, 8191, 8193, 12288, 65535,
+                                    65537, 4096 * 37 + 5])
+def test_tile_boundary_lengths(length):
+    """COO lengths straddling the warp, tile (4096) and multi-tile boundaries of the sort and tail
+    kernels: assembly (both formats, f32), transpose, add and every SpMV kernel against the oracle."""
+    import torch
+    rng = np.random.default_rng(length)
+    n, m = max(2, length // 7 + 3), max(2, length // 5 + 2)
+    r = rng.integers(0, n, length).astype(np.uint64)
+    c = rng.integers(0, m, length).astype(np.uint64)
+    v = rng.standard_normal(length).astype(np.float32)
+    if length > 4:
+        r[-2:], c[-2:] = r[:2], c[:2]                     # duplicates across the whole list
+        v[-1] = -v[1]
+    trip = orc.make_triplets(r, c, v)
+    coo = sp.CooMatrix.with_triplets(n, m, r, c, v)
+    A = sp.CsrMatrix.from_coo(coo)
+    want = orc.compress_from_coo(n, m, trip, "row")
+    same(arrays(A), want, "csr")
+    same(arrays(sp.CscMatrix.from_coo(coo)), orc.compress_from_coo(n, m, trip, "col"), "csc")
+    same(arrays(A.transpose()), orc.recompress(n, m, *want), "transpose")
+    same(arrays(A + A), orc.addsub(0, n, m, want, want), "add")
+    x = rng.standard_normal(m).astype(np.float32)
+    yw = orc.csr_spmv(n, *want, x)
+    sc = orc.csr_spmv(n, want[0], want[1], np.abs(want[2]), np.abs(x))
+    xd = torch.from_numpy(x).cuda()
+    for kernel, lanes in ((1, 1), (1, 4), (1, 32), (2, 0), (3, 0)):
+        yd = torch.full((n,), 7.0, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
+        sp.default_context().sync()
+        assert np.all(np.abs(yd.cpu().numpy() - yw) <= 1e-5 * np.maximum(sc, 1e-30)), (kernel, lanes)
