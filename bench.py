@@ -94,6 +94,23 @@ def cpu_assembly_baseline():
             "sample": f"2-D Laplacian 512^2, {len(av)} shuffled triplets, f64, COO->CSR"}
 
 
+def cpu_mul_baseline():
+    """A * A on the CPU: the oracle port of impl Mul for &CsrMatrix (src/csr/ops/mul.rs:5-60: three
+    transposes + Gustavson) on a 256^2 Laplacian, one core."""
+    import oracle as orc
+    from spalinalg_b200 import synthetic as syn
+    r, c, v = syn.laplacian_2d(256)
+    nn = 256 * 256
+    a = orc.compress_from_coo(nn, nn, orc.make_triplets(r, c, v), "row")
+    out = orc.csr_mul(nn, nn, nn, a, a)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out = orc.csr_mul(nn, nn, nn, a, a)
+    s_ = (time.perf_counter() - t0) / 3
+    return {"value": len(out[1]) / s_ / 1e6, "unit": "Mnnz_out/s", "cores": 1,
+            "sample": f"A * A, 2-D Laplacian 256^2, nnz(C)={len(out[1])}, f64"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -116,7 +133,7 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count(), "assembly": asm},
+                         "host_cores": os.cpu_count(), "assembly": asm, "mul": cpu_mul_baseline()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -454,7 +471,7 @@ def main():
             orc.csr_spmv(sn, sptr, sind, sval, sx)
         rowdot = (time.perf_counter() - t0) / 5
         cpu = {"value": sb / statistics.median(ts) / 1e9, "unit": "GB/s", "cores": 1,
-               "assembly": cpu_assembly_baseline(),
+               "assembly": cpu_assembly_baseline(), "mul": cpu_mul_baseline(),
                "kind": "port", "host_cores": os.cpu_count(),
                "sample": f"27-point stencil {m}^3 (n={sn}, nnz={len(sval)}), f64; reference route "
                          f"&A * &X (3 transposes + Gustavson), 3 reps median",
@@ -683,6 +700,18 @@ def secondary_metrics(torch, sp, ctx, A, wl):
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
+
+    # the reference's Mul on a general right-hand side: A * A on the config-1 matrix
+    A1m = sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(),
+                                          values.data_ptr(), np.float64, validate=False, ctx=ctx)
+    keepm = {}
+
+    def mul():
+        keepm["C"] = A1m * A1m
+    ms = timed(mul, reps=5, warm=2)
+    out["mul_laplace2d_1024_f64"] = {"workload": "A * A, 2-D Laplacian 1024^2 (impl Mul for &CsrMatrix)", "ms": ms,
+                                     "nnz_out": keepm["C"].nnz(), "mnnz_out_per_s": keepm["C"].nnz() / ms / 1e3}
+    del A1m, keepm
 
     peak, _ = peaks()
     # config 1 SpMV, 4 rotating copies (4 x 80 MB > L2)

@@ -3,7 +3,9 @@
 // Reference: impl Mul for &CsrMatrix (src/csr/ops/mul.rs:5-60) and &CscMatrix
 // (src/csc/ops/mul.rs:5-61): Gustavson on the transposes with a dense accumulator; each
 // C[i,j] = sum over ascending k of round(A[i,k]*B[k,j]), the first term copied, the pattern the
-// structural union (explicit zeros kept).  Device formulation (expand - sort - compress):
+// structural union (explicit zeros kept).  Two device formulations: rows whose products fit a warp's
+// shared-memory hash table accumulate row-wise in ascending k (spgemm_hash_kernel, no sort); anything
+// else goes through expand - sort - compress:
 // every A entry emits its products against B's row k in storage order, which is ascending k
 // for a fixed (i,j); a stable sort by (i,j) keeps that order and the in-order segmented sum
 // of assembly (dedup=1, dropzero=0) reproduces the accumulation bit for bit.
@@ -12,6 +14,8 @@
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+
+#include <algorithm>
 
 namespace spl {
 
@@ -53,6 +57,173 @@ expand_kernel(uint32_t an, uint32_t annz, const uint32_t *__restrict__ aptr,
     }
 }
 
+// ---- row-wise hash accumulation (rows with at most HS_MAX_PRODUCTS products) -------------------
+// One warp owns one row i of C and a private hash table in shared memory (column j -> running
+// value).  It walks A's row in storage order — ascending k, one entry per step — and in each step
+// its lanes take the entries of B's row k: their columns are distinct, so within a step no two lanes
+// touch the same cell, and across steps the warp is sequential.  Every C[i,j] therefore accumulates
+// round(a*b) in ascending k with the first product copied, exactly the reference's order
+// (src/csr/ops/mul.rs:25-40) — no sort of the products, which never leave the SM.  A symbolic
+// pass (same walk, keys only) counts the distinct columns per row, the scan gives rowptr, the
+// numeric pass accumulates, then ranks the row's columns (ascending, as the reference's final
+// transpose leaves them) and writes them out.
+constexpr int HS_THREADS = 256;
+constexpr int HS_WARPS = HS_THREADS / 32;
+constexpr uint32_t HS_SLOTS = 256;            // per warp, power of two
+constexpr int HS_SLOT_BITS = 8;
+constexpr uint32_t HS_MAX_PRODUCTS = 128;     // load factor <= 0.5
+constexpr uint32_t HS_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t hs_hash(uint32_t j) { return (j * 2654435761u) >> (32 - HS_SLOT_BITS); }
+
+// slot of column j in the warp's table, inserting it if absent; *fresh tells whether it was inserted
+__device__ __forceinline__ uint32_t hs_find_or_insert(uint32_t *keys, uint32_t j, bool *fresh) {
+    uint32_t s = hs_hash(j);
+    for (;;) {
+        const uint32_t seen = atomicCAS(keys + s, HS_EMPTY, j);
+        if (seen == HS_EMPTY) { *fresh = true; return s; }
+        if (seen == j) { *fresh = false; return s; }
+        s = (s + 1) & (HS_SLOTS - 1);
+    }
+}
+
+__global__ void row_products_kernel(const uint32_t *__restrict__ aptr, const uint32_t *__restrict__ off,
+                                    uint32_t an, uint32_t *__restrict__ max_out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < an; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, off[aptr[i + 1]] - off[aptr[i]]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane_id() == 0 && m) atomicMax(max_out, m);
+}
+
+// Memory is touched in two round trips per 32 entries of A's row: the lanes fetch (k, a, B's row
+// range) of one entry each, then every product of those entries is fetched at once — lane t takes
+// product t, found by a search over the scanned row lengths — and only then do the steps run, in
+// ascending k, out of registers.
+template <typename T, bool NUMERIC>
+__global__ void __launch_bounds__(HS_THREADS)
+spgemm_hash_kernel(uint32_t an, const uint32_t *__restrict__ aptr, const uint32_t *__restrict__ aind,
+                   const T *__restrict__ aval, const uint32_t *__restrict__ bptr,
+                   const uint32_t *__restrict__ bind, const T *__restrict__ bval,
+                   uint32_t *__restrict__ cnt, const uint32_t *__restrict__ cptr, uint32_t *__restrict__ cind,
+                   T *__restrict__ cval) {
+    __shared__ uint32_t s_keys[HS_WARPS][HS_SLOTS];
+    __shared__ uint32_t s_dk[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_MAX_PRODUCTS : 1];
+    __shared__ T s_vals[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_SLOTS : 1];
+    __shared__ T s_dv[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_MAX_PRODUCTS : 1];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t *keys = s_keys[warp];
+    T *vals = s_vals[NUMERIC ? warp : 0];
+    for (uint64_t i = (uint64_t)blockIdx.x * HS_WARPS + warp; i < an; i += (uint64_t)gridDim.x * HS_WARPS) {
+        for (uint32_t s = lane; s < HS_SLOTS; s += 32) keys[s] = HS_EMPTY;
+        __syncwarp();
+        uint32_t mine = 0;                                  // columns this lane inserted
+        const uint32_t pa = __ldg(aptr + i), ea = __ldg(aptr + i + 1);
+        for (uint32_t p0 = pa; p0 < ea; p0 += 32) {         // 32 entries of A's row per trip, ascending k
+            const uint32_t p = p0 + lane;
+            const bool valid = p < ea;
+            const uint32_t k = valid ? __ldg(aind + p) : 0u;
+            T a = (T)0;
+            if (NUMERIC && valid) a = __ldg(aval + p);
+            const uint32_t qb = valid ? __ldg(bptr + k) : 0u;
+            const uint32_t len = valid ? __ldg(bptr + k + 1) - qb : 0u;
+            const uint32_t incl = warp_inclusive_scan(len);
+            const uint32_t excl = incl - len;
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t t0 = 0; t0 < total; t0 += 32) {   // 32 products per batch, in emission order
+                const uint32_t t = t0 + lane;
+                const bool has = t < total;
+                // step of product t = first lane whose inclusive count exceeds t
+                uint32_t lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    const uint32_t im = __shfl_sync(0xffffffffu, incl, mid);
+                    if (im <= t) lo = mid + 1; else hi = mid;
+                }
+                const uint32_t step = has ? lo : 31u;
+                const uint32_t q = __shfl_sync(0xffffffffu, qb, step) + (t - __shfl_sync(0xffffffffu, excl, step));
+                const T av = __shfl_sync(0xffffffffu, a, step);
+                const uint32_t j = has ? __ldg(bind + q) : 0u;
+                T prod = (T)0;
+                if (NUMERIC && has) prod = av * __ldg(bval + q);     // rounded product (no FMA), then the add
+                const uint32_t first = __shfl_sync(0xffffffffu, step, 0);
+                const unsigned live = __ballot_sync(0xffffffffu, has);
+                const uint32_t last = __shfl_sync(0xffffffffu, step, 31 - __clz(live));
+                for (uint32_t sgo = first; sgo <= last; ++sgo) {      // one k at a time: columns distinct inside a step
+                    if (has && step == sgo) {
+                        bool fresh;
+                        const uint32_t s = hs_find_or_insert(keys, j, &fresh);
+                        mine += fresh;
+                        if (NUMERIC) vals[s] = fresh ? prod : vals[s] + prod;
+                    }
+                    __syncwarp();                                     // the next k sees this step's cells
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (!NUMERIC) {
+            if (lane == 0) cnt[i] = mine;
+            __syncwarp();
+            continue;
+        }
+        // dense list of the stored columns, then rank = number of stored columns below: ascending order out
+        uint32_t *dk = s_dk[warp];
+        T *dv = s_dv[warp];
+        uint32_t filled = 0;
+        for (uint32_t c0 = 0; c0 < HS_SLOTS; c0 += 32) {
+            const uint32_t key = keys[c0 + lane];
+            const bool occ = key != HS_EMPTY;
+            const unsigned bal = __ballot_sync(0xffffffffu, occ);
+            if (occ) {
+                const uint32_t pos = filled + __popc(bal & lanemask_lt());
+                dk[pos] = key;
+                dv[pos] = vals[c0 + lane];
+            }
+            filled += __popc(bal);
+        }
+        __syncwarp();
+        const uint32_t base = __ldg(cptr + i);
+        for (uint32_t e = lane; e < mine; e += 32) {
+            const uint32_t j = dk[e];
+            uint32_t rank = 0;
+            for (uint32_t t = 0; t < mine; ++t) rank += dk[t] < j;
+            cind[base + rank] = j;
+            cval[base + rank] = dv[e];
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+spl_mat *spgemm_hash(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uint32_t out_cols, uint32_t an,
+                     const spl_mat *a, const spl_mat *b) {
+    Tmp<uint32_t> cnt(ctx, an);
+    Tmp<uint32_t> cptr(ctx, (size_t)an + 1);
+    const unsigned grid = std::min<unsigned>(div_up(an, HS_WARPS), (unsigned)ctx->num_sms * 8u);
+    spgemm_hash_kernel<T, false><<<grid, HS_THREADS, 0, ctx->stream>>>(
+        an, a->ptr, a->ind, nullptr, b->ptr, b->ind, nullptr, cnt, nullptr, nullptr, nullptr);
+    check_launch(ctx, "spgemm_hash_symbolic");
+    exclusive_scan_u32(ctx, cnt, an, cptr);
+    uint32_t nnz = 0;
+    read_back(ctx, cptr.p + an, &nnz, 1);      // exact-size output
+    spl_mat *c = new_mat(ctx, format, dtype, out_rows, out_cols, nnz);
+    dfree(ctx, c->ptr);
+    c->ptr = cptr.release();
+    try {
+        spgemm_hash_kernel<T, true><<<grid, HS_THREADS, 0, ctx->stream>>>(
+            an, a->ptr, a->ind, (const T *)a->val, b->ptr, b->ind, (const T *)b->val, nullptr, c->ptr, c->ind,
+            (T *)c->val);
+        check_launch(ctx, "spgemm_hash_numeric");
+    } catch (...) {
+        free_mat(ctx, c);
+        throw;
+    }
+    return c;
+}
+
 template <typename K, typename T, typename VB>
 spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uint32_t out_cols,
                      uint32_t an, uint32_t bn, const spl_mat *a, const spl_mat *b) {
@@ -72,6 +243,17 @@ spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
                     "mul: more than 2^32 intermediate products (expand-sort-compress limit)");
         total = t64[0];
         exclusive_scan_u32(ctx, cnt, annz, off);
+        // rows whose products fit the warp's hash table take the row-wise path (no sort)
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        row_products_kernel<<<std::min<unsigned>(div_up(an, 256), (unsigned)ctx->num_sms * 8u), 256, 0, ctx->stream>>>(
+            a->ptr, off, an, ctx->d_scratch);
+        check_launch(ctx, "row_products");
+        uint32_t max_products = 0;
+        read_back(ctx, ctx->d_scratch, &max_products, 1);
+#ifndef SPL_NO_HASH_SPGEMM
+        if (max_products <= HS_MAX_PRODUCTS && bn > 1)
+            return spgemm_hash<T>(ctx, format, dtype, out_rows, out_cols, an, a, b);
+#endif
     }
     const int minor_bits = bits_for(bn);
     const int bits = bits_for(an) + minor_bits;
