@@ -57,7 +57,7 @@ expand_kernel(uint32_t an, uint32_t annz, const uint32_t *__restrict__ aptr,
     }
 }
 
-// ---- row-wise hash accumulation (rows with at most HS_MAX_PRODUCTS products) -------------------
+// ---- row-wise hash accumulation (rows with at most 1 024 products) ---------------------------
 // One warp owns one row i of C and a private hash table in shared memory (column j -> running
 // value).  It walks A's row in storage order — ascending k, one entry per step — and in each step
 // its lanes take the entries of B's row k: their columns are distinct, so within a step no two lanes
@@ -67,23 +67,23 @@ expand_kernel(uint32_t an, uint32_t annz, const uint32_t *__restrict__ aptr,
 // pass (same walk, keys only) counts the distinct columns per row, the scan gives rowptr, the
 // numeric pass accumulates, then ranks the row's columns (ascending, as the reference's final
 // transpose leaves them) and writes them out.
-constexpr int HS_THREADS = 256;
-constexpr int HS_WARPS = HS_THREADS / 32;
-constexpr uint32_t HS_SLOTS = 256;            // per warp, power of two
-constexpr int HS_SLOT_BITS = 8;
-constexpr uint32_t HS_MAX_PRODUCTS = 128;     // load factor <= 0.5
+// Two table sizes: 256 slots (rows of up to 128 products, 8 warps per CTA) and 2 048 slots (up to
+// 1 024 products, 4 warps per CTA, dynamic shared memory).
 constexpr uint32_t HS_EMPTY = 0xffffffffu;
+constexpr uint32_t HS_SMALL_PRODUCTS = 128, HS_LARGE_PRODUCTS = 1024;
 
-__device__ __forceinline__ uint32_t hs_hash(uint32_t j) { return (j * 2654435761u) >> (32 - HS_SLOT_BITS); }
+template <int SLOT_BITS>
+__device__ __forceinline__ uint32_t hs_hash(uint32_t j) { return (j * 2654435761u) >> (32 - SLOT_BITS); }
 
 // slot of column j in the warp's table, inserting it if absent; *fresh tells whether it was inserted
+template <int SLOT_BITS>
 __device__ __forceinline__ uint32_t hs_find_or_insert(uint32_t *keys, uint32_t j, bool *fresh) {
-    uint32_t s = hs_hash(j);
+    uint32_t s = hs_hash<SLOT_BITS>(j);
     for (;;) {
         const uint32_t seen = atomicCAS(keys + s, HS_EMPTY, j);
         if (seen == HS_EMPTY) { *fresh = true; return s; }
         if (seen == j) { *fresh = false; return s; }
-        s = (s + 1) & (HS_SLOTS - 1);
+        s = (s + 1) & ((1u << SLOT_BITS) - 1u);
     }
 }
 
@@ -97,26 +97,35 @@ __global__ void row_products_kernel(const uint32_t *__restrict__ aptr, const uin
     if (lane_id() == 0 && m) atomicMax(max_out, m);
 }
 
+template <typename T, bool NUMERIC, int SLOT_BITS, int WARPS>
+constexpr size_t hs_smem_bytes() {
+    constexpr size_t slots = (size_t)1 << SLOT_BITS, maxp = slots / 2;
+    return WARPS * (slots * 4 + (NUMERIC ? slots * sizeof(T) + maxp * 4 + maxp * sizeof(T) : 0));
+}
+
 // Memory is touched in two round trips per 32 entries of A's row: the lanes fetch (k, a, B's row
 // range) of one entry each, then every product of those entries is fetched at once — lane t takes
 // product t, found by a search over the scanned row lengths — and only then do the steps run, in
 // ascending k, out of registers.
-template <typename T, bool NUMERIC>
-__global__ void __launch_bounds__(HS_THREADS)
+template <typename T, bool NUMERIC, int SLOT_BITS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 spgemm_hash_kernel(uint32_t an, const uint32_t *__restrict__ aptr, const uint32_t *__restrict__ aind,
                    const T *__restrict__ aval, const uint32_t *__restrict__ bptr,
                    const uint32_t *__restrict__ bind, const T *__restrict__ bval,
                    uint32_t *__restrict__ cnt, const uint32_t *__restrict__ cptr, uint32_t *__restrict__ cind,
                    T *__restrict__ cval) {
-    __shared__ uint32_t s_keys[HS_WARPS][HS_SLOTS];
-    __shared__ uint32_t s_dk[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_MAX_PRODUCTS : 1];
-    __shared__ T s_vals[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_SLOTS : 1];
-    __shared__ T s_dv[NUMERIC ? HS_WARPS : 1][NUMERIC ? HS_MAX_PRODUCTS : 1];
+    constexpr uint32_t SLOTS = 1u << SLOT_BITS, MAXP = SLOTS / 2;
+    extern __shared__ __align__(16) unsigned char hs_raw[];
+    // layout: values first (8-byte aligned), then the 4-byte arrays
+    T *vals_all = reinterpret_cast<T *>(hs_raw);
+    T *dv_all = vals_all + (NUMERIC ? (size_t)WARPS * SLOTS : 0);
+    uint32_t *keys_all = reinterpret_cast<uint32_t *>(dv_all + (NUMERIC ? (size_t)WARPS * MAXP : 0));
+    uint32_t *dk_all = keys_all + (size_t)WARPS * SLOTS;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    uint32_t *keys = s_keys[warp];
-    T *vals = s_vals[NUMERIC ? warp : 0];
-    for (uint64_t i = (uint64_t)blockIdx.x * HS_WARPS + warp; i < an; i += (uint64_t)gridDim.x * HS_WARPS) {
-        for (uint32_t s = lane; s < HS_SLOTS; s += 32) keys[s] = HS_EMPTY;
+    uint32_t *keys = keys_all + (size_t)warp * SLOTS;
+    T *vals = vals_all + (NUMERIC ? (size_t)warp * SLOTS : 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * WARPS + warp; i < an; i += (uint64_t)gridDim.x * WARPS) {
+        for (uint32_t s = lane; s < SLOTS; s += 32) keys[s] = HS_EMPTY;
         __syncwarp();
         uint32_t mine = 0;                                  // columns this lane inserted
         const uint32_t pa = __ldg(aptr + i), ea = __ldg(aptr + i + 1);
@@ -154,7 +163,7 @@ spgemm_hash_kernel(uint32_t an, const uint32_t *__restrict__ aptr, const uint32_
                 for (uint32_t sgo = first; sgo <= last; ++sgo) {      // one k at a time: columns distinct inside a step
                     if (has && step == sgo) {
                         bool fresh;
-                        const uint32_t s = hs_find_or_insert(keys, j, &fresh);
+                        const uint32_t s = hs_find_or_insert<SLOT_BITS>(keys, j, &fresh);
                         mine += fresh;
                         if (NUMERIC) vals[s] = fresh ? prod : vals[s] + prod;
                     }
@@ -170,10 +179,10 @@ spgemm_hash_kernel(uint32_t an, const uint32_t *__restrict__ aptr, const uint32_
             continue;
         }
         // dense list of the stored columns, then rank = number of stored columns below: ascending order out
-        uint32_t *dk = s_dk[warp];
-        T *dv = s_dv[warp];
+        uint32_t *dk = dk_all + (size_t)warp * MAXP;
+        T *dv = dv_all + (size_t)warp * MAXP;
         uint32_t filled = 0;
-        for (uint32_t c0 = 0; c0 < HS_SLOTS; c0 += 32) {
+        for (uint32_t c0 = 0; c0 < SLOTS; c0 += 32) {
             const uint32_t key = keys[c0 + lane];
             const bool occ = key != HS_EMPTY;
             const unsigned bal = __ballot_sync(0xffffffffu, occ);
@@ -197,14 +206,21 @@ spgemm_hash_kernel(uint32_t an, const uint32_t *__restrict__ aptr, const uint32_
     }
 }
 
-template <typename T>
+template <typename T, int SLOT_BITS, int WARPS>
 spl_mat *spgemm_hash(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uint32_t out_cols, uint32_t an,
                      const spl_mat *a, const spl_mat *b) {
     Tmp<uint32_t> cnt(ctx, an);
     Tmp<uint32_t> cptr(ctx, (size_t)an + 1);
-    const unsigned grid = std::min<unsigned>(div_up(an, HS_WARPS), (unsigned)ctx->num_sms * 8u);
-    spgemm_hash_kernel<T, false><<<grid, HS_THREADS, 0, ctx->stream>>>(
-        an, a->ptr, a->ind, nullptr, b->ptr, b->ind, nullptr, cnt, nullptr, nullptr, nullptr);
+    auto ksym = spgemm_hash_kernel<T, false, SLOT_BITS, WARPS>;
+    auto knum = spgemm_hash_kernel<T, true, SLOT_BITS, WARPS>;
+    constexpr size_t sm_sym = hs_smem_bytes<T, false, SLOT_BITS, WARPS>();
+    constexpr size_t sm_num = hs_smem_bytes<T, true, SLOT_BITS, WARPS>();
+    SPL_CUDA(cudaFuncSetAttribute(ksym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_sym));
+    SPL_CUDA(cudaFuncSetAttribute(knum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_num));
+    SPL_CUDA(cudaFuncSetAttribute(knum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const unsigned grid = std::min<unsigned>(div_up(an, WARPS), (unsigned)ctx->num_sms * 8u);
+    ksym<<<grid, WARPS * 32, sm_sym, ctx->stream>>>(an, a->ptr, a->ind, nullptr, b->ptr, b->ind, nullptr, cnt,
+                                                    nullptr, nullptr, nullptr);
     check_launch(ctx, "spgemm_hash_symbolic");
     exclusive_scan_u32(ctx, cnt, an, cptr);
     uint32_t nnz = 0;
@@ -213,9 +229,8 @@ spl_mat *spgemm_hash(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
     dfree(ctx, c->ptr);
     c->ptr = cptr.release();
     try {
-        spgemm_hash_kernel<T, true><<<grid, HS_THREADS, 0, ctx->stream>>>(
-            an, a->ptr, a->ind, (const T *)a->val, b->ptr, b->ind, (const T *)b->val, nullptr, c->ptr, c->ind,
-            (T *)c->val);
+        knum<<<grid, WARPS * 32, sm_num, ctx->stream>>>(an, a->ptr, a->ind, (const T *)a->val, b->ptr, b->ind,
+                                                        (const T *)b->val, nullptr, c->ptr, c->ind, (T *)c->val);
         check_launch(ctx, "spgemm_hash_numeric");
     } catch (...) {
         free_mat(ctx, c);
@@ -251,8 +266,10 @@ spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
         uint32_t max_products = 0;
         read_back(ctx, ctx->d_scratch, &max_products, 1);
 #ifndef SPL_NO_HASH_SPGEMM
-        if (max_products <= HS_MAX_PRODUCTS && bn > 1)
-            return spgemm_hash<T>(ctx, format, dtype, out_rows, out_cols, an, a, b);
+        if (max_products <= HS_SMALL_PRODUCTS && bn > 1)
+            return spgemm_hash<T, 8, 8>(ctx, format, dtype, out_rows, out_cols, an, a, b);
+        if (max_products <= HS_LARGE_PRODUCTS && bn > 1)
+            return spgemm_hash<T, 11, 4>(ctx, format, dtype, out_rows, out_cols, an, a, b);
 #endif
     }
     const int minor_bits = bits_for(bn);

@@ -229,7 +229,8 @@ def test_add_sub_random(dtype, n, m, density):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n,k,m,density", [(5, 3, 4, 0.6), (60, 80, 50, 0.1), (2000, 1500, 1800, 0.004),
-                                           (300, 400, 500, 0.08)])   # last: > 128 products per row, sort path
+                                           (400, 300, 600, 0.05),    # 128..1024 products per row: large hash table
+                                           (300, 400, 500, 0.08)])   # > 1024 products per row: sort path
 def test_mul_random(dtype, n, k, m, density):
     rng = np.random.default_rng(n * k + m)
     a = _rand_csr(rng, n, k, density, dtype)
