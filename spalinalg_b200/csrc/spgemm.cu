@@ -68,7 +68,7 @@ expand_kernel(uint32_t an, uint32_t annz, const uint32_t *__restrict__ aptr,
 // numeric pass accumulates, then ranks the row's columns (ascending, as the reference's final
 // transpose leaves them) and writes them out.
 // Two table sizes: 256 slots (rows of up to 128 products, 8 warps per CTA) and 2 048 slots (up to
-// 1 024 products, 4 warps per CTA, dynamic shared memory).
+// 1 024 products; 6 warps per CTA for f64, 8 for f32: one CTA fills an SM's shared memory).
 constexpr uint32_t HS_EMPTY = 0xffffffffu;
 constexpr uint32_t HS_SMALL_PRODUCTS = 128, HS_LARGE_PRODUCTS = 1024;
 
@@ -269,7 +269,7 @@ spl_mat *spgemm_impl(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uin
         if (max_products <= HS_SMALL_PRODUCTS && bn > 1)
             return spgemm_hash<T, 8, 8>(ctx, format, dtype, out_rows, out_cols, an, a, b);
         if (max_products <= HS_LARGE_PRODUCTS && bn > 1)
-            return spgemm_hash<T, 11, 4>(ctx, format, dtype, out_rows, out_cols, an, a, b);
+            return spgemm_hash<T, 11, (sizeof(T) == 8 ? 6 : 8)>(ctx, format, dtype, out_rows, out_cols, an, a, b);
 #endif
     }
     const int minor_bits = bits_for(bn);
