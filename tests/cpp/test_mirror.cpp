@@ -111,6 +111,27 @@ static int run() {
         CHECK(a.values() == (D{2, 4, 6, 8}) && a.matvec(D{10, 20, 30}) == (D{140, 0, 360}));
         CHECK(panics([&] { (void)(x * a); }));                                             // mul.rs:9
     }
+    {   // src/csc/ops/add.rs:77-100, src/csc/ops/sub.rs:77-103, src/csc/ops/neg.rs:25-36 (CSC twins), f32 values
+        using F = std::vector<float>;
+        CscMatrix<float> lhs(4, 4, V{0, 2, 4, 6, 7}, V{0, 1, 2, 3, 1, 3, 3}, F{1, 2, 4, 5, 3, 6, 7});
+        CscMatrix<float> rhs(4, 4, V{0, 1, 2, 4, 5}, V{0, 3, 0, 1, 2}, F{2, 6, 4, 8, 10});
+        auto add = lhs + rhs;
+        CHECK(add.colptr() == (V{0, 2, 4, 7, 9}) && add.rowind() == (V{0, 1, 2, 3, 0, 1, 3, 2, 3}) &&
+              add.values() == (F{3, 2, 4, 11, 4, 11, 6, 10, 7}));
+        auto sub = lhs - rhs;
+        CHECK(sub.colptr() == add.colptr() && sub.rowind() == add.rowind() &&
+              sub.values() == (F{-1, 2, 4, -1, -4, -5, 6, -10, 7}));
+        CscMatrix<float> one(1, 2, V{0, 1, 2}, V{0, 0}, F{1, 2});
+        CHECK((-one).values() == (F{-1, -2}) && (-one).colptr() == one.colptr());
+        CHECK(panics([] { CscMatrix<float>(2, 1, V{0, 2}, V{1, 0}, F{1, 2}); }));               // rowind increasing
+        // CooMatrix shell: push bounds, pop, get (src/coo.rs tests)
+        CooMatrix<float> coo(2, 2);
+        coo.push(0, 1, 1.0f);
+        CHECK(panics([&] { coo.push(2, 0, 1.0f); }) && panics([&] { coo.push(0, 2, 1.0f); }));
+        CHECK(coo.length() == 1 && coo.get(0).has_value() && !coo.get(1).has_value());
+        CHECK(coo.transpose().rowind() == (V{1}) && coo.pop().has_value() && coo.length() == 0);
+        CHECK(panics([] { CooMatrix<float>(0, 1); }) && panics([] { DokMatrix<float>(1, 0); }));
+    }
     if (failures == 0) std::printf("cpp mirror: all reference tests passed\n");
     return failures == 0 ? 0 : 1;
 }
