@@ -2,9 +2,11 @@
 // (src/csr.rs:358-406), CscMatrix::transpose (src/csc.rs:358-406) and the CSR<->CSC
 // conversions (src/csc/conv/csr.rs:3-53, src/csr/conv/csc.rs:3-53): histogram of the minor
 // index, exclusive scan, stable scatter (major ascending inside each output segment).
-// On the device the three steps run once per 8-bit digit of the minor index (stable LSD radix
-// sort carrying (major, value)); only ceil(log2(nminor)) bits are sorted.  The output pointer
-// array is read off the sorted minor keys.
+// Two device routes.  Near-diagonal matrices with short output segments: the three steps as they
+// are, the scatter taking its slot from an atomic counter, followed by a per-segment repair that
+// restores the major-ascending order (recompress_by_scatter).  Everything else: the three steps
+// once per 8-bit digit of the minor index (stable LSD radix sort carrying (major, value)); only
+// ceil(log2(nminor)) bits are sorted and the output pointer array is read off the sorted keys.
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"

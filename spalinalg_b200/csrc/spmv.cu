@@ -3,15 +3,21 @@
 // The reference has no SpMV; its pinned meaning is `&A * &X` with X an n x 1 matrix
 // (src/csr/ops/mul.rs:5-60): per row the column-ascending sum of round(a*x).  Parity bar
 // (BASELINE.json north_star): 1e-12 (f64) / 1e-5 (f32) relative, so the in-row reduction
-// order is free.  Two hand-written kernels:
+// order is free.  Three hand-written kernels:
 //   vector  LPR lanes per row (1..32) with 4 entries in flight per lane: consecutive lanes read
 //           consecutive entries (col/val loads coalesce, neighbouring columns share x-gather
-//           sectors), shuffle reduction.  Regular rows (stencils, bands, uniform random).
+//           sectors), shuffle reduction.  Regular rows (stencils, bands, uniform random).  The x
+//           access is a template policy: one local array, or the slice of the rank that owns the
+//           column (peer memory over NVLink: the row-sharded product without a collective).
+//   split   merge-path's balance at warp granularity: every warp owns a fixed chunk of stored
+//           entries, rows are found from a per-chunk start row, rows that straddle chunks go
+//           through a deterministic carry fix-up.  Skewed (power-law) rows; with a shared-memory
+//           cache of the hottest x values from the second product on a matrix.
 //   merge   merge-path tiles over (row ends, nnz): every CTA takes the same number of
 //           (row + nnz) items; its contiguous col/val slice arrives in shared memory by TMA bulk
 //           copies (cp.async.bulk + mbarrier), products are formed in place, rows are reduced by
 //           a balanced per-thread path walk and a segmented shuffle scan; partial rows go to a
-//           deterministic fix-up.  Skewed (power-law) rows.
+//           deterministic fix-up.  Kept selectable; the split kernel replaced it in the planner.
 // 128-bit per-lane loads of col/val were measured and rejected for the gather-bound patterns:
 // they put entries 4 apart on neighbouring lanes and triple the L1 wavefronts of the x gathers
 // ("SpMV").
