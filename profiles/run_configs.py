@@ -105,6 +105,12 @@ def c1():
     res = {"config": "C1 2-D Laplacian 1024^2 f64", "nrows": n}
     A, res["assembly_row_ordered"] = assembly(n, n, rows, col, val, np.float64, 8)
     _, res["assembly_shuffled"] = assembly(n, n, *shuffled(rows, col, val), np.float64, 8)
+    # row by row, but the columns of every row in descending order (rows sorted, columns not)
+    pos = torch.arange(col.numel(), device="cuda", dtype=torch.int64)
+    first, last = ptr[:-1].long()[rows.long()], ptr[1:].long()[rows.long()] - 1
+    rev = first + (last - pos)
+    _, res["assembly_rows_sorted_cols_reversed"] = assembly(n, n, rows, col[rev].contiguous(), val[rev].contiguous(),
+                                                            np.float64, 8)
     _, res["assembly_shuffled_csc"] = assembly(n, n, *shuffled(rows, col, val), np.float64, 8, "csc")
     res["spmv_l2_flushed"] = spmv_rows(A, 8, torch.float64, small=True)
     res["spmv_l2_resident"] = spmv_rows(A, 8, torch.float64, small=False)

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256)
 prepare_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor,
                const VB *__restrict__ val, uint32_t n, uint32_t nmajor, uint32_t nminor, int minor_bits,
                K *__restrict__ keys, VB *__restrict__ vals, uint32_t *__restrict__ flags) {
-    uint32_t bad = 0, unsorted = 0;
+    uint32_t bad = 0, unsorted = 0, major_unsorted = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t mj = major[i], mn = minor[i];
@@ -282,12 +282,68 @@ prepare_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ 
         keys[i] = k;
         vals[i] = val[i];
         if (i + 1 < n) {
-            const K kn = (K)(((uint64_t)major[i + 1] << minor_bits) | (uint64_t)minor[i + 1]);
+            const uint32_t mjn = major[i + 1];
+            const K kn = (K)(((uint64_t)mjn << minor_bits) | (uint64_t)minor[i + 1]);
             unsorted |= kn < k;
+            major_unsorted |= mjn < mj;
         }
     }
     if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flags, 1u);
     if (__any_sync(0xffffffffu, unsorted) && lane_id() == 0) atomicOr(flags + 1, 1u);
+    if (__any_sync(0xffffffffu, major_unsorted) && lane_id() == 0) atomicOr(flags + 2, 1u);
+}
+
+// Triplets that already come major by major (row by row) only need each segment put in (minor,
+// position) order: LPS lanes own one segment of at most 2*LPS records and rank it by shuffles.  The
+// position is the tie-break, so duplicates of a cell keep their insertion order (what the stable sort
+// guarantees on the general path).  Out of place: (keys, vals) -> (out_k, out_v).
+template <typename K, typename VB, int LPS>
+__global__ void __launch_bounds__(256)
+segment_sort_kernel(const uint32_t *__restrict__ segptr, uint32_t nseg, const K *__restrict__ keys,
+                    const VB *__restrict__ vals, K *__restrict__ out_k, VB *__restrict__ out_v) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t seg = gtid / LPS;
+    const unsigned sub = (unsigned)(gtid % LPS);
+    const unsigned group_base = lane_id() - sub;
+    uint32_t lo = 0, len = 0;
+    if (seg < nseg) {
+        lo = __ldg(segptr + seg);
+        len = __ldg(segptr + seg + 1) - lo;
+    }
+    K k[2] = {~(K)0, ~(K)0};
+    VB v[2] = {};
+    bool have[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const uint32_t e = sub + u * LPS;
+        have[u] = e < len;
+        if (have[u]) { k[u] = keys[lo + e]; v[u] = vals[lo + e]; }
+    }
+    uint32_t rank[2] = {0, 0};
+#pragma unroll
+    for (int u2 = 0; u2 < 2; ++u2) {
+#pragma unroll
+        for (int t = 0; t < LPS; ++t) {
+            const K other = __shfl_sync(0xffffffffu, k[u2], group_base + t);
+            const bool there = __shfl_sync(0xffffffffu, (int)have[u2], group_base + t) != 0;
+            const uint32_t opos = t + u2 * LPS;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                rank[u] += there && (other < k[u] || (other == k[u] && opos < sub + u * LPS));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (have[u]) { out_k[lo + rank[u]] = k[u]; out_v[lo + rank[u]] = v[u]; }
+}
+
+__global__ void max_seglen_kernel(const uint32_t *__restrict__ segptr, uint32_t nseg, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, segptr[i + 1] - segptr[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane_id() == 0 && m) atomicMax(out, m);
 }
 
 template <typename K, typename VB>
@@ -297,21 +353,48 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
     const uint32_t nmajor = format == SPL_CSR ? nrows : ncols, nminor = format == SPL_CSR ? ncols : nrows;
     Tmp<K> k0(ctx, len), k1(ctx, len);
     Tmp<VB> v0(ctx, len), v1(ctx, len);
-    uint32_t flags[2] = {0, 0};
+    uint32_t flags[3] = {0, 0, 0};
     if (len) {
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(uint32_t), ctx->stream));
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 4 * sizeof(uint32_t), ctx->stream));
         unsigned grid = div_up(len, 256 * 4);
         if (grid > (unsigned)ctx->num_sms * 16u) grid = (unsigned)ctx->num_sms * 16u;
         prepare_kernel<K, VB><<<grid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len, nmajor, nminor,
                                                              minor_bits, k0, v0, ctx->d_scratch);
         check_launch(ctx, "prepare");
-        read_back(ctx, ctx->d_scratch, flags, 2);
+        read_back(ctx, ctx->d_scratch, flags, 3);
         SPL_REQUIRE(flags[0] == 0, SPL_ERR_ARG,
                     "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
     }
     K *keys = k0;
     VB *vals = v0;
-    if (flags[1]) {       // pass 0 reads (k0, v0) and writes (k1, v1); later passes ping-pong
+    bool sorted_now = !flags[1];
+    if (!sorted_now && !flags[2]) {       // majors already in order: sort inside the segments only
+        Tmp<uint32_t> segptr(ctx, (size_t)nmajor + 1);
+        fill_ptr(ctx, major_idx, len, nmajor, segptr);
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        unsigned g = div_up(nmajor, 256);
+        if (g > (unsigned)ctx->num_sms * 16u) g = (unsigned)ctx->num_sms * 16u;
+        max_seglen_kernel<<<g, 256, 0, ctx->stream>>>(segptr, nmajor, ctx->d_scratch);
+        check_launch(ctx, "max_seglen");
+        uint32_t longest = 0;
+        read_back(ctx, ctx->d_scratch, &longest, 1);
+        if (longest <= 64) {
+            if (longest <= 16)
+                segment_sort_kernel<K, VB, 8><<<div_up((uint64_t)nmajor * 8, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            else if (longest <= 32)
+                segment_sort_kernel<K, VB, 16><<<div_up((uint64_t)nmajor * 16, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            else
+                segment_sort_kernel<K, VB, 32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            check_launch(ctx, "segment_sort");
+            keys = k1;
+            vals = v1;
+            sorted_now = true;
+        }
+    }
+    if (!sorted_now) {    // pass 0 reads (k0, v0) and writes (k1, v1); later passes ping-pong
         K *kb[2] = {k1, k0};
         VB *vb[2] = {v1, v0};
         NoPayload *nb[2] = {nullptr, nullptr};

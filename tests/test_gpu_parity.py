@@ -318,6 +318,29 @@ def test_long_runs_of_empty_rows_and_columns():
     same(arrays(A + A), orc.addsub(0, n, m, want, want), "add")
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fmt,longest", [("row", 12), ("row", 40), ("col", 60), ("row", 200)])
+def test_assembly_of_major_sorted_triplets(dtype, fmt, longest):
+    """Triplets that come row by row (column by column for CSC) with the minor indices in arbitrary
+    order and duplicates inside the segments: the per-segment sort route (segments up to 64) and, for
+    the 200-entry case, the radix route must both equal the oracle bit for bit — duplicates summed
+    in insertion order."""
+    rng = np.random.default_rng(longest)
+    n, m = 3000, 2500
+    nmaj, nmin = (n, m) if fmt == "row" else (m, n)
+    lens = rng.integers(0, longest + 1, nmaj)
+    lens[5] = longest                                         # the longest segment decides the route
+    maj = np.repeat(np.arange(nmaj, dtype=np.uint64), lens)
+    mino = rng.integers(0, min(nmin, 3 * longest), len(maj)).astype(np.uint64)     # many duplicates per segment
+    v = rng.standard_normal(len(maj)).astype(dtype)
+    v[::7] = -v[1::7][: len(v[::7])] if len(v[1::7]) >= len(v[::7]) else v[::7]
+    r, c = (maj, mino) if fmt == "row" else (mino, maj)
+    cls = sp.CsrMatrix if fmt == "row" else sp.CscMatrix
+    got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+    want = orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), fmt)
+    same(arrays(got), want, f"{fmt} longest {longest}")
+
+
 def test_dok_round_trip_through_device():
     """From<&DokMatrix> for CsrMatrix / CscMatrix (src/csr/conv/dok.rs:3-76) and back
     (src/dok.rs:676-720): explicit zeros survive both ways, nothing is summed or dropped."""
