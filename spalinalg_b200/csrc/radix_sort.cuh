@@ -347,13 +347,13 @@ rs_scatter_kernel(LoadK lk, LoadA la, LoadB lb, uint32_t n, uint32_t tiles_per_b
 }
 
 // ---- driver ----------------------------------------------------------------------------------
-// Sorts n records by the low `bits` bits of the key.  Pass 0 reads through the loaders and
+// Sorts n records by `bits` bits of the key starting at bit `first_bit` (default: the low bits).  Pass 0 reads through the loaders and
 // writes buffer set 0; pass p writes set p&1.  Returns the index (0/1) of the set that holds
 // the sorted result, i.e. (passes-1)&1.  A/B = NoPayload (with LoadNone, null buffers) drops
 // that payload.
 template <typename K, typename A, typename B, typename LoadK, typename LoadA, typename LoadB>
 int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB lb0, K *k_buf[2],
-               A *a_buf[2], B *b_buf[2]) {
+               A *a_buf[2], B *b_buf[2], int first_bit = 0) {
     const int passes = rs_num_passes(bits);
     if (n == 0) return (passes - 1) & 1;
     if (bits <= 0) bits = 1;
@@ -376,9 +376,9 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
     Tmp<uint32_t> counts(ctx, (size_t)RS_BINS * grid);
     Tmp<uint32_t> totals(ctx, RS_BINS);
 
-    int shift = 0;
+    int shift = first_bit, done = 0;       // sorts key bits [first_bit, first_bit + bits)
     for (int p = 0; p < passes; ++p) {
-        const int nb = (bits - shift + (passes - p) - 1) / (passes - p);   // even split
+        const int nb = (bits - done + (passes - p) - 1) / (passes - p);   // even split
         const uint32_t mask = (1u << nb) - 1u;
         K *ok = k_buf[p & 1];
         A *oa = a_buf[p & 1];
@@ -417,6 +417,7 @@ int radix_sort(spl_ctx *ctx, uint32_t n, int bits, LoadK lk0, LoadA la0, LoadB l
             check_launch(ctx, "rs_scatter");
         }
         shift += nb;
+        done += nb;
     }
     return (passes - 1) & 1;
 }
