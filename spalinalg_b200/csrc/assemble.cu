@@ -387,27 +387,33 @@ __global__ void block_hist_kernel(const K *__restrict__ keys, uint32_t n, int S,
         atomicAdd(bcount + (uint32_t)(keys[i] >> S), 1u);
 }
 
-template <typename K, typename VB>
+// LK: type of the key inside the block.  All records of a block share the key bits above S, so
+// only the low S bits (local row, minor) are kept — 32 bits whenever S <= 32, which halves the
+// shared memory per record and raises the number of resident CTAs.
+template <typename K, typename VB, typename LK>
 __global__ void __launch_bounds__(BL_THREADS)
 block_finish_kernel(const K *__restrict__ keys, const VB *__restrict__ vals, const uint32_t *__restrict__ bptr,
                     int minor_bits, int row_bits, K *__restrict__ out_k, VB *__restrict__ out_v) {
-    extern __shared__ __align__(16) unsigned char bl_raw[];   // BL_CAP * (sizeof(K) + sizeof(VB) + 2) bytes
-    K *s_key = reinterpret_cast<K *>(bl_raw);
-    VB *s_val = reinterpret_cast<VB *>(s_key + BL_CAP);
-    uint16_t *s_slot = reinterpret_cast<uint16_t *>(s_val + BL_CAP);   // position (arrival index) of the record in a slot
+    extern __shared__ __align__(16) unsigned char bl_raw[];   // BL_CAP * (sizeof(LK) + sizeof(VB) + 2) bytes
+    constexpr bool kValFirst = sizeof(VB) > sizeof(LK);       // the wider array first: alignment
+    VB *s_val = reinterpret_cast<VB *>(bl_raw + (kValFirst ? 0 : sizeof(LK) * BL_CAP));
+    LK *s_key = reinterpret_cast<LK *>(bl_raw + (kValFirst ? sizeof(VB) * BL_CAP : 0));
+    uint16_t *s_slot = reinterpret_cast<uint16_t *>(bl_raw + (sizeof(LK) + sizeof(VB)) * BL_CAP);   // arrival index per slot
     __shared__ uint32_t s_off[(1 << BL_MAX_ROW_BITS) + 1];
     __shared__ uint32_t s_cur[1 << BL_MAX_ROW_BITS];
     __shared__ uint32_t ws[BL_THREADS / 32 + 1];
     const uint32_t lo = bptr[blockIdx.x], cnt = bptr[blockIdx.x + 1] - lo;
     if (cnt == 0) return;
-    const uint32_t R = 1u << row_bits, rmask = R - 1u;
+    const int S = minor_bits + row_bits;
+    const K low_mask = S >= (int)(8 * sizeof(K)) ? ~(K)0 : (((K)1 << S) - 1);
+    const uint32_t R = 1u << row_bits;
     for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS) s_cur[r] = 0;
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
-        const K k = keys[lo + e];
+        const LK k = (LK)(keys[lo + e] & low_mask);
         s_key[e] = k;
         s_val[e] = vals[lo + e];
-        atomicAdd(&s_cur[(uint32_t)(k >> minor_bits) & rmask], 1u);
+        atomicAdd(&s_cur[(uint32_t)(k >> minor_bits)], 1u);
     }
     __syncthreads();
     {   // exclusive scan of the row counts (R <= 1024: four per thread), counters reset for the scatter
@@ -430,22 +436,23 @@ block_finish_kernel(const K *__restrict__ keys, const VB *__restrict__ vals, con
     }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
-        const uint32_t r = (uint32_t)(s_key[e] >> minor_bits) & rmask;
+        const uint32_t r = (uint32_t)(s_key[e] >> minor_bits);
         s_slot[s_off[r] + atomicAdd(&s_cur[r], 1u)] = (uint16_t)e;
     }
     __syncthreads();
+    const K high = (K)blockIdx.x << (S >= (int)(8 * sizeof(K)) ? 0 : S);
     for (uint32_t slot = threadIdx.x; slot < cnt; slot += BL_THREADS) {
         const uint32_t e = s_slot[slot];
-        const K k = s_key[e];
-        const uint32_t r = (uint32_t)(k >> minor_bits) & rmask;
+        const LK k = s_key[e];
+        const uint32_t r = (uint32_t)(k >> minor_bits);
         const uint32_t a = s_off[r], b = s_off[r + 1];
         uint32_t rank = 0;
-        for (uint32_t t = a; t < b; ++t) {
+        for (uint32_t t = a; t < b; ++t) {                    // (minor, arrival) order inside the row
             const uint32_t et = s_slot[t];
-            const K kt = s_key[et];
+            const LK kt = s_key[et];
             rank += kt < k || (kt == k && et < e);
         }
-        out_k[lo + a + rank] = k;
+        out_k[lo + a + rank] = high | (K)k;
         out_v[lo + a + rank] = s_val[e];
     }
 }
@@ -453,13 +460,25 @@ block_finish_kernel(const K *__restrict__ keys, const VB *__restrict__ vals, con
 // bptr[b] = first position whose block id is >= b, read off the block-sorted keys (same bracket
 // logic as fill_ptr_kernel; block ids ascend)
 template <typename K>
-__global__ void block_bounds_kernel(const K *__restrict__ keys, uint32_t n, int S, uint32_t nblocks,
-                                    uint32_t *__restrict__ bptr, GapQueue gq) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > n) return;
-    const uint64_t lo = p == 0 ? 0 : (uint64_t)(keys[p - 1] >> S) + 1;
-    const uint64_t hi = p == n ? (uint64_t)nblocks : (uint64_t)(keys[p] >> S);
-    emit_ptr(bptr, lo, hi, (uint32_t)p, gq);
+__global__ void __launch_bounds__(256)
+block_bounds_kernel(const K *__restrict__ keys, uint32_t n, int S, uint32_t nblocks,
+                    uint32_t *__restrict__ bptr, GapQueue gq) {
+    constexpr int U = 4;                                   // positions per thread, loads issued together
+    const uint64_t base = ((uint64_t)blockIdx.x * blockDim.x) * U + threadIdx.x;
+    uint32_t cur[U], prev[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint64_t p = base + (uint64_t)u * blockDim.x;
+        cur[u] = p < n ? (uint32_t)(keys[p] >> S) : nblocks;             // position n closes the last block
+        prev[u] = (p > 0 && p <= n) ? (uint32_t)(keys[p - 1] >> S) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint64_t p = base + (uint64_t)u * blockDim.x;
+        if (p > n) continue;
+        const uint64_t lo = p == 0 ? 0 : (uint64_t)prev[u] + 1;
+        if (lo <= (uint64_t)cur[u]) emit_ptr(bptr, lo, cur[u], (uint32_t)p, gq);   // most positions: same block, nothing to do
+    }
 }
 
 // Sorts the records by the hybrid route.  Input (k0, v0); on success *sorted_k / *sorted_v point at
@@ -509,8 +528,8 @@ void hybrid_sort(spl_ctx *ctx, uint32_t len, uint32_t nmajor, int major_bits, in
     *sorted_v = iv;
     {   // exact block boundaries and the longest block, from the block-sorted keys
         GapQueueOwner gaps(ctx);
-        block_bounds_kernel<K><<<div_up((uint64_t)len + 1, 256), 256, 0, ctx->stream>>>(ik, len, S, nblocks, bptr,
-                                                                                     gaps.q);
+        block_bounds_kernel<K><<<div_up((uint64_t)len + 1, 256 * 4), 256, 0, ctx->stream>>>(ik, len, S, nblocks, bptr,
+                                                                                         gaps.q);
         check_launch(ctx, "block_bounds");
         gaps.drain(ctx, bptr);
         SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
@@ -521,12 +540,18 @@ void hybrid_sort(spl_ctx *ctx, uint32_t len, uint32_t nmajor, int major_bits, in
         read_back(ctx, ctx->d_scratch, &longest, 1);
         if (longest > BL_CAP) return;              // the caller sorts (ik, iv) fully; the passes so far were stable
     }
-    constexpr size_t kSmem = (size_t)BL_CAP * (sizeof(K) + sizeof(VB) + 2);
-    SPL_CUDA(cudaFuncSetAttribute(block_finish_kernel<K, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-    SPL_CUDA(cudaFuncSetAttribute(block_finish_kernel<K, VB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  cudaSharedmemCarveoutMaxShared));
-    block_finish_kernel<K, VB><<<nblocks, BL_THREADS, kSmem, ctx->stream>>>(ik, iv, bptr, minor_bits, row_bits, ok, ov);
-    check_launch(ctx, "block_finish");
+    auto finish = [&](auto lk_tag) {
+        using LK = decltype(lk_tag);
+        constexpr size_t kSmem = (size_t)BL_CAP * (sizeof(LK) + sizeof(VB) + 2);
+        auto kern = block_finish_kernel<K, VB, LK>;
+        SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        kern<<<nblocks, BL_THREADS, kSmem, ctx->stream>>>(ik, iv, bptr, minor_bits, row_bits, ok, ov);
+        check_launch(ctx, "block_finish");
+    };
+    if (S <= 32) finish(uint32_t{});
+    else finish(K{});
     *sorted_k = ok;
     *sorted_v = ov;
     *done = true;
