@@ -685,7 +685,32 @@ def secondary_metrics(torch, sp, ctx, A, wl):
                                     "len": int(coo_h[2].numel()), "ms": hs * 1e3,
                                     "mnnz_per_s": coo_h[2].numel() / hs / 1e6,
                                     "h2d_bytes": int(coo_h[2].numel()) * 24}
-    del coo_h
+
+    # the same triplets through the streaming CooMatrix storage (spl_coo): the fill
+    # (extend from the host arrays, chunks sent while the rest is copied in) and the conversion
+    # (flush of the last partial chunk + device assembly) timed separately and together
+    np_trip = [t.numpy() for t in coo_h]
+    np_trip = (np_trip[0].view(np.uint64), np_trip[1].view(np.uint64), np_trip[2])
+    ln = int(np_trip[2].shape[0])
+    fill_s, conv_s = [], []
+    for it in range(6):
+        pc = sp.PinnedCooMatrix.with_capacity(n, n, ln, np.float64, ctx=ctx)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pc.extend_triplets(*np_trip)
+        t1 = time.perf_counter()
+        M_ = sp.CsrMatrix.from_coo(pc, ctx=ctx)
+        ctx.sync()
+        t2 = time.perf_counter()
+        if it:
+            fill_s.append(t1 - t0); conv_s.append(t2 - t1)
+        del M_, pc
+    fill_ms, conv_ms = 1e3 * float(np.median(fill_s)), 1e3 * float(np.median(conv_s))
+    out["assembly_shuffled_streamed"] = {
+        "workload": "laplace2d_1024_f64: PinnedCooMatrix filled from host usize triplets, then CsrMatrix::from(&coo)",
+        "len": ln, "fill_ms": fill_ms, "convert_ms": conv_ms, "total_ms": fill_ms + conv_ms,
+        "convert_mnnz_per_s": ln / conv_ms / 1e3, "total_mnnz_per_s": ln / (fill_ms + conv_ms) / 1e3}
+    del coo_h, np_trip
 
     def spmv_rate(M, x, y, copies=1, reps=100):
         """Back-to-back launches; `copies` > 1 rotates over independent (A, x, y) sets whose total

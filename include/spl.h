@@ -94,6 +94,39 @@ int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, ui
                          uint64_t len, const uint32_t *row_dev, const uint32_t *col_dev,
                          const void *val_dev, int dedup, int dropzero, spl_mat **out);
 
+/* ---- CooMatrix storage that streams to the device while it is filled ----
+ * spl_coo is the storage of a CooMatrix<T> (src/coo.rs:52-57): insertion-ordered triplets kept as
+ * three PINNED host arrays (row usize, col usize, value).  Every time another 2^19 triplets are
+ * complete they are sent on the builder's own copy stream (indices narrowed to uint32 on the
+ * device), so the host keeps pushing while the DMA engine works and the conversion finds its input
+ * already in HBM.  One builder per host thread at a time (`&mut self` in the reference).
+ *   spl_coo_create    CooMatrix::new / with_capacity   src/coo.rs:104-112, 162-170
+ *   spl_coo_push      CooMatrix::push                  src/coo.rs:431-435 (bounds -> SPL_ERR_ARG)
+ *   spl_coo_extend    Extend for CooMatrix             src/coo.rs:566-573 (all entries asserted
+ *                                                      before any is stored); with_triplets :254-288
+ *   spl_coo_truncate  pop / clear                      src/coo.rs:450-452, 467-469
+ *   spl_coo_len / _capacity                            src/coo.rs:349-351, 331-333
+ *   spl_coo_host_ptrs get / iter (borrowed, valid until the next push/extend/reserve)
+ *                                                      src/coo.rs:386-390, 491-495
+ *   spl_mat_from_coo_builder   From<&CooMatrix> for CsrMatrix / CscMatrix (as spl_mat_from_coo);
+ *                     the builder stays valid and can be pushed to and converted again. */
+typedef struct spl_coo spl_coo;
+int spl_coo_create(spl_ctx *ctx, int dtype, uint64_t nrows, uint64_t ncols, uint64_t capacity,
+                   spl_coo **out);
+int spl_coo_free(spl_coo *coo);
+const char *spl_coo_last_error(const spl_coo *coo);
+int spl_coo_push(spl_coo *coo, uint64_t row, uint64_t col, const void *value);
+int spl_coo_extend(spl_coo *coo, uint64_t len, const uint64_t *row, const uint64_t *col, const void *val);
+int spl_coo_reserve(spl_coo *coo, uint64_t capacity);
+int spl_coo_truncate(spl_coo *coo, uint64_t len);
+uint64_t spl_coo_len(const spl_coo *coo);
+uint64_t spl_coo_capacity(const spl_coo *coo);
+/* Entries already handed to the copy stream (diagnostic). */
+uint64_t spl_coo_streamed(const spl_coo *coo);
+int spl_coo_host_ptrs(const spl_coo *coo, const uint64_t **row, const uint64_t **col, const void **val);
+int spl_mat_from_coo_builder(spl_ctx *ctx, spl_coo *coo, int format, int dedup, int dropzero,
+                             spl_mat **out);
+
 /* CsrMatrix::new (src/csr.rs:137-164) / CscMatrix::new (src/csc.rs:137-164):
  * validating constructor from host arrays.  ptr is rowptr (CSR) or colptr (CSC). */
 int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,

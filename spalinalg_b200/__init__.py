@@ -5,8 +5,8 @@ CsrMatrix, DokMatrix.  Device work goes through libspalinalg_b200.so (include/sp
 with `python -m spalinalg_b200.build`.  No CPU fallback.
 """
 from . import matrix
-from .matrix import (Context, CooMatrix, CscMatrix, CsrMatrix, DeviceError, DokMatrix, Panic,
+from .matrix import (Context, CooMatrix, CscMatrix, CsrMatrix, DeviceError, DokMatrix, Panic, PinnedCooMatrix,
                      default_context, set_default_context)
 
-__all__ = ["Context", "CooMatrix", "CscMatrix", "CsrMatrix", "DokMatrix", "Panic", "DeviceError",
+__all__ = ["Context", "CooMatrix", "CscMatrix", "CsrMatrix", "DokMatrix", "Panic", "DeviceError", "PinnedCooMatrix",
            "default_context", "set_default_context"]

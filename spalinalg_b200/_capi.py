@@ -63,6 +63,18 @@ SIGNATURES = {
     "spl_peer_pull": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
     "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "spl_coo_create": (_i, [_vp, _i, _u64, _u64, _u64, _pp]),
+    "spl_coo_free": (_i, [_vp]),
+    "spl_coo_last_error": (C.c_char_p, [_vp]),
+    "spl_coo_push": (_i, [_vp, _u64, _u64, _vp]),
+    "spl_coo_extend": (_i, [_vp, _u64, _vp, _vp, _vp]),
+    "spl_coo_reserve": (_i, [_vp, _u64]),
+    "spl_coo_truncate": (_i, [_vp, _u64]),
+    "spl_coo_len": (_u64, [_vp]),
+    "spl_coo_capacity": (_u64, [_vp]),
+    "spl_coo_streamed": (_u64, [_vp]),
+    "spl_coo_host_ptrs": (_i, [_vp, _pp, _pp, _pp]),
+    "spl_mat_from_coo_builder": (_i, [_vp, _vp, _i, _i, _i, _pp]),
 }
 
 _lib = None

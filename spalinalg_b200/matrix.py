@@ -271,6 +271,133 @@ class CooMatrix:
         return cls.with_entries(dok.nrows(), dok.ncols(), items, dtype=dok.dtype)
 
 
+class PinnedCooMatrix(CooMatrix):
+    """CooMatrix whose storage is an spl_coo (include/spl.h): pinned host SoA
+    arrays, streamed to the device chunk by chunk while they are filled, so that
+    CsrMatrix.from_coo / CscMatrix.from_coo find the triplets already in HBM.  Same surface as
+    CooMatrix (push, extend, pop, clear, get, iter, length, capacity ...; src/coo.rs); needs a
+    CUDA device — there is no CPU fallback for this storage."""
+
+    def __init__(self, nrows: int, ncols: int, dtype=np.float64, capacity: int = 0, ctx=None):
+        if not nrows > 0:
+            raise Panic("assertion failed: nrows > 0")
+        if not ncols > 0:
+            raise Panic("assertion failed: ncols > 0")
+        self._nrows, self._ncols = int(nrows), int(ncols)
+        self._dtype = np.dtype(dtype)
+        code = _dtype_code(self._dtype)
+        self._ctx = ctx or default_context()
+        self._lib = self._ctx._lib
+        h = C.c_void_p()
+        self._ctx.check(self._lib.spl_coo_create(self._ctx._h, code, self._nrows, self._ncols,
+                                                 int(capacity), C.byref(h)))
+        self._b = h
+
+    def __del__(self):
+        b = getattr(self, "_b", None)
+        if b:
+            self._lib.spl_coo_free(b)
+            self._b = None
+
+    def _check(self, status: int):
+        if status == capi.SPL_OK:
+            return
+        msg = self._lib.spl_coo_last_error(self._b).decode(errors="replace")
+        if status in (capi.SPL_ERR_ARG, capi.SPL_ERR_INVALID, capi.SPL_ERR_SHAPE):
+            raise Panic(msg)
+        raise DeviceError(f"{capi.STATUS_NAMES.get(status, status)}: {msg}")
+
+    # constructors (src/coo.rs:104-112, 162-170, 204-220, 254-288) -----------------
+    @classmethod
+    def new(cls, nrows, ncols, dtype=np.float64, ctx=None):
+        return cls(nrows, ncols, dtype, 0, ctx)
+
+    @classmethod
+    def with_capacity(cls, nrows, ncols, capacity, dtype=np.float64, ctx=None):
+        return cls(nrows, ncols, dtype, capacity, ctx)
+
+    @classmethod
+    def with_triplets(cls, nrows, ncols, rowind, colind, values, dtype=None, ctx=None):
+        values = np.asarray(values) if dtype is None else np.asarray(values, dtype=dtype)
+        if values.dtype not in (np.float32, np.float64):
+            values = values.astype(np.float64)
+        if len(rowind) != len(values):
+            raise Panic("assertion failed: rowind.len() == values.len()")
+        if len(colind) != len(values):
+            raise Panic("assertion failed: colind.len() == values.len()")
+        m = cls(nrows, ncols, values.dtype, len(values), ctx)
+        m.extend_triplets(rowind, colind, values)
+        return m
+
+    @classmethod
+    def with_entries(cls, nrows, ncols, entries, dtype=np.float64, ctx=None):
+        ents = list(entries)
+        return cls.with_triplets(nrows, ncols, [e[0] for e in ents], [e[1] for e in ents],
+                                 np.array([e[2] for e in ents], dtype=dtype), ctx=ctx)
+
+    # accessors ---------------------------------------------------------------------
+    @property
+    def _len(self):
+        return int(self._lib.spl_coo_len(self._b))
+
+    def length(self): return self._len
+    def capacity(self): return int(self._lib.spl_coo_capacity(self._b))
+    def streamed(self): return int(self._lib.spl_coo_streamed(self._b))
+
+    def triplets(self):
+        """Views of the pinned arrays (valid until the next push / extend / reserve)."""
+        n = self._len
+        r, c, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.spl_coo_host_ptrs(self._b, C.byref(r), C.byref(c), C.byref(v)))
+        if n == 0:
+            return np.empty(0, np.uint64), np.empty(0, np.uint64), np.empty(0, self._dtype)
+        ct = C.c_float if self._dtype == np.float32 else C.c_double
+        row = np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_uint64)), (n,))
+        col = np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_uint64)), (n,))
+        val = np.ctypeslib.as_array(C.cast(v, C.POINTER(ct)), (n,))
+        return row, col, val
+
+    def get(self, index: int):
+        if 0 <= index < self._len:
+            r, c, v = self.triplets()
+            return (int(r[index]), int(c[index]), v[index].item())
+        return None
+
+    def _reserve(self, cap: int):
+        self._check(self._lib.spl_coo_reserve(self._b, int(cap)))
+
+    def push(self, row: int, col: int, value: float):                   # coo.rs:431-435
+        if row < 0 or col < 0:
+            raise Panic("index must be non-negative (usize)")
+        v = np.array([value], dtype=self._dtype)
+        self._check(self._lib.spl_coo_push(self._b, int(row), int(col), _ptr(v)))
+
+    def extend_triplets(self, rowind, colind, values):
+        """Bulk push of SoA triplets (with_triplets, coo.rs:254-288 / Extend, coo.rs:566-573)."""
+        r = np.ascontiguousarray(rowind, dtype=np.uint64)
+        c = np.ascontiguousarray(colind, dtype=np.uint64)
+        v = np.ascontiguousarray(values, dtype=self._dtype)
+        if not (len(r) == len(v) and len(c) == len(v)):
+            raise Panic("assertion failed: rowind.len() == colind.len() == values.len()")
+        self._check(self._lib.spl_coo_extend(self._b, len(v), _ptr(r), _ptr(c), _ptr(v)))
+
+    def extend(self, entries):
+        ents = list(entries)
+        if ents:
+            self.extend_triplets([e[0] for e in ents], [e[1] for e in ents], [e[2] for e in ents])
+
+    def pop(self):                                                      # coo.rs:450-452
+        n = self._len
+        if n == 0:
+            return None
+        last = self.get(n - 1)
+        self._check(self._lib.spl_coo_truncate(self._b, n - 1))
+        return last
+
+    def clear(self):                                                    # coo.rs:467-469
+        self._check(self._lib.spl_coo_truncate(self._b, 0))
+
+
 # --------------------------------------------------------------------------- DOK (host shell)
 class DokMatrix:
     """Dictionary-of-keys matrix (src/dok.rs:53-58): unordered, keys unique."""
@@ -438,8 +565,11 @@ class _Compressed:
     def from_coo(cls, coo: CooMatrix, ctx=None):
         """From<&CooMatrix<T>> (src/csr/conv/coo.rs:3-116, src/csc/conv/coo.rs:3-116)."""
         ctx = ctx or default_context()
-        r, c, v = coo.triplets()
         h = C.c_void_p()
+        if isinstance(coo, PinnedCooMatrix):         # triplets already streamed to the device
+            ctx.check(ctx._lib.spl_mat_from_coo_builder(ctx._h, coo._b, cls._FORMAT, 1, 1, C.byref(h)))
+            return cls._wrap(ctx, h)
+        r, c, v = coo.triplets()
         ctx.check(ctx._lib.spl_mat_from_coo(ctx._h, cls._FORMAT, _dtype_code(v.dtype), coo.nrows(),
                                             coo.ncols(), len(v), _ptr(r), _ptr(c), _ptr(v), 1, 1,
                                             C.byref(h)))

@@ -541,3 +541,81 @@ def test_tile_boundary_lengths(length):
         A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
         sp.default_context().sync()
         assert np.all(np.abs(yd.cpu().numpy() - yw) <= 1e-5 * np.maximum(sc, 1e-30)), (kernel, lanes)
+
+
+# ------------------------------------------------------------------ pinned, streaming CooMatrix (8f-4)
+def test_pinned_coo_golden(goldens):
+    """The reference's COO->CSR/CSC test (src/csr/conv/coo.rs:129-145) through the streamed storage."""
+    g = goldens["coo_pushes"]
+    coo = sp.PinnedCooMatrix.new(g["nrows"], g["ncols"])
+    for r, c, v in g["entries"]:
+        coo.push(int(r), int(c), v)
+    assert coo.length() == len(g["entries"]) and coo.get(0) == (1, 2, 5.0) and coo.get(99) is None
+    csr = sp.CsrMatrix.from_coo(coo)
+    assert csr.rowptr().tolist() == g["csr"][2] and csr.colind().tolist() == g["csr"][3]
+    assert csr.values().tolist() == g["csr"][4]
+    csc = sp.CscMatrix.from_coo(coo)                       # the builder stays valid
+    assert csc.colptr().tolist() == g["csc"][2] and csc.rowind().tolist() == g["csc"][3]
+    assert csc.values().tolist() == g["csc"][4]
+    with pytest.raises(sp.Panic):
+        coo.push(2, 0, 1.0)                                # src/coo.rs:432
+    with pytest.raises(sp.Panic):
+        coo.push(0, 3, 1.0)                                # src/coo.rs:433
+    with pytest.raises(sp.Panic):
+        coo.extend([(0, 0, 1.0), (5, 0, 1.0)])             # Extend asserts before storing anything
+    assert coo.length() == len(g["entries"])
+    with pytest.raises(sp.Panic):
+        sp.PinnedCooMatrix.new(0, 3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fmt", ["row", "col"])
+def test_pinned_coo_streams_chunks_and_matches_the_oracle(dtype, fmt):
+    """More than two transfer chunks (2^19 each), growth from a small capacity, duplicates,
+    cancellations; pop / clear below the streamed watermark; conversion twice with pushes between."""
+    rng = np.random.default_rng(11)
+    n, m, length = 3000, 2500, (1 << 20) + 300_001
+    r = rng.integers(0, n, length).astype(np.uint64)
+    c = rng.integers(0, m, length).astype(np.uint64)
+    v = rng.standard_normal(length).astype(dtype)
+    v[1000:2000] = -v[0:1000]; r[1000:2000] = r[0:1000]; c[1000:2000] = c[0:1000]
+    cls = sp.CsrMatrix if fmt == "row" else sp.CscMatrix
+    coo = sp.PinnedCooMatrix.with_capacity(n, m, 1000, dtype)
+    cut = 700_003
+    coo.extend_triplets(r[:cut], c[:cut], v[:cut])
+    assert coo.streamed() == 1 << 19 and coo.length() == cut and coo.capacity() >= cut
+    first = cls.from_coo(coo)
+    same(arrays(first), orc.compress_from_coo(n, m, orc.make_triplets(r[:cut], c[:cut], v[:cut]), fmt), "first")
+    assert coo.streamed() == cut
+    for i in range(cut, cut + 5):                                    # single pushes after a conversion
+        coo.push(int(r[i]), int(c[i]), v[i])
+    coo.extend_triplets(r[cut + 5:], c[cut + 5:], v[cut + 5:])
+    tr = coo.triplets()
+    assert np.array_equal(tr[0], r) and np.array_equal(tr[1], c) and tr[2].tobytes() == v.tobytes()
+    same(arrays(cls.from_coo(coo)), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), fmt), "all")
+    # pop below the watermark, refill with other entries: the positions are sent again
+    assert coo.pop() == (int(r[-1]), int(c[-1]), v[-1].item())
+    keep = 600_000
+    while coo.length() > length - 3:
+        coo.pop()
+    coo._check(coo._lib.spl_coo_truncate(coo._b, keep))
+    assert coo.length() == keep and coo.streamed() == keep
+    r2, c2, v2 = r[::-1][:200_000].copy(), c[::-1][:200_000].copy(), (v[::-1][:200_000] * 2).astype(dtype)
+    coo.extend_triplets(r2, c2, v2)
+    want = orc.compress_from_coo(n, m, orc.make_triplets(np.concatenate([r[:keep], r2]),
+                                                       np.concatenate([c[:keep], c2]),
+                                                       np.concatenate([v[:keep], v2])), fmt)
+    same(arrays(cls.from_coo(coo)), want, "after truncate")
+    coo.clear()
+    assert coo.length() == 0 and coo.pop() is None
+    empty = cls.from_coo(coo)
+    assert empty.nnz() == 0 and arrays(empty)[0].tolist() == [0] * ((n if fmt == "row" else m) + 1)
+
+
+def test_pinned_coo_with_triplets_equals_plain():
+    r, c, v = syn.laplacian_2d(96)
+    rng = np.random.default_rng(5)
+    p = rng.permutation(len(v))
+    a = sp.CsrMatrix.from_coo(sp.PinnedCooMatrix.with_triplets(96 * 96, 96 * 96, r[p], c[p], v[p]))
+    b = sp.CsrMatrix.from_coo(sp.CooMatrix.with_triplets(96 * 96, 96 * 96, r[p], c[p], v[p]))
+    same(arrays(a), arrays(b))
