@@ -390,30 +390,54 @@ __global__ void block_hist_kernel(const K *__restrict__ keys, uint32_t n, int S,
 // LK: type of the key inside the block.  All records of a block share the key bits above S, so
 // only the low S bits (local row, minor) are kept — 32 bits whenever S <= 32, which halves the
 // shared memory per record and raises the number of resident CTAs.
-template <typename K, typename VB, typename LK>
+//
+// The kernel is the whole tail of the assembly for its block, not only the sort: a block holds
+// whole rows, so every run of equal keys (one matrix cell) is inside it.  After the ranking the
+// sorted order sits in shared memory; the head of each run adds the run left to right in insertion
+// order (src/csr/conv/coo.rs:43-52, one rounding per addend), the zero test runs on the rounded sum
+// (:60-73), and the survivors leave compacted to the front of the block's own range of the
+// temporary arrays, as (minor index, value) — 4 + V bytes instead of the sorted 8 + V.  What is
+// left for the global level is the survivor count per block, the pointer entries relative to the
+// block, and one gather pass (block_gather_kernel) once the exact nnz is known.
+template <typename K, typename T, typename LK>
 __global__ void __launch_bounds__(BL_THREADS)
-block_finish_kernel(const K *__restrict__ keys, const VB *__restrict__ vals, const uint32_t *__restrict__ bptr,
-                    int minor_bits, int row_bits, K *__restrict__ out_k, VB *__restrict__ out_v) {
-    extern __shared__ __align__(16) unsigned char bl_raw[];   // BL_CAP * (sizeof(LK) + sizeof(VB) + 2) bytes
-    constexpr bool kValFirst = sizeof(VB) > sizeof(LK);       // the wider array first: alignment
-    VB *s_val = reinterpret_cast<VB *>(bl_raw + (kValFirst ? 0 : sizeof(LK) * BL_CAP));
-    LK *s_key = reinterpret_cast<LK *>(bl_raw + (kValFirst ? sizeof(VB) * BL_CAP : 0));
-    uint16_t *s_slot = reinterpret_cast<uint16_t *>(bl_raw + (sizeof(LK) + sizeof(VB)) * BL_CAP);   // arrival index per slot
+block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, const uint32_t *__restrict__ bptr,
+                    int minor_bits, int row_bits, int dedup, int dropzero, uint32_t nmajor,
+                    uint32_t *__restrict__ tmp_ind, T *__restrict__ tmp_val, uint32_t *__restrict__ block_kept,
+                    uint32_t *__restrict__ local_ptr) {
+    constexpr int IPT = BL_CAP / BL_THREADS;                  // 16 sorted positions per thread
+    constexpr int W = BL_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char bl_raw[];   // BL_CAP * (sizeof(LK) + sizeof(T) + 2) bytes
+    constexpr bool kValFirst = sizeof(T) > sizeof(LK);        // the wider array first: alignment
+    T *s_val = reinterpret_cast<T *>(bl_raw + (kValFirst ? 0 : sizeof(LK) * BL_CAP));
+    LK *s_key = reinterpret_cast<LK *>(bl_raw + (kValFirst ? sizeof(T) * BL_CAP : 0));
+    // arrival index per slot (records grouped by row), later per sorted position
+    uint16_t *s_slot = reinterpret_cast<uint16_t *>(bl_raw + (sizeof(LK) + sizeof(T)) * BL_CAP);
     __shared__ uint32_t s_off[(1 << BL_MAX_ROW_BITS) + 1];
     __shared__ uint32_t s_cur[1 << BL_MAX_ROW_BITS];
     __shared__ uint32_t ws[BL_THREADS / 32 + 1];
+    __shared__ uint32_t s_cnt[IPT * W + 1];                   // survivors before each (step, warp)
+    __shared__ uint32_t s_bal[IPT * W];                       // survivor lanes of each (step, warp)
+    const uint32_t R = 1u << row_bits;
     const uint32_t lo = bptr[blockIdx.x], cnt = bptr[blockIdx.x + 1] - lo;
-    if (cnt == 0) return;
+    const uint64_t first_row = (uint64_t)blockIdx.x << row_bits;
+    if (cnt == 0) {
+        for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS)
+            if (first_row + r < nmajor) local_ptr[first_row + r] = 0u;
+        if (threadIdx.x == 0) block_kept[blockIdx.x] = 0u;
+        return;
+    }
     const int S = minor_bits + row_bits;
     const K low_mask = S >= (int)(8 * sizeof(K)) ? ~(K)0 : (((K)1 << S) - 1);
-    const uint32_t R = 1u << row_bits;
+    const LK minor_mask = minor_bits >= (int)(8 * sizeof(LK)) ? ~(LK)0 : (LK)(((LK)1 << minor_bits) - 1);
+    auto row_of = [&](LK k) -> uint32_t { return row_bits ? (uint32_t)(k >> minor_bits) : 0u; };
     for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS) s_cur[r] = 0;
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
         const LK k = (LK)(keys[lo + e] & low_mask);
         s_key[e] = k;
         s_val[e] = vals[lo + e];
-        atomicAdd(&s_cur[(uint32_t)(k >> minor_bits)], 1u);
+        atomicAdd(&s_cur[row_of(k)], 1u);
     }
     __syncthreads();
     {   // exclusive scan of the row counts (R <= 1024: four per thread), counters reset for the scatter
@@ -436,25 +460,127 @@ block_finish_kernel(const K *__restrict__ keys, const VB *__restrict__ vals, con
     }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
-        const uint32_t r = (uint32_t)(s_key[e] >> minor_bits);
+        const uint32_t r = row_of(s_key[e]);
         s_slot[s_off[r] + atomicAdd(&s_cur[r], 1u)] = (uint16_t)e;
     }
     __syncthreads();
-    const K high = (K)blockIdx.x << (S >= (int)(8 * sizeof(K)) ? 0 : S);
-    for (uint32_t slot = threadIdx.x; slot < cnt; slot += BL_THREADS) {
-        const uint32_t e = s_slot[slot];
-        const LK k = s_key[e];
-        const uint32_t r = (uint32_t)(k >> minor_bits);
-        const uint32_t a = s_off[r], b = s_off[r + 1];
-        uint32_t rank = 0;
-        for (uint32_t t = a; t < b; ++t) {                    // (minor, arrival) order inside the row
-            const uint32_t et = s_slot[t];
-            const LK kt = s_key[et];
-            rank += kt < k || (kt == k && et < e);
+    // rank inside the row by (minor, arrival); the sorted position and the record stay in a register
+    // until every thread is done reading the slots, then s_slot becomes the sorted order
+    uint32_t packed[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t slot = threadIdx.x + (uint32_t)i * BL_THREADS;
+        packed[i] = 0xffffffffu;
+        if (slot < cnt) {
+            const uint32_t e = s_slot[slot];
+            const LK k = s_key[e];
+            const uint32_t r = row_of(k);
+            const uint32_t a = s_off[r], b = s_off[r + 1];
+            uint32_t rank = 0;
+            for (uint32_t t = a; t < b; ++t) {
+                const uint32_t et = s_slot[t];
+                const LK kt = s_key[et];
+                rank += kt < k || (kt == k && et < e);
+            }
+            packed[i] = ((a + rank) << 16) | e;
         }
-        out_k[lo + a + rank] = high | (K)k;
-        out_v[lo + a + rank] = s_val[e];
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (packed[i] != 0xffffffffu) s_slot[packed[i] >> 16] = (uint16_t)(packed[i] & 0xffffu);
+    __syncthreads();
+    // heads of runs of equal keys: in-order sum (stored in the head's own slot), zero test
+    uint32_t keepbits = 0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t p = threadIdx.x + (uint32_t)i * BL_THREADS;
+        if (p < cnt) {
+            const uint32_t e = s_slot[p];
+            const LK k = s_key[e];
+            const bool head = !dedup || p == 0 || s_key[s_slot[p - 1]] != k;
+            if (head) {
+                T acc = s_val[e];
+                if (dedup) {
+                    bool more = false;
+                    for (uint32_t j = p + 1; j < cnt; ++j) {
+                        const uint32_t ej = s_slot[j];
+                        if (s_key[ej] != k) break;
+                        acc = acc + s_val[ej];
+                        more = true;
+                    }
+                    if (more) s_val[e] = acc;      // nobody else reads a head's value
+                }
+                keepbits |= (uint32_t)(!dropzero || acc != (T)0) << i;
+            }
+        }
+    }
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (keepbits >> i) & 1u);
+        if (lane == 0) { s_cnt[i * W + warp] = __popc(bal); s_bal[i * W + warp] = bal; }
+    }
+    __syncthreads();
+    if (warp == 0) {                       // exclusive scan of the IPT*W (= 128) counts: 4 per lane
+        constexpr int PER = IPT * W / 32;
+        uint32_t c[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { c[q] = s_cnt[lane * PER + q]; sum += c[q]; }
+        const uint32_t incl = warp_inclusive_scan(sum);
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { s_cnt[lane * PER + q] = run; run += c[q]; }
+        if (lane == 31) s_cnt[IPT * W] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        if ((keepbits >> i) & 1u) {
+            const uint32_t p = threadIdx.x + (uint32_t)i * BL_THREADS;
+            const uint32_t e = s_slot[p];
+            const uint32_t lp = s_cnt[i * W + warp] + __popc(s_bal[i * W + warp] & lanemask_lt());
+            tmp_ind[lo + lp] = (uint32_t)(s_key[e] & minor_mask);
+            tmp_val[lo + lp] = s_val[e];
+        }
+    }
+    // pointer entries relative to the block: survivors before the first sorted position of the row
+    const uint32_t total = s_cnt[IPT * W];
+    for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS) {
+        if (first_row + r >= nmajor) break;
+        const uint32_t p = s_off[r];
+        uint32_t before = total;
+        if (p < cnt) {
+            const uint32_t cell = (p / BL_THREADS) * W + ((p % BL_THREADS) >> 5);
+            before = s_cnt[cell] + __popc(s_bal[cell] & ((1u << (p & 31u)) - 1u));
+        }
+        local_ptr[first_row + r] = before;
+    }
+    if (threadIdx.x == 0) block_kept[blockIdx.x] = total;
+}
+
+// Survivors of every block to their final place (the exact nnz is known by now) and the pointer
+// array: base of the block + the entry relative to it.  One CTA per block; coalesced both ways.
+template <typename T>
+__global__ void __launch_bounds__(256)
+block_gather_kernel(const uint32_t *__restrict__ tmp_ind, const T *__restrict__ tmp_val,
+                    const uint32_t *__restrict__ bptr, const uint32_t *__restrict__ block_base,
+                    const uint32_t *__restrict__ local_ptr, int row_bits, uint32_t nmajor,
+                    uint32_t *__restrict__ out_ind, T *__restrict__ out_val, uint32_t *__restrict__ ptr) {
+    const uint32_t lo = bptr[blockIdx.x], base = block_base[blockIdx.x];
+    const uint32_t kept = block_base[blockIdx.x + 1] - base;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < kept; i += 256) {
+        out_ind[base + i] = tmp_ind[lo + i];
+        out_val[base + i] = tmp_val[lo + i];
+    }
+    const uint32_t R = 1u << row_bits;
+    const uint64_t first_row = (uint64_t)blockIdx.x << row_bits;
+    for (uint32_t r = threadIdx.x; r < R; r += 256) {
+        if (first_row + r >= nmajor) break;
+        ptr[first_row + r] = base + local_ptr[first_row + r];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) ptr[nmajor] = block_base[gridDim.x];
 }
 
 // bptr[b] = first position whose block id is >= b, read off the block-sorted keys (same bracket
@@ -481,16 +607,18 @@ block_bounds_kernel(const K *__restrict__ keys, uint32_t n, int S, uint32_t nblo
     }
 }
 
-// Sorts the records by the hybrid route.  Input (k0, v0); on success *sorted_k / *sorted_v point at
-// the sorted records (in k0/v0 or k1/v1).  On failure (a block would not fit: skewed rows) the
-// records are left, still in a stable order, in *sorted_k / *sorted_v with *done = false and the
-// caller runs the full radix sort from there; if nothing was touched the pointers are k0 / v0.
+// Assembles by the hybrid route.  Input (k0, v0); on success *result is the finished matrix (the
+// tail runs inside the block kernel).  On failure (a block would not fit: skewed rows) *result stays
+// NULL, the records are left, still in a stable order, in *sorted_k / *sorted_v and the caller runs
+// the full radix sort and the streaming tail from there; if nothing was touched the pointers are
+// k0 / v0.
 template <typename K, typename VB>
-void hybrid_sort(spl_ctx *ctx, uint32_t len, uint32_t nmajor, int major_bits, int minor_bits, K *k0, VB *v0,
-                 K *k1, VB *v1, K **sorted_k, VB **sorted_v, bool *done) {
+void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, int dedup, int dropzero,
+                 uint32_t len, uint32_t nmajor, int major_bits, int minor_bits, K *k0, VB *v0,
+                 K *k1, VB *v1, K **sorted_k, VB **sorted_v, spl_mat **result) {
     *sorted_k = k0;
     *sorted_v = v0;
-    *done = false;
+    *result = nullptr;
     if (len < (1u << 22) || major_bits < 1) return;                // small lists: the extra launches cost more
     // rows per block: the largest power of two that keeps the average block at BL_TARGET records
     const double rows_per_block = (double)BL_TARGET * (double)nmajor / (double)len;
@@ -540,21 +668,42 @@ void hybrid_sort(spl_ctx *ctx, uint32_t len, uint32_t nmajor, int major_bits, in
         read_back(ctx, ctx->d_scratch, &longest, 1);
         if (longest > BL_CAP) return;              // the caller sorts (ik, iv) fully; the passes so far were stable
     }
-    auto finish = [&](auto lk_tag) {
+    // one CTA per block: sort, in-order sum, zero drop, compaction inside the block's range of (ok, ov)
+    Tmp<uint32_t> block_kept(ctx, nblocks), block_base(ctx, (size_t)nblocks + 1), local_ptr(ctx, nmajor);
+    uint32_t *tmp_ind = reinterpret_cast<uint32_t *>(ok);
+    auto finish = [&](auto lk_tag, auto t_tag) -> spl_mat * {
         using LK = decltype(lk_tag);
-        constexpr size_t kSmem = (size_t)BL_CAP * (sizeof(LK) + sizeof(VB) + 2);
-        auto kern = block_finish_kernel<K, VB, LK>;
+        using T = decltype(t_tag);
+        static_assert(sizeof(T) == sizeof(VB), "value container and scalar must have one size");
+        constexpr size_t kSmem = (size_t)BL_CAP * (sizeof(LK) + sizeof(T) + 2);
+        auto kern = block_finish_kernel<K, T, LK>;
         SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
         SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
-        kern<<<nblocks, BL_THREADS, kSmem, ctx->stream>>>(ik, iv, bptr, minor_bits, row_bits, ok, ov);
+        kern<<<nblocks, BL_THREADS, kSmem, ctx->stream>>>(ik, reinterpret_cast<const T *>(iv), bptr, minor_bits,
+                                                         row_bits, dedup, dropzero, nmajor, tmp_ind,
+                                                         reinterpret_cast<T *>(ov), block_kept, local_ptr);
         check_launch(ctx, "block_finish");
+        exclusive_scan_u32(ctx, block_kept, nblocks, block_base);
+        uint32_t nnz = 0;
+        read_back(ctx, block_base.p + nblocks, &nnz, 1);      // the one host sync of the tail: exact-size output
+        spl_mat *m = new_mat(ctx, format, dtype, nrows, ncols, nnz);
+        block_gather_kernel<T><<<nblocks, 256, 0, ctx->stream>>>(tmp_ind, reinterpret_cast<const T *>(ov), bptr,
+                                                               block_base, local_ptr, row_bits, nmajor, m->ind,
+                                                               static_cast<T *>(m->val), m->ptr);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            free_mat(ctx, m);
+            throw Error{SPL_ERR_CUDA, std::string("block_gather: ") + cudaGetErrorString(e)};
+        }
+        count_launch(ctx);
+        return m;
     };
-    if (S <= 32) finish(uint32_t{});
-    else finish(K{});
-    *sorted_k = ok;
-    *sorted_v = ov;
-    *done = true;
+    if (dtype == SPL_F32) {
+        if constexpr (sizeof(VB) == 4) *result = S <= 32 ? finish(uint32_t{}, float{}) : finish(K{}, float{});
+    } else {
+        if constexpr (sizeof(VB) == 8) *result = S <= 32 ? finish(uint32_t{}, double{}) : finish(K{}, double{});
+    }
 }
 
 template <typename K, typename VB>
@@ -609,13 +758,10 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
     VB *src_v = v0;
 #ifndef SPL_NO_HYBRID_SORT
     if (!sorted_now) {
-        bool done = false;
-        hybrid_sort<K, VB>(ctx, len, nmajor, bits - minor_bits, minor_bits, k0.p, v0.p, k1.p, v1.p, &src_k, &src_v, &done);
-        if (done) {
-            keys = src_k;
-            vals = src_v;
-            sorted_now = true;
-        }
+        spl_mat *fused = nullptr;      // the hybrid route ends in the finished matrix (tail fused into its last kernel)
+        hybrid_sort<K, VB>(ctx, format, dtype, nrows, ncols, dedup, dropzero, len, nmajor, bits - minor_bits,
+                           minor_bits, k0.p, v0.p, k1.p, v1.p, &src_k, &src_v, &fused);
+        if (fused) return fused;
     }
 #endif
     if (!sorted_now) {    // full radix sort of (src_k, src_v): pass 0 writes the other pair, then ping-pong

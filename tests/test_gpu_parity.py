@@ -619,3 +619,45 @@ def test_pinned_coo_with_triplets_equals_plain():
     a = sp.CsrMatrix.from_coo(sp.PinnedCooMatrix.with_triplets(96 * 96, 96 * 96, r[p], c[p], v[p]))
     b = sp.CsrMatrix.from_coo(sp.CooMatrix.with_triplets(96 * 96, 96 * 96, r[p], c[p], v[p]))
     same(arrays(a), arrays(b))
+
+
+# ------------------------------------------------------------------ hybrid route (>= 2^22 triplets): tail fused into the block kernel
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("fmt", ["row", "col"])
+def test_hybrid_assembly_gaps_duplicates_zeros(dtype, fmt):
+    """5 M triplets: a band of 100 000 empty majors (empty blocks), a last block that is not full,
+    cells with 2..5 duplicates (order-sensitive sums), exact cancellations and explicit zeros."""
+    rng = np.random.default_rng(21)
+    n, m, length = 300_001, 70_001, 5_000_000
+    if fmt == "col":
+        n, m = m, n
+    nmaj = n if fmt == "row" else m
+    maj = rng.integers(0, nmaj - 100_000, length)
+    maj = np.where(maj >= 100_000, maj + 100_000, maj)
+    mnr = rng.integers(0, m if fmt == "row" else n, length)
+    v = (rng.standard_normal(length) * 10.0 ** rng.integers(-6, 6, length)).astype(dtype)
+    src = rng.integers(0, length // 2, 400_000)                # duplicates of earlier cells
+    dst = length // 2 + np.arange(400_000)
+    maj[dst], mnr[dst] = maj[src], mnr[src]
+    v[dst[:50_000]] = -v[src[:50_000]]                          # many of these cancel exactly
+    v[rng.integers(0, length, 1000)] = 0.0
+    p = rng.permutation(length)
+    maj, mnr, v = maj[p].astype(np.uint64), mnr[p].astype(np.uint64), v[p]
+    r, c = (maj, mnr) if fmt == "row" else (mnr, maj)
+    cls = sp.CsrMatrix if fmt == "row" else sp.CscMatrix
+    got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+    same(arrays(got), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), fmt), "dedup")
+    # DOK route: unique keys, explicit zeros kept, nothing summed
+    key = maj * np.uint64(1 << 20) + mnr
+    _, first = np.unique(key, return_index=True)
+    first = rng.permutation(first)
+    assert len(first) >= 1 << 22
+    r1, c1, v1 = r[first], c[first], v[first]
+    h = sp.default_context()
+    import ctypes as C
+    out = C.c_void_p()
+    h.check(h._lib.spl_mat_from_coo(h._h, cls._FORMAT, sp.matrix._dtype_code(v1.dtype), n, m, len(v1),
+                                    r1.ctypes.data_as(C.c_void_p), c1.ctypes.data_as(C.c_void_p),
+                                    v1.ctypes.data_as(C.c_void_p), 0, 0, C.byref(out)))
+    same(arrays(cls._wrap(h, out)),
+         orc.compress_from_coo(n, m, orc.make_triplets(r1, c1, v1), fmt, dedup=False, dropzero=False), "dok")
