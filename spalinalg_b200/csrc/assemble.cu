@@ -271,26 +271,25 @@ spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint
                                   reinterpret_cast<double *>(vb[r]), minor_bits, dedup, dropzero);
 }
 
-// First pass over the caller's triplets: the bounds of CooMatrix::push (src/coo.rs:432-433), the
-// packed sort key major << minor_bits | minor, a private copy of the values (the tail sums in place
-// and the input must stay untouched) and whether the keys are already non-decreasing.  A sorted
-// list — triplets emitted row by row, column by column, as element loops and stencil generators do
-// — needs no sort at all: a stable sort would leave it where it is.
-template <typename K, typename VB>
+// First pass over the caller's triplets, reading the indices only: the bounds of CooMatrix::push
+// (src/coo.rs:432-433), whether the packed keys major << minor_bits | minor are already
+// non-decreasing and whether at least the majors are.  A sorted list — triplets emitted row by row,
+// column by column, as element loops and stencil generators do — needs no sort at all: a stable
+// sort would leave it where it is.  The general route never materialises the unsorted keys: its
+// first radix pass packs them on the fly from the caller's arrays (LoadPack) and reads the values
+// in place.
+template <typename K>
 __global__ void __launch_bounds__(256)
-prepare_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor,
-               const VB *__restrict__ val, uint32_t n, uint32_t nmajor, uint32_t nminor, int minor_bits,
-               K *__restrict__ keys, VB *__restrict__ vals, uint32_t *__restrict__ flags) {
+coo_scan_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor, uint32_t n,
+                uint32_t nmajor, uint32_t nminor, int minor_bits, uint32_t *__restrict__ flags) {
     uint32_t bad = 0, unsorted = 0, major_unsorted = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t mj = major[i], mn = minor[i];
         bad |= (mj >= nmajor) | (mn >= nminor);
-        const K k = (K)(((uint64_t)mj << minor_bits) | (uint64_t)mn);
-        keys[i] = k;
-        vals[i] = val[i];
         if (i + 1 < n) {
             const uint32_t mjn = major[i + 1];
+            const K k = (K)(((uint64_t)mj << minor_bits) | (uint64_t)mn);
             const K kn = (K)(((uint64_t)mjn << minor_bits) | (uint64_t)minor[i + 1]);
             unsorted |= kn < k;
             major_unsorted |= mjn < mj;
@@ -299,6 +298,19 @@ prepare_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ 
     if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(flags, 1u);
     if (__any_sync(0xffffffffu, unsorted) && lane_id() == 0) atomicOr(flags + 1, 1u);
     if (__any_sync(0xffffffffu, major_unsorted) && lane_id() == 0) atomicOr(flags + 2, 1u);
+}
+
+// Packed keys and a private copy of the values for the routes that skip the global sort (the tail
+// sums in place and the caller's arrays must stay untouched).
+template <typename K, typename VB>
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint32_t *__restrict__ major, const uint32_t *__restrict__ minor, const VB *__restrict__ val,
+            uint32_t n, int minor_bits, K *__restrict__ keys, VB *__restrict__ vals) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        keys[i] = (K)(((uint64_t)major[i] << minor_bits) | (uint64_t)minor[i]);
+        vals[i] = val[i];
+    }
 }
 
 // Triplets that already come major by major (row by row) only need each segment put in (minor,
@@ -379,12 +391,12 @@ constexpr uint32_t BL_TARGET = 2700;
 constexpr int BL_MAX_ROW_BITS = 10;            // at most 1 024 rows per block
 constexpr int BL_THREADS = 256;
 
-template <typename K>
-__global__ void block_hist_kernel(const K *__restrict__ keys, uint32_t n, int S, uint32_t step,
-                                  uint32_t *__restrict__ bcount) {
+template <typename K, typename LoadK>
+__global__ void block_hist_kernel(LoadK lk, uint32_t n, int S, uint32_t step, uint32_t *__restrict__ bcount) {
+    uint32_t state = 0;
     for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * step; i < n;
          i += (uint64_t)gridDim.x * blockDim.x * step)
-        atomicAdd(bcount + (uint32_t)(keys[i] >> S), 1u);
+        atomicAdd(bcount + (uint32_t)((K)lk((uint32_t)i, state) >> S), 1u);
 }
 
 // LK: type of the key inside the block.  All records of a block share the key bits above S, so
@@ -607,17 +619,17 @@ block_bounds_kernel(const K *__restrict__ keys, uint32_t n, int S, uint32_t nblo
     }
 }
 
-// Assembles by the hybrid route.  Input (k0, v0); on success *result is the finished matrix (the
-// tail runs inside the block kernel).  On failure (a block would not fit: skewed rows) *result stays
-// NULL, the records are left, still in a stable order, in *sorted_k / *sorted_v and the caller runs
-// the full radix sort and the streaming tail from there; if nothing was touched the pointers are
-// k0 / v0.
-template <typename K, typename VB>
+// Assembles by the hybrid route.  Input: the loaders (lk, lv) over the caller's triplets; (k0, v0)
+// and (k1, v1) are scratch pairs.  On success *result is the finished matrix (the tail runs inside
+// the block kernel).  On failure *result stays NULL: either nothing was touched (*sorted_k == NULL,
+// the caller sorts from the loaders), or a block would not fit (skewed rows) and the records are
+// left, in a stable order, in *sorted_k / *sorted_v for the caller's full radix sort.
+template <typename K, typename VB, typename LoadK, typename LoadV>
 void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, int dedup, int dropzero,
-                 uint32_t len, uint32_t nmajor, int major_bits, int minor_bits, K *k0, VB *v0,
+                 uint32_t len, uint32_t nmajor, int major_bits, int minor_bits, LoadK lk, LoadV lv, K *k0, VB *v0,
                  K *k1, VB *v1, K **sorted_k, VB **sorted_v, spl_mat **result) {
-    *sorted_k = k0;
-    *sorted_v = v0;
+    *sorted_k = nullptr;
+    *sorted_v = nullptr;
     *result = nullptr;
     if (len < (1u << 22) || major_bits < 1) return;                // small lists: the extra launches cost more
     // rows per block: the largest power of two that keeps the average block at BL_TARGET records
@@ -636,7 +648,7 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
         Tmp<uint32_t> bcount(ctx, nblocks);
         SPL_CUDA(cudaMemsetAsync(bcount, 0, sizeof(uint32_t) * (size_t)nblocks, ctx->stream));
         SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
-        block_hist_kernel<K><<<sgrid, 256, 0, ctx->stream>>>(k0, len, S, 64u, bcount);
+        block_hist_kernel<K, LoadK><<<sgrid, 256, 0, ctx->stream>>>(lk, len, S, 64u, bcount);
         check_launch(ctx, "block_hist");
         unsigned g = div_up(nblocks, 256);
         max_seglen_counts_kernel<<<g < sgrid ? g : sgrid, 256, 0, ctx->stream>>>(bcount, nblocks, ctx->d_scratch);
@@ -648,8 +660,7 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
     K *kb[2] = {k1, k0};
     VB *vb[2] = {v1, v0};
     NoPayload *nb[2] = {nullptr, nullptr};
-    const int r = radix_sort<K, VB, NoPayload>(ctx, len, H, LoadPlain<K>{k0}, LoadPlain<VB>{v0}, LoadNone{}, kb, vb,
-                                               nb, S);
+    const int r = radix_sort<K, VB, NoPayload>(ctx, len, H, lk, lv, LoadNone{}, kb, vb, nb, S);
     K *ik = kb[r], *ok = kb[r ^ 1];
     VB *iv = vb[r], *ov = vb[r ^ 1];
     *sorted_k = ik;
@@ -714,31 +725,46 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
     Tmp<K> k0(ctx, len), k1(ctx, len);
     Tmp<VB> v0(ctx, len), v1(ctx, len);
     uint32_t flags[3] = {0, 0, 0};
+    const unsigned sgrid = (unsigned)ctx->num_sms * 16u;
     if (len) {
         SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 4 * sizeof(uint32_t), ctx->stream));
-        unsigned grid = div_up(len, 256 * 4);
-        if (grid > (unsigned)ctx->num_sms * 16u) grid = (unsigned)ctx->num_sms * 16u;
-        prepare_kernel<K, VB><<<grid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len, nmajor, nminor,
-                                                             minor_bits, k0, v0, ctx->d_scratch);
-        check_launch(ctx, "prepare");
+        const unsigned grid = div_up(len, 256 * 4);
+        coo_scan_kernel<K><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, len, nmajor,
+                                                                               nminor, minor_bits, ctx->d_scratch);
+        check_launch(ctx, "coo_scan");
         read_back(ctx, ctx->d_scratch, flags, 3);
         SPL_REQUIRE(flags[0] == 0, SPL_ERR_ARG,
                     "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
     }
-    K *keys = k0;
-    VB *vals = v0;
-    bool sorted_now = !flags[1];
-    if (!sorted_now && !flags[2]) {       // majors already in order: sort inside the segments only
+    auto finish = [&](K *keys, VB *vals) {
+        if (dtype == SPL_F32)
+            return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, keys,
+                                         reinterpret_cast<float *>(vals), minor_bits, dedup, dropzero);
+        return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, keys,
+                                      reinterpret_cast<double *>(vals), minor_bits, dedup, dropzero);
+    };
+    auto pack = [&]() {
+        if (!len) return;
+        const unsigned grid = div_up(len, 256 * 4);
+        pack_kernel<K, VB><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len,
+                                                                               minor_bits, k0, v0);
+        check_launch(ctx, "pack");
+    };
+    if (!flags[1]) {                      // already sorted: no sort at all
+        pack();
+        return finish(k0, v0);
+    }
+    if (!flags[2]) {                      // majors already in order: sort inside the segments only
         Tmp<uint32_t> segptr(ctx, (size_t)nmajor + 1);
         fill_ptr(ctx, major_idx, len, nmajor, segptr);
         SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
         unsigned g = div_up(nmajor, 256);
-        if (g > (unsigned)ctx->num_sms * 16u) g = (unsigned)ctx->num_sms * 16u;
-        max_seglen_kernel<<<g, 256, 0, ctx->stream>>>(segptr, nmajor, ctx->d_scratch);
+        max_seglen_kernel<<<g < sgrid ? g : sgrid, 256, 0, ctx->stream>>>(segptr, nmajor, ctx->d_scratch);
         check_launch(ctx, "max_seglen");
         uint32_t longest = 0;
         read_back(ctx, ctx->d_scratch, &longest, 1);
         if (longest <= 64) {
+            pack();
             if (longest <= 16)
                 segment_sort_kernel<K, VB, 8><<<div_up((uint64_t)nmajor * 8, 256), 256, 0, ctx->stream>>>(
                     segptr, nmajor, k0, v0, k1, v1);
@@ -749,37 +775,34 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
                 segment_sort_kernel<K, VB, 32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(
                     segptr, nmajor, k0, v0, k1, v1);
             check_launch(ctx, "segment_sort");
-            keys = k1;
-            vals = v1;
-            sorted_now = true;
+            return finish(k1, v1);
         }
     }
-    K *src_k = k0;
-    VB *src_v = v0;
+    // general route: keys packed on the fly by the first pass, values read in place
+    const LoadPack<K> lk{major_idx, minor_idx, minor_bits};
+    const LoadPlain<VB> lv{val};
+    K *src_k = nullptr;
+    VB *src_v = nullptr;
 #ifndef SPL_NO_HYBRID_SORT
-    if (!sorted_now) {
+    {
         spl_mat *fused = nullptr;      // the hybrid route ends in the finished matrix (tail fused into its last kernel)
         hybrid_sort<K, VB>(ctx, format, dtype, nrows, ncols, dedup, dropzero, len, nmajor, bits - minor_bits,
-                           minor_bits, k0.p, v0.p, k1.p, v1.p, &src_k, &src_v, &fused);
+                           minor_bits, lk, lv, k0.p, v0.p, k1.p, v1.p, &src_k, &src_v, &fused);
         if (fused) return fused;
     }
 #endif
-    if (!sorted_now) {    // full radix sort of (src_k, src_v): pass 0 writes the other pair, then ping-pong
-        K *other_k = src_k == k0.p ? k1.p : k0.p;
-        VB *other_v = src_v == v0.p ? v1.p : v0.p;
-        K *kb[2] = {other_k, src_k};
-        VB *vb[2] = {other_v, src_v};
-        NoPayload *nb[2] = {nullptr, nullptr};
+    NoPayload *nb[2] = {nullptr, nullptr};
+    if (src_k) {          // stable partial order left by the hybrid route: pass 0 writes the other pair
+        K *kb[2] = {src_k == k0.p ? k1.p : k0.p, src_k};
+        VB *vb[2] = {src_v == v0.p ? v1.p : v0.p, src_v};
         const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, LoadPlain<K>{src_k}, LoadPlain<VB>{src_v},
                                                    LoadNone{}, kb, vb, nb);
-        keys = kb[r];
-        vals = vb[r];
+        return finish(kb[r], vb[r]);
     }
-    if (dtype == SPL_F32)
-        return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, keys,
-                                     reinterpret_cast<float *>(vals), minor_bits, dedup, dropzero);
-    return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, keys,
-                                  reinterpret_cast<double *>(vals), minor_bits, dedup, dropzero);
+    K *kb[2] = {k0.p, k1.p};
+    VB *vb[2] = {v0.p, v1.p};
+    const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, lk, lv, LoadNone{}, kb, vb, nb);
+    return finish(kb[r], vb[r]);
 }
 
 // ---- row-sharded assembly: routing of triplets to their owners ----------------
