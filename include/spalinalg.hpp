@@ -6,6 +6,7 @@
 // names, argument meaning and error behaviour as the crate (paths under /root/reference):
 //   CooMatrix<T>  src/coo.rs:52-57      builder, insertion-ordered triplets (host, SoA)
 //   DokMatrix<T>  src/dok.rs:53-58      builder, hash map (host)
+//   PinnedCooMatrix<T>                  CooMatrix on pinned storage streamed to the device (spl_coo)
 //   CsrMatrix<T>  src/csr.rs:65-72      device resident; rowptr()/colind()/values() are host
 //   CscMatrix<T>  src/csc.rs:65-72      copies made on first use, exactly sized, usize indices
 //   T in {float, double}                src/scalar.rs:55-57
@@ -72,6 +73,7 @@ private:
 template <typename T> class CsrMatrix;
 template <typename T> class CscMatrix;
 template <typename T> class DokMatrix;
+template <typename T> class PinnedCooMatrix;
 
 // ---------------------------------------------------------------------------- CooMatrix
 template <typename T>
@@ -140,6 +142,65 @@ private:
     std::size_t nrows_, ncols_;
     std::vector<std::size_t> rows_, cols_;      // SoA: what spl_mat_from_coo takes as is
     std::vector<T> vals_;
+};
+
+// ---------------------------------------------------------------------------- PinnedCooMatrix
+// CooMatrix whose storage is an spl_coo (spl.h): pinned host SoA arrays streamed to
+// the device chunk by chunk while they are filled, so CsrMatrix::from / CscMatrix::from find the
+// triplets already in HBM.  Same surface as CooMatrix (src/coo.rs); needs a CUDA device.
+template <typename T>
+class PinnedCooMatrix {
+public:
+    PinnedCooMatrix(std::size_t nrows, std::size_t ncols, std::size_t capacity = 0) : nrows_(nrows), ncols_(ncols) {
+        if (!(nrows > 0)) throw Panic("assertion failed: nrows > 0");                     // coo.rs:105-106
+        if (!(ncols > 0)) throw Panic("assertion failed: ncols > 0");
+        Context &c = Context::current();
+        c.check(spl_coo_create(c.raw(), Scalar<T>::dtype, nrows, ncols, capacity, &b_));
+    }
+    static PinnedCooMatrix with_capacity(std::size_t nrows, std::size_t ncols, std::size_t capacity) {
+        return PinnedCooMatrix(nrows, ncols, capacity);                                   // coo.rs:162-170
+    }
+    ~PinnedCooMatrix() { if (b_) spl_coo_free(b_); }
+    PinnedCooMatrix(PinnedCooMatrix &&o) noexcept : nrows_(o.nrows_), ncols_(o.ncols_), b_(o.b_) { o.b_ = nullptr; }
+    PinnedCooMatrix(const PinnedCooMatrix &) = delete;
+    PinnedCooMatrix &operator=(const PinnedCooMatrix &) = delete;
+    std::size_t nrows() const { return nrows_; }
+    std::size_t ncols() const { return ncols_; }
+    std::size_t length() const { return spl_coo_len(b_); }                                // coo.rs:349-351
+    std::size_t capacity() const { return spl_coo_capacity(b_); }
+    void push(std::size_t row, std::size_t col, T value) { check(spl_coo_push(b_, row, col, &value)); }   // coo.rs:431-435
+    void extend(const std::vector<std::size_t> &rowind, const std::vector<std::size_t> &colind,
+                const std::vector<T> &values) {                                           // coo.rs:566-573
+        if (rowind.size() != values.size() || colind.size() != values.size())
+            throw Panic("assertion `left == right` failed: triplet lengths differ");
+        check(spl_coo_extend(b_, values.size(), reinterpret_cast<const std::uint64_t *>(rowind.data()),
+                             reinterpret_cast<const std::uint64_t *>(colind.data()), values.data()));
+    }
+    std::optional<std::tuple<std::size_t, std::size_t, T>> get(std::size_t index) const { // coo.rs:386-390
+        if (index >= length()) return std::nullopt;
+        const std::uint64_t *r = nullptr, *c = nullptr;
+        const void *v = nullptr;
+        spl_coo_host_ptrs(b_, &r, &c, &v);
+        return std::make_tuple((std::size_t)r[index], (std::size_t)c[index], static_cast<const T *>(v)[index]);
+    }
+    std::optional<std::tuple<std::size_t, std::size_t, T>> pop() {                        // coo.rs:450-452
+        const std::size_t n = length();
+        if (n == 0) return std::nullopt;
+        auto e = get(n - 1);
+        check(spl_coo_truncate(b_, n - 1));
+        return e;
+    }
+    void clear() { check(spl_coo_truncate(b_, 0)); }                                      // coo.rs:467-469
+    spl_coo *raw() const { return b_; }
+private:
+    void check(int status) const {
+        if (status == SPL_OK) return;
+        const std::string msg = spl_coo_last_error(b_);
+        if (status == SPL_ERR_SHAPE || status == SPL_ERR_INVALID || status == SPL_ERR_ARG) throw Panic(msg);
+        throw DeviceError(msg);
+    }
+    std::size_t nrows_, ncols_;
+    spl_coo *b_ = nullptr;
 };
 
 // ---------------------------------------------------------------------------- DokMatrix
@@ -286,6 +347,11 @@ public:
         return CsrMatrix(m);
     }
     static CsrMatrix from(const CooMatrix<T> &coo) { CsrMatrix r; r.from_triplets(coo, 1, 1); return r; }   // csr/conv/coo.rs:3-116
+    static CsrMatrix from(const PinnedCooMatrix<T> &coo) {                                // same, triplets already streamed
+        spl_mat *m = nullptr;
+        Base::ctx().check(spl_mat_from_coo_builder(Base::ctx().raw(), coo.raw(), SPL_CSR, 1, 1, &m));
+        return CsrMatrix(m);
+    }
     static CsrMatrix from(const DokMatrix<T> &dok) {                                      // csr/conv/dok.rs:3-76
         CsrMatrix r; r.from_triplets(CooMatrix<T>::from(dok), 0, 0); return r;
     }
@@ -339,6 +405,11 @@ public:
         return CscMatrix(m);
     }
     static CscMatrix from(const CooMatrix<T> &coo) { CscMatrix r; r.from_triplets(coo, 1, 1); return r; }   // csc/conv/coo.rs:3-116
+    static CscMatrix from(const PinnedCooMatrix<T> &coo) {
+        spl_mat *m = nullptr;
+        Base::ctx().check(spl_mat_from_coo_builder(Base::ctx().raw(), coo.raw(), SPL_CSC, 1, 1, &m));
+        return CscMatrix(m);
+    }
     static CscMatrix from(const DokMatrix<T> &dok) {                                      // csc/conv/dok.rs:3-76
         CscMatrix r; r.from_triplets(CooMatrix<T>::from(dok), 0, 0); return r;
     }

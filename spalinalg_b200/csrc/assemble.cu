@@ -3,10 +3,15 @@
 // Reference semantics (src/csr/conv/coo.rs:3-116, src/csc/conv/coo.rs:3-116): entries ordered
 // by (major, minor); duplicates of one cell added left to right in insertion order, the first
 // value copied (:43-52); cells whose sum == 0 removed (:60-73); exactly sized outputs.
-// Device formulation: one pass checks bounds, packs key = major << minor_bits | minor and detects
-// already sorted input (no sort then); otherwise a stable LSD radix sort of the key carrying the
-// value; then one sequential in-order sum per run of equal keys (a tree reduction would change
-// the rounding and, through the zero drop, the structure), flag, compact, build the pointers.
+// Device formulation: one pass over the indices checks bounds and detects already sorted input (no
+// sort then).  Otherwise the key major << minor_bits | minor is sorted stably, carrying the value:
+// large lists by the hybrid route (global radix passes on the high key bits, packing the key on the
+// fly; then one CTA per block of whole rows finishes the sort in shared memory AND runs the tail
+// there), the rest by full LSD radix passes and the streaming tail.  The tail is one sequential
+// in-order sum per run of equal keys (a tree reduction would change the rounding and, through the
+// zero drop, the structure), flag, compact, build the pointers.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -386,10 +391,10 @@ __global__ void max_seglen_kernel(const uint32_t *__restrict__ segptr, uint32_t 
 // Two global passes instead of five or six on the benchmark shapes.  Blocks are sized for ~2 700
 // records; if any block would exceed the 4 096 the kernel holds (skewed rows), the full radix sort
 // runs instead — decided from an exact histogram of the block ids, after a cheap sampled one.
-constexpr uint32_t BL_CAP = 4096;
+constexpr uint32_t BL_CAP = 4096;             // records a block kernel holds (256 threads)
+constexpr uint32_t BL_CAP_BIG = 8192;         // ... with 512 threads: f32 values and 32-bit in-block keys only
 constexpr uint32_t BL_TARGET = 2700;
 constexpr int BL_MAX_ROW_BITS = 10;            // at most 1 024 rows per block
-constexpr int BL_THREADS = 256;
 
 template <typename K, typename LoadK>
 __global__ void block_hist_kernel(LoadK lk, uint32_t n, int S, uint32_t step, uint32_t *__restrict__ bcount) {
@@ -411,30 +416,40 @@ __global__ void block_hist_kernel(LoadK lk, uint32_t n, int S, uint32_t step, ui
 // temporary arrays, as (minor index, value) — 4 + V bytes instead of the sorted 8 + V.  What is
 // left for the global level is the survivor count per block, the pointer entries relative to the
 // block, and one gather pass (block_gather_kernel) once the exact nnz is known.
-template <typename K, typename T, typename LK>
-__global__ void __launch_bounds__(BL_THREADS)
+// resident CTAs per SM: what the shared memory allows (227 KB, ~10.5 KB static + reserved per CTA), at most 1 024 threads
+constexpr int bl_min_ctas(int cap, int rec_bytes) {
+    const int by_smem = (227 * 1024) / (cap * rec_bytes + 10752);
+    const int by_threads = 16384 / cap;
+    return by_smem < 1 ? 1 : (by_smem < by_threads ? by_smem : by_threads);
+}
+
+template <typename K, typename T, typename LK, int CAP>
+__global__ void __launch_bounds__(CAP / 16, bl_min_ctas(CAP, (int)(sizeof(LK) + sizeof(T) + 2)))
 block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, const uint32_t *__restrict__ bptr,
                     int minor_bits, int row_bits, int dedup, int dropzero, uint32_t nmajor,
                     uint32_t *__restrict__ tmp_ind, T *__restrict__ tmp_val, uint32_t *__restrict__ block_kept,
                     uint32_t *__restrict__ local_ptr) {
-    constexpr int IPT = BL_CAP / BL_THREADS;                  // 16 sorted positions per thread
-    constexpr int W = BL_THREADS / 32;
-    extern __shared__ __align__(16) unsigned char bl_raw[];   // BL_CAP * (sizeof(LK) + sizeof(T) + 2) bytes
+    constexpr int IPT = 16;                                   // sorted positions per thread
+    constexpr int THREADS = CAP / IPT;
+    constexpr int W = THREADS / 32;
+    extern __shared__ __align__(16) unsigned char bl_raw[];   // CAP * (sizeof(LK) + sizeof(T) + 2) bytes
     constexpr bool kValFirst = sizeof(T) > sizeof(LK);        // the wider array first: alignment
-    T *s_val = reinterpret_cast<T *>(bl_raw + (kValFirst ? 0 : sizeof(LK) * BL_CAP));
-    LK *s_key = reinterpret_cast<LK *>(bl_raw + (kValFirst ? sizeof(T) * BL_CAP : 0));
-    // arrival index per slot (records grouped by row), later per sorted position
-    uint16_t *s_slot = reinterpret_cast<uint16_t *>(bl_raw + (sizeof(LK) + sizeof(T)) * BL_CAP);
+    // values stay in ARRIVAL order (coalesced in); keys go to slot order (grouped by row), then
+    // to sorted order in place
+    T *s_val = reinterpret_cast<T *>(bl_raw + (kValFirst ? 0 : sizeof(LK) * CAP));
+    LK *s_key = reinterpret_cast<LK *>(bl_raw + (kValFirst ? sizeof(T) * CAP : 0));
+    // arrival index of the record in a slot (the tie-break); later: of the record at a sorted position
+    uint16_t *s_arr = reinterpret_cast<uint16_t *>(bl_raw + (sizeof(LK) + sizeof(T)) * CAP);
     __shared__ uint32_t s_off[(1 << BL_MAX_ROW_BITS) + 1];
     __shared__ uint32_t s_cur[1 << BL_MAX_ROW_BITS];
-    __shared__ uint32_t ws[BL_THREADS / 32 + 1];
+    __shared__ uint32_t ws[W + 1];
     __shared__ uint32_t s_cnt[IPT * W + 1];                   // survivors before each (step, warp)
     __shared__ uint32_t s_bal[IPT * W];                       // survivor lanes of each (step, warp)
     const uint32_t R = 1u << row_bits;
     const uint32_t lo = bptr[blockIdx.x], cnt = bptr[blockIdx.x + 1] - lo;
     const uint64_t first_row = (uint64_t)blockIdx.x << row_bits;
     if (cnt == 0) {
-        for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS)
+        for (uint32_t r = threadIdx.x; r < R; r += THREADS)
             if (first_row + r < nmajor) local_ptr[first_row + r] = 0u;
         if (threadIdx.x == 0) block_kept[blockIdx.x] = 0u;
         return;
@@ -443,17 +458,30 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
     const K low_mask = S >= (int)(8 * sizeof(K)) ? ~(K)0 : (((K)1 << S) - 1);
     const LK minor_mask = minor_bits >= (int)(8 * sizeof(LK)) ? ~(LK)0 : (LK)(((LK)1 << minor_bits) - 1);
     auto row_of = [&](LK k) -> uint32_t { return row_bits ? (uint32_t)(k >> minor_bits) : 0u; };
-    for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS) s_cur[r] = 0;
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
-        const LK k = (LK)(keys[lo + e] & low_mask);
-        s_key[e] = k;
-        s_val[e] = vals[lo + e];
-        atomicAdd(&s_cur[row_of(k)], 1u);
+    for (uint32_t r = threadIdx.x; r < R; r += THREADS) s_cur[r] = 0;
+    // all of a thread's loads are issued before the first dependent instruction
+    LK kreg[IPT];
+    {
+        T vreg[IPT];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t e = threadIdx.x + (uint32_t)i * THREADS;
+            kreg[i] = e < cnt ? (LK)(keys[lo + e] & low_mask) : (LK)0;
+            vreg[i] = e < cnt ? vals[lo + e] : (T)0;
+        }
+        __syncthreads();                                          // counters are zero
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t e = threadIdx.x + (uint32_t)i * THREADS;
+            if (e < cnt) {
+                s_val[e] = vreg[i];
+                atomicAdd(&s_cur[row_of(kreg[i])], 1u);           // records per row
+            }
+        }
     }
     __syncthreads();
-    {   // exclusive scan of the row counts (R <= 1024: four per thread), counters reset for the scatter
-        constexpr int PER = (1 << BL_MAX_ROW_BITS) / BL_THREADS;
+    {   // exclusive scan of the row counts (R <= 1024), counters reset for the placement
+        constexpr int PER = (1 << BL_MAX_ROW_BITS) / THREADS;
         uint32_t c[PER], sum = 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
@@ -468,57 +496,70 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
             if (r < R) { s_off[r] = run; s_cur[r] = 0; }
             run += c[q];
         }
-        if (threadIdx.x == BL_THREADS - 1) s_off[R] = run;
+        if (threadIdx.x == THREADS - 1) s_off[R] = run;
     }
     __syncthreads();
-    for (uint32_t e = threadIdx.x; e < cnt; e += BL_THREADS) {
-        const uint32_t r = row_of(s_key[e]);
-        s_slot[s_off[r] + atomicAdd(&s_cur[r], 1u)] = (uint16_t)e;
+    // every key (and its arrival index) into a slot of its row's segment; the order inside a
+    // segment is whatever the atomics give
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t e = threadIdx.x + (uint32_t)i * THREADS;
+        if (e < cnt) {
+            const uint32_t r = row_of(kreg[i]);
+            const uint32_t slot = s_off[r] + atomicAdd(&s_cur[r], 1u);
+            s_key[slot] = kreg[i];
+            s_arr[slot] = (uint16_t)e;
+        }
     }
     __syncthreads();
-    // rank inside the row by (minor, arrival); the sorted position and the record stay in a register
-    // until every thread is done reading the slots, then s_slot becomes the sorted order
+    // rank inside the row by (minor, arrival): one shared-memory word per comparison, no branch;
+    // arrival indices are looked at only when the row really holds the key more than once.  Key,
+    // sorted position and arrival index stay in registers until every thread is done reading.
     uint32_t packed[IPT];
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const uint32_t slot = threadIdx.x + (uint32_t)i * BL_THREADS;
+        const uint32_t slot = threadIdx.x + (uint32_t)i * THREADS;
         packed[i] = 0xffffffffu;
         if (slot < cnt) {
-            const uint32_t e = s_slot[slot];
-            const LK k = s_key[e];
+            const LK k = s_key[slot];
+            const uint32_t e = s_arr[slot];
             const uint32_t r = row_of(k);
             const uint32_t a = s_off[r], b = s_off[r + 1];
-            uint32_t rank = 0;
+            uint32_t lt = 0, eq = 0;
             for (uint32_t t = a; t < b; ++t) {
-                const uint32_t et = s_slot[t];
-                const LK kt = s_key[et];
-                rank += kt < k || (kt == k && et < e);
+                const LK kt = s_key[t];
+                lt += kt < k;
+                eq += kt == k;
             }
-            packed[i] = ((a + rank) << 16) | e;
+            if (eq > 1)
+                for (uint32_t t = a; t < b; ++t) lt += (s_key[t] == k) & (s_arr[t] < e);
+            kreg[i] = k;
+            packed[i] = ((a + lt) << 16) | e;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
-        if (packed[i] != 0xffffffffu) s_slot[packed[i] >> 16] = (uint16_t)(packed[i] & 0xffffu);
+        if (packed[i] != 0xffffffffu) {                           // keys and arrival indices in sorted order
+            s_key[packed[i] >> 16] = kreg[i];
+            s_arr[packed[i] >> 16] = (uint16_t)(packed[i] & 0xffffu);
+        }
     __syncthreads();
     // heads of runs of equal keys: in-order sum (stored in the head's own slot), zero test
     uint32_t keepbits = 0;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const uint32_t p = threadIdx.x + (uint32_t)i * BL_THREADS;
+        const uint32_t p = threadIdx.x + (uint32_t)i * THREADS;
         if (p < cnt) {
-            const uint32_t e = s_slot[p];
-            const LK k = s_key[e];
-            const bool head = !dedup || p == 0 || s_key[s_slot[p - 1]] != k;
+            const LK k = s_key[p];
+            const bool head = !dedup || p == 0 || s_key[p - 1] != k;
             if (head) {
+                const uint32_t e = s_arr[p];
                 T acc = s_val[e];
                 if (dedup) {
                     bool more = false;
-                    for (uint32_t j = p + 1; j < cnt; ++j) {
-                        const uint32_t ej = s_slot[j];
-                        if (s_key[ej] != k) break;
-                        acc = acc + s_val[ej];
+                    for (uint32_t j = p + 1; j < cnt && s_key[j] == k; ++j) {
+                        acc = acc + s_val[s_arr[j]];
                         more = true;
                     }
                     if (more) s_val[e] = acc;      // nobody else reads a head's value
@@ -534,7 +575,7 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
         if (lane == 0) { s_cnt[i * W + warp] = __popc(bal); s_bal[i * W + warp] = bal; }
     }
     __syncthreads();
-    if (warp == 0) {                       // exclusive scan of the IPT*W (= 128) counts: 4 per lane
+    if (warp == 0) {                       // exclusive scan of the IPT*W counts: PER per lane
         constexpr int PER = IPT * W / 32;
         uint32_t c[PER], sum = 0;
 #pragma unroll
@@ -549,21 +590,20 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         if ((keepbits >> i) & 1u) {
-            const uint32_t p = threadIdx.x + (uint32_t)i * BL_THREADS;
-            const uint32_t e = s_slot[p];
+            const uint32_t p = threadIdx.x + (uint32_t)i * THREADS;
             const uint32_t lp = s_cnt[i * W + warp] + __popc(s_bal[i * W + warp] & lanemask_lt());
-            tmp_ind[lo + lp] = (uint32_t)(s_key[e] & minor_mask);
-            tmp_val[lo + lp] = s_val[e];
+            tmp_ind[lo + lp] = (uint32_t)(s_key[p] & minor_mask);
+            tmp_val[lo + lp] = s_val[s_arr[p]];
         }
     }
     // pointer entries relative to the block: survivors before the first sorted position of the row
     const uint32_t total = s_cnt[IPT * W];
-    for (uint32_t r = threadIdx.x; r < R; r += BL_THREADS) {
+    for (uint32_t r = threadIdx.x; r < R; r += THREADS) {
         if (first_row + r >= nmajor) break;
         const uint32_t p = s_off[r];
         uint32_t before = total;
         if (p < cnt) {
-            const uint32_t cell = (p / BL_THREADS) * W + ((p % BL_THREADS) >> 5);
+            const uint32_t cell = (p / THREADS) * W + ((p % THREADS) >> 5);
             before = s_cnt[cell] + __popc(s_bal[cell] & ((1u << (p & 31u)) - 1u));
         }
         local_ptr[first_row + r] = before;
@@ -631,13 +671,25 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
     *sorted_k = nullptr;
     *sorted_v = nullptr;
     *result = nullptr;
-    if (len < (1u << 22) || major_bits < 1) return;                // small lists: the extra launches cost more
+    // small lists: the extra launches cost more (SPL_HYBRID_MIN_LEN lowers the bar: tests of this route at oracle sizes)
+    const char *knob = std::getenv("SPL_HYBRID_MIN_LEN");
+    const uint32_t min_len = knob ? (uint32_t)std::strtoul(knob, nullptr, 10) : (1u << 22);
+    if (len < min_len || major_bits < 1) return;
     // rows per block: the largest power of two that keeps the average block at BL_TARGET records
     const double rows_per_block = (double)BL_TARGET * (double)nmajor / (double)len;
     if (rows_per_block < 1.0) return;                              // rows longer than a block on average
     int row_bits = 0;
     while (row_bits < BL_MAX_ROW_BITS && (double)(2u << row_bits) <= rows_per_block) ++row_bits;
     if (row_bits > major_bits) row_bits = major_bits;
+    // Blocks twice as large (and twice the threads) when that saves a whole global pass and the block
+    // still fits two to an SM: 4-byte values, 32-bit in-block keys (config 3: 17 -> 16 key bits).
+    uint32_t cap = BL_CAP;
+    if (sizeof(VB) == 4 && row_bits + 1 <= BL_MAX_ROW_BITS && row_bits + 1 <= major_bits &&
+        minor_bits + row_bits + 1 <= 32 && major_bits - row_bits - 1 >= 1 &&
+        rs_num_passes(major_bits - row_bits - 1) < rs_num_passes(major_bits - row_bits)) {
+        ++row_bits;
+        cap = BL_CAP_BIG;
+    }
     const int H = major_bits - row_bits;                           // key bits sorted globally
     if (H < 1 || H > 24) return;
     const int S = minor_bits + row_bits;                           // block id = key >> S
@@ -655,7 +707,7 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
         check_launch(ctx, "max_block");
         uint32_t m = 0;
         read_back(ctx, ctx->d_scratch, &m, 1);
-        if ((uint64_t)m * 64 > (uint64_t)BL_CAP + BL_CAP / 2) return;          // clearly skewed
+        if ((uint64_t)m * 64 > (uint64_t)cap + cap / 2) return;                // clearly skewed
     }
     K *kb[2] = {k1, k0};
     VB *vb[2] = {v1, v0};
@@ -677,21 +729,22 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
         check_launch(ctx, "max_block");
         uint32_t longest = 0;
         read_back(ctx, ctx->d_scratch, &longest, 1);
-        if (longest > BL_CAP) return;              // the caller sorts (ik, iv) fully; the passes so far were stable
+        if (longest > cap) return;                 // the caller sorts (ik, iv) fully; the passes so far were stable
     }
     // one CTA per block: sort, in-order sum, zero drop, compaction inside the block's range of (ok, ov)
     Tmp<uint32_t> block_kept(ctx, nblocks), block_base(ctx, (size_t)nblocks + 1), local_ptr(ctx, nmajor);
     uint32_t *tmp_ind = reinterpret_cast<uint32_t *>(ok);
-    auto finish = [&](auto lk_tag, auto t_tag) -> spl_mat * {
+    auto finish = [&](auto lk_tag, auto t_tag, auto cap_tag) -> spl_mat * {
         using LK = decltype(lk_tag);
         using T = decltype(t_tag);
+        constexpr int CAP = decltype(cap_tag)::value;
         static_assert(sizeof(T) == sizeof(VB), "value container and scalar must have one size");
-        constexpr size_t kSmem = (size_t)BL_CAP * (sizeof(LK) + sizeof(T) + 2);
-        auto kern = block_finish_kernel<K, T, LK>;
+        constexpr size_t kSmem = (size_t)CAP * (sizeof(LK) + sizeof(T) + 2);
+        auto kern = block_finish_kernel<K, T, LK, CAP>;
         SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
         SPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
-        kern<<<nblocks, BL_THREADS, kSmem, ctx->stream>>>(ik, reinterpret_cast<const T *>(iv), bptr, minor_bits,
+        kern<<<nblocks, CAP / 16, kSmem, ctx->stream>>>(ik, reinterpret_cast<const T *>(iv), bptr, minor_bits,
                                                          row_bits, dedup, dropzero, nmajor, tmp_ind,
                                                          reinterpret_cast<T *>(ov), block_kept, local_ptr);
         check_launch(ctx, "block_finish");
@@ -710,10 +763,16 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
         count_launch(ctx);
         return m;
     };
+    using Small = std::integral_constant<int, (int)BL_CAP>;
+    using Big = std::integral_constant<int, (int)BL_CAP_BIG>;
     if (dtype == SPL_F32) {
-        if constexpr (sizeof(VB) == 4) *result = S <= 32 ? finish(uint32_t{}, float{}) : finish(K{}, float{});
+        if constexpr (sizeof(VB) == 4)
+            *result = cap == BL_CAP_BIG ? finish(uint32_t{}, float{}, Big{})
+                      : S <= 32         ? finish(uint32_t{}, float{}, Small{})
+                                        : finish(K{}, float{}, Small{});
     } else {
-        if constexpr (sizeof(VB) == 8) *result = S <= 32 ? finish(uint32_t{}, double{}) : finish(K{}, double{});
+        if constexpr (sizeof(VB) == 8)
+            *result = S <= 32 ? finish(uint32_t{}, double{}, Small{}) : finish(K{}, double{}, Small{});
     }
 }
 

@@ -46,6 +46,19 @@ static int run() {
         CHECK(csc.colptr() == (V{0, 1, 2, 4}) && csc.rowind() == (V{0, 0, 0, 1}) && csc.values() == (D{3, 3, 4, 5}));
         CHECK(csr.values().capacity() >= csr.values().size() && csr.nnz() == 4);
     }
+    {   // the same test through the streamed pinned storage (spl_coo)
+        PinnedCooMatrix<double> coo(2, 3);
+        coo.push(1, 2, 5.0); coo.push(0, 2, 4.0); coo.push(0, 1, 3.0); coo.push(0, 0, 1.0);
+        coo.push(0, 0, 2.0); coo.push(1, 0, 0.0); coo.push(1, 1, 1.0); coo.push(1, 1, -1.0);
+        coo.push(0, 0, 9.0);
+        CHECK(coo.length() == 9 && std::get<2>(*coo.pop()) == 9.0 && coo.length() == 8);
+        CHECK(panics([&] { coo.push(2, 0, 1.0); }) && panics([&] { coo.push(0, 3, 1.0); }));
+        auto csr = CsrMatrix<double>::from(coo);
+        CHECK(csr.rowptr() == (V{0, 3, 4}) && csr.colind() == (V{0, 1, 2, 2}) && csr.values() == (D{3, 3, 4, 5}));
+        auto csc = CscMatrix<double>::from(coo);
+        CHECK(csc.colptr() == (V{0, 1, 2, 4}) && csc.rowind() == (V{0, 0, 0, 1}) && csc.values() == (D{3, 3, 4, 5}));
+        CHECK(panics([] { PinnedCooMatrix<float> bad(0, 1); }));
+    }
     {   // src/csr.rs:352-356 (transpose doctest), src/csc.rs:352-356
         CsrMatrix<double> m(2, 2, V{0, 2, 3}, V{0, 1, 1}, D{1, 2, 3});
         auto t = m.transpose();

@@ -661,3 +661,30 @@ def test_hybrid_assembly_gaps_duplicates_zeros(dtype, fmt):
                                     v1.ctypes.data_as(C.c_void_p), 0, 0, C.byref(out)))
     same(arrays(cls._wrap(h, out)),
          orc.compress_from_coo(n, m, orc.make_triplets(r1, c1, v1), fmt, dedup=False, dropzero=False), "dok")
+
+
+@pytest.mark.parametrize("fmt", ["row", "col"])
+def test_hybrid_assembly_big_blocks(fmt, monkeypatch):
+    """The 8 192-record / 512-thread block kernel (f32, taken when it saves a global pass: 9 -> 8 high
+    key bits here, 17 -> 16 on config 3), reached at an oracle-sized list by lowering the route's
+    length threshold."""
+    monkeypatch.setenv("SPL_HYBRID_MIN_LEN", "100000")
+    rng = np.random.default_rng(33)
+    nmaj, nmin, length = 65_536, 60_000, 1_310_720
+    maj = rng.integers(0, nmaj, length)
+    mnr = rng.integers(0, nmin, length)
+    v = rng.standard_normal(length).astype(np.float32)
+    src = rng.integers(0, length // 2, 100_000)
+    dst = length // 2 + np.arange(100_000)
+    maj[dst], mnr[dst] = maj[src], mnr[src]
+    v[dst[:20_000]] = -v[src[:20_000]]
+    p = rng.permutation(length)
+    maj, mnr, v = maj[p].astype(np.uint64), mnr[p].astype(np.uint64), v[p]
+    n, m = (nmaj, nmin) if fmt == "row" else (nmin, nmaj)
+    r, c = (maj, mnr) if fmt == "row" else (mnr, maj)
+    cls = sp.CsrMatrix if fmt == "row" else sp.CscMatrix
+    got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+    same(arrays(got), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), fmt), "big blocks")
+    # the same list in f64 takes the 4 096-record kernel
+    got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v.astype(np.float64)))
+    same(arrays(got), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v.astype(np.float64)), fmt), "f64")
