@@ -513,7 +513,9 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
     }
     __syncthreads();
     // rank inside the row by (minor, arrival): one shared-memory word per comparison, no branch;
-    // arrival indices are looked at only when the row really holds the key more than once.  Key,
+    // arrival indices are looked at only when the row really holds the key more than once (ncu: the
+    // kernel is issue-bound on this loop, and with 5 % duplicates nearly every warp has one lane
+    // that needs the tie-break).  Key,
     // sorted position and arrival index stay in registers until every thread is done reading.
     uint32_t packed[IPT];
 #pragma unroll
@@ -525,13 +527,17 @@ block_finish_kernel(const K *__restrict__ keys, const T *__restrict__ vals, cons
             const uint32_t e = s_arr[slot];
             const uint32_t r = row_of(k);
             const uint32_t a = s_off[r], b = s_off[r + 1];
-            uint32_t lt = 0, eq = 0;
+            uint32_t lt = 0, eq = 0, xs = 0;
             for (uint32_t t = a; t < b; ++t) {
                 const LK kt = s_key[t];
+                const bool same = kt == k;
                 lt += kt < k;
-                eq += kt == k;
+                eq += same;
+                xs ^= same ? t : 0u;                      // slots holding this key, xor-ed (own slot included)
             }
-            if (eq > 1)
+            if (eq == 2)                                  // the usual duplicate: one partner, found without a second pass
+                lt += s_arr[xs ^ slot] < e;
+            else if (eq > 2)
                 for (uint32_t t = a; t < b; ++t) lt += (s_key[t] == k) & (s_arr[t] < e);
             kreg[i] = k;
             packed[i] = ((a + lt) << 16) | e;

@@ -626,15 +626,19 @@ def test_pinned_coo_with_triplets_equals_plain():
 @pytest.mark.parametrize("fmt", ["row", "col"])
 def test_hybrid_assembly_gaps_duplicates_zeros(dtype, fmt):
     """5 M triplets: a band of 100 000 empty majors (empty blocks), a last block that is not full,
-    cells with 2..5 duplicates (order-sensitive sums), exact cancellations and explicit zeros."""
+    cells with 2..5 duplicates (order-sensitive sums), exact cancellations, explicit zeros and three
+    majors with 1 000 records each (ranked by counting instead of the per-thread insertion sort)."""
     rng = np.random.default_rng(21)
-    n, m, length = 300_001, 70_001, 5_000_000
+    n, m, length = 400_001, 70_001, 5_000_000
     if fmt == "col":
         n, m = m, n
     nmaj = n if fmt == "row" else m
     maj = rng.integers(0, nmaj - 100_000, length)
     maj = np.where(maj >= 100_000, maj + 100_000, maj)
     mnr = rng.integers(0, m if fmt == "row" else n, length)
+    for heavy in (5, 250_017, nmaj - 1):                       # rows too long for the per-thread insertion sort
+        at = rng.choice(length, 1000, replace=False)
+        maj[at], mnr[at] = heavy, rng.integers(0, 300, 1000)   # ~3 records per cell
     v = (rng.standard_normal(length) * 10.0 ** rng.integers(-6, 6, length)).astype(dtype)
     src = rng.integers(0, length // 2, 400_000)                # duplicates of earlier cells
     dst = length // 2 + np.arange(400_000)
