@@ -258,24 +258,6 @@ spl_mat *finish_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32
     return m;
 }
 
-template <typename K, typename VB, typename LoadK>
-spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
-                       uint32_t len, LoadK lk, const VB *val, int minor_bits, int bits, int dedup,
-                       int dropzero) {
-    Tmp<K> k0(ctx, len), k1(ctx, len);
-    Tmp<VB> v0(ctx, len), v1(ctx, len);
-    K *kb[2] = {k0, k1};
-    VB *vb[2] = {v0, v1};
-    NoPayload *nb[2] = {nullptr, nullptr};
-    LoadPlain<VB> lv{val};
-    const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, lk, lv, LoadNone{}, kb, vb, nb);
-    if (dtype == SPL_F32)
-        return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, kb[r],
-                                     reinterpret_cast<float *>(vb[r]), minor_bits, dedup, dropzero);
-    return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, kb[r],
-                                  reinterpret_cast<double *>(vb[r]), minor_bits, dedup, dropzero);
-}
-
 // First pass over the caller's triplets, reading the indices only: the bounds of CooMatrix::push
 // (src/coo.rs:432-433), whether the packed keys major << minor_bits | minor are already
 // non-decreasing and whether at least the majors are.  A sorted list — triplets emitted row by row,
@@ -782,25 +764,17 @@ void hybrid_sort(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
     }
 }
 
-template <typename K, typename VB>
-spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
-                      const uint32_t *major_idx, const uint32_t *minor_idx, const VB *val, int minor_bits,
-                      int bits, int dedup, int dropzero) {
-    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols, nminor = format == SPL_CSR ? ncols : nrows;
+// General route, shared by the COO front (keys packed on the fly from the caller's index arrays)
+// and the receive side of the sharded assembly (packed keys as routed): hybrid route first, full
+// LSD radix passes and the streaming tail when it does not apply.
+template <typename K, typename VB, typename LoadK>
+spl_mat *assemble_impl(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols,
+                       uint32_t len, LoadK lk, const VB *val, int minor_bits, int bits, int dedup,
+                       int dropzero) {
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols;
     Tmp<K> k0(ctx, len), k1(ctx, len);
     Tmp<VB> v0(ctx, len), v1(ctx, len);
-    uint32_t flags[3] = {0, 0, 0};
-    const unsigned sgrid = (unsigned)ctx->num_sms * 16u;
-    if (len) {
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 4 * sizeof(uint32_t), ctx->stream));
-        const unsigned grid = div_up(len, 256 * 4);
-        coo_scan_kernel<K><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, len, nmajor,
-                                                                               nminor, minor_bits, ctx->d_scratch);
-        check_launch(ctx, "coo_scan");
-        read_back(ctx, ctx->d_scratch, flags, 3);
-        SPL_REQUIRE(flags[0] == 0, SPL_ERR_ARG,
-                    "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
-    }
+    const LoadPlain<VB> lv{val};
     auto finish = [&](K *keys, VB *vals) {
         if (dtype == SPL_F32)
             return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, keys,
@@ -808,44 +782,6 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
         return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, keys,
                                       reinterpret_cast<double *>(vals), minor_bits, dedup, dropzero);
     };
-    auto pack = [&]() {
-        if (!len) return;
-        const unsigned grid = div_up(len, 256 * 4);
-        pack_kernel<K, VB><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len,
-                                                                               minor_bits, k0, v0);
-        check_launch(ctx, "pack");
-    };
-    if (!flags[1]) {                      // already sorted: no sort at all
-        pack();
-        return finish(k0, v0);
-    }
-    if (!flags[2]) {                      // majors already in order: sort inside the segments only
-        Tmp<uint32_t> segptr(ctx, (size_t)nmajor + 1);
-        fill_ptr(ctx, major_idx, len, nmajor, segptr);
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
-        unsigned g = div_up(nmajor, 256);
-        max_seglen_kernel<<<g < sgrid ? g : sgrid, 256, 0, ctx->stream>>>(segptr, nmajor, ctx->d_scratch);
-        check_launch(ctx, "max_seglen");
-        uint32_t longest = 0;
-        read_back(ctx, ctx->d_scratch, &longest, 1);
-        if (longest <= 64) {
-            pack();
-            if (longest <= 16)
-                segment_sort_kernel<K, VB, 8><<<div_up((uint64_t)nmajor * 8, 256), 256, 0, ctx->stream>>>(
-                    segptr, nmajor, k0, v0, k1, v1);
-            else if (longest <= 32)
-                segment_sort_kernel<K, VB, 16><<<div_up((uint64_t)nmajor * 16, 256), 256, 0, ctx->stream>>>(
-                    segptr, nmajor, k0, v0, k1, v1);
-            else
-                segment_sort_kernel<K, VB, 32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(
-                    segptr, nmajor, k0, v0, k1, v1);
-            check_launch(ctx, "segment_sort");
-            return finish(k1, v1);
-        }
-    }
-    // general route: keys packed on the fly by the first pass, values read in place
-    const LoadPack<K> lk{major_idx, minor_idx, minor_bits};
-    const LoadPlain<VB> lv{val};
     K *src_k = nullptr;
     VB *src_v = nullptr;
 #ifndef SPL_NO_HYBRID_SORT
@@ -868,6 +804,74 @@ spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint3
     VB *vb[2] = {v0.p, v1.p};
     const int r = radix_sort<K, VB, NoPayload>(ctx, len, bits, lk, lv, LoadNone{}, kb, vb, nb);
     return finish(kb[r], vb[r]);
+}
+
+template <typename K, typename VB>
+spl_mat *assemble_coo(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t len,
+                      const uint32_t *major_idx, const uint32_t *minor_idx, const VB *val, int minor_bits,
+                      int bits, int dedup, int dropzero) {
+    const uint32_t nmajor = format == SPL_CSR ? nrows : ncols, nminor = format == SPL_CSR ? ncols : nrows;
+    uint32_t flags[3] = {0, 0, 0};
+    const unsigned sgrid = (unsigned)ctx->num_sms * 16u;
+    if (len) {
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 4 * sizeof(uint32_t), ctx->stream));
+        const unsigned grid = div_up(len, 256 * 4);
+        coo_scan_kernel<K><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, len, nmajor,
+                                                                               nminor, minor_bits, ctx->d_scratch);
+        check_launch(ctx, "coo_scan");
+        read_back(ctx, ctx->d_scratch, flags, 3);
+        SPL_REQUIRE(flags[0] == 0, SPL_ERR_ARG,
+                    "COO entry out of bounds (CooMatrix::push asserts row < nrows, col < ncols)");
+    }
+    auto finish = [&](K *keys, VB *vals) {
+        if (dtype == SPL_F32)
+            return finish_impl<K, float>(ctx, format, dtype, nrows, ncols, len, keys,
+                                         reinterpret_cast<float *>(vals), minor_bits, dedup, dropzero);
+        return finish_impl<K, double>(ctx, format, dtype, nrows, ncols, len, keys,
+                                      reinterpret_cast<double *>(vals), minor_bits, dedup, dropzero);
+    };
+    auto pack = [&](K *keys, VB *vals) {
+        if (!len) return;
+        const unsigned grid = div_up(len, 256 * 4);
+        pack_kernel<K, VB><<<grid < sgrid ? grid : sgrid, 256, 0, ctx->stream>>>(major_idx, minor_idx, val, len,
+                                                                               minor_bits, keys, vals);
+        check_launch(ctx, "pack");
+    };
+    if (!flags[1]) {                      // already sorted: no sort at all
+        Tmp<K> k0(ctx, len);
+        Tmp<VB> v0(ctx, len);
+        pack(k0, v0);
+        return finish(k0, v0);
+    }
+    if (!flags[2]) {                      // majors already in order: sort inside the segments only
+        Tmp<uint32_t> segptr(ctx, (size_t)nmajor + 1);
+        fill_ptr(ctx, major_idx, len, nmajor, segptr);
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        unsigned g = div_up(nmajor, 256);
+        max_seglen_kernel<<<g < sgrid ? g : sgrid, 256, 0, ctx->stream>>>(segptr, nmajor, ctx->d_scratch);
+        check_launch(ctx, "max_seglen");
+        uint32_t longest = 0;
+        read_back(ctx, ctx->d_scratch, &longest, 1);
+        if (longest <= 64) {
+            Tmp<K> k0(ctx, len), k1(ctx, len);
+            Tmp<VB> v0(ctx, len), v1(ctx, len);
+            pack(k0, v0);
+            if (longest <= 16)
+                segment_sort_kernel<K, VB, 8><<<div_up((uint64_t)nmajor * 8, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            else if (longest <= 32)
+                segment_sort_kernel<K, VB, 16><<<div_up((uint64_t)nmajor * 16, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            else
+                segment_sort_kernel<K, VB, 32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(
+                    segptr, nmajor, k0, v0, k1, v1);
+            check_launch(ctx, "segment_sort");
+            return finish(k1, v1);
+        }
+    }
+    // general route: keys packed on the fly by the first pass, values read in place
+    return assemble_impl<K, VB>(ctx, format, dtype, nrows, ncols, len, LoadPack<K>{major_idx, minor_idx, minor_bits},
+                                val, minor_bits, bits, dedup, dropzero);
 }
 
 // ---- row-sharded assembly: routing of triplets to their owners ----------------

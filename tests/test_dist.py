@@ -156,6 +156,42 @@ def test_route_and_packed_assembly_device(dtype, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,ncols", [(np.float32, 3000), (np.float64, 3000), (np.float32, 1 << 20)])
+def test_packed_assembly_takes_the_hybrid_route(dtype, ncols, monkeypatch):
+    """The receive side of the sharded assembly at a size where its list goes through the hybrid
+    route (global passes on the high row bits, block kernel with the tail inside), reached at an
+    oracle-sized list by lowering the route's threshold; 32-bit packed keys (3 000 columns) and
+    64-bit ones (2^20 columns)."""
+    import spalinalg_b200 as sp
+    from spalinalg_b200 import _capi as capi
+    monkeypatch.setenv("SPL_HYBRID_MIN_LEN", "50000")
+    ctx = sp.default_context()
+    n, world = 40_000, 2
+    r, c, v = make_coo(n, ncols, 600_000, 5, dtype)
+    full = orc.compress_from_coo(n, ncols, orc.make_triplets(r, c, v), "row")
+    starts = spd.partition_starts(n, world)
+    parts = []
+    for src in range(world):
+        a, b = syn_block(len(v), world, src)
+        keys, vals, counts = spd.route_device(ctx, torch, capi.SPL_CSR, n, ncols, _t(r[a:b], np.int32),
+                                              _t(c[a:b], np.int32), _t(v[a:b], dtype), starts)
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        parts.append([(keys[offs[g]:offs[g + 1]], vals[offs[g]:offs[g + 1]]) for g in range(world)])
+    for dst in range(world):
+        rk = torch.cat([parts[src][dst][0] for src in range(world)]).contiguous()
+        rv = torch.cat([parts[src][dst][1] for src in range(world)]).contiguous()
+        h = C.c_void_p()
+        ctx.check(ctx._lib.spl_mat_from_packed_dev(
+            ctx._h, capi.SPL_CSR, capi.SPL_F32 if dtype == np.float32 else capi.SPL_F64,
+            starts[dst + 1] - starts[dst], ncols, int(rk.numel()), C.c_void_p(rk.data_ptr()),
+            C.c_void_p(rv.data_ptr()), 1, 1, C.byref(h)))
+        m = sp.CsrMatrix._wrap(ctx, h)
+        want = shard_of(full, starts, dst)
+        assert np.array_equal(m.rowptr(), want[0]) and np.array_equal(m.colind(), want[1])
+        assert m.values().tobytes() == want[2].tobytes()
+
+
+@pytest.mark.gpu
 def test_route_rejects_out_of_bounds():
     import spalinalg_b200 as sp
     from spalinalg_b200 import _capi as capi
