@@ -53,8 +53,12 @@ typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:
 
 /* SpMV kernel choice (spl_spmv_ex): auto picks by row-length statistics — VECTOR (1..32 lanes per
  * row) for regular rows, SPLIT (fixed chunks of stored entries per warp, the merge-path balance at
- * warp granularity) for skewed rows; MERGE is the block-level merge-path kernel, selectable. */
-typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3 } spl_spmv_kernel;
+ * warp granularity) for skewed rows; MERGE is the block-level merge-path kernel, selectable.  SLICED
+ * is the lane-per-row kernel over a second copy of the matrix kept in slices of 32 rows, column-major
+ * inside the slice (every load a full line; the row sum runs in ascending column order, i.e. it is
+ * bit-identical to the reference's `&A * &X`); AUTO builds the copy for regular matrices when they
+ * come back for a second product and the padding stays small. */
+typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3, SPL_SPMV_SLICED = 4 } spl_spmv_kernel;
 
 /* ---- context ------------------------------------------------------------ */
 

@@ -45,7 +45,7 @@ def spmv_rows(A, V, tdt, small):
     y = torch.empty(n, device="cuda", dtype=tdt)
     b = nnz * (4 + V) + (n + m) * V
     out = {"algorithmic_bytes": b, "planned": A.spmv_choice()}
-    variants = [("auto", 0, 0), ("merge", 2, 0), ("split", 3, 0)] + [(f"vector{l}", 1, l) for l in (1, 2, 4, 8, 16, 32)]
+    variants = [("auto", 0, 0), ("merge", 2, 0), ("split", 3, 0), ("sliced", 4, 0)] + [(f"vector{l}", 1, l) for l in (1, 2, 4, 8, 16, 32)]
     for name, k, l in variants:
         try:
             med, mn = timed(lambda: A.spmv_device(x.data_ptr(), y.data_ptr(), k, l), reps=15, warm=3, flush_l2=small)

@@ -81,6 +81,14 @@ struct spl_mat {
     uint32_t hot_count = 0;
     std::atomic<int> hot_state{0};    // 0 not tried, 1 one split product done, 2 decided (ind_rank set or not)
     double hot_coverage = 0.0;        // share of the stored entries that fall in the hot columns
+    // sliced copy for the vector-class SpMV (regular rows): slices of 32 consecutive rows stored
+    // column-major inside the slice (entry k of the 32 rows contiguous), padded to the slice's
+    // longest row.  slice_ptr[s] = sum of the widths of the slices before s (offset = 32 * that).
+    uint32_t *slice_ptr = nullptr;
+    uint32_t *slice_ind = nullptr;
+    void *slice_val = nullptr;
+    uint64_t slice_entries = 0;       // padded entries stored
+    std::atomic<int> slice_state{0};  // 0 not tried, 1 one vector product done, 2 decided (slice_ptr set or not)
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

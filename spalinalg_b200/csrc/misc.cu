@@ -197,6 +197,9 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->split_rows);
     dfree(ctx, m->ind_rank);
     dfree(ctx, m->col_order);
+    dfree(ctx, m->slice_ptr);
+    dfree(ctx, m->slice_ind);
+    dfree(ctx, m->slice_val);
     delete m;
 }
 

@@ -26,6 +26,7 @@
 
 #include "kernels.cuh"
 #include "radix_sort.cuh"
+#include "scan.cuh"
 
 namespace spl {
 
@@ -129,6 +130,120 @@ void spmv_peer_t(spl_ctx *ctx, const spl_mat *a, const PeerX &px, T *y, int lane
     spmv_vector<T>(ctx, a, xg, y, lanes);
 }
 
+
+// ------------------------------------------------------------------ sliced kernel
+// The vector kernel with more than one lane per row spends its L1 bandwidth on partial sectors (a
+// warp's load touches 32/LPR rows, 16-32 useful bytes of each line) and its rows pay a shuffle
+// reduction; with one lane per row on CSR the loads of a warp are a stride of one row length apart.
+// Regular matrices therefore get a second copy in slices of 32 consecutive rows, stored column-major
+// inside the slice and padded to the slice's longest row: lane = row, step k of a warp reads one
+// full line of indices and one or two of values, no shuffles, and the sum runs in ascending column
+// order — bit-identical to the reference's `&A * &X` (src/csr/ops/mul.rs:25-40).  Padded slots are
+// never multiplied (0, never 0 * inf).
+__global__ void slice_width_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t nslices,
+                                   uint32_t *__restrict__ width) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t slice = gtid >> 5;
+    if (slice >= nslices) return;
+    uint32_t len = gtid < nrows ? ptr[gtid + 1] - ptr[gtid] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane_id() == 0) width[slice] = len;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+slice_fill_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, const T *__restrict__ val,
+                  uint32_t nrows, uint32_t nslices, const uint32_t *__restrict__ slice_ptr,
+                  uint32_t *__restrict__ slice_ind, T *__restrict__ slice_val) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t slice = gtid >> 5;
+    if (slice >= nslices) return;
+    const uint32_t p0 = gtid < nrows ? ptr[gtid] : 0u;
+    const uint32_t len = gtid < nrows ? ptr[gtid + 1] - p0 : 0u;
+    const uint64_t base = (uint64_t)slice_ptr[slice] * 32u + lane_id();
+    const uint32_t width = slice_ptr[slice + 1] - slice_ptr[slice];
+    for (uint32_t k = 0; k < width; ++k) {
+        const bool real = k < len;
+        slice_ind[base + (uint64_t)k * 32u] = real ? ind[p0 + k] : 0u;
+        slice_val[base + (uint64_t)k * 32u] = real ? val[p0 + k] : (T)0;
+    }
+}
+
+template <typename T, typename XG>
+__global__ void __launch_bounds__(256, 8)
+spmv_sliced_kernel(uint32_t nrows, uint32_t nslices, const uint32_t *__restrict__ ptr,
+                   const uint32_t *__restrict__ slice_ptr, const uint32_t *__restrict__ slice_ind,
+                   const T *__restrict__ slice_val, const XG xg, T *__restrict__ y) {
+    constexpr int U = 4;   // entries in flight per lane
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t slice = row >> 5;
+    if (slice >= nslices) return;
+    const uint32_t len = row < nrows ? __ldg(ptr + row + 1) - __ldg(ptr + row) : 0u;
+    const uint32_t s0 = __ldg(slice_ptr + slice), width = __ldg(slice_ptr + slice + 1) - s0;
+    const uint32_t *__restrict__ ci = slice_ind + (uint64_t)s0 * 32u + lane_id();
+    const T *__restrict__ cv = slice_val + (uint64_t)s0 * 32u + lane_id();
+    T acc = (T)0;
+    for (uint32_t k = 0; k < width; k += U) {
+        uint32_t c[U];
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t ku = k + u < width ? k + u : k;      // k itself is in range: safe dummy
+            c[u] = __ldg(ci + (uint64_t)ku * 32u);
+            v[u] = __ldg(cv + (uint64_t)ku * 32u);
+        }
+        T xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = k + u < len ? xg(c[u]) : (T)0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += k + u < len ? v[u] * xv[u] : (T)0;     // ascending column order
+    }
+    if (row < nrows) y[row] = acc;
+}
+
+// Builds the sliced copy if the padding stays within `max_ratio` of the stored entries; returns
+// whether it exists afterwards.  Caller holds a->plan_mu.
+template <typename T>
+bool build_slices(spl_ctx *ctx, spl_mat *a, double max_ratio) {
+    if (a->slice_ptr) return true;
+    if (a->nnz == 0) return false;
+    const uint32_t nslices = div_up(a->nrows, 32);
+    Tmp<uint32_t> width(ctx, nslices);
+    Tmp<uint32_t> sp(ctx, (size_t)nslices + 1);
+    slice_width_kernel<<<div_up((uint64_t)nslices * 32, 256), 256, 0, ctx->stream>>>(a->ptr, a->nrows, nslices, width);
+    check_launch(ctx, "slice_width");
+    exclusive_scan_u32(ctx, width, nslices, sp);
+    uint32_t total_width = 0;
+    read_back(ctx, sp.p + nslices, &total_width, 1);
+    const uint64_t padded = (uint64_t)total_width * 32u;
+    if ((double)padded > max_ratio * (double)a->nnz + 4096.0) return false;
+    uint32_t *si = nullptr;
+    T *sv = nullptr;
+    if (cudaMallocAsync((void **)&si, padded * sizeof(uint32_t), ctx->stream) != cudaSuccess ||
+        cudaMallocAsync((void **)&sv, padded * sizeof(T), ctx->stream) != cudaSuccess) {
+        cudaGetLastError();                      // no room for a second copy: stay with CSR
+        if (si) cudaFreeAsync(si, ctx->stream);
+        return false;
+    }
+    slice_fill_kernel<T><<<div_up((uint64_t)nslices * 32, 256), 256, 0, ctx->stream>>>(
+        a->ptr, a->ind, static_cast<const T *>(a->val), a->nrows, nslices, sp, si, sv);
+    check_launch(ctx, "slice_fill");
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    a->slice_ind = si;
+    a->slice_val = sv;
+    a->slice_entries = padded;
+    a->slice_ptr = sp.release();
+    return true;
+}
+
+template <typename T, typename XG>
+void spmv_sliced(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y) {
+    const uint32_t nslices = div_up(a->nrows, 32);
+    spmv_sliced_kernel<T, XG><<<div_up((uint64_t)nslices * 32, 256), 256, 0, ctx->stream>>>(
+        a->nrows, nslices, a->ptr, a->slice_ptr, a->slice_ind, static_cast<const T *>(a->slice_val), xg, y);
+    check_launch(ctx, "spmv_sliced");
+}
 
 // ------------------------------------------------------------------ merge-path kernel
 // Merge path over A = row end offsets ptr[1..nrows] and B = 0..nnz-1 (Merrill & Garland): the
@@ -757,6 +872,19 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
     if (kernel == SPL_SPMV_VECTOR && lanes == 0) {
         spmv_plan(ctx, const_cast<spl_mat *>(a));
         lanes = a->plan_lanes;
+    }
+    if (kernel == SPL_SPMV_SLICED) {     // forced: build the copy now, whatever the padding (within reason)
+        spl_mat *m = const_cast<spl_mat *>(a);
+        spmv_plan(ctx, m);
+        if (m->slice_state.load(std::memory_order_acquire) != 2 || !m->slice_ptr) {
+            std::lock_guard<std::mutex> lock(m->plan_mu);
+            const bool ok = a->dtype == SPL_F32 ? build_slices<float>(ctx, m, 4.0) : build_slices<double>(ctx, m, 4.0);
+            m->slice_state.store(2, std::memory_order_release);
+            SPL_REQUIRE(ok, SPL_ERR_UNSUPPORTED, "sliced copy not built: padding above 4x or out of memory");
+        }
+        if (a->dtype == SPL_F32) spmv_sliced<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y);
+        else spmv_sliced<double>(ctx, a, XLocal<double>{(const double *)x}, (double *)y);
+        return;
     }
     if (kernel == SPL_SPMV_VECTOR) {
         if (a->dtype == SPL_F32) spmv_vector<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y, lanes);

@@ -391,6 +391,19 @@ def test_spmv_random(dtype, n, m, density):
         sp.default_context().sync()
         got = yd.cpu().numpy()
         assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), (kernel, lanes)
+    # sliced kernel (slices of 32 rows, lane per row): ascending-column sum, i.e. the reference's
+    # `&A * &X` bit for bit; the copy is refused when the padding would exceed 4x
+    lens = np.diff(a[0].astype(np.int64))
+    padded = sum(32 * int(lens[i:i + 32].max()) for i in range(0, n, 32))
+    yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+    torch.cuda.synchronize()
+    if padded <= 4 * len(a[1]) + 4096 and len(a[1]):
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=4)
+        sp.default_context().sync()
+        assert yd.cpu().numpy().tobytes() == want.tobytes(), "sliced: not bit-identical to the sequential row sum"
+    else:
+        with pytest.raises(sp.DeviceError):
+            A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=4)
 
 
 def test_spmv_skewed_rows():
