@@ -120,6 +120,10 @@ int spl_ctx_destroy(spl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    for (cudaEvent_t e : ctx->pipe_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SPL_OK;
@@ -383,9 +387,11 @@ int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_ho
     SPL_REQUIRE(a && x_host && y_host, SPL_ERR_ARG, "NULL argument");
     const size_t vs = a->vsize();
     Tmp<unsigned char> x(ctx, (size_t)a->ncols * vs), y(ctx, (size_t)a->nrows * vs);
-    SPL_CUDA(cudaMemcpyAsync(x, x_host, (size_t)a->ncols * vs, cudaMemcpyHostToDevice, ctx->stream));
-    spmv(ctx, a, x, y, SPL_SPMV_AUTO, 0);
-    SPL_CUDA(cudaMemcpyAsync(y_host, y, (size_t)a->nrows * vs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!spmv_host_pipelined(ctx, a, x_host, y_host, x, y)) {
+        SPL_CUDA(cudaMemcpyAsync(x, x_host, (size_t)a->ncols * vs, cudaMemcpyHostToDevice, ctx->stream));
+        spmv(ctx, a, x, y, SPL_SPMV_AUTO, 0);
+        SPL_CUDA(cudaMemcpyAsync(y_host, y, (size_t)a->nrows * vs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }

@@ -52,6 +52,11 @@ struct spl_ctx {
     uint64_t launches = 0;
     uint32_t *h_scratch = nullptr;   // pinned, 64 words: small device->host read-backs
     uint32_t *d_scratch = nullptr;   // device, 64 words
+    // host-vector SpMV pipeline (spl_spmv_host): upload and download streams and the events that
+    // order them against the compute stream; created on first use
+    static constexpr int kPipeChunks = 8;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t pipe_ev[2 * kPipeChunks + 2] = {};
 };
 
 struct spl_mat {
@@ -88,6 +93,11 @@ struct spl_mat {
     uint32_t *slice_ind = nullptr;
     void *slice_val = nullptr;
     uint64_t slice_entries = 0;       // padded entries stored
+    // host-vector SpMV pipeline: row chunks and, per chunk, how long a prefix of x its rows need
+    // (1 + the largest column index in the chunks up to it); pipe_state 0 = not planned yet
+    uint32_t pipe_rows[spl_ctx::kPipeChunks + 1] = {};
+    uint32_t pipe_need[spl_ctx::kPipeChunks] = {};
+    std::atomic<int> pipe_state{0};
     std::atomic<int> slice_state{0};  // 0 not tried, 1 one vector product done, 2 decided (slice_ptr set or not)
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }

@@ -41,6 +41,13 @@ void recompress(spl_ctx *ctx, int dtype, uint32_t nmajor, uint32_t nminor, uint3
 // spmv.cu — y = A x, CSR (a-6 restricted to B = n x 1, dense vectors)
 void spmv_plan(spl_ctx *ctx, spl_mat *a);
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes);
+// `&A * &x` with host vectors, pipelined: x goes up in prefixes, row chunks run as soon as the prefix
+// they need is there, their part of y goes down while the next chunk runs (PCIe both ways at once).
+// x_dev / y_dev are device buffers of ncols / nrows values.  Returns false (nothing done) when the
+// matrix is not one for the vector kernel or too small to be worth it; the caller then does the
+// plain upload - product - download.  Does not synchronise the compute stream.
+bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host, void *x_dev,
+                         void *y_dev);
 
 // x gathered from the slice that owns the column (local HBM or a peer's over NVLink)
 struct PeerX {

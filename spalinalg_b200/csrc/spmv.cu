@@ -921,6 +921,130 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
     throw Error{SPL_ERR_UNSUPPORTED, "unknown SpMV kernel"};
 }
 
+// ------------------------------------------------------------------ host vectors, pipelined
+// The reference-facing product takes x from host memory and returns y there.  Done as upload,
+// product, download it is PCIe time twice over with the kernel in between; but a row chunk only
+// needs the prefix of x up to its largest column, and its part of y can leave while the next chunk
+// runs.  So x goes up in the prefixes the chunks need (stencils, bands: about a chunk's worth each;
+// random columns: everything before the first chunk), the vector kernel runs chunk by chunk on the
+// compute stream behind the upload events, and each chunk of y is copied down on a third stream
+// behind the chunk's event: both directions of the link are busy at once.
+namespace {
+
+__global__ void chunk_need_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, uint32_t nrows,
+                                  uint32_t rows_per_chunk, uint32_t *__restrict__ need) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;                                     // 1 + last (= largest) column of the row, 0 if empty
+    if (r < nrows) {
+        const uint32_t lo = ptr[r], hi = ptr[r + 1];
+        if (hi > lo) m = ind[hi - 1] + 1u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // rows_per_chunk is a multiple of 32: a warp never straddles two chunks
+    if (lane_id() == 0 && m && r < nrows) atomicMax(need + (uint32_t)(r / rows_per_chunk), m);
+}
+
+template <typename T, int LPR>
+void launch_vector_rows(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, uint32_t r0, uint32_t r1) {
+    const uint64_t threads = (uint64_t)(r1 - r0) * LPR;
+    spmv_vector_kernel<T, LPR, XLocal<T>><<<div_up(threads, 256), 256, 0, ctx->stream>>>(
+        r1 - r0, a->ptr + r0, a->ind, static_cast<const T *>(a->val), XLocal<T>{x}, y + r0);
+    check_launch(ctx, "spmv_vector");
+}
+
+template <typename T>
+void spmv_vector_rows(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, int lanes, uint32_t r0, uint32_t r1) {
+    switch (lanes) {
+        case 1: launch_vector_rows<T, 1>(ctx, a, x, y, r0, r1); break;
+        case 2: launch_vector_rows<T, 2>(ctx, a, x, y, r0, r1); break;
+        case 4: launch_vector_rows<T, 4>(ctx, a, x, y, r0, r1); break;
+        case 8: launch_vector_rows<T, 8>(ctx, a, x, y, r0, r1); break;
+        case 16: launch_vector_rows<T, 16>(ctx, a, x, y, r0, r1); break;
+        default: launch_vector_rows<T, 32>(ctx, a, x, y, r0, r1); break;
+    }
+}
+
+void plan_pipeline(spl_ctx *ctx, spl_mat *a) {
+    constexpr int K = spl_ctx::kPipeChunks;
+    std::lock_guard<std::mutex> lock(a->plan_mu);
+    if (a->pipe_state.load(std::memory_order_relaxed)) return;
+    const uint32_t per = (uint32_t)((((uint64_t)a->nrows + K - 1) / K + 255) / 256 * 256);
+    for (int c = 0; c <= K; ++c) a->pipe_rows[c] = (uint32_t)std::min<uint64_t>((uint64_t)c * per, a->nrows);
+    uint32_t need[K] = {};
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, K * sizeof(uint32_t), ctx->stream));
+    chunk_need_kernel<<<div_up(a->nrows, 256), 256, 0, ctx->stream>>>(a->ptr, a->ind, a->nrows, per, ctx->d_scratch);
+    check_launch(ctx, "chunk_need");
+    read_back(ctx, ctx->d_scratch, need, K);
+    uint32_t run = 0;
+    for (int c = 0; c < K; ++c) {                        // prefix maximum: what has to be up before chunk c runs
+        run = std::max(run, need[c]);
+        a->pipe_need[c] = run;
+    }
+    a->pipe_state.store(1, std::memory_order_release);
+}
+
+}  // namespace
+
+bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host, void *x_dev,
+                         void *y_dev) {
+    constexpr int K = spl_ctx::kPipeChunks;
+    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
+    const size_t vs = a->vsize();
+    if ((size_t)a->nrows * vs < (1u << 20) || a->nnz == 0) return false;      // small: one copy each way
+    {   // pageable host memory makes every cudaMemcpyAsync block the host: nothing would overlap
+        cudaPointerAttributes ax{}, ay{};
+        const bool okx = cudaPointerGetAttributes(&ax, x_host) == cudaSuccess && ax.type == cudaMemoryTypeHost;
+        const bool oky = cudaPointerGetAttributes(&ay, y_host) == cudaSuccess && ay.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!okx || !oky) return false;
+    }
+    spl_mat *m = const_cast<spl_mat *>(a);
+    spmv_plan(ctx, m);
+    if (a->plan_kernel != SPL_SPMV_VECTOR) return false;                      // skewed rows: whole-matrix kernels
+    if (!a->pipe_state.load(std::memory_order_acquire)) plan_pipeline(ctx, m);
+    if (!ctx->up_stream) {
+        SPL_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+        SPL_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : ctx->pipe_ev) SPL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t *up_ev = ctx->pipe_ev, *run_ev = ctx->pipe_ev + K;
+    cudaEvent_t start_ev = ctx->pipe_ev[2 * K], end_ev = ctx->pipe_ev[2 * K + 1];
+    const unsigned char *xh = static_cast<const unsigned char *>(x_host);
+    unsigned char *yh = static_cast<unsigned char *>(y_host);
+    unsigned char *xd = static_cast<unsigned char *>(x_dev), *yd = static_cast<unsigned char *>(y_dev);
+    // the device buffers were allocated in compute-stream order: the copy streams start behind that point
+    SPL_CUDA(cudaEventRecord(start_ev, ctx->stream));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->up_stream, start_ev, 0));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->down_stream, start_ev, 0));
+    uint32_t up = 0;
+    for (int c = 0; c < K; ++c) {
+        const uint32_t r0 = a->pipe_rows[c], r1 = a->pipe_rows[c + 1];
+        if (r1 <= r0) continue;
+        const uint32_t need = std::min(a->pipe_need[c], a->ncols);
+        if (need > up) {
+            SPL_CUDA(cudaMemcpyAsync(xd + (size_t)up * vs, xh + (size_t)up * vs, (size_t)(need - up) * vs,
+                                     cudaMemcpyHostToDevice, ctx->up_stream));
+            up = need;
+        }
+        SPL_CUDA(cudaEventRecord(up_ev[c], ctx->up_stream));
+        SPL_CUDA(cudaStreamWaitEvent(ctx->stream, up_ev[c], 0));
+        if (a->dtype == SPL_F32)
+            spmv_vector_rows<float>(ctx, a, (const float *)x_dev, (float *)y_dev, a->plan_lanes, r0, r1);
+        else
+            spmv_vector_rows<double>(ctx, a, (const double *)x_dev, (double *)y_dev, a->plan_lanes, r0, r1);
+        SPL_CUDA(cudaEventRecord(run_ev[c], ctx->stream));
+        SPL_CUDA(cudaStreamWaitEvent(ctx->down_stream, run_ev[c], 0));
+        SPL_CUDA(cudaMemcpyAsync(yh + (size_t)r0 * vs, yd + (size_t)r0 * vs, (size_t)(r1 - r0) * vs,
+                                 cudaMemcpyDeviceToHost, ctx->down_stream));
+    }
+    // the compute stream (which the caller synchronises, and on which the buffers are freed) ends
+    // behind the last download
+    SPL_CUDA(cudaEventRecord(end_ev, ctx->down_stream));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->stream, end_ev, 0));
+    return true;
+}
+
 // Row-sharded SpMV with x left in its owners' memory: the vector kernel with the
 // peer gather.  Skewed shards should all-gather x and use the merge kernel instead.
 void spmv_peer(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *y) {

@@ -705,3 +705,47 @@ def test_hybrid_assembly_big_blocks(fmt, monkeypatch):
     # the same list in f64 takes the 4 096-record kernel
     got = cls.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v.astype(np.float64)))
     same(arrays(got), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v.astype(np.float64)), fmt), "f64")
+
+
+# ------------------------------------------------------------------ `&A * &x` with pinned host vectors: the pipelined path
+@pytest.mark.parametrize("kind", ["laplace", "random", "tall"])
+def test_spmv_host_pipelined_matches_device_product(kind):
+    """spl_spmv_host with pinned x, y and >= 1 MB of rows runs in row chunks behind prefix uploads of
+    x, downloads overlapping the next chunk: same kernel, so the bytes must equal the one-shot device
+    product; and both must be within tolerance of the oracle."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(17)
+    if kind == "laplace":                                   # chunk c needs about a chunk of x more
+        g = 600
+        n = m = g * g
+        r, c, v = syn.laplacian_2d(g)
+    elif kind == "random":                                  # the first chunk already needs all of x
+        n = m = 300_000
+        r = np.repeat(np.arange(n, dtype=np.uint64), 6)
+        c = rng.integers(0, m, len(r)).astype(np.uint64)
+        v = rng.standard_normal(len(r))
+    else:                                                   # more rows than columns, many empty rows
+        n, m = 400_000, 1000
+        r = np.sort(rng.integers(0, n, 900_000)).astype(np.uint64)
+        c = rng.integers(0, m, len(r)).astype(np.uint64)
+        v = rng.standard_normal(len(r))
+    A = sp.CsrMatrix.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+    a = arrays(A)
+    x = rng.standard_normal(m)
+    hx = torch.from_numpy(x).pin_memory()
+    hy = torch.full((n,), 7.0, dtype=torch.float64).pin_memory()
+    ctx = sp.default_context()
+    for _ in range(2):                                      # second call: plan cached, events reused
+        hy.fill_(7.0)
+        ctx.check(ctx._lib.spl_spmv_host(ctx._h, A._h, C.c_void_p(hx.data_ptr()), C.c_void_p(hy.data_ptr())))
+        xd = hx.cuda()
+        yd = torch.empty(n, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        A.spmv_device(xd.data_ptr(), yd.data_ptr())
+        ctx.sync()
+        assert torch.equal(hy, yd.cpu()), "pipelined host product differs from the device product"
+    want = orc.csr_spmv(n, *a, x)
+    scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x))
+    assert np.all(np.abs(hy.numpy() - want) <= 1e-12 * np.maximum(scale, 1e-300))
+    assert np.array_equal(A.matvec(x), hy.numpy())          # pageable vectors: the plain path, same result
