@@ -172,7 +172,10 @@ int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev);
 /* kernel: spl_spmv_kernel in bits 0-7; bits 8-15 optionally force the vector kernel's lanes per
  * row (1, 2, 4, 8, 16 or 32; 0 = planned value). */
 int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel);
-/* Host-buffer form: uploads x, runs spl_spmv, downloads y, synchronises. */
+/* Host-buffer form (the reference-facing `&A * &x`): uploads x, runs spl_spmv, downloads y,
+ * synchronises.  With pinned vectors of a megabyte or more and a matrix for the vector kernel the
+ * three steps are pipelined over row chunks (x in the prefixes the chunks need, y chunk by chunk
+ * behind the kernels), so both directions of the PCIe link work at once; same result bit for bit. */
 int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host);
 /* Which kernel AUTO resolves to for this matrix (SPL_SPMV_VECTOR / _SPLIT) and the vector kernel's
  * lanes per row. */
