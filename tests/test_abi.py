@@ -54,6 +54,11 @@ def test_fails_loudly_without_cuda(lib):
         sp.CsrMatrix.eye(2)
     with pytest.raises(sp.DeviceError):
         sp.CsrMatrix.from_coo(sp.CooMatrix.with_entries(2, 2, [(0, 0, 1.0)]))
+    with pytest.raises(sp.DeviceError):                       # the streamed CooMatrix storage has no host-only form
+        sp.PinnedCooMatrix.new(2, 2)
+    assert lib.spl_coo_free(None) == _capi.SPL_ERR_ARG and lib.spl_coo_len(None) == 0
+    with pytest.raises(sp.Panic):                             # the reference's assert comes before any device work
+        sp.PinnedCooMatrix.new(0, 2)
 
 
 def test_coo_shell_mirrors_reference_panics():
