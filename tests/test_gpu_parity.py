@@ -749,3 +749,23 @@ def test_spmv_host_pipelined_matches_device_product(kind):
     scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x))
     assert np.all(np.abs(hy.numpy() - want) <= 1e-12 * np.maximum(scale, 1e-300))
     assert np.array_equal(A.matvec(x), hy.numpy())          # pageable vectors: the plain path, same result
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_hybrid_assembly_wide_minor_index(dtype, monkeypatch):
+    """2^27 columns: minor bits + in-block row bits exceed 32, so the block kernel keeps 64-bit keys in
+    shared memory (its other instantiation); reached at an oracle-sized list through the threshold knob."""
+    monkeypatch.setenv("SPL_HYBRID_MIN_LEN", "100000")
+    rng = np.random.default_rng(44)
+    n, m, length = 65_536, 1 << 27, 1_310_720
+    r = rng.integers(0, n, length)
+    c = rng.integers(0, m, length)
+    v = rng.standard_normal(length).astype(dtype)
+    src = rng.integers(0, length // 2, 100_000)
+    dst = length // 2 + np.arange(100_000)
+    r[dst], c[dst] = r[src], c[src]
+    v[dst[:20_000]] = -v[src[:20_000]]
+    p = rng.permutation(length)
+    r, c, v = r[p].astype(np.uint64), c[p].astype(np.uint64), v[p]
+    got = sp.CsrMatrix.from_coo(sp.CooMatrix.with_triplets(n, m, r, c, v))
+    same(arrays(got), orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), "row"), "wide minor")
