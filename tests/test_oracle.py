@@ -173,3 +173,64 @@ def test_expand_round_trip():
     back = orc.compress_from_coo(9, 6, t, "row", dedup=False, dropzero=False)
     assert back[0].tolist() == a[0].tolist() and back[1].tolist() == a[1].tolist()
     assert back[2].tobytes() == a[2].tobytes()
+
+
+# ------------------------------------------------------------------ second opinion: scipy.sparse
+# The goldens pin the oracle on the reference's own small cases; here an independent implementation
+# agrees with it on random inputs.  Values are small integers stored as floats, so every summation
+# order gives the same bits and the comparison can be exact in structure AND values.
+def _int_coo(rng, n, m, length, dtype):
+    r = rng.integers(0, n, length).astype(np.uint64)
+    c = rng.integers(0, m, length).astype(np.uint64)
+    v = rng.integers(-3, 4, length).astype(dtype)            # zeros and cancellations happen
+    return r, c, v
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("major", ["row", "col"])
+def test_oracle_agrees_with_scipy_on_assembly_and_conversions(dtype, major):
+    sps = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(101)
+    n, m = 300, 211
+    r, c, v = _int_coo(rng, n, m, 6000, dtype)
+    got = orc.compress_from_coo(n, m, orc.make_triplets(r, c, v), major)
+    S = sps.coo_matrix((v, (r.astype(np.int64), c.astype(np.int64))), shape=(n, m))
+    S = S.tocsr() if major == "row" else S.tocsc()
+    S.sum_duplicates(); S.eliminate_zeros(); S.sort_indices()
+    assert np.array_equal(got[0], S.indptr) and np.array_equal(got[1], S.indices)
+    assert np.array_equal(got[2], S.data.astype(dtype))
+    # the other format of the same matrix, and the transpose
+    nmaj, nmin = (n, m) if major == "row" else (m, n)
+    other = orc.recompress(nmaj, nmin, *got)
+    T = S.tocsc() if major == "row" else S.tocsr()
+    T.sort_indices()
+    assert np.array_equal(other[0], T.indptr) and np.array_equal(other[1], T.indices)
+    assert np.array_equal(other[2], T.data.astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_agrees_with_scipy_on_add_sub_mul_spmv(dtype):
+    sps = pytest.importorskip("scipy.sparse")
+    rng = np.random.default_rng(202)
+    n = 180
+    a = orc.compress_from_coo(n, n, orc.make_triplets(*_int_coo(rng, n, n, 2500, dtype)), "row")
+    b = orc.compress_from_coo(n, n, orc.make_triplets(*_int_coo(rng, n, n, 2500, dtype)), "row")
+    A = sps.csr_matrix((a[2], a[1].astype(np.int64), a[0].astype(np.int64)), shape=(n, n))
+    B = sps.csr_matrix((b[2], b[1].astype(np.int64), b[0].astype(np.int64)), shape=(n, n))
+    for sub in (0, 1):
+        got = orc.addsub(sub, n, n, a, b)
+        # the reference keeps explicit zeros (pattern union): compare against the union pattern
+        U = (abs(A) + abs(B)).tocsr(); U.sort_indices()
+        want = (A - B if sub else A + B).tocsr()
+        assert np.array_equal(got[0], U.indptr) and np.array_equal(got[1], U.indices)
+        dense = np.asarray(want.todense())
+        rows = np.repeat(np.arange(n), np.diff(U.indptr))
+        assert np.array_equal(got[2], dense[rows, U.indices].astype(dtype))
+    got = orc.csr_mul(n, n, n, a, b)
+    P = (abs(A) @ abs(B)).tocsr(); P.sort_indices()             # structural product: no cancellation
+    assert np.array_equal(got[0], P.indptr) and np.array_equal(got[1], P.indices)
+    dense = np.asarray((A @ B).todense())
+    rows = np.repeat(np.arange(n), np.diff(P.indptr))
+    assert np.array_equal(got[2], dense[rows, P.indices].astype(dtype))
+    x = rng.integers(-2, 3, n).astype(dtype)
+    assert np.array_equal(orc.csr_spmv(n, *a, x), (A @ x).astype(dtype))
