@@ -190,7 +190,7 @@ public:
         check(spl_coo_truncate(b_, n - 1));
         return e;
     }
-    void clear() { check(spl_coo_truncate(b_, 0)); }                                      // coo.rs:467-469
+    void clear() { check(spl_coo_truncate(b_, 0)); }                                      // coo.rs:470-472
     spl_coo *raw() const { return b_; }
 private:
     void check(int status) const {

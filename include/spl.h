@@ -108,8 +108,8 @@ int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, ui
  *   spl_coo_push      CooMatrix::push                  src/coo.rs:431-435 (bounds -> SPL_ERR_ARG)
  *   spl_coo_extend    Extend for CooMatrix             src/coo.rs:566-573 (all entries asserted
  *                                                      before any is stored); with_triplets :254-288
- *   spl_coo_truncate  pop / clear                      src/coo.rs:450-452, 467-469
- *   spl_coo_len / _capacity                            src/coo.rs:349-351, 331-333
+ *   spl_coo_truncate  pop / clear                      src/coo.rs:450-452, 470-472
+ *   spl_coo_len / _capacity                            src/coo.rs:349-351, 366-368
  *   spl_coo_host_ptrs get / iter (borrowed, valid until the next push/extend/reserve)
  *                                                      src/coo.rs:386-390, 491-495
  *   spl_mat_from_coo_builder   From<&CooMatrix> for CsrMatrix / CscMatrix (as spl_mat_from_coo);

@@ -1,0 +1,90 @@
+//! `CsrMatrix<T>` (reference: src/csr.rs:65-72 and src/csr/conv/*, src/csr/ops/*).
+use std::ops::{Add, Mul, Neg, Sub};
+
+use crate::compressed::Compressed;
+use crate::coo::CooMatrix;
+use crate::csc::CscMatrix;
+use crate::dok::DokMatrix;
+use crate::ffi::*;
+use crate::scalar::Scalar;
+
+pub struct CsrMatrix<T: Scalar>(Compressed<T>);
+
+impl<T: Scalar> CsrMatrix<T> {
+    /// src/csr.rs:137-164 — panics like the reference on the first failing assertion
+    pub fn new(nrows: usize, ncols: usize, rowptr: Vec<usize>, colind: Vec<usize>, values: Vec<T>) -> Self {
+        CsrMatrix(Compressed::new(SPL_CSR, nrows, ncols, rowptr, colind, values))
+    }
+    /// src/csr.rs:179-188
+    pub fn eye(size: usize) -> Self { CsrMatrix(Compressed::eye(SPL_CSR, size)) }
+
+    pub fn nrows(&self) -> usize { self.0.nrows }
+    pub fn ncols(&self) -> usize { self.0.ncols }
+    pub fn shape(&self) -> (usize, usize) { (self.0.nrows, self.0.ncols) }
+    /// src/csr.rs:287-289
+    pub fn nnz(&self) -> usize { self.0.nnz }
+    /// src/csr.rs:228-258
+    pub fn rowptr(&self) -> &[usize] { &self.0.host().ptr }
+    pub fn colind(&self) -> &[usize] { &self.0.host().ind }
+    pub fn values(&self) -> &[T] { &self.0.host().val }
+    /// src/csr.rs:270-272
+    pub fn values_mut(&mut self) -> &mut [T] { self.0.values_mut() }
+
+    /// src/csr.rs:303-316: (row, col, value) in storage order
+    pub fn iter(&self) -> impl Iterator<Item = (usize, usize, &T)> + '_ {
+        let h = self.0.host();
+        (0..self.0.nrows).flat_map(move |r| (h.ptr[r]..h.ptr[r + 1]).map(move |p| (r, h.ind[p], &h.val[p])))
+    }
+
+    /// src/csr.rs:358-406
+    pub fn transpose(&self) -> Self { CsrMatrix(self.0.unary(spl_mat_transpose)) }
+
+    /// Extension: y = A x with dense host vectors (`&A * &X`, X n x 1, src/csr/ops/mul.rs:5-60).
+    pub fn matvec(&self, x: &[T]) -> Vec<T> { self.0.matvec(x) }
+
+    pub(crate) fn inner(&self) -> &Compressed<T> { &self.0 }
+    pub(crate) fn wrap(c: Compressed<T>) -> Self { CsrMatrix(c) }
+}
+
+/// src/csr/conv/coo.rs:3-116 (owned form :118-122)
+impl<T: Scalar> From<&CooMatrix<T>> for CsrMatrix<T> {
+    fn from(coo: &CooMatrix<T>) -> Self { CsrMatrix(Compressed::from_coo(SPL_CSR, coo)) }
+}
+impl<T: Scalar> From<CooMatrix<T>> for CsrMatrix<T> {
+    fn from(coo: CooMatrix<T>) -> Self { Self::from(&coo) }
+}
+/// src/csr/conv/dok.rs:3-76 (:78-82)
+impl<T: Scalar> From<&DokMatrix<T>> for CsrMatrix<T> {
+    fn from(dok: &DokMatrix<T>) -> Self { CsrMatrix(Compressed::from_dok(SPL_CSR, dok)) }
+}
+impl<T: Scalar> From<DokMatrix<T>> for CsrMatrix<T> {
+    fn from(dok: DokMatrix<T>) -> Self { Self::from(&dok) }
+}
+/// src/csr/conv/csc.rs:3-53 (:55-59)
+impl<T: Scalar> From<&CscMatrix<T>> for CsrMatrix<T> {
+    fn from(csc: &CscMatrix<T>) -> Self { CsrMatrix(csc.inner().convert(SPL_CSR)) }
+}
+impl<T: Scalar> From<CscMatrix<T>> for CsrMatrix<T> {
+    fn from(csc: CscMatrix<T>) -> Self { Self::from(&csc) }
+}
+
+/// src/csr/ops/add.rs:5-75 — shapes asserted equal (SPL_ERR_SHAPE -> panic)
+impl<T: Scalar> Add for &CsrMatrix<T> {
+    type Output = CsrMatrix<T>;
+    fn add(self, rhs: Self) -> Self::Output { CsrMatrix(self.0.binary(&rhs.0, spl_mat_add)) }
+}
+/// src/csr/ops/sub.rs:5-75
+impl<T: Scalar> Sub for &CsrMatrix<T> {
+    type Output = CsrMatrix<T>;
+    fn sub(self, rhs: Self) -> Self::Output { CsrMatrix(self.0.binary(&rhs.0, spl_mat_sub)) }
+}
+/// src/csr/ops/mul.rs:5-60 — `self.ncols() == rhs.nrows()` asserted
+impl<T: Scalar> Mul for &CsrMatrix<T> {
+    type Output = CsrMatrix<T>;
+    fn mul(self, rhs: Self) -> Self::Output { CsrMatrix(self.0.binary(&rhs.0, spl_mat_mul)) }
+}
+/// src/csr/ops/neg.rs:5-18
+impl<T: Scalar> Neg for &CsrMatrix<T> {
+    type Output = CsrMatrix<T>;
+    fn neg(self) -> Self::Output { CsrMatrix(self.0.unary(spl_mat_neg)) }
+}

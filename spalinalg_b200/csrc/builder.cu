@@ -1,6 +1,6 @@
 // builder.cu — CooMatrix storage in pinned host memory with the triplets streamed to the device
 // while they are pushed (CooMatrix::push src/coo.rs:431-435, with_capacity
-// :162-170, extend :548-574, pop :450-452, clear :467-469).
+// :162-170, extend :548-574, pop :450-452, clear :470-472).
 //
 // The reference keeps a Vec<(usize, usize, T)> and hands it to the conversion as a whole.  Done the
 // same way here the assembly call starts with 16 + V bytes per triplet over PCIe (C1: 126 MB, 2.4 ms

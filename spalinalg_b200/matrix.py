@@ -394,7 +394,7 @@ class PinnedCooMatrix(CooMatrix):
         self._check(self._lib.spl_coo_truncate(self._b, n - 1))
         return last
 
-    def clear(self):                                                    # coo.rs:467-469
+    def clear(self):                                                    # coo.rs:470-472
         self._check(self._lib.spl_coo_truncate(self._b, 0))
 
 
