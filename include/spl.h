@@ -57,8 +57,14 @@ typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:
  * is the lane-per-row kernel over a second copy of the matrix kept in slices of 32 rows, column-major
  * inside the slice (every load a full line; the row sum runs in ascending column order, i.e. it is
  * bit-identical to the reference's `&A * &X`); AUTO builds the copy for regular matrices when they
- * come back for a second product and the padding stays small. */
-typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3, SPL_SPMV_SLICED = 4 } spl_spmv_kernel;
+ * come back for a second product and the padding stays small.  STREAM is the persistent kernel for
+ * regular rows: one producer thread per CTA moves the contiguous col/val slice of a tile of rows
+ * into a ring of shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier) several tiles
+ * ahead, the other warps consume the stages (x gathers, row sums with LPR lanes per row; with one
+ * lane per row the sum runs in ascending column order, bit-identical to `&A * &X`).  Launched with
+ * programmatic dependent launch: the matrix prefetch of a product overlaps the tail of the one before. */
+typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3, SPL_SPMV_SLICED = 4,
+               SPL_SPMV_STREAM = 5 } spl_spmv_kernel;
 
 /* ---- context ------------------------------------------------------------ */
 

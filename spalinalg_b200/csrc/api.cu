@@ -11,6 +11,8 @@ using namespace spl;
 #define API_BEGIN(ctx)                         \
     if (!(ctx)) return SPL_ERR_ARG;            \
     try {                                      \
+        (ctx)->pdl_prev = (ctx)->pdl_chain;    \
+        (ctx)->pdl_chain = false;              \
         SPL_CUDA(cudaSetDevice((ctx)->device));
 
 #define API_END(ctx)                                   \

@@ -57,6 +57,11 @@ struct spl_ctx {
     static constexpr int kPipeChunks = 8;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t pipe_ev[2 * kPipeChunks + 2] = {};
+    // programmatic dependent launch: true while the last thing this context put on its stream was a
+    // stream-kernel SpMV (whose CTAs signal launch_dependents); the next one may then start its
+    // matrix prefetch under the tail of that product.  Any other entry point clears it.
+    bool pdl_chain = false;
+    bool pdl_prev = false;     // pdl_chain as the current entry point found it
 };
 
 struct spl_mat {
@@ -99,6 +104,12 @@ struct spl_mat {
     uint32_t pipe_need[spl_ctx::kPipeChunks] = {};
     std::atomic<int> pipe_state{0};
     std::atomic<int> slice_state{0};  // 0 not tried, 1 one vector product done, 2 decided (slice_ptr set or not)
+    // stream kernel (persistent, TMA-pipelined; regular rows): tiles of stream_rows consecutive rows,
+    // stream_cap = shared-memory stage capacity in entries (0: a tile would not fit, kernel not usable),
+    // stream_xhi[t] = 1 + the largest column index of tile t (0 for an empty tile): the producer
+    // prefetches the leading edge of x into L2 from it
+    uint32_t *stream_xhi = nullptr;
+    uint32_t stream_tiles = 0, stream_rows = 0, stream_cap = 0;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

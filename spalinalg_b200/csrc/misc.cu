@@ -200,6 +200,7 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->slice_ptr);
     dfree(ctx, m->slice_ind);
     dfree(ctx, m->slice_val);
+    dfree(ctx, m->stream_xhi);
     delete m;
 }
 

@@ -22,7 +22,9 @@
 // they put entries 4 apart on neighbouring lanes and triple the L1 wavefronts of the x gathers
 // ("SpMV").
 // Algorithmic bytes per launch: nnz*(4+V) + (ncols+nrows)*V  (SURVEY.md 8d); HBM-bound.
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "kernels.cuh"
 #include "radix_sort.cuh"
@@ -455,6 +457,222 @@ void spmv_merge(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
     check_launch(ctx, "spmv_merge_fixup");
 }
 
+// ------------------------------------------------------------------ stream kernel
+// Persistent CTAs, the matrix stream decoupled from the threads that use it.  The vector kernel
+// hides DRAM latency with resident threads: every lane's chain ptr -> col/val -> x is three
+// dependent round trips, and an 80 MB matrix (config 1) is over before the pipeline is full.  Here a
+// tile is R = 256 / LPR consecutive rows; its col/val entries are one contiguous slice of the CSR
+// arrays, so ONE producer thread per CTA fetches it with two TMA bulk copies (cp.async.bulk,
+// completion on an mbarrier) into a ring of S shared-memory stages, S - 1 tiles ahead of the eight
+// consumer warps.  Bytes in flight per SM = CTAs x (S - 1) x stage bytes (100-140 KB), whatever the
+// occupancy, at zero registers.  The consumers read indices and values from shared memory, gather x
+// (LPR lanes per row, U gathers in flight per lane), reduce, and free the stage (empty barrier).
+//   * x: the producer also prefetches the leading edge of x into L2 (cp.async.bulk.prefetch.L2):
+//     for banded / stencil matrices the only x bytes a tile touches first are (xhi[t-1], xhi[t]],
+//     which the plan recorded per tile; the consumers' gathers then hit L2 instead of waiting on HBM.
+//   * programmatic dependent launch: the kernel is launched with
+//     cudaLaunchAttributeProgrammaticStreamSerialization; producers start their matrix prefetch at
+//     once (the matrix is immutable), consumers wait (griddepcontrol.wait) before the first x gather
+//     and y store, then release the next launch (griddepcontrol.launch_dependents).  Back-to-back
+//     products (solver iterations) overlap one product's ramp with the tail of the one before.
+//   * with one lane per row the row sum runs in ascending column order: bit-identical to the
+//     reference's `&A * &X` (src/csr/ops/mul.rs:25-40), like the sliced kernel.
+constexpr int ST_CONSUMERS = 256;
+constexpr int ST_THREADS = ST_CONSUMERS + 32;
+constexpr uint32_t kStreamXEdgeMax = 1u << 15;     // longest leading edge of x one tile prefetches (elements)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// per tile: 1 + largest column (rows are column-sorted: the last entry of a row), and the largest tile
+__global__ void stream_plan_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, uint32_t nrows,
+                                   uint32_t rows_per_tile, uint32_t *__restrict__ xhi, uint32_t *__restrict__ max_tile) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const uint32_t lo = ptr[r], hi = ptr[r + 1];
+    if (hi > lo) atomicMax(xhi + (uint32_t)(r / rows_per_tile), ind[hi - 1] + 1u);
+    if (r % rows_per_tile == 0) {
+        const uint64_t e = r + rows_per_tile < nrows ? r + rows_per_tile : nrows;
+        atomicMax(max_tile, ptr[e] - lo);
+    }
+}
+
+template <typename T, int LPR, int U, typename XG>
+__global__ void __launch_bounds__(ST_THREADS, 3)
+spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
+                   const T *__restrict__ val, const XG xg, T *__restrict__ y, uint32_t ntiles, uint32_t cap,
+                   uint32_t stages, const uint32_t *__restrict__ xhi, const T *__restrict__ x_edge, uint32_t ncols) {
+    constexpr uint32_t R = ST_CONSUMERS / LPR;
+    extern __shared__ __align__(128) unsigned char st_raw[];
+    uint32_t *s_ind = reinterpret_cast<uint32_t *>(st_raw);                            // [stages][cap]
+    T *s_val = reinterpret_cast<T *>(st_raw + (size_t)stages * cap * sizeof(uint32_t));   // [stages][cap]
+    uint64_t *full = reinterpret_cast<uint64_t *>(st_raw + (size_t)stages * cap * (sizeof(uint32_t) + sizeof(T)));
+    uint64_t *empty = full + stages;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, ST_CONSUMERS / 32);
+        }
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= ST_CONSUMERS) {
+        // ---- producer: one thread, S - 1 tiles ahead of the consumers ----
+        if (threadIdx.x != ST_CONSUMERS) return;
+        uint32_t t = blockIdx.x, s = 0, phase = 0;
+        if (t >= ntiles) return;
+        auto bounds = [&](uint32_t tile, uint32_t &lo, uint32_t &hi, uint32_t &x0, uint32_t &x1) {
+            const uint64_t r0 = (uint64_t)tile * R, r1 = r0 + R < nrows ? r0 + R : nrows;
+            lo = __ldg(ptr + r0);
+            hi = __ldg(ptr + r1);
+            x0 = tile ? __ldg(xhi + tile - 1) : 0u;
+            x1 = __ldg(xhi + tile);
+        };
+        uint32_t lo, hi, x0, x1;
+        bounds(t, lo, hi, x0, x1);
+        for (uint32_t i = 0;; ++i) {
+            const uint32_t tn = t + gridDim.x;
+            uint32_t nlo = 0, nhi = 0, nx0 = 0, nx1 = 0;
+            if (tn < ntiles) bounds(tn, nlo, nhi, nx0, nx1);       // next tile's bounds: in flight during the wait
+            if (i >= stages) mbar_wait(empty + s, phase ^ 1u);       // the consumers are done with this stage
+            const uint32_t za = lo & ~3u, zb = (hi + 3u) & ~3u;      // 16-byte aligned superset; arrays carry slack
+            const uint32_t cnt = zb - za;
+            mbar_expect_tx(full + s, cnt * (uint32_t)(sizeof(uint32_t) + sizeof(T)));
+            if (cnt) {
+                tma_bulk_g2s(s_ind + (size_t)s * cap, ind + za, cnt * (uint32_t)sizeof(uint32_t), full + s);
+                tma_bulk_g2s(s_val + (size_t)s * cap, val + za, cnt * (uint32_t)sizeof(T), full + s);
+            }
+            if (x_edge && x1 > x0 && x1 - x0 <= kStreamXEdgeMax) {   // leading edge of x -> L2
+                constexpr uint32_t per16 = 16 / sizeof(T);          // whole 16-byte units, inside x[0, ncols)
+                const uint32_t a = x0 & ~(per16 - 1u);
+                uint32_t b = (x1 + per16 - 1u) & ~(per16 - 1u);
+                if (b > ncols) b = ncols & ~(per16 - 1u);
+                if (b > a) l2_prefetch_bulk(x_edge + a, (b - a) * (uint32_t)sizeof(T));
+            }
+            if (tn >= ntiles) break;
+            t = tn; lo = nlo; hi = nhi; x0 = nx0; x1 = nx1;
+            if (++s == stages) { s = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    // ---- consumers: 256 threads, LPR lanes per row ----
+    const uint32_t rl = threadIdx.x / LPR, sub = threadIdx.x % LPR;
+    uint32_t t = blockIdx.x, s = 0, phase = 0;
+    uint32_t lo = 0, p0 = 0, p1 = 0;
+    auto rows = [&](uint32_t tile, uint32_t &tlo, uint32_t &a, uint32_t &b) {
+        const uint64_t r0 = (uint64_t)tile * R, r = r0 + rl;
+        tlo = __ldg(ptr + r0);
+        a = b = 0;
+        if (r < nrows) { a = __ldg(ptr + r); b = __ldg(ptr + r + 1); }
+    };
+    if (t < ntiles) rows(t, lo, p0, p1);
+    griddep_wait();                    // x (and y's previous readers) belong to the launch before this one
+    if (threadIdx.x == 0) griddep_launch();
+    while (t < ntiles) {
+        const uint32_t tn = t + gridDim.x;
+        uint32_t nlo = 0, np0 = 0, np1 = 0;
+        if (tn < ntiles) rows(tn, nlo, np0, np1);
+        mbar_wait(full + s, phase);
+        const uint32_t za = lo & ~3u;
+        const uint32_t *ci = s_ind + (size_t)s * cap;
+        const T *cv = s_val + (size_t)s * cap;
+        const uint32_t e = p1 - za;
+        T acc = (T)0;
+        for (uint32_t j = p0 - za + sub; j < e; j += U * LPR) {
+            uint32_t c[U];
+            T xv[U], v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = j + u * LPR < e ? ci[j + u * LPR] : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = c[u] != 0xffffffffu ? xg(c[u]) : (T)0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = j + u * LPR < e ? cv[j + u * LPR] : (T)0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += j + u * LPR < e ? v[u] * xv[u] : (T)0;      // 0, never 0 * inf
+        }
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(empty + s);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const uint64_t r = (uint64_t)t * R + rl;
+        if (sub == 0 && r < nrows) y[r] = acc;
+        t = tn; lo = nlo; p0 = np0; p1 = np1;
+        if (++s == stages) { s = 0; phase ^= 1u; }
+    }
+}
+
+// stages and CTAs per SM for a stage of `stage_bytes`: as many bytes in flight as fit (~200 KB per SM)
+struct StreamShape { uint32_t stages, ctas; size_t smem; };
+inline StreamShape stream_shape(size_t stage_bytes) {
+    // SPL_STREAM_STAGES / SPL_STREAM_CTAS: measurement knobs (read per call: a sweep changes them in-process)
+    const char *es = std::getenv("SPL_STREAM_STAGES"), *ec = std::getenv("SPL_STREAM_CTAS");
+    const int want_stages = es ? std::atoi(es) : 0, want_ctas = ec ? std::atoi(ec) : 0;
+    const size_t budget = 220 * 1024;               // 227 KB per SM less 1 KB per CTA and the barriers
+    static const int order[][2] = {{3, 4}, {4, 3}, {3, 3}, {2, 4}, {2, 3}, {1, 4}, {1, 3}, {1, 2}};   // {CTAs, stages}
+    for (const auto &o : order) {
+        const uint32_t ctas = want_ctas ? (uint32_t)want_ctas : (uint32_t)o[0];
+        const uint32_t stages = want_stages ? (uint32_t)want_stages : (uint32_t)o[1];
+        const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+        if (ctas * (smem + 1024) <= budget) return {stages, ctas, smem};
+    }
+    return {0, 0, 0};
+}
+
+template <typename T, int LPR, int U, typename XG>
+void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
+    const StreamShape sh = stream_shape((size_t)a->stream_cap * (sizeof(uint32_t) + sizeof(T)));
+    SPL_REQUIRE(sh.stages >= 2, SPL_ERR_UNSUPPORTED, "stream SpMV: a tile of rows does not fit in shared memory");
+    auto k = spmv_stream_kernel<T, LPR, U, XG>;
+    SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+    cudaLaunchConfig_t cfg{};
+    int resident = 0;                                  // registers may allow fewer CTAs than shared memory does
+    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k, ST_THREADS, sh.smem));
+    SPL_REQUIRE(resident >= 1, SPL_ERR_CUDA, "stream SpMV: no CTA fits on an SM");
+    cfg.gridDim = dim3(std::min<uint32_t>(a->stream_tiles, (uint32_t)ctx->num_sms * std::min<uint32_t>(sh.ctas, (uint32_t)resident)));
+    cfg.blockDim = dim3(ST_THREADS);
+    cfg.dynamicSmemBytes = sh.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool no_pdl = std::getenv("SPL_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->pdl_prev && !no_pdl) ? 1 : 0;     // only behind another stream-kernel product
+    SPL_CUDA(cudaLaunchKernelEx(&cfg, k, a->nrows, (const uint32_t *)a->ptr, (const uint32_t *)a->ind,
+                                static_cast<const T *>(a->val), xg, y, a->stream_tiles, a->stream_cap, sh.stages,
+                                (const uint32_t *)a->stream_xhi,
+                                ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
+    check_launch(ctx, "spmv_stream");
+    ctx->pdl_chain = true;
+}
+
+template <typename T, int LPR, typename XG>
+void spmv_stream_u(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
+    // entries per lane and trip: one trip for the short rows of stencils and bands
+    const double per_lane = a->nrows ? (double)a->nnz / a->nrows / LPR : 0.0;
+    if (per_lane > 4.0) launch_stream<T, LPR, 8>(ctx, a, xg, y, x_edge);
+    else launch_stream<T, LPR, 4>(ctx, a, xg, y, x_edge);
+}
+
+template <typename T, typename XG>
+void spmv_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
+    switch (a->plan_lanes) {
+        case 1: spmv_stream_u<T, 1>(ctx, a, xg, y, x_edge); break;
+        case 2: spmv_stream_u<T, 2>(ctx, a, xg, y, x_edge); break;
+        case 4: spmv_stream_u<T, 4>(ctx, a, xg, y, x_edge); break;
+        case 8: spmv_stream_u<T, 8>(ctx, a, xg, y, x_edge); break;
+        case 16: spmv_stream_u<T, 16>(ctx, a, xg, y, x_edge); break;
+        default: spmv_stream_u<T, 32>(ctx, a, xg, y, x_edge); break;
+    }
+}
+
 // ------------------------------------------------------------------ nnz-split kernel
 // Merge-path's balance at warp granularity, without a block barrier: every warp owns a fixed chunk
 // of K = 32*IPL consecutive stored entries, whatever the rows look like (a 700 000-entry row of a
@@ -486,37 +704,56 @@ __global__ void split_partition_kernel(const uint32_t *__restrict__ ptr, uint32_
 constexpr uint32_t kHotFlag = 0x80000000u;   // column index = slot in the hot-column cache
 constexpr uint32_t kHotBytes = 128 * 1024;    // shared memory given to the hot x values per CTA
 
+// The registers of one chunk on one lane: IPL (index, value) pairs and the chunk's row range.
+template <typename T, int IPL>
+struct ChunkRegs {
+    uint32_t c[IPL];
+    T v[IPL];
+    uint32_t R0, R1;
+};
+
+// Issues the loads of chunk w (coalesced, streaming) without using them: the hot kernel calls this one
+// chunk ahead, so the col/val stream of the next chunk is in flight while this one's gathers are.
+template <typename T, int IPL>
+__device__ __forceinline__ void
+split_load(ChunkRegs<T, IPL> &q, uint32_t w, uint32_t nrows, uint32_t nnz, uint32_t nchunks,
+           const uint32_t *__restrict__ ind, const T *__restrict__ val, const uint32_t *__restrict__ chunk_row) {
+    constexpr uint32_t K = 32 * IPL;
+    const unsigned lane = lane_id();
+    const uint32_t base = w * K;
+    const uint32_t count = nnz - base < K ? nnz - base : K;
+    q.R0 = __ldg(chunk_row + w);
+    q.R1 = w + 1 == nchunks ? nrows : __ldg(chunk_row + w + 1);
+#pragma unroll
+    for (int u = 0; u < IPL; ++u) {
+        const uint32_t j = lane + 32 * u;
+        const uint32_t p = base + (j < count ? j : 0u);     // entry `base` exists: safe dummy
+        q.c[u] = ld_stream(ind + p);
+        q.v[u] = ld_stream(val + p);
+    }
+}
+
 // One warp, one chunk.  HOT: indices carrying kHotFlag name a slot of the CTA's shared-memory copy of
 // the hottest x values instead of a column.
 template <typename T, int IPL, bool HOT>
 __device__ __forceinline__ void
-split_chunk(uint32_t w, uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
-            const uint32_t *__restrict__ ind, const T *__restrict__ val, const T *__restrict__ x,
-            T *__restrict__ y, const uint32_t *__restrict__ chunk_row, uint32_t *__restrict__ carry_row,
+split_chunk(const ChunkRegs<T, IPL> &q, uint32_t w, uint32_t nrows, uint32_t nnz, uint32_t nchunks,
+            const uint32_t *__restrict__ ptr, const T *__restrict__ x,
+            T *__restrict__ y, uint32_t *__restrict__ carry_row,
             T *__restrict__ carry_val, T *sp, const T *s_hot) {
     constexpr uint32_t K = 32 * IPL;
     const unsigned lane = lane_id();
     const uint32_t base = w * K;
     const uint32_t count = nnz - base < K ? nnz - base : K;
     const bool last = w + 1 == nchunks;
-    const uint32_t R0 = __ldg(chunk_row + w);
-    const uint32_t R1 = last ? nrows : __ldg(chunk_row + w + 1);
+    const uint32_t R0 = q.R0, R1 = q.R1;
 
-    uint32_t c[IPL];
-    T v[IPL];
-#pragma unroll
-    for (int u = 0; u < IPL; ++u) {
-        const uint32_t j = lane + 32 * u;
-        const uint32_t p = base + (j < count ? j : 0u);     // entry `base` exists: safe dummy
-        c[u] = ld_stream(ind + p);
-        v[u] = ld_stream(val + p);
-    }
     T prod[IPL];
 #pragma unroll
     for (int u = 0; u < IPL; ++u)
-        prod[u] = (HOT && (c[u] & kHotFlag)) ? s_hot[c[u] & ~kHotFlag] : __ldg(x + c[u]);
+        prod[u] = (HOT && (q.c[u] & kHotFlag)) ? s_hot[q.c[u] & ~kHotFlag] : __ldg(x + q.c[u]);
 #pragma unroll
-    for (int u = 0; u < IPL; ++u) prod[u] = lane + 32 * u < count ? v[u] * prod[u] : (T)0;
+    for (int u = 0; u < IPL; ++u) prod[u] = lane + 32 * u < count ? q.v[u] * prod[u] : (T)0;
 
     if (R0 == R1) {          // the whole chunk lies inside the open row
         T s = prod[0];
@@ -584,16 +821,18 @@ spmv_split_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t
     __shared__ T s_prod[SP_WARPS][32 * IPL];
     const uint32_t w = blockIdx.x * SP_WARPS + (threadIdx.x >> 5);
     if (w >= nchunks) return;
-    split_chunk<T, IPL, false>(w, nrows, nnz, nchunks, ptr, ind, val, x, y, chunk_row, carry_row, carry_val,
+    ChunkRegs<T, IPL> q;
+    split_load<T, IPL>(q, w, nrows, nnz, nchunks, ind, val, chunk_row);
+    split_chunk<T, IPL, false>(q, w, nrows, nnz, nchunks, ptr, x, y, carry_row, carry_val,
                                s_prod[threadIdx.x >> 5], nullptr);
 }
 
-// Hot-column variant: one persistent CTA of 1 024 threads per SM keeps the x values of the `nhot`
-// hottest columns in shared memory (loaded once per launch through the hot-column list) and its 32
-// warps walk the chunks with a grid stride.  Gathers of hot columns never leave the SM.
-constexpr int SPH_THREADS = 1024;
-template <typename T, int IPL>
-__global__ void __launch_bounds__(SPH_THREADS, 1)
+// Hot-column variant: one persistent CTA per SM keeps the x values of the `nhot` hottest columns in
+// shared memory (loaded once per launch through the hot-column list) and its warps walk the chunks
+// with a grid stride, the col/val stream of the next chunk loaded (registers) while the gathers of
+// the current one are in flight.  Gathers of hot columns never leave the SM.
+template <typename T, int IPL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 spmv_split_hot_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint32_t *__restrict__ ptr,
                       const uint32_t *__restrict__ ind_hot, const T *__restrict__ val,
                       const T *__restrict__ x, T *__restrict__ y, const uint32_t *__restrict__ chunk_row,
@@ -602,13 +841,21 @@ spmv_split_hot_kernel(uint32_t nrows, uint32_t nnz, uint32_t nchunks, const uint
     extern __shared__ __align__(16) unsigned char sph_raw[];
     T *s_hot = reinterpret_cast<T *>(sph_raw);
     T *s_prod = s_hot + nhot;
-    for (uint32_t j = threadIdx.x; j < nhot; j += SPH_THREADS) s_hot[j] = __ldg(x + __ldg(hot_cols + j));
+    const uint32_t warp = threadIdx.x >> 5, warps = THREADS / 32;
+    uint32_t w = blockIdx.x * warps + warp;
+    const uint32_t stride = gridDim.x * warps;
+    ChunkRegs<T, IPL> cur, nxt;
+    if (w < nchunks) split_load<T, IPL>(cur, w, nrows, nnz, nchunks, ind_hot, val, chunk_row);   // under the table fill
+    for (uint32_t j = threadIdx.x; j < nhot; j += THREADS) s_hot[j] = __ldg(x + __ldg(hot_cols + j));
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, warps = SPH_THREADS / 32;
-    for (uint32_t w = blockIdx.x * warps + warp; w < nchunks; w += gridDim.x * warps) {
-        split_chunk<T, IPL, true>(w, nrows, nnz, nchunks, ptr, ind_hot, val, x, y, chunk_row, carry_row, carry_val,
+    while (w < nchunks) {
+        const uint32_t wn = w + stride;
+        if (wn < nchunks) split_load<T, IPL>(nxt, wn, nrows, nnz, nchunks, ind_hot, val, chunk_row);
+        split_chunk<T, IPL, true>(cur, w, nrows, nnz, nchunks, ptr, x, y, carry_row, carry_val,
                                   s_prod + warp * (32 * IPL), s_hot);
         __syncwarp();          // the product buffer is reused by the warp's next chunk
+        cur = nxt;
+        w = wn;
     }
 }
 
@@ -690,12 +937,18 @@ void spmv_split(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
     SPL_CUDA(cudaMemsetAsync(n_long, 0, sizeof(uint32_t), ctx->stream));
     if (a->hot_state.load(std::memory_order_acquire) == 2 && a->ind_rank) {   // hot columns: persistent CTAs, hottest x values in shared memory
         const uint32_t nhot = a->hot_count;
-        const size_t smem = (size_t)nhot * sizeof(T) + (size_t)(SPH_THREADS / 32) * 32 * IPL * sizeof(T);
-        auto k = spmv_split_hot_kernel<T, IPL>;
-        SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<ctx->num_sms, SPH_THREADS, smem, ctx->stream>>>(
-            a->nrows, a->nnz, nchunks, a->ptr, a->ind_rank, static_cast<const T *>(a->val), x, y,
-            a->split_rows, carry_row, carry_val, a->col_order, nhot);
+        const char *te = std::getenv("SPL_HOT_THREADS");
+        const int threads = te ? std::atoi(te) : 1024;
+        const size_t smem = (size_t)nhot * sizeof(T) + (size_t)(threads / 32) * 32 * IPL * sizeof(T);
+        auto go = [&](auto k) {
+            SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<ctx->num_sms, threads, smem, ctx->stream>>>(
+                a->nrows, a->nnz, nchunks, a->ptr, a->ind_rank, static_cast<const T *>(a->val), x, y,
+                a->split_rows, carry_row, carry_val, a->col_order, nhot);
+        };
+        if (threads == 512) go(spmv_split_hot_kernel<T, IPL, 512>);
+        else if (threads == 768) go(spmv_split_hot_kernel<T, IPL, 768>);
+        else go(spmv_split_hot_kernel<T, IPL, 1024>);
         check_launch(ctx, "spmv_split_hot");
     } else {
         spmv_split_kernel<T, IPL><<<div_up(nchunks, SP_WARPS), SP_THREADS, 0, ctx->stream>>>(
@@ -762,7 +1015,9 @@ __global__ void renumber_kernel(const uint32_t *__restrict__ ind, uint32_t nnz, 
 }
 void plan_hot_columns(spl_ctx *ctx, spl_mat *a) {
     const uint32_t ncols = a->ncols, nnz = a->nnz;
-    const uint32_t kHotColumns = kHotBytes / (uint32_t)a->vsize();      // 32 768 (f32) / 16 384 (f64)
+    const char *hot_kb = std::getenv("SPL_HOT_KB");        // table size (measurement knob); default 128 KB
+    const uint32_t hot_bytes = hot_kb ? (uint32_t)std::atoi(hot_kb) * 1024u : kHotBytes;
+    const uint32_t kHotColumns = hot_bytes / (uint32_t)a->vsize();      // 32 768 (f32) / 16 384 (f64) by default
     if (ncols < 4 * kHotColumns || nnz == 0) return;       // small x: nothing to gain
     Tmp<uint32_t> counts(ctx, ncols);
     SPL_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)ncols, ctx->stream));
@@ -835,6 +1090,22 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     if (mean > 12.0) lanes = 4;
     while (lanes < 32 && lanes * 10 < mean) lanes *= 2;
     a->plan_lanes = lanes;
+    // stream kernel: tiles of 256 / lanes rows; the largest tile sizes the shared-memory stages
+    if (a->nnz) {
+        const uint32_t rpt = ST_CONSUMERS / (uint32_t)lanes;
+        a->stream_rows = rpt;
+        a->stream_tiles = div_up(a->nrows, rpt);
+        a->stream_xhi = dalloc<uint32_t>(ctx, a->stream_tiles);
+        SPL_CUDA(cudaMemsetAsync(a->stream_xhi, 0, sizeof(uint32_t) * (size_t)a->stream_tiles, ctx->stream));
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 1, 0, sizeof(uint32_t), ctx->stream));
+        stream_plan_kernel<<<div_up(a->nrows, 256), 256, 0, ctx->stream>>>(a->ptr, a->ind, a->nrows, rpt, a->stream_xhi,
+                                                                          ctx->d_scratch + 1);
+        check_launch(ctx, "stream_plan");
+        uint32_t max_tile = 0;
+        read_back(ctx, ctx->d_scratch + 1, &max_tile, 1);
+        const uint32_t cap = (max_tile + 6u + 3u) & ~3u;          // the 16-byte aligned superset of the largest slice
+        a->stream_cap = stream_shape((size_t)cap * (4 + a->vsize())).stages >= 2 ? cap : 0u;
+    }
     // merge-path tile starts (matrix-only data, cached)
     const int ipt = a->dtype == SPL_F64 ? merge_ipt<double>() : merge_ipt<float>();
     const uint32_t items = MG_THREADS * ipt;
@@ -868,6 +1139,26 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         spmv_plan(ctx, const_cast<spl_mat *>(a));
         kernel = a->plan_kernel;
         lanes = 0;
+        // SPL_SPMV_KERNEL=vector|stream|split|merge overrides the planner (measurement / triage)
+        const char *force = std::getenv("SPL_SPMV_KERNEL");
+        if (force) {
+            if (!std::strcmp(force, "vector")) kernel = SPL_SPMV_VECTOR;
+            else if (!std::strcmp(force, "stream") && a->stream_cap) kernel = SPL_SPMV_STREAM;
+            else if (!std::strcmp(force, "split")) kernel = SPL_SPMV_SPLIT;
+            else if (!std::strcmp(force, "merge")) kernel = SPL_SPMV_MERGE;
+        }
+    }
+    if (kernel == SPL_SPMV_STREAM) {
+        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        SPL_REQUIRE(a->nnz == 0 || a->stream_cap, SPL_ERR_UNSUPPORTED,
+                    "stream SpMV: a tile of rows does not fit in shared memory (skewed rows: use SPLIT)");
+        if (a->nnz == 0) {
+            SPL_CUDA(cudaMemsetAsync(y, 0, a->vsize() * (size_t)a->nrows, ctx->stream));
+            return;
+        }
+        if (a->dtype == SPL_F32) spmv_stream<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y, (const float *)x);
+        else spmv_stream<double>(ctx, a, XLocal<double>{(const double *)x}, (double *)y, (const double *)x);
+        return;
     }
     if (kernel == SPL_SPMV_VECTOR && lanes == 0) {
         spmv_plan(ctx, const_cast<spl_mat *>(a));

@@ -384,13 +384,15 @@ def test_spmv_random(dtype, n, m, density):
     assert np.all(got[np.diff(a[0].astype(np.int64)) == 0] == 0)          # empty rows give 0
     import torch
     xd = torch.from_numpy(x).cuda()
-    for kernel, lanes in [(1, l) for l in (1, 2, 4, 8, 16, 32)] + [(2, 0), (3, 0)]:   # vector x6, merge, split
+    for kernel, lanes in [(1, l) for l in (1, 2, 4, 8, 16, 32)] + [(2, 0), (3, 0), (5, 0)]:   # vector x6, merge, split, stream
         yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
         torch.cuda.synchronize()
         A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
         sp.default_context().sync()
         got = yd.cpu().numpy()
         assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny)), (kernel, lanes)
+        if kernel == 5 and A.spmv_choice()[1] == 1:       # stream kernel, one lane per row: ascending-column sum
+            assert got.tobytes() == want.tobytes(), "stream (1 lane/row): not bit-identical to the sequential row sum"
     # sliced kernel (slices of 32 rows, lane per row): ascending-column sum, i.e. the reference's
     # `&A * &X` bit for bit; the copy is refused when the padding would exceed 4x
     lens = np.diff(a[0].astype(np.int64))
@@ -472,6 +474,74 @@ def test_spmv_split_long_runs_and_edges(dtype):
         assert np.array_equal(np.isnan(got), np.isnan(w2)) and np.array_equal(np.isinf(got), np.isinf(w2)), kernel
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", ["laplace", "band9", "stencil27", "ragged"])
+def test_spmv_stream_kernel(dtype, shape):
+    """The persistent TMA-pipelined kernel (SPL_SPMV_STREAM): row counts that are not a multiple of the
+    tile, tiles without entries, more tiles than CTAs (the ring wraps many times), and a chain of
+    products y_t -> x_{t+1} launched back to back (programmatic dependent launch between them)
+    against the oracle's sequential iteration.  One lane per row => bit-identical to `&A * &X`."""
+    import torch
+    rng = np.random.default_rng(11)
+    if shape == "laplace":
+        g = 301
+        r, c, v = syn.laplacian_2d(g)
+        n = g * g
+        order = np.lexsort((c, r))
+        a = (syn.csr_from_sorted_triplets(n, r, c, v)[0], c[order], v[order])
+    elif shape == "band9":
+        n = 700_001
+        rows = np.repeat(np.arange(n), 9)
+        cols = rows + np.tile(np.arange(-4, 5), n)
+        ok = (cols >= 0) & (cols < n)
+        rows, cols = rows[ok].astype(np.uint64), cols[ok].astype(np.uint64)
+        a = (np.concatenate([[0], np.cumsum(np.bincount(rows.astype(np.int64), minlength=n))]).astype(np.uint64), cols,
+             rng.standard_normal(len(cols)))
+    elif shape == "stencil27":
+        m_ = 40
+        r, c, v = syn.stencil_27(m_)
+        n = m_ ** 3
+        a = syn.csr_from_sorted_triplets(n, r, c, v)
+    else:                                                       # empty tiles, rows of 0..40 entries, a ragged end
+        n = 70_003
+        lens = rng.integers(0, 41, n)
+        lens[1000:3000] = 0
+        lens[-5:] = 0
+        ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        ind = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens if l]).astype(np.uint64)
+        a = (ptr, ind, rng.standard_normal(len(ind)))
+    a = (a[0], a[1], (np.asarray(a[2]) * 0.05).astype(dtype))   # scaled: the chain below neither blows up nor dies
+    A = sp.CsrMatrix.new(n, n, *a)
+    lanes = A.spmv_choice()[1]
+    x0 = rng.standard_normal(n).astype(dtype)
+    rtol = SPMV_RTOL[np.dtype(dtype)]
+    xd = torch.from_numpy(x0).cuda()
+    yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+    torch.cuda.synchronize()
+    A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=5)
+    sp.default_context().sync()
+    want = orc.csr_spmv(n, *a, x0)
+    scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x0))
+    got = yd.cpu().numpy()
+    assert np.all(np.abs(got - want) <= rtol * np.maximum(scale, np.finfo(dtype).tiny))
+    if lanes == 1:
+        assert got.tobytes() == want.tobytes()
+    # chain: 12 products back to back on two buffers, no host synchronisation in between
+    bufs = [xd.clone(), torch.empty_like(xd)]
+    torch.cuda.synchronize()
+    for it in range(12):
+        A.spmv_device(bufs[it % 2].data_ptr(), bufs[(it + 1) % 2].data_ptr(), kernel=5)
+    sp.default_context().sync()
+    ref = x0
+    for it in range(12):
+        ref = orc.csr_spmv(n, *a, ref)
+    got = bufs[0].cpu().numpy()
+    if lanes == 1:
+        assert got.tobytes() == ref.tobytes(), "chained stream products differ from the sequential iteration"
+    else:
+        assert np.allclose(got, ref, rtol=1e3 * rtol, atol=1e3 * rtol * float(np.abs(ref).max() + 1e-30))
+
+
 # ------------------------------------------------------------------ BASELINE shapes, properties
 def test_c1_laplacian_assembly_and_spmv():
     """Config 1 at full size: shuffled COO -> CSR equals the generator's canonical CSR bit for
@@ -548,7 +618,7 @@ def test_tile_boundary_lengths(length):
     yw = orc.csr_spmv(n, *want, x)
     sc = orc.csr_spmv(n, want[0], want[1], np.abs(want[2]), np.abs(x))
     xd = torch.from_numpy(x).cuda()
-    for kernel, lanes in ((1, 1), (1, 4), (1, 32), (2, 0), (3, 0)):
+    for kernel, lanes in ((1, 1), (1, 4), (1, 32), (2, 0), (3, 0), (5, 0)):
         yd = torch.full((n,), 7.0, dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
         A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=kernel, lanes=lanes)
