@@ -105,11 +105,13 @@ struct spl_mat {
     std::atomic<int> pipe_state{0};
     std::atomic<int> slice_state{0};  // 0 not tried, 1 one vector product done, 2 decided (slice_ptr set or not)
     // stream kernel (persistent, TMA-pipelined; regular rows): tiles of stream_rows consecutive rows,
-    // stream_cap = shared-memory stage capacity in entries (0: a tile would not fit, kernel not usable),
-    // stream_xhi[t] = 1 + the largest column index of tile t (0 for an empty tile): the producer
-    // prefetches the leading edge of x into L2 from it
-    uint32_t *stream_xhi = nullptr;
-    uint32_t stream_tiles = 0, stream_rows = 0, stream_cap = 0;
+    // stream_cap = shared-memory stage capacity in entries (0: a window of stream_rows rows does not fit:
+    // kernel not usable).  For a grid of stream_grid CTAs: stream_cta_rows[b] = first row of CTA b (ranges
+    // balanced on rows + stored entries), stream_xhi[b * stream_max_tiles + k] = 1 + the largest column of
+    // CTA b's tile k (0 if it has no entry), stream_xlo0[b] = smallest column of its first tile: the
+    // producer prefetches the leading edge of x into L2 from them
+    uint32_t *stream_cta_rows = nullptr, *stream_xhi = nullptr, *stream_xlo0 = nullptr;
+    uint32_t stream_rows = 0, stream_cap = 0, stream_grid = 0, stream_max_tiles = 0;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }

@@ -201,6 +201,8 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->slice_ind);
     dfree(ctx, m->slice_val);
     dfree(ctx, m->stream_xhi);
+    dfree(ctx, m->stream_cta_rows);
+    dfree(ctx, m->stream_xlo0);
     delete m;
 }
 

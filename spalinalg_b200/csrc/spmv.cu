@@ -460,25 +460,26 @@ void spmv_merge(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
 // ------------------------------------------------------------------ stream kernel
 // Persistent CTAs, the matrix stream decoupled from the threads that use it.  The vector kernel
 // hides DRAM latency with resident threads: every lane's chain ptr -> col/val -> x is three
-// dependent round trips, and an 80 MB matrix (config 1) is over before the pipeline is full.  Here a
-// tile is R = 256 / LPR consecutive rows; its col/val entries are one contiguous slice of the CSR
-// arrays, so ONE producer thread per CTA fetches it with two TMA bulk copies (cp.async.bulk,
-// completion on an mbarrier) into a ring of S shared-memory stages, S - 1 tiles ahead of the eight
-// consumer warps.  Bytes in flight per SM = CTAs x (S - 1) x stage bytes (100-140 KB), whatever the
-// occupancy, at zero registers.  The consumers read indices and values from shared memory, gather x
-// (LPR lanes per row, U gathers in flight per lane), reduce, and free the stage (empty barrier).
+// dependent round trips, and an 80 MB matrix (config 1) is over before the pipeline is full.  Here
+// every CTA owns one contiguous range of rows (ranges balanced on rows + stored entries, so all CTAs
+// finish together) and walks it in tiles of R = CONS / LPR rows.  A tile's col/val entries are one
+// contiguous slice of the CSR arrays, so ONE producer thread per CTA fetches it with two TMA bulk
+// copies (cp.async.bulk, completion on an mbarrier) into a ring of S shared-memory stages, ahead of
+// the consumer warps: the bytes in flight cost no registers.  The consumers read indices and values
+// from shared memory, gather x (LPR lanes per row, U gathers in flight per lane), reduce, and free
+// the stage (empty barrier).
 //   * x: the producer also prefetches the leading edge of x into L2 (cp.async.bulk.prefetch.L2):
-//     for banded / stencil matrices the only x bytes a tile touches first are (xhi[t-1], xhi[t]],
-//     which the plan recorded per tile; the consumers' gathers then hit L2 instead of waiting on HBM.
-//   * programmatic dependent launch: the kernel is launched with
+//     for banded / stencil matrices the only x bytes a tile touches first are those above the
+//     largest column of the tiles before it, which the plan recorded per tile; the consumers'
+//     gathers then hit L2 (or L1: consecutive tiles of a CTA overlap) instead of waiting on HBM.
+//   * programmatic dependent launch: behind another product of this kind the kernel is launched with
 //     cudaLaunchAttributeProgrammaticStreamSerialization; producers start their matrix prefetch at
 //     once (the matrix is immutable), consumers wait (griddepcontrol.wait) before the first x gather
 //     and y store, then release the next launch (griddepcontrol.launch_dependents).  Back-to-back
 //     products (solver iterations) overlap one product's ramp with the tail of the one before.
-//   * with one lane per row the row sum runs in ascending column order: bit-identical to the
-//     reference's `&A * &X` (src/csr/ops/mul.rs:25-40), like the sliced kernel.
-constexpr int ST_CONSUMERS = 256;
-constexpr int ST_THREADS = ST_CONSUMERS + 32;
+//   * lanes take the entries of a row exactly as the vector kernel does, so the two kernels give the
+//     same bits; with one lane per row the row sum runs in ascending column order: bit-identical to
+//     the reference's `&A * &X` (src/csr/ops/mul.rs:25-40).
 constexpr uint32_t kStreamXEdgeMax = 1u << 15;     // longest leading edge of x one tile prefetches (elements)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -490,25 +491,65 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *gmem, uint32_t byte
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// per tile: 1 + largest column (rows are column-sorted: the last entry of a row), and the largest tile
-__global__ void stream_plan_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, uint32_t nrows,
-                                   uint32_t rows_per_tile, uint32_t *__restrict__ xhi, uint32_t *__restrict__ max_tile) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
-    const uint32_t lo = ptr[r], hi = ptr[r + 1];
-    if (hi > lo) atomicMax(xhi + (uint32_t)(r / rows_per_tile), ind[hi - 1] + 1u);
-    if (r % rows_per_tile == 0) {
-        const uint64_t e = r + rows_per_tile < nrows ? r + rows_per_tile : nrows;
-        atomicMax(max_tile, ptr[e] - lo);
+// largest number of stored entries in any window of `rows` consecutive rows (bounds every tile)
+__global__ void stream_window_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t rows,
+                                     uint32_t *__restrict__ max_window) {
+    uint32_t m = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = r + rows < nrows ? r + rows : nrows;
+        m = max(m, ptr[e] - ptr[r]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane_id() == 0 && m) atomicMax(max_window, m);
+}
+
+// cta_rows[b] = first row of CTA b: the smallest r with ptr[r] + r >= b * (nnz + nrows) / grid
+__global__ void stream_partition_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t nnz, uint32_t grid,
+                                        uint32_t rows_per_tile, uint32_t *__restrict__ cta_rows,
+                                        uint32_t *__restrict__ max_tiles) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid) return;
+    auto first_row = [&](uint32_t q) -> uint32_t {
+        if (q == 0) return 0u;
+        if (q >= grid) return nrows;
+        const uint64_t target = ((uint64_t)nnz + nrows) * q / grid;
+        uint32_t lo = 0, hi = nrows;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if ((uint64_t)__ldg(ptr + mid) + mid < target) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    const uint32_t r0 = first_row(b);
+    cta_rows[b] = r0;
+    if (b < grid) atomicMax(max_tiles, (first_row(b + 1) - r0 + rows_per_tile - 1) / rows_per_tile);
+}
+
+// per tile: 1 + its largest column (rows are column-sorted: the last entry of a row); per CTA: the
+// smallest column of its first tile
+__global__ void stream_edges_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
+                                    const uint32_t *__restrict__ cta_rows, uint32_t rows_per_tile, uint32_t max_tiles,
+                                    uint32_t *__restrict__ xhi, uint32_t *__restrict__ xlo0) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t rs = cta_rows[b], re = cta_rows[b + 1];
+    for (uint32_t r = rs + threadIdx.x; r < re; r += blockDim.x) {
+        const uint32_t lo = ptr[r], hi = ptr[r + 1];
+        if (hi == lo) continue;
+        const uint32_t k = (r - rs) / rows_per_tile;
+        atomicMax(xhi + (size_t)b * max_tiles + k, ind[hi - 1] + 1u);
+        if (k == 0) atomicMin(xlo0 + b, ind[lo]);
     }
 }
 
-template <typename T, int LPR, int U, typename XG>
-__global__ void __launch_bounds__(ST_THREADS, 3)
+template <typename T, int LPR, int U, int CONS, typename XG>
+__global__ void __launch_bounds__(CONS + 32, 1024 / CONS)
 spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
-                   const T *__restrict__ val, const XG xg, T *__restrict__ y, uint32_t ntiles, uint32_t cap,
-                   uint32_t stages, const uint32_t *__restrict__ xhi, const T *__restrict__ x_edge, uint32_t ncols) {
-    constexpr uint32_t R = ST_CONSUMERS / LPR;
+                   const T *__restrict__ val, const XG xg, T *__restrict__ y, const uint32_t *__restrict__ cta_rows,
+                   const uint32_t *__restrict__ xhi, const uint32_t *__restrict__ xlo0, uint32_t max_tiles,
+                   uint32_t cap, uint32_t stages, const T *__restrict__ x_edge, uint32_t ncols) {
+    constexpr uint32_t R = CONS / LPR;
     extern __shared__ __align__(128) unsigned char st_raw[];
     uint32_t *s_ind = reinterpret_cast<uint32_t *>(st_raw);                            // [stages][cap]
     T *s_val = reinterpret_cast<T *>(st_raw + (size_t)stages * cap * sizeof(uint32_t));   // [stages][cap]
@@ -517,68 +558,67 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < stages; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, ST_CONSUMERS / 32);
+            mbar_init(empty + s, CONS / 32);
         }
     }
     __syncthreads();
+    const uint32_t rs = __ldg(cta_rows + blockIdx.x), re = __ldg(cta_rows + blockIdx.x + 1);
+    const uint32_t ntiles = (re - rs + R - 1) / R;
 
-    if (threadIdx.x >= ST_CONSUMERS) {
-        // ---- producer: one thread, S - 1 tiles ahead of the consumers ----
-        if (threadIdx.x != ST_CONSUMERS) return;
-        uint32_t t = blockIdx.x, s = 0, phase = 0;
-        if (t >= ntiles) return;
-        auto bounds = [&](uint32_t tile, uint32_t &lo, uint32_t &hi, uint32_t &x0, uint32_t &x1) {
-            const uint64_t r0 = (uint64_t)tile * R, r1 = r0 + R < nrows ? r0 + R : nrows;
-            lo = __ldg(ptr + r0);
-            hi = __ldg(ptr + r1);
-            x0 = tile ? __ldg(xhi + tile - 1) : 0u;
-            x1 = __ldg(xhi + tile);
-        };
-        uint32_t lo, hi, x0, x1;
-        bounds(t, lo, hi, x0, x1);
-        for (uint32_t i = 0;; ++i) {
-            const uint32_t tn = t + gridDim.x;
-            uint32_t nlo = 0, nhi = 0, nx0 = 0, nx1 = 0;
-            if (tn < ntiles) bounds(tn, nlo, nhi, nx0, nx1);       // next tile's bounds: in flight during the wait
-            if (i >= stages) mbar_wait(empty + s, phase ^ 1u);       // the consumers are done with this stage
-            const uint32_t za = lo & ~3u, zb = (hi + 3u) & ~3u;      // 16-byte aligned superset; arrays carry slack
+    if (threadIdx.x >= CONS) {
+        // ---- producer: one thread, up to S tiles ahead of the consumers ----
+        if (threadIdx.x != CONS || ntiles == 0) return;
+        const uint32_t *hi_edge = xhi + (size_t)blockIdx.x * max_tiles;
+        uint32_t s = 0, phase = 0;
+        uint32_t edge = __ldg(xlo0 + blockIdx.x);                 // x below this is somebody else's first touch
+        uint32_t lo = __ldg(ptr + rs), hi = __ldg(ptr + (rs + R < re ? rs + R : re)), x1 = __ldg(hi_edge);
+        for (uint32_t k = 0; k < ntiles; ++k) {
+            uint32_t nhi = 0, nx1 = 0;
+            if (k + 1 < ntiles) {                                  // next tile's bounds: in flight during the wait
+                const uint32_t r1 = rs + (k + 2) * R;
+                nhi = __ldg(ptr + (r1 < re ? r1 : re));
+                nx1 = __ldg(hi_edge + k + 1);
+            }
+            if (k >= stages) mbar_wait(empty + s, phase ^ 1u);     // the consumers are done with this stage
+            const uint32_t za = lo & ~3u, zb = (hi + 3u) & ~3u;    // 16-byte aligned superset; the arrays carry slack
             const uint32_t cnt = zb - za;
             mbar_expect_tx(full + s, cnt * (uint32_t)(sizeof(uint32_t) + sizeof(T)));
             if (cnt) {
                 tma_bulk_g2s(s_ind + (size_t)s * cap, ind + za, cnt * (uint32_t)sizeof(uint32_t), full + s);
                 tma_bulk_g2s(s_val + (size_t)s * cap, val + za, cnt * (uint32_t)sizeof(T), full + s);
             }
-            if (x_edge && x1 > x0 && x1 - x0 <= kStreamXEdgeMax) {   // leading edge of x -> L2
-                constexpr uint32_t per16 = 16 / sizeof(T);          // whole 16-byte units, inside x[0, ncols)
-                const uint32_t a = x0 & ~(per16 - 1u);
-                uint32_t b = (x1 + per16 - 1u) & ~(per16 - 1u);
-                if (b > ncols) b = ncols & ~(per16 - 1u);
-                if (b > a) l2_prefetch_bulk(x_edge + a, (b - a) * (uint32_t)sizeof(T));
+            if (x_edge && x1 > edge) {                             // leading edge of x -> L2
+                if (x1 - edge <= kStreamXEdgeMax) {
+                    constexpr uint32_t per16 = 16 / sizeof(T);     // whole 16-byte units, inside x[0, ncols)
+                    const uint32_t a = edge & ~(per16 - 1u);
+                    uint32_t b = (x1 + per16 - 1u) & ~(per16 - 1u);
+                    if (b > ncols) b = ncols & ~(per16 - 1u);
+                    if (b > a) l2_prefetch_bulk(x_edge + a, (b - a) * (uint32_t)sizeof(T));
+                }
+                edge = x1;
             }
-            if (tn >= ntiles) break;
-            t = tn; lo = nlo; hi = nhi; x0 = nx0; x1 = nx1;
+            lo = hi; hi = nhi; x1 = nx1;
             if (++s == stages) { s = 0; phase ^= 1u; }
         }
         return;
     }
 
-    // ---- consumers: 256 threads, LPR lanes per row ----
+    // ---- consumers: CONS threads, LPR lanes per row ----
     const uint32_t rl = threadIdx.x / LPR, sub = threadIdx.x % LPR;
-    uint32_t t = blockIdx.x, s = 0, phase = 0;
+    uint32_t s = 0, phase = 0;
     uint32_t lo = 0, p0 = 0, p1 = 0;
-    auto rows = [&](uint32_t tile, uint32_t &tlo, uint32_t &a, uint32_t &b) {
-        const uint64_t r0 = (uint64_t)tile * R, r = r0 + rl;
+    auto rows = [&](uint32_t k, uint32_t &tlo, uint32_t &a, uint32_t &b) {
+        const uint32_t r0 = rs + k * R, r = r0 + rl;
         tlo = __ldg(ptr + r0);
         a = b = 0;
-        if (r < nrows) { a = __ldg(ptr + r); b = __ldg(ptr + r + 1); }
+        if (r < re) { a = __ldg(ptr + r); b = __ldg(ptr + r + 1); }
     };
-    if (t < ntiles) rows(t, lo, p0, p1);
+    if (ntiles) rows(0, lo, p0, p1);
     griddep_wait();                    // x (and y's previous readers) belong to the launch before this one
     if (threadIdx.x == 0) griddep_launch();
-    while (t < ntiles) {
-        const uint32_t tn = t + gridDim.x;
+    for (uint32_t k = 0; k < ntiles; ++k) {
         uint32_t nlo = 0, np0 = 0, np1 = 0;
-        if (tn < ntiles) rows(tn, nlo, np0, np1);
+        if (k + 1 < ntiles) rows(k + 1, nlo, np0, np1);
         mbar_wait(full + s, phase);
         const uint32_t za = lo & ~3u;
         const uint32_t *ci = s_ind + (size_t)s * cap;
@@ -601,54 +641,113 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
         if (lane_id() == 0) mbar_arrive(empty + s);
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const uint64_t r = (uint64_t)t * R + rl;
-        if (sub == 0 && r < nrows) y[r] = acc;
-        t = tn; lo = nlo; p0 = np0; p1 = np1;
+        const uint32_t r = rs + k * R + rl;
+        if (sub == 0 && r < re) y[r] = acc;
+        lo = nlo; p0 = np0; p1 = np1;
         if (++s == stages) { s = 0; phase ^= 1u; }
     }
 }
 
-// stages and CTAs per SM for a stage of `stage_bytes`: as many bytes in flight as fit (~200 KB per SM)
-struct StreamShape { uint32_t stages, ctas; size_t smem; };
-inline StreamShape stream_shape(size_t stage_bytes) {
-    // SPL_STREAM_STAGES / SPL_STREAM_CTAS: measurement knobs (read per call: a sweep changes them in-process)
-    const char *es = std::getenv("SPL_STREAM_STAGES"), *ec = std::getenv("SPL_STREAM_CTAS");
-    const int want_stages = es ? std::atoi(es) : 0, want_ctas = ec ? std::atoi(ec) : 0;
-    const size_t budget = 220 * 1024;               // 227 KB per SM less 1 KB per CTA and the barriers
-    static const int order[][2] = {{3, 4}, {4, 3}, {3, 3}, {2, 4}, {2, 3}, {1, 4}, {1, 3}, {1, 2}};   // {CTAs, stages}
-    for (const auto &o : order) {
-        const uint32_t ctas = want_ctas ? (uint32_t)want_ctas : (uint32_t)o[0];
-        const uint32_t stages = want_stages ? (uint32_t)want_stages : (uint32_t)o[1];
-        const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
-        if (ctas * (smem + 1024) <= budget) return {stages, ctas, smem};
-    }
-    return {0, 0, 0};
+inline int env_int(const char *name, int fallback) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : fallback;
 }
 
-template <typename T, int LPR, int U, typename XG>
+// consumer threads per CTA (SPL_STREAM_CONS: measurement knob)
+inline int stream_consumers() { return env_int("SPL_STREAM_CONS", 256) == 128 ? 128 : 256; }
+
+// Largest window of R rows -> stage capacity in entries (0: a tile does not fit in shared memory).
+// Caller holds a->plan_mu or is the planner.
+void stream_capacity(spl_ctx *ctx, spl_mat *a, uint32_t rows_per_tile) {
+    if (a->stream_rows == rows_per_tile) return;
+    a->stream_rows = rows_per_tile;
+    a->stream_cap = 0;
+    a->stream_grid = 0;
+    if (a->nnz == 0) return;
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 1, 0, sizeof(uint32_t), ctx->stream));
+    stream_window_kernel<<<std::min<unsigned>(div_up(a->nrows, 256), (unsigned)ctx->num_sms * 8u), 256, 0, ctx->stream>>>(
+        a->ptr, a->nrows, rows_per_tile, ctx->d_scratch + 1);
+    check_launch(ctx, "stream_window");
+    uint32_t max_window = 0;
+    read_back(ctx, ctx->d_scratch + 1, &max_window, 1);
+    const uint32_t cap = (max_window + 6u + 3u) & ~3u;            // the 16-byte aligned superset of the largest slice
+    // two stages of it must fit beside the barriers
+    if (2 * (size_t)cap * (4 + a->vsize()) + 64 <= 226 * 1024) a->stream_cap = cap;
+}
+
+// Row range per CTA and the x edges per tile for a grid of `grid` CTAs.  Cached; rebuilt when the grid changes.
+void stream_partition(spl_ctx *ctx, spl_mat *a, uint32_t grid) {
+    if (a->stream_grid == grid) return;
+    std::lock_guard<std::mutex> lock(a->plan_mu);
+    if (a->stream_grid == grid) return;
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));                  // nobody is reading the old arrays
+    dfree(ctx, a->stream_cta_rows); dfree(ctx, a->stream_xhi); dfree(ctx, a->stream_xlo0);
+    a->stream_cta_rows = a->stream_xhi = a->stream_xlo0 = nullptr;
+    a->stream_cta_rows = dalloc<uint32_t>(ctx, (size_t)grid + 1);
+    SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 1, 0, sizeof(uint32_t), ctx->stream));
+    stream_partition_kernel<<<div_up((uint64_t)grid + 1, 128), 128, 0, ctx->stream>>>(
+        a->ptr, a->nrows, a->nnz, grid, a->stream_rows, a->stream_cta_rows, ctx->d_scratch + 1);
+    check_launch(ctx, "stream_partition");
+    uint32_t max_tiles = 0;
+    read_back(ctx, ctx->d_scratch + 1, &max_tiles, 1);
+    max_tiles = std::max(max_tiles, 1u);
+    a->stream_max_tiles = max_tiles;
+    a->stream_xhi = dalloc<uint32_t>(ctx, (size_t)grid * max_tiles);
+    a->stream_xlo0 = dalloc<uint32_t>(ctx, grid);
+    SPL_CUDA(cudaMemsetAsync(a->stream_xhi, 0, sizeof(uint32_t) * (size_t)grid * max_tiles, ctx->stream));
+    SPL_CUDA(cudaMemsetAsync(a->stream_xlo0, 0xff, sizeof(uint32_t) * (size_t)grid, ctx->stream));
+    stream_edges_kernel<<<grid, 256, 0, ctx->stream>>>(a->ptr, a->ind, a->stream_cta_rows, a->stream_rows, max_tiles,
+                                                      a->stream_xhi, a->stream_xlo0);
+    check_launch(ctx, "stream_edges");
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));                  // visible to any other stream from here on
+    a->stream_grid = grid;
+}
+
+template <typename T, int LPR, int U, int CONS, typename XG>
 void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
-    const StreamShape sh = stream_shape((size_t)a->stream_cap * (sizeof(uint32_t) + sizeof(T)));
-    SPL_REQUIRE(sh.stages >= 2, SPL_ERR_UNSUPPORTED, "stream SpMV: a tile of rows does not fit in shared memory");
-    auto k = spmv_stream_kernel<T, LPR, U, XG>;
-    SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+    auto k = spmv_stream_kernel<T, LPR, U, CONS, XG>;
+    // shape: two stages are enough once the CTAs overlap each other (measured: profiles/r2_spmv_notes.md);
+    // as many CTAs as fit, one slot of the SM left free when programmatic launches chain, so that the
+    // next product's CTAs are resident (barriers set up, first tiles in flight) before this one ends
+    const size_t stage_bytes = (size_t)a->stream_cap * (sizeof(uint32_t) + sizeof(T));
+    const uint32_t stages = (uint32_t)std::max(2, env_int("SPL_STREAM_STAGES", 2));
+    const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+    SPL_REQUIRE(smem <= 227 * 1024, SPL_ERR_UNSUPPORTED, "stream SpMV: the stages do not fit in shared memory");
+    static std::atomic<size_t> smem_set{0};                       // per instantiation
+    if (smem > smem_set.load(std::memory_order_relaxed)) {
+        SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set.store(smem, std::memory_order_relaxed);
+    }
+    static std::atomic<uint64_t> occ_cache{0};                    // (smem << 8) | resident CTAs
+    uint64_t oc = occ_cache.load(std::memory_order_relaxed);
+    if ((oc >> 8) != smem) {
+        int resident = 0;
+        SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k, CONS + 32, smem));
+        SPL_REQUIRE(resident >= 1, SPL_ERR_CUDA, "stream SpMV: no CTA fits on an SM");
+        oc = ((uint64_t)smem << 8) | (uint64_t)resident;
+        occ_cache.store(oc, std::memory_order_relaxed);
+    }
+    const uint32_t resident = (uint32_t)(oc & 0xff);
+    const uint32_t spare = (uint32_t)env_int("SPL_STREAM_SPARE", 0);
+    uint32_t ctas = (uint32_t)env_int("SPL_STREAM_CTAS", 0);
+    if (ctas == 0) ctas = resident > spare ? resident - spare : 1u;
+    ctas = std::min(ctas, resident);
+    const uint32_t grid = (uint32_t)ctx->num_sms * ctas;
+    stream_partition(ctx, const_cast<spl_mat *>(a), grid);
     cudaLaunchConfig_t cfg{};
-    int resident = 0;                                  // registers may allow fewer CTAs than shared memory does
-    SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k, ST_THREADS, sh.smem));
-    SPL_REQUIRE(resident >= 1, SPL_ERR_CUDA, "stream SpMV: no CTA fits on an SM");
-    cfg.gridDim = dim3(std::min<uint32_t>(a->stream_tiles, (uint32_t)ctx->num_sms * std::min<uint32_t>(sh.ctas, (uint32_t)resident)));
-    cfg.blockDim = dim3(ST_THREADS);
-    cfg.dynamicSmemBytes = sh.smem;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CONS + 32);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    const bool no_pdl = std::getenv("SPL_NO_PDL") != nullptr;
     cfg.attrs = attr;
-    cfg.numAttrs = (ctx->pdl_prev && !no_pdl) ? 1 : 0;     // only behind another stream-kernel product
+    cfg.numAttrs = (ctx->pdl_prev && !std::getenv("SPL_NO_PDL")) ? 1 : 0;     // only behind another stream-kernel product
     SPL_CUDA(cudaLaunchKernelEx(&cfg, k, a->nrows, (const uint32_t *)a->ptr, (const uint32_t *)a->ind,
-                                static_cast<const T *>(a->val), xg, y, a->stream_tiles, a->stream_cap, sh.stages,
-                                (const uint32_t *)a->stream_xhi,
-                                ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
+                                static_cast<const T *>(a->val), xg, y, (const uint32_t *)a->stream_cta_rows,
+                                (const uint32_t *)a->stream_xhi, (const uint32_t *)a->stream_xlo0, a->stream_max_tiles,
+                                a->stream_cap, stages, ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
     check_launch(ctx, "spmv_stream");
     ctx->pdl_chain = true;
 }
@@ -656,9 +755,14 @@ void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *
 template <typename T, int LPR, typename XG>
 void spmv_stream_u(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
     // entries per lane and trip: one trip for the short rows of stencils and bands
-    const double per_lane = a->nrows ? (double)a->nnz / a->nrows / LPR : 0.0;
-    if (per_lane > 4.0) launch_stream<T, LPR, 8>(ctx, a, xg, y, x_edge);
-    else launch_stream<T, LPR, 4>(ctx, a, xg, y, x_edge);
+    const bool wide = (a->max_row_len + LPR - 1) / LPR > 4;
+    if (a->stream_rows * LPR == 128) {
+        if (wide) launch_stream<T, LPR, 8, 128>(ctx, a, xg, y, x_edge);
+        else launch_stream<T, LPR, 4, 128>(ctx, a, xg, y, x_edge);
+    } else {
+        if (wide) launch_stream<T, LPR, 8, 256>(ctx, a, xg, y, x_edge);
+        else launch_stream<T, LPR, 4, 256>(ctx, a, xg, y, x_edge);
+    }
 }
 
 template <typename T, typename XG>
@@ -1090,22 +1194,8 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     if (mean > 12.0) lanes = 4;
     while (lanes < 32 && lanes * 10 < mean) lanes *= 2;
     a->plan_lanes = lanes;
-    // stream kernel: tiles of 256 / lanes rows; the largest tile sizes the shared-memory stages
-    if (a->nnz) {
-        const uint32_t rpt = ST_CONSUMERS / (uint32_t)lanes;
-        a->stream_rows = rpt;
-        a->stream_tiles = div_up(a->nrows, rpt);
-        a->stream_xhi = dalloc<uint32_t>(ctx, a->stream_tiles);
-        SPL_CUDA(cudaMemsetAsync(a->stream_xhi, 0, sizeof(uint32_t) * (size_t)a->stream_tiles, ctx->stream));
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 1, 0, sizeof(uint32_t), ctx->stream));
-        stream_plan_kernel<<<div_up(a->nrows, 256), 256, 0, ctx->stream>>>(a->ptr, a->ind, a->nrows, rpt, a->stream_xhi,
-                                                                          ctx->d_scratch + 1);
-        check_launch(ctx, "stream_plan");
-        uint32_t max_tile = 0;
-        read_back(ctx, ctx->d_scratch + 1, &max_tile, 1);
-        const uint32_t cap = (max_tile + 6u + 3u) & ~3u;          // the 16-byte aligned superset of the largest slice
-        a->stream_cap = stream_shape((size_t)cap * (4 + a->vsize())).stages >= 2 ? cap : 0u;
-    }
+    // stream kernel: the largest window of 256 / lanes rows sizes its shared-memory stages
+    stream_capacity(ctx, a, (uint32_t)stream_consumers() / (uint32_t)lanes);
     // merge-path tile starts (matrix-only data, cached)
     const int ipt = a->dtype == SPL_F64 ? merge_ipt<double>() : merge_ipt<float>();
     const uint32_t items = MG_THREADS * ipt;
@@ -1149,7 +1239,13 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
         }
     }
     if (kernel == SPL_SPMV_STREAM) {
-        spmv_plan(ctx, const_cast<spl_mat *>(a));
+        spl_mat *m = const_cast<spl_mat *>(a);
+        spmv_plan(ctx, m);
+        if (a->stream_rows != (uint32_t)stream_consumers() / (uint32_t)a->plan_lanes) {     // measurement knob changed
+            std::lock_guard<std::mutex> lock(m->plan_mu);
+            SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+            stream_capacity(ctx, m, (uint32_t)stream_consumers() / (uint32_t)a->plan_lanes);
+        }
         SPL_REQUIRE(a->nnz == 0 || a->stream_cap, SPL_ERR_UNSUPPORTED,
                     "stream SpMV: a tile of rows does not fit in shared memory (skewed rows: use SPLIT)");
         if (a->nnz == 0) {

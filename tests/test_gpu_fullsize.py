@@ -63,7 +63,65 @@ def same_host(A, want):
     assert A.values().tobytes() == want[2].tobytes()
 
 
+def host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:                                             # noqa: BLE001
+        return 0.0
+
+
+def aos_triplets_from_device(r, c, v):
+    """The oracle's input — the reference's Vec<(usize, usize, T)> (src/coo.rs:52-57), 24 bytes per
+    entry — built on the device and brought down in one copy (numpy would spend longer converting the
+    three arrays than the oracle spends assembling them)."""
+    n = r.numel()
+    aos = torch.empty((n, 3), dtype=torch.int64, device="cuda")
+    aos[:, 0] = r.long() & 0xFFFFFFFF                             # int32 tensors hold uint32 bit patterns
+    aos[:, 1] = c.long() & 0xFFFFFFFF
+    if v.dtype == torch.float32:
+        aos[:, 2] = v.view(torch.int32).long() & 0xFFFFFFFF       # value in the low 4 bytes, padding above
+    else:
+        aos[:, 2] = v.view(torch.int64)
+    host = aos.cpu().numpy()
+    del aos
+    return host.reshape(-1).view(orc.triplet_dtype(np.float32 if v.dtype == torch.float32 else np.float64))
+
+
+def same_compressed_big(A, want):
+    """Bit-exact comparison of a large device matrix with the oracle's arrays: pointers and indices on
+    the host (uint64), values as raw bytes."""
+    ptr, ind, val = (A.rowptr(), A.colind(), A.values()) if isinstance(A, sp.CsrMatrix) else (A.colptr(), A.rowind(), A.values())
+    assert len(ind) == len(want[1]), (len(ind), len(want[1]))
+    assert np.array_equal(ptr, want[0]), "pointers differ"
+    assert np.array_equal(ind, want[1]), "indices differ"
+    assert val.tobytes() == np.asarray(want[2]).tobytes(), "values differ (bitwise)"
+
+
 # ------------------------------------------------------------------ config 3
+def test_c3_full_size_bit_exact_vs_oracle():
+    """Config 3 at its full size (168 M triplets, 5 % duplicates incl. exact cancellations and >= 3-fold
+    cells) against the oracle's restatement of src/csr/conv/coo.rs:4-115, bit for bit; then the
+    assembled matrix CSR -> CSC against src/csc/conv/csr.rs:4-52."""
+    if host_ram_gb() < 24:
+        pytest.skip(f"host RAM {host_ram_gb():.0f} GB < 24 GB: the oracle needs the 4 GB AoS list plus ~8 GB of work arrays")
+    sd = gen()
+    n = 10_000_000
+    r, c, v = sd.random_uniform_coo_device(torch, n, 16, 8_000_000, torch.float32, seed=1)
+    assert r.numel() == 168_000_000
+    A = sp.CsrMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    trip = aos_triplets_from_device(r, c, v)
+    del r, c, v
+    torch.cuda.empty_cache()
+    want = orc.compress_from_coo(n, n, trip, "row")
+    del trip
+    same_compressed_big(A, want)
+    C = A.to_csc()
+    wantc = orc.recompress(n, n, *want)
+    del want
+    same_compressed_big(C, wantc)
+
+
 def test_c3_reduced_bit_exact_vs_oracle():
     sd = gen()
     n = 1_000_000
@@ -134,6 +192,24 @@ def test_c4_reduced_bit_exact_and_merge_path():
     T = A.transpose()
     wt = orc.recompress(n, n, *want)
     same_host(T, wt)
+
+
+def test_c4_full_size_bit_exact_vs_oracle():
+    """Config 4 at its full size (R-MAT scale 24, 2^29 generated edges, heavy duplicate merging in the
+    hot cells, rows of up to ~10^6 entries) against the oracle, bit for bit."""
+    if host_ram_gb() < 56:
+        pytest.skip(f"host RAM {host_ram_gb():.0f} GB < 56 GB: the oracle needs the 12.9 GB AoS list plus ~25 GB of work arrays")
+    sd = gen()
+    scale = 24
+    n = 1 << scale
+    r, c, v = sd.rmat_coo_device(torch, scale, 32, torch.float32, seed=3)
+    A = sp.CsrMatrix.from_device_triplets(n, n, r.numel(), r.data_ptr(), c.data_ptr(), v.data_ptr(), np.float32)
+    trip = aos_triplets_from_device(r, c, v)
+    del r, c, v
+    torch.cuda.empty_cache()
+    want = orc.compress_from_coo(n, n, trip, "row")
+    del trip
+    same_compressed_big(A, want)
 
 
 def test_c4_full_size_properties():

@@ -475,6 +475,26 @@ def test_spmv_split_long_runs_and_edges(dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,density", [(1, 1, 1.0), (37, 91, 0.2), (4000, 2500, 0.01), (120000, 90000, 0.0001)])
+def test_to_coo_random_matches_the_oracle(dtype, n, m, density):
+    """From<&CsrMatrix> / From<&CscMatrix> for CooMatrix (src/coo.rs:629-705): storage-order expansion
+    (row of every entry from rowptr, src/csr.rs:303-316), compared entry by entry with the oracle."""
+    rng = np.random.default_rng(n * 7 + m)
+    a = _rand_csr(rng, n, m, density, dtype)
+    A = sp.CsrMatrix.new(n, m, *a)
+    for M, major, nmaj in ((A, "row", n), (A.to_csc(), "col", m)):
+        arr = arrays(M)
+        want = orc.expand_to_coo(nmaj, arr[0], arr[1], arr[2], major)
+        r, c, v = M.to_coo().triplets()
+        assert r.dtype == np.uint64 and c.dtype == np.uint64 and len(v) == M.nnz()
+        assert np.array_equal(r, want["row"]) and np.array_equal(c, want["col"]), major
+        assert v.tobytes() == want["val"].tobytes(), major
+        # and back: CooMatrix -> the same compressed matrix (round trip through the builder format)
+        back = type(M).from_coo(M.to_coo())
+        same(arrays(back), arr, f"round trip through COO ({major})")       # values are non-zero: nothing is dropped
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", ["laplace", "band9", "stencil27", "ragged"])
 def test_spmv_stream_kernel(dtype, shape):
     """The persistent TMA-pipelined kernel (SPL_SPMV_STREAM): row counts that are not a multiple of the
