@@ -65,7 +65,7 @@ def sweep_regular(name, make, V, tdt, copies, reps):
         res[key] = {"ms": round(ms, 5), "gbps": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / PEAK, 4)}
         print(name, key, res[key], flush=True)
 
-    knobs = dict(SPL_STREAM_STAGES=None, SPL_STREAM_CTAS=None, SPL_NO_PDL=None, SPL_STREAM_CONS=None, SPL_STREAM_SPARE=None)
+    knobs = dict(SPL_STREAM_STAGES=None, SPL_STREAM_CTAS=None, SPL_NO_PDL=None, SPL_STREAM_TIGHT=None)
     setenv(**knobs)
     put("vector", rate(As, xs, ys, 1, 0, reps))
     # check the stream kernel against the vector kernel once: same lanes, same order => same bits
@@ -77,15 +77,16 @@ def sweep_regular(name, make, V, tdt, copies, reps):
     setenv(SPL_NO_PDL=1)
     put("stream_default_nopdl", rate(As, xs, ys, 5, 0, reps))
     setenv(SPL_NO_PDL=None)
-    for cons in (256, 128):
-        for spare in (0, 1, 2):
-            for stages in (2, 3):
-                setenv(SPL_STREAM_STAGES=stages, SPL_STREAM_CONS=cons, SPL_STREAM_SPARE=spare)
+    for tight in (0, 1):
+        for ctas in (0, 2, 3):
+            for stages in (2, 3, 4):
+                setenv(SPL_STREAM_STAGES=stages, SPL_STREAM_TIGHT=tight, SPL_STREAM_CTAS=ctas or None)
+                key = f"stream_tight{tight}_ctas{ctas or 'max'}_s{stages}"
                 try:
-                    put(f"stream_cons{cons}_spare{spare}_s{stages}", rate(As, xs, ys, 5, 0, reps))
+                    put(key, rate(As, xs, ys, 5, 0, reps))
                 except Exception as e:                                   # noqa: BLE001
-                    res[f"stream_cons{cons}_spare{spare}_s{stages}"] = {"error": str(e)[:60]}
-                    print(name, cons, spare, stages, "error", str(e)[:60], flush=True)
+                    res[key] = {"error": str(e)[:60]}
+                    print(name, key, "error", str(e)[:60], flush=True)
     setenv(**knobs)
     if copies > 1:
         put("vector_l2_resident", rate(As[:1], xs[:1], ys[:1], 1, 0, reps))

@@ -221,7 +221,7 @@ spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract) 
                 "add/sub: nnz(A)+nnz(B) must stay below 2^32 - 65536");
     const uint32_t nmajor = a->nmajor();
     Tmp<uint32_t> cnt(ctx, nmajor);
-    Tmp<uint32_t> cptr(ctx, (size_t)nmajor + 1);
+    Tmp<uint32_t> cptr(ctx, (size_t)nmajor + 1 + 4);      // becomes the result's pointer array: same slack as new_mat
     const BlockPlan bp = plan_blocks(a, b);
     {
         auto k = union_block_kernel<float, false, false>;       // symbolic: indices only

@@ -109,8 +109,9 @@ struct spl_mat {
     // kernel not usable).  For a grid of stream_grid CTAs: stream_cta_rows[b] = first row of CTA b (ranges
     // balanced on rows + stored entries), stream_xhi[b * stream_max_tiles + k] = 1 + the largest column of
     // CTA b's tile k (0 if it has no entry), stream_xlo0[b] = smallest column of its first tile: the
-    // producer prefetches the leading edge of x into L2 from them
-    uint32_t *stream_cta_rows = nullptr, *stream_xhi = nullptr, *stream_xlo0 = nullptr;
+    // producer prefetches the leading edge of x into L2 from them; stream_tile_lo = position of every
+    // tile's first stored entry (same layout, one more slot per CTA)
+    uint32_t *stream_cta_rows = nullptr, *stream_xhi = nullptr, *stream_xlo0 = nullptr, *stream_tile_lo = nullptr;
     uint32_t stream_rows = 0, stream_cap = 0, stream_grid = 0, stream_max_tiles = 0;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }

@@ -177,7 +177,8 @@ spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
     m->ncols = ncols;
     m->nnz = nnz;
     try {
-        m->ptr = dalloc<uint32_t>(ctx, (size_t)m->nmajor() + 1);
+        // +4 pointers of slack: the stream SpMV fetches pointer slices in whole 16-byte units
+        m->ptr = dalloc<uint32_t>(ctx, (size_t)m->nmajor() + 1 + 4);
         // +16 entries of slack: the SpMV kernels read aligned groups of four entries
         m->ind = dalloc<uint32_t>(ctx, (size_t)nnz + 16);
         m->val = dalloc_bytes(ctx, ((size_t)nnz + 16) * m->vsize());
@@ -203,6 +204,7 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     dfree(ctx, m->stream_xhi);
     dfree(ctx, m->stream_cta_rows);
     dfree(ctx, m->stream_xlo0);
+    dfree(ctx, m->stream_tile_lo);
     delete m;
 }
 

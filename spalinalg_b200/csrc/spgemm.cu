@@ -210,7 +210,7 @@ template <typename T, int SLOT_BITS, int WARPS>
 spl_mat *spgemm_hash(spl_ctx *ctx, int format, int dtype, uint32_t out_rows, uint32_t out_cols, uint32_t an,
                      const spl_mat *a, const spl_mat *b) {
     Tmp<uint32_t> cnt(ctx, an);
-    Tmp<uint32_t> cptr(ctx, (size_t)an + 1);
+    Tmp<uint32_t> cptr(ctx, (size_t)an + 1 + 4);            // becomes the result's pointer array: same slack as new_mat
     auto ksym = spgemm_hash_kernel<T, false, SLOT_BITS, WARPS>;
     auto knum = spgemm_hash_kernel<T, true, SLOT_BITS, WARPS>;
     constexpr size_t sm_sym = hs_smem_bytes<T, false, SLOT_BITS, WARPS>();

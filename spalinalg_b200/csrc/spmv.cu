@@ -42,6 +42,7 @@ template <typename T>
 struct XLocal {
     const T *x;
     __device__ __forceinline__ T operator()(uint32_t c) const { return __ldg(x + c); }
+    __device__ __forceinline__ bool poisoned() const { return false; }
 };
 template <typename T>
 struct XPeer {
@@ -50,6 +51,10 @@ struct XPeer {
     const T *slice[SPL_MAX_PEERS];
     uint32_t start[SPL_MAX_PEERS + 1];
     int world;
+    const uint32_t *barrier_failed;          // set by a peer barrier that timed out on this context
+    // A product behind a barrier that gave up would read a peer's slice before it is final: its rows
+    // come out as NaN instead of plausible numbers (the status call reports the timeout itself).
+    __device__ __forceinline__ bool poisoned() const { return *reinterpret_cast<const volatile uint32_t *>(barrier_failed) != 0u; }
     __device__ __forceinline__ T operator()(uint32_t c) const {
         const uint32_t o = c - my_start;
         if (o < my_len) return __ldg(mine + o);
@@ -95,7 +100,7 @@ spmv_vector_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr,
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0 && row < nrows) y[row] = acc;
+    if (sub == 0 && row < nrows) y[row] = xg.poisoned() ? (T)NAN : acc;
 }
 
 template <typename T, int LPR, typename XG>
@@ -129,6 +134,7 @@ void spmv_peer_t(spl_ctx *ctx, const spl_mat *a, const PeerX &px, T *y, int lane
     xg.mine = xg.slice[px.rank];
     xg.my_start = px.start[px.rank];
     xg.my_len = px.start[px.rank + 1] - px.start[px.rank];
+    xg.barrier_failed = ctx->d_scratch + 32;
     spmv_vector<T>(ctx, a, xg, y, lanes);
 }
 
@@ -504,7 +510,8 @@ __global__ void stream_window_kernel(const uint32_t *__restrict__ ptr, uint32_t 
     if (lane_id() == 0 && m) atomicMax(max_window, m);
 }
 
-// cta_rows[b] = first row of CTA b: the smallest r with ptr[r] + r >= b * (nnz + nrows) / grid
+// cta_rows[b] = first row of CTA b: the smallest r with ptr[r] + r >= b * (nnz + nrows) / grid, rounded
+// down to a multiple of 4 rows (the pointer slice of a tile is fetched by a 16-byte aligned bulk copy)
 __global__ void stream_partition_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t nnz, uint32_t grid,
                                         uint32_t rows_per_tile, uint32_t *__restrict__ cta_rows,
                                         uint32_t *__restrict__ max_tiles) {
@@ -520,40 +527,57 @@ __global__ void stream_partition_kernel(const uint32_t *__restrict__ ptr, uint32
             if ((uint64_t)__ldg(ptr + mid) + mid < target) lo = mid + 1;
             else hi = mid;
         }
-        return lo;
+        return lo & ~3u;
     };
     const uint32_t r0 = first_row(b);
     cta_rows[b] = r0;
     if (b < grid) atomicMax(max_tiles, (first_row(b + 1) - r0 + rows_per_tile - 1) / rows_per_tile);
 }
 
-// per tile: 1 + its largest column (rows are column-sorted: the last entry of a row); per CTA: the
-// smallest column of its first tile
+// Per CTA b, slots [b * (max_tiles + 1) ...]: tile_lo[k] = position of tile k's first stored entry
+// (k = number of tiles: the end of the range); xhi[k] = 1 + the largest column of tile k (rows are
+// column-sorted: the last entry of a row), 0 if the tile has no entry; xlo0[b] = the smallest column of
+// the CTA's first tile.
 __global__ void stream_edges_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
                                     const uint32_t *__restrict__ cta_rows, uint32_t rows_per_tile, uint32_t max_tiles,
-                                    uint32_t *__restrict__ xhi, uint32_t *__restrict__ xlo0) {
+                                    uint32_t *__restrict__ tile_lo, uint32_t *__restrict__ xhi,
+                                    uint32_t *__restrict__ xlo0) {
     const uint32_t b = blockIdx.x;
     const uint32_t rs = cta_rows[b], re = cta_rows[b + 1];
+    const size_t base = (size_t)b * (max_tiles + 1);
+    for (uint32_t k = threadIdx.x; k <= max_tiles; k += blockDim.x) {
+        const uint64_t r = (uint64_t)rs + (uint64_t)k * rows_per_tile;
+        tile_lo[base + k] = ptr[r < re ? r : re];
+    }
     for (uint32_t r = rs + threadIdx.x; r < re; r += blockDim.x) {
         const uint32_t lo = ptr[r], hi = ptr[r + 1];
         if (hi == lo) continue;
         const uint32_t k = (r - rs) / rows_per_tile;
-        atomicMax(xhi + (size_t)b * max_tiles + k, ind[hi - 1] + 1u);
+        atomicMax(xhi + base + k, ind[hi - 1] + 1u);
         if (k == 0) atomicMin(xlo0 + b, ind[lo]);
     }
 }
 
-template <typename T, int LPR, int U, int CONS, typename XG>
-__global__ void __launch_bounds__(CONS + 32, 1024 / CONS)
+constexpr int ST_CONSUMERS = 256;
+
+// TIGHT: registers held to 56 so that four CTAs fit on an SM; otherwise three CTAs with room for
+// eight f64 gathers and values in flight per lane.
+template <typename T, int LPR, int U, bool TIGHT, typename XG>
+__global__ void __launch_bounds__(ST_CONSUMERS + 32, TIGHT ? 4 : 3)
 spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
                    const T *__restrict__ val, const XG xg, T *__restrict__ y, const uint32_t *__restrict__ cta_rows,
-                   const uint32_t *__restrict__ xhi, const uint32_t *__restrict__ xlo0, uint32_t max_tiles,
-                   uint32_t cap, uint32_t stages, const T *__restrict__ x_edge, uint32_t ncols) {
+                   const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ xhi,
+                   const uint32_t *__restrict__ xlo0, uint32_t max_tiles, uint32_t cap, uint32_t stages,
+                   const T *__restrict__ x_edge, uint32_t ncols) {
+    constexpr uint32_t CONS = ST_CONSUMERS;
     constexpr uint32_t R = CONS / LPR;
+    constexpr uint32_t PTRS = R + 4;           // pointer slots per stage: R + 1 needed, whole 16-byte units
     extern __shared__ __align__(128) unsigned char st_raw[];
-    uint32_t *s_ind = reinterpret_cast<uint32_t *>(st_raw);                            // [stages][cap]
-    T *s_val = reinterpret_cast<T *>(st_raw + (size_t)stages * cap * sizeof(uint32_t));   // [stages][cap]
-    uint64_t *full = reinterpret_cast<uint64_t *>(st_raw + (size_t)stages * cap * (sizeof(uint32_t) + sizeof(T)));
+    // per stage: [cap] indices, [cap] values, [PTRS] row pointers; then the barriers
+    uint32_t *s_ind = reinterpret_cast<uint32_t *>(st_raw);
+    T *s_val = reinterpret_cast<T *>(st_raw + (size_t)stages * cap * sizeof(uint32_t));
+    uint32_t *s_ptr = reinterpret_cast<uint32_t *>(st_raw + (size_t)stages * cap * (sizeof(uint32_t) + sizeof(T)));
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_ptr + (size_t)stages * PTRS);
     uint64_t *empty = full + stages;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < stages; ++s) {
@@ -568,21 +592,21 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
     if (threadIdx.x >= CONS) {
         // ---- producer: one thread, up to S tiles ahead of the consumers ----
         if (threadIdx.x != CONS || ntiles == 0) return;
-        const uint32_t *hi_edge = xhi + (size_t)blockIdx.x * max_tiles;
+        const size_t base = (size_t)blockIdx.x * (max_tiles + 1);
+        const uint32_t *t_lo = tile_lo + base, *t_xhi = xhi + base;
         uint32_t s = 0, phase = 0;
         uint32_t edge = __ldg(xlo0 + blockIdx.x);                 // x below this is somebody else's first touch
-        uint32_t lo = __ldg(ptr + rs), hi = __ldg(ptr + (rs + R < re ? rs + R : re)), x1 = __ldg(hi_edge);
+        uint32_t lo = __ldg(t_lo);
         for (uint32_t k = 0; k < ntiles; ++k) {
-            uint32_t nhi = 0, nx1 = 0;
-            if (k + 1 < ntiles) {                                  // next tile's bounds: in flight during the wait
-                const uint32_t r1 = rs + (k + 2) * R;
-                nhi = __ldg(ptr + (r1 < re ? r1 : re));
-                nx1 = __ldg(hi_edge + k + 1);
-            }
+            const uint32_t hi = __ldg(t_lo + k + 1), x1 = __ldg(t_xhi + k);     // consecutive words: L1 hits
             if (k >= stages) mbar_wait(empty + s, phase ^ 1u);     // the consumers are done with this stage
             const uint32_t za = lo & ~3u, zb = (hi + 3u) & ~3u;    // 16-byte aligned superset; the arrays carry slack
             const uint32_t cnt = zb - za;
-            mbar_expect_tx(full + s, cnt * (uint32_t)(sizeof(uint32_t) + sizeof(T)));
+            const uint32_t r0 = rs + k * R;                        // multiple of 4
+            const uint32_t left = (nrows + 1u - r0 + 3u) & ~3u;    // pointer entries from r0 to the end (+ slack)
+            const uint32_t np = left < PTRS ? left : PTRS;
+            mbar_expect_tx(full + s, cnt * (uint32_t)(sizeof(uint32_t) + sizeof(T)) + np * (uint32_t)sizeof(uint32_t));
+            tma_bulk_g2s(s_ptr + (size_t)s * PTRS, ptr + r0, np * (uint32_t)sizeof(uint32_t), full + s);
             if (cnt) {
                 tma_bulk_g2s(s_ind + (size_t)s * cap, ind + za, cnt * (uint32_t)sizeof(uint32_t), full + s);
                 tma_bulk_g2s(s_val + (size_t)s * cap, val + za, cnt * (uint32_t)sizeof(T), full + s);
@@ -597,35 +621,28 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
                 }
                 edge = x1;
             }
-            lo = hi; hi = nhi; x1 = nx1;
+            lo = hi;
             if (++s == stages) { s = 0; phase ^= 1u; }
         }
         return;
     }
 
-    // ---- consumers: CONS threads, LPR lanes per row ----
+    // ---- consumers: CONS threads, LPR lanes per row; nothing but x comes from global memory ----
     const uint32_t rl = threadIdx.x / LPR, sub = threadIdx.x % LPR;
     uint32_t s = 0, phase = 0;
-    uint32_t lo = 0, p0 = 0, p1 = 0;
-    auto rows = [&](uint32_t k, uint32_t &tlo, uint32_t &a, uint32_t &b) {
-        const uint32_t r0 = rs + k * R, r = r0 + rl;
-        tlo = __ldg(ptr + r0);
-        a = b = 0;
-        if (r < re) { a = __ldg(ptr + r); b = __ldg(ptr + r + 1); }
-    };
-    if (ntiles) rows(0, lo, p0, p1);
     griddep_wait();                    // x (and y's previous readers) belong to the launch before this one
     if (threadIdx.x == 0) griddep_launch();
     for (uint32_t k = 0; k < ntiles; ++k) {
-        uint32_t nlo = 0, np0 = 0, np1 = 0;
-        if (k + 1 < ntiles) rows(k + 1, nlo, np0, np1);
         mbar_wait(full + s, phase);
-        const uint32_t za = lo & ~3u;
+        const uint32_t *cp = s_ptr + (size_t)s * PTRS;
         const uint32_t *ci = s_ind + (size_t)s * cap;
         const T *cv = s_val + (size_t)s * cap;
-        const uint32_t e = p1 - za;
+        const uint32_t r = rs + k * R + rl;
+        const uint32_t za = cp[0] & ~3u;
+        uint32_t p0 = 0, e = 0;
+        if (r < re) { p0 = cp[rl] - za; e = cp[rl + 1] - za; }
         T acc = (T)0;
-        for (uint32_t j = p0 - za + sub; j < e; j += U * LPR) {
+        for (uint32_t j = p0 + sub; j < e; j += U * LPR) {
             uint32_t c[U];
             T xv[U], v[U];
 #pragma unroll
@@ -641,9 +658,7 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
         if (lane_id() == 0) mbar_arrive(empty + s);
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const uint32_t r = rs + k * R + rl;
         if (sub == 0 && r < re) y[r] = acc;
-        lo = nlo; p0 = np0; p1 = np1;
         if (++s == stages) { s = 0; phase ^= 1u; }
     }
 }
@@ -653,8 +668,10 @@ inline int env_int(const char *name, int fallback) {
     return e ? std::atoi(e) : fallback;
 }
 
-// consumer threads per CTA (SPL_STREAM_CONS: measurement knob)
-inline int stream_consumers() { return env_int("SPL_STREAM_CONS", 256) == 128 ? 128 : 256; }
+inline int stream_consumers() { return ST_CONSUMERS; }
+inline size_t stream_stage_bytes(const spl_mat *a) {
+    return (size_t)a->stream_cap * (4 + a->vsize()) + ((size_t)a->stream_rows + 4) * 4;
+}
 
 // Largest window of R rows -> stage capacity in entries (0: a tile does not fit in shared memory).
 // Caller holds a->plan_mu or is the planner.
@@ -671,8 +688,8 @@ void stream_capacity(spl_ctx *ctx, spl_mat *a, uint32_t rows_per_tile) {
     uint32_t max_window = 0;
     read_back(ctx, ctx->d_scratch + 1, &max_window, 1);
     const uint32_t cap = (max_window + 6u + 3u) & ~3u;            // the 16-byte aligned superset of the largest slice
-    // two stages of it must fit beside the barriers
-    if (2 * (size_t)cap * (4 + a->vsize()) + 64 <= 226 * 1024) a->stream_cap = cap;
+    // two stages of it (with the pointer slices) must fit beside the barriers
+    if (2 * ((size_t)cap * (4 + a->vsize()) + ((size_t)rows_per_tile + 4) * 4) + 64 <= 226 * 1024) a->stream_cap = cap;
 }
 
 // Row range per CTA and the x edges per tile for a grid of `grid` CTAs.  Cached; rebuilt when the grid changes.
@@ -681,8 +698,8 @@ void stream_partition(spl_ctx *ctx, spl_mat *a, uint32_t grid) {
     std::lock_guard<std::mutex> lock(a->plan_mu);
     if (a->stream_grid == grid) return;
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));                  // nobody is reading the old arrays
-    dfree(ctx, a->stream_cta_rows); dfree(ctx, a->stream_xhi); dfree(ctx, a->stream_xlo0);
-    a->stream_cta_rows = a->stream_xhi = a->stream_xlo0 = nullptr;
+    dfree(ctx, a->stream_cta_rows); dfree(ctx, a->stream_xhi); dfree(ctx, a->stream_xlo0); dfree(ctx, a->stream_tile_lo);
+    a->stream_cta_rows = a->stream_xhi = a->stream_xlo0 = a->stream_tile_lo = nullptr;
     a->stream_cta_rows = dalloc<uint32_t>(ctx, (size_t)grid + 1);
     SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 1, 0, sizeof(uint32_t), ctx->stream));
     stream_partition_kernel<<<div_up((uint64_t)grid + 1, 128), 128, 0, ctx->stream>>>(
@@ -692,24 +709,26 @@ void stream_partition(spl_ctx *ctx, spl_mat *a, uint32_t grid) {
     read_back(ctx, ctx->d_scratch + 1, &max_tiles, 1);
     max_tiles = std::max(max_tiles, 1u);
     a->stream_max_tiles = max_tiles;
-    a->stream_xhi = dalloc<uint32_t>(ctx, (size_t)grid * max_tiles);
+    const size_t slots = (size_t)grid * (max_tiles + 1);
+    a->stream_xhi = dalloc<uint32_t>(ctx, slots);
+    a->stream_tile_lo = dalloc<uint32_t>(ctx, slots);
     a->stream_xlo0 = dalloc<uint32_t>(ctx, grid);
-    SPL_CUDA(cudaMemsetAsync(a->stream_xhi, 0, sizeof(uint32_t) * (size_t)grid * max_tiles, ctx->stream));
+    SPL_CUDA(cudaMemsetAsync(a->stream_xhi, 0, sizeof(uint32_t) * slots, ctx->stream));
     SPL_CUDA(cudaMemsetAsync(a->stream_xlo0, 0xff, sizeof(uint32_t) * (size_t)grid, ctx->stream));
     stream_edges_kernel<<<grid, 256, 0, ctx->stream>>>(a->ptr, a->ind, a->stream_cta_rows, a->stream_rows, max_tiles,
-                                                      a->stream_xhi, a->stream_xlo0);
+                                                      a->stream_tile_lo, a->stream_xhi, a->stream_xlo0);
     check_launch(ctx, "stream_edges");
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));                  // visible to any other stream from here on
     a->stream_grid = grid;
 }
 
-template <typename T, int LPR, int U, int CONS, typename XG>
+template <typename T, int LPR, int U, bool TIGHT, typename XG>
 void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
-    auto k = spmv_stream_kernel<T, LPR, U, CONS, XG>;
-    // shape: two stages are enough once the CTAs overlap each other (measured: profiles/r2_spmv_notes.md);
-    // as many CTAs as fit, one slot of the SM left free when programmatic launches chain, so that the
-    // next product's CTAs are resident (barriers set up, first tiles in flight) before this one ends
-    const size_t stage_bytes = (size_t)a->stream_cap * (sizeof(uint32_t) + sizeof(T));
+    auto k = spmv_stream_kernel<T, LPR, U, TIGHT, XG>;
+    constexpr int CONS = ST_CONSUMERS;
+    // shape: two stages are enough once the CTAs overlap each other, and more CTAs beat deeper rings
+    // (measured: profiles/r2_spmv_notes.md)
+    const size_t stage_bytes = stream_stage_bytes(a);
     const uint32_t stages = (uint32_t)std::max(2, env_int("SPL_STREAM_STAGES", 2));
     const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
     SPL_REQUIRE(smem <= 227 * 1024, SPL_ERR_UNSUPPORTED, "stream SpMV: the stages do not fit in shared memory");
@@ -728,10 +747,8 @@ void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *
         occ_cache.store(oc, std::memory_order_relaxed);
     }
     const uint32_t resident = (uint32_t)(oc & 0xff);
-    const uint32_t spare = (uint32_t)env_int("SPL_STREAM_SPARE", 0);
     uint32_t ctas = (uint32_t)env_int("SPL_STREAM_CTAS", 0);
-    if (ctas == 0) ctas = resident > spare ? resident - spare : 1u;
-    ctas = std::min(ctas, resident);
+    if (ctas == 0 || ctas > resident) ctas = resident;
     const uint32_t grid = (uint32_t)ctx->num_sms * ctas;
     stream_partition(ctx, const_cast<spl_mat *>(a), grid);
     cudaLaunchConfig_t cfg{};
@@ -746,8 +763,9 @@ void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *
     cfg.numAttrs = (ctx->pdl_prev && !std::getenv("SPL_NO_PDL")) ? 1 : 0;     // only behind another stream-kernel product
     SPL_CUDA(cudaLaunchKernelEx(&cfg, k, a->nrows, (const uint32_t *)a->ptr, (const uint32_t *)a->ind,
                                 static_cast<const T *>(a->val), xg, y, (const uint32_t *)a->stream_cta_rows,
-                                (const uint32_t *)a->stream_xhi, (const uint32_t *)a->stream_xlo0, a->stream_max_tiles,
-                                a->stream_cap, stages, ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
+                                (const uint32_t *)a->stream_tile_lo, (const uint32_t *)a->stream_xhi,
+                                (const uint32_t *)a->stream_xlo0, a->stream_max_tiles, a->stream_cap, stages,
+                                ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
     check_launch(ctx, "spmv_stream");
     ctx->pdl_chain = true;
 }
@@ -756,12 +774,13 @@ template <typename T, int LPR, typename XG>
 void spmv_stream_u(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
     // entries per lane and trip: one trip for the short rows of stencils and bands
     const bool wide = (a->max_row_len + LPR - 1) / LPR > 4;
-    if (a->stream_rows * LPR == 128) {
-        if (wide) launch_stream<T, LPR, 8, 128>(ctx, a, xg, y, x_edge);
-        else launch_stream<T, LPR, 4, 128>(ctx, a, xg, y, x_edge);
+    const bool tight = env_int("SPL_STREAM_TIGHT", 0) != 0;
+    if (wide) {
+        if (tight) launch_stream<T, LPR, 8, true>(ctx, a, xg, y, x_edge);
+        else launch_stream<T, LPR, 8, false>(ctx, a, xg, y, x_edge);
     } else {
-        if (wide) launch_stream<T, LPR, 8, 256>(ctx, a, xg, y, x_edge);
-        else launch_stream<T, LPR, 4, 256>(ctx, a, xg, y, x_edge);
+        if (tight) launch_stream<T, LPR, 4, true>(ctx, a, xg, y, x_edge);
+        else launch_stream<T, LPR, 4, false>(ctx, a, xg, y, x_edge);
     }
 }
 

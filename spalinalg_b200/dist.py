@@ -61,6 +61,13 @@ def exchange_routed(dist, torch, keys, vals, counts: Sequence[int], group=None):
     return rk, rv, recv_counts
 
 
+def _torch_to_ctx(torch):
+    """Device tensors handed to the library were written on torch's current stream; the library works on
+    the context's stream.  When the two are one stream (bench.py, the tests) this costs nothing."""
+    if torch.cuda.is_available():
+        torch.cuda.current_stream().synchronize()
+
+
 def route_device(ctx: Context, torch, fmt: int, nrows: int, ncols: int, row, col, val, starts):
     """Device stable partition by owner (spl_coo_route_dev) of uint32 row/col (int32 tensors) and
     f32/f64 values.  Returns (keys int64 tensor, vals tensor, counts list)."""
@@ -83,6 +90,7 @@ def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col
     through peer memory and assemble the own shard.  Returns (spl_mat handle, major partition)."""
     ctx, group = exchange.ctx, exchange.group
     world, rank = exchange.world, exchange.rank
+    _torch_to_ctx(torch)                      # row/col/val were produced on torch's stream
     nmajor = nrows if fmt == capi.SPL_CSR else ncols
     starts = partition_starts(nmajor, world)
     n = int(val.numel())
@@ -108,6 +116,8 @@ def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col
         C.c_void_p(col.data_ptr()), C.c_void_p(val.data_ptr()), world, C.cast(st, C.c_void_p),
         C.cast(kb, C.c_void_p), C.cast(vb, C.c_void_p), C.cast(off, C.c_void_p)))
     exchange.barrier()                                        # every record has landed
+    exchange.check()          # a barrier that gave up must not let a half-filled buffer be assembled (host sync:
+    #                           the assembly below synchronises for its output size anyway)
     nloc = max(starts[rank + 1] - starts[rank], 1)
     h = C.c_void_p()
     ctx.check(ctx._lib.spl_mat_from_packed_dev(
@@ -153,6 +163,7 @@ class DistCsrMatrix:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         starts = partition_starts(nrows, world)
         timing = os.environ.get("SPL_DIST_TIMING") and rank == 0
+        _torch_to_ctx(torch)                  # row/col/val were produced on torch's stream
         t0 = time.perf_counter()
         keys, vals, counts = route_device(ctx, torch, capi.SPL_CSR, nrows, ncols, row, col, val, starts)
         t1 = time.perf_counter()
@@ -211,6 +222,7 @@ class DistCsrMatrix:
         r0, r1 = self.local_rows()
         nnz = self.local.nnz()
         tdt = torch.float32 if self.local.dtype == np.float32 else torch.float64
+        ctx.sync()        # the matrix may still have tail kernels queued on the context's stream; torch reads it below
         p_ptr, p_ind, p_val = self.local.device_ptrs()
         ptr = device_view(torch, p_ptr, r1 - r0 + 1, torch.int32)
         if nnz:
@@ -347,32 +359,60 @@ class PeerExchange:
 
 class PeerVector:
     """x sharded conformally with the columns: rank g's slice holds x[starts[g]:starts[g+1]] in
-    peer-visible memory; `barrier()` orders one iteration's writes before the next one's reads."""
+    peer-visible memory.  Two buffers per rank: peers read the PUBLISHED one (`ptrs`, what
+    spl_spmv_peer gathers from) while the rank fills the other (`local_ptr`, e.g. as the y of its own
+    product: y_t becomes x_{t+1} without a copy); `publish()` runs the device-side barrier and swaps
+    them.  That is what makes one barrier per iteration enough: rank A may write its next slice while a
+    slower rank B is still gathering the current one, because they are different buffers, and the
+    buffer A writes at iteration t+1 is the one read at t-1, which every rank left before it arrived
+    at barrier t (stream order).  With a single buffer a second, read-side barrier would be needed.
+    `barrier()` is the same barrier without the swap, for products that re-read an unchanged x."""
 
-    def __init__(self, ctx: Context, dist, n: int, dtype, starts: Optional[Sequence[int]] = None, group=None):
+    def __init__(self, ctx: Context, dist, n: int, dtype, starts: Optional[Sequence[int]] = None, group=None,
+                 buffers: int = 2):
         self.ctx, self.dtype = ctx, np.dtype(dtype)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.starts = list(starts) if starts is not None else partition_starts(n, self.world)
         self.n = int(n)
         longest = max(self.starts[g + 1] - self.starts[g] for g in range(self.world))
-        self._data = PeerBuffer(ctx, dist, max(longest, 1) * self.dtype.itemsize, group)
+        assert buffers in (1, 2)
+        self._data = [PeerBuffer(ctx, dist, max(longest, 1) * self.dtype.itemsize, group) for _ in range(buffers)]
         self._flags = PeerBuffer(ctx, dist, 4 * capi.SPL_MAX_PEERS, group)
-        self.ptrs = self._data.ptrs
-        self.local_ptr = self._data.local
+        self._cur = 0                          # the published buffer
         self.local_len = self.starts[self.rank + 1] - self.starts[self.rank]
         self._epoch = 0
         dist.barrier(group=group)              # every flag block exists (and is zero) before first use
 
+    @property
+    def ptrs(self) -> List[int]:
+        """Every rank's slice of the published x (own slice included): what the products read."""
+        return self._data[self._cur].ptrs
+
+    @property
+    def published_ptr(self) -> int:
+        return self._data[self._cur].local
+
+    @property
+    def local_ptr(self) -> int:
+        """This rank's slice of the NEXT x: write here, then publish()."""
+        return self._data[(self._cur + 1) % len(self._data)].local
+
     def barrier(self, timeout_ms: int = 2000):
-        """Device-side barrier on the context's stream (no host synchronisation)."""
+        """Device-side barrier on the context's stream (no host synchronisation), no swap."""
         self._epoch += 1
         fl = (C.c_void_p * self.world)(*self._flags.ptrs)
         self.ctx.check(self.ctx._lib.spl_peer_barrier(self.ctx._h, self.world, self.rank,
                                                       C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms)))
 
+    def publish(self, timeout_ms: int = 2000):
+        """The slice at `local_ptr` is final: barrier, then it becomes the published buffer."""
+        self.barrier(timeout_ms)
+        self._cur = (self._cur + 1) % len(self._data)
+
     def pull(self, x_full_dev: int):
-        """All-gather by pulling: copies every peer's slice into the local full-length vector at
-        `x_full_dev` (device address, n elements).  The own slice is left to the caller."""
+        """All-gather by pulling: copies every peer's slice of the published x into the local
+        full-length vector at `x_full_dev` (device address, n elements).  The own slice is left to
+        the caller."""
         st = (C.c_uint64 * (self.world + 1))(*self.starts)
         sl = (C.c_void_p * self.world)(*self.ptrs)
         self.ctx.check(self.ctx._lib.spl_peer_pull(self.ctx._h, _dtype_code(self.dtype), self.world, self.rank,
@@ -380,12 +420,14 @@ class PeerVector:
                                                    C.c_void_p(x_full_dev)))
 
     def check(self):
-        """Raises if a barrier timed out (synchronises the stream)."""
+        """Raises if a barrier timed out (synchronises the stream).  A product launched behind a
+        barrier that timed out writes NaN, never a result computed from a half-written x."""
         t = C.c_int()
         self.ctx.check(self.ctx._lib.spl_peer_barrier_status(self.ctx._h, C.byref(t)))
 
     def close(self, dist=None, group=None):
-        self._data.close(dist, group)
+        for d in self._data:
+            d.close(dist, group)
         self._flags.close(dist, group)
 
 

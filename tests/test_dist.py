@@ -308,14 +308,28 @@ def test_sharded_front_end_world1_nccl():
         device_view(torch, xv.local_ptr, n, torch.float64).copy_(torch.from_numpy(x))
         y = torch.zeros(n, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
+        xv.publish()                                          # the written buffer becomes the one products read
         for _ in range(2):
-            xv.barrier()
             D.spmv_peer(xv, y.data_ptr())
+            xv.barrier()                                      # x unchanged: barrier without the swap
         ctx.sync()
         xv.check()
         yw = orc.csr_spmv(n, *full, x)
         sc = orc.csr_spmv(n, full[0], full[1], np.abs(full[2]), np.abs(x))
         assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
+        # y_t -> x_{t+1} without a copy: the product writes the next x into the unpublished buffer
+        A1 = 0.05 * np.asarray(full[2])
+        D1 = spd.DistCsrMatrix(type(D.local).new(n, n, full[0], full[1], A1, ctx=ctx), D.starts, 0, n, n)
+        ref = x
+        for _ in range(6):
+            D1.spmv_peer(xv, xv.local_ptr)
+            xv.publish()
+            ref = orc.csr_spmv(n, full[0], full[1], A1, ref)
+        ctx.sync()
+        xv.check()
+        got = device_view(torch, xv.published_ptr, n, torch.float64).cpu().numpy()
+        scale = np.abs(ref).max() + 1e-300
+        assert np.all(np.abs(got - ref) <= 1e-10 * scale)
         S = D + D
         w = orc.addsub(0, n, n, full, full)
         assert np.array_equal(S.local.colind(), w[1]) and S.local.values().tobytes() == w[2].tobytes()

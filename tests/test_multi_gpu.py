@@ -69,9 +69,10 @@ def _worker(rank, world, port, out):
         from spalinalg_b200.synthetic_device import device_view
         device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(x[r0:r1]))
         y = torch.zeros(r1 - r0, dtype=torch.float64, device="cuda")
-        for _ in range(3):                            # several epochs of the flag barrier
-            xv.barrier()
+        xv.publish()                                  # barrier + the written buffer becomes the published one
+        for _ in range(3):                            # several epochs of the flag barrier, x unchanged
             D.spmv_peer(xv, y.data_ptr())
+            xv.barrier()
         torch.cuda.synchronize()
         xv.check()
         ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
@@ -89,13 +90,22 @@ def _worker(rank, world, port, out):
         x_full[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
         torch.cuda.synchronize()
         xv.barrier()
-        xv.pull(x_full.data_ptr())
+        xv.pull(x_full.data_ptr())                    # pulls the published buffer
         y.zero_()
         L.spmv_device(x_full.data_ptr(), y.data_ptr())
         torch.cuda.synchronize()
         xv.check()
         ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
         assert ok, "pulled all-gather SpMV differs from the oracle"
+
+        # an iteration whose x changes every step: y_t is written straight into the unpublished buffer
+        # and published as x_{t+1} (one barrier per step).  One rank is held back by a spin kernel at a
+        # different point of every step, so the fast rank runs ahead as far as the barrier lets it; with
+        # a single buffer it would overwrite a slice its peer is still gathering (write after read).
+        # Banded matrix, one lane per row: the sharded iteration must equal the oracle's sequential one
+        # bit for bit.
+        ok &= iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50)
+        assert ok, "changing-x iteration over peer memory differs from the oracle's sequential iteration"
 
         # add / sub / neg on the shared partition
         r2, c2, v2 = make_coo(n, n, 300000, 321)
@@ -129,6 +139,45 @@ def _worker(rank, world, port, out):
         if rank == 0:
             out.put(int(flag.item()))
         dist.destroy_process_group()
+
+
+def iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50, n=300_007, delay_cycles=3_000_000):
+    """x_{t+1} = A x_t over a PeerVector, `iters` steps, against the oracle's sequential iteration.
+    Returns True when this rank's slice of the last x equals the oracle's bit for bit."""
+    from spalinalg_b200.synthetic_device import device_view
+    rows = np.repeat(np.arange(n), 9)
+    cols = rows + np.tile(np.arange(-4, 5), n)
+    keep = (cols >= 0) & (cols < n)
+    rows, cols = rows[keep], cols[keep]
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.uint64)
+    val = (0.11 + 0.001 * ((rows * 7 + cols * 3) % 13)).astype(np.float64)     # row sums ~ 1: the iteration stays O(1)
+    x0 = np.sin(np.arange(n) * 1e-2) + 1.5
+    starts = spd.partition_starts(n, world)
+    r0, r1 = starts[rank], starts[rank + 1]
+    lo, hi = int(ptr[r0]), int(ptr[r1])
+    A = sp.CsrMatrix.new(r1 - r0, n, (ptr[r0:r1 + 1] - ptr[r0]).astype(np.uint64), cols[lo:hi].astype(np.uint64),
+                         val[lo:hi], ctx=ctx)
+    dA = spd.DistCsrMatrix(A, starts, rank, n, n)
+    xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+    device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(x0[r0:r1]))
+    xv.publish()
+    for t in range(iters):
+        slow = (t % world) == rank                    # the late rank changes every step
+        if slow and t % 2 == 0:
+            torch.cuda._sleep(delay_cycles)           # late before its product: peers wait at the barrier
+        dA.spmv_peer(xv, xv.local_ptr)                # y_t -> the unpublished buffer
+        if slow and t % 2 == 1:
+            torch.cuda._sleep(delay_cycles)           # late after its product, before the barrier
+        xv.publish()
+    torch.cuda.synchronize()
+    xv.check()
+    got = device_view(torch, xv.published_ptr, r1 - r0, torch.float64).cpu().numpy()
+    ref = x0
+    for _ in range(iters):
+        ref = orc.csr_spmv(n, ptr, cols.astype(np.uint64), val, ref)
+    same = got.tobytes() == ref[r0:r1].tobytes()
+    xv.close(dist)
+    return bool(same)
 
 
 def _free_port():
