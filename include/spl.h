@@ -62,9 +62,11 @@ typedef enum { SPL_F32 = 0, SPL_F64 = 1 } spl_dtype;   /* Scalar: src/scalar.rs:
  * into a ring of shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier) several tiles
  * ahead, the other warps consume the stages (x gathers, row sums with LPR lanes per row; with one
  * lane per row the sum runs in ascending column order, bit-identical to `&A * &X`).  Launched with
- * programmatic dependent launch: the matrix prefetch of a product overlaps the tail of the one before. */
+ * programmatic dependent launch: the matrix prefetch of a product overlaps the tail of the one before.
+ * SCATTER is for CSC matrices only: column by column with atomic adds into y, no second copy of the
+ * matrix (every other choice runs a CSC matrix on its cached CSR form, see spl_spmv). */
 typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_SPMV_SPLIT = 3, SPL_SPMV_SLICED = 4,
-               SPL_SPMV_STREAM = 5 } spl_spmv_kernel;
+               SPL_SPMV_STREAM = 5, SPL_SPMV_SCATTER = 6 } spl_spmv_kernel;
 
 /* ---- context ------------------------------------------------------------ */
 
@@ -171,9 +173,12 @@ int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out)
 int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out);
 
 /* y = A*x with dense device vectors (extension; the reference's only route is
- * `&A * &X` with X n x 1, src/csr/ops/mul.rs:5-60, whose values this matches to
- * 1e-12 (f64) / 1e-5 (f32) relative; rows without entries give 0).  A must be
- * CSR.  x has ncols elements, y nrows. */
+ * `&A * &X` with X n x 1, src/csr/ops/mul.rs:5-60 and src/csc/ops/mul.rs:5-61, whose values
+ * this matches to 1e-12 (f64) / 1e-5 (f32) relative; rows without entries give 0).  x has
+ * ncols elements, y nrows.  A may be CSR or CSC: the first product on a CSC matrix builds
+ * its CSR form on the device (as spl_mat_convert would) and keeps it with the matrix, so
+ * later products cost the same as on a CsrMatrix.  With A = the CSC view of a CSR matrix B
+ * (same arrays, dims swapped) this is y = B^T x. */
 int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev);
 /* kernel: spl_spmv_kernel in bits 0-7; bits 8-15 optionally force the vector kernel's lanes per
  * row (1, 2, 4, 8, 16 or 32; 0 = planned value). */

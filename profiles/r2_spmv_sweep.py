@@ -65,7 +65,7 @@ def sweep_regular(name, make, V, tdt, copies, reps):
         res[key] = {"ms": round(ms, 5), "gbps": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / PEAK, 4)}
         print(name, key, res[key], flush=True)
 
-    knobs = dict(SPL_STREAM_STAGES=None, SPL_STREAM_CTAS=None, SPL_NO_PDL=None, SPL_STREAM_TIGHT=None)
+    knobs = dict(SPL_STREAM_STAGES=None, SPL_STREAM_CTAS=None, SPL_NO_PDL=None, SPL_STREAM_TIGHT=None, SPL_STREAM_L2HINT=None)
     setenv(**knobs)
     put("vector", rate(As, xs, ys, 1, 0, reps))
     # check the stream kernel against the vector kernel once: same lanes, same order => same bits
@@ -77,11 +77,11 @@ def sweep_regular(name, make, V, tdt, copies, reps):
     setenv(SPL_NO_PDL=1)
     put("stream_default_nopdl", rate(As, xs, ys, 5, 0, reps))
     setenv(SPL_NO_PDL=None)
-    for tight in (0, 1):
-        for ctas in (0, 2, 3):
-            for stages in (2, 3, 4):
-                setenv(SPL_STREAM_STAGES=stages, SPL_STREAM_TIGHT=tight, SPL_STREAM_CTAS=ctas or None)
-                key = f"stream_tight{tight}_ctas{ctas or 'max'}_s{stages}"
+    for hint in (0, 1):
+        for tight in (0, 1):
+            for stages in (2, 3):
+                setenv(SPL_STREAM_STAGES=stages, SPL_STREAM_TIGHT=tight, SPL_STREAM_L2HINT=hint)
+                key = f"stream_hint{hint}_tight{tight}_s{stages}"
                 try:
                     put(key, rate(As, xs, ys, 5, 0, reps))
                 except Exception as e:                                   # noqa: BLE001

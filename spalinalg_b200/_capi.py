@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libspalinalg_b200.so")
 SPL_OK, SPL_ERR_SHAPE, SPL_ERR_INVALID, SPL_ERR_CUDA, SPL_ERR_UNSUPPORTED, SPL_ERR_OOM, SPL_ERR_ARG = range(7)
 SPL_CSR, SPL_CSC = 0, 1
 SPL_F32, SPL_F64 = 0, 1
-SPL_SPMV_AUTO, SPL_SPMV_VECTOR, SPL_SPMV_MERGE, SPL_SPMV_SPLIT, SPL_SPMV_SLICED, SPL_SPMV_STREAM = 0, 1, 2, 3, 4, 5
+SPL_SPMV_AUTO, SPL_SPMV_VECTOR, SPL_SPMV_MERGE, SPL_SPMV_SPLIT, SPL_SPMV_SLICED, SPL_SPMV_STREAM, SPL_SPMV_SCATTER = 0, 1, 2, 3, 4, 5, 6
 SPL_MAX_PEERS, SPL_IPC_HANDLE_BYTES = 8, 64
 
 STATUS_NAMES = {0: "SPL_OK", 1: "SPL_ERR_SHAPE", 2: "SPL_ERR_INVALID", 3: "SPL_ERR_CUDA",

@@ -401,7 +401,7 @@ int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_ho
 int spl_spmv_choice(spl_ctx *ctx, const spl_mat *a, int *kernel, int *lanes_per_row) {
     API_BEGIN(ctx)
     SPL_REQUIRE(a, SPL_ERR_ARG, "NULL handle");
-    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
+    a = csr_form(ctx, a);                 // a CSC matrix is planned on its CSR form
     spmv_plan(ctx, const_cast<spl_mat *>(a));
     if (kernel) *kernel = a->plan_kernel;
     if (lanes_per_row) *lanes_per_row = a->plan_lanes;
@@ -445,6 +445,7 @@ int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val) {
     if (m->nnz) {
         SPL_CUDA(cudaMemcpyAsync(m->val, val, (size_t)m->nnz * m->vsize(), cudaMemcpyHostToDevice, ctx->stream));
         SPL_CUDA(cudaStreamSynchronize(ctx->stream));      // the caller may reuse its buffer at once
+        drop_value_copies(ctx, m);                         // copies of the old values: CSR twin, sliced SpMV copy
     }
     API_END(ctx)
 }

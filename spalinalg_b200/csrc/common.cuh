@@ -114,6 +114,11 @@ struct spl_mat {
     uint32_t *stream_cta_rows = nullptr, *stream_xhi = nullptr, *stream_xlo0 = nullptr, *stream_tile_lo = nullptr;
     uint32_t stream_rows = 0, stream_cap = 0, stream_grid = 0, stream_max_tiles = 0;
 
+    // CSR form of a CSC matrix (same matrix, other format), built by the first product y = A x on it
+    // and kept: products on a CscMatrix then run the row kernels at full speed and in the reference's
+    // summation order.  Owned by this matrix; dropped when the values change.
+    std::atomic<spl_mat *> twin{nullptr};
+
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }
     size_t vsize() const { return dtype == SPL_F32 ? 4 : 8; }

@@ -38,8 +38,13 @@ void recompress(spl_ctx *ctx, int dtype, uint32_t nmajor, uint32_t nminor, uint3
                 const uint32_t *ptr, const uint32_t *ind, const void *val, uint32_t *out_ptr,
                 uint32_t *out_ind, void *out_val);
 
-// spmv.cu — y = A x, CSR (a-6 restricted to B = n x 1, dense vectors)
+// spmv.cu — y = A x (a-6 restricted to B = n x 1, dense vectors).  CSR runs the row kernels; a CSC
+// matrix runs them on its cached CSR form (csr_form), or scatters column by column (SPL_SPMV_SCATTER).
 void spmv_plan(spl_ctx *ctx, spl_mat *a);
+// `a` itself if it is CSR, else its CSR twin (built on first use, kept with the matrix)
+const spl_mat *csr_form(spl_ctx *ctx, const spl_mat *a);
+// forget everything derived from the values (after values_mut): CSR twin, sliced copy
+void drop_value_copies(spl_ctx *ctx, spl_mat *m);
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes);
 // `&A * &x` with host vectors, pipelined: x goes up in prefixes, row chunks run as soon as the prefix
 // they need is there, their part of y goes down while the next chunk runs (PCIe both ways at once).

@@ -191,6 +191,7 @@ spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
 
 void free_mat(spl_ctx *ctx, spl_mat *m) {
     if (!m) return;
+    free_mat(ctx, m->twin.exchange(nullptr));
     dfree(ctx, m->ptr);
     dfree(ctx, m->ind);
     dfree(ctx, m->val);

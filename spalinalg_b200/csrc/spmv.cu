@@ -488,6 +488,21 @@ void spmv_merge(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
 //     the reference's `&A * &X` (src/csr/ops/mul.rs:25-40).
 constexpr uint32_t kStreamXEdgeMax = 1u << 15;     // longest leading edge of x one tile prefetches (elements)
 
+// L2 eviction policy for the matrix stream: read once, so it should not push x (re-read by other
+// tiles) out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                  uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -568,7 +583,7 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
                    const T *__restrict__ val, const XG xg, T *__restrict__ y, const uint32_t *__restrict__ cta_rows,
                    const uint32_t *__restrict__ tile_lo, const uint32_t *__restrict__ xhi,
                    const uint32_t *__restrict__ xlo0, uint32_t max_tiles, uint32_t cap, uint32_t stages,
-                   const T *__restrict__ x_edge, uint32_t ncols) {
+                   const T *__restrict__ x_edge, uint32_t ncols, int l2_hint) {
     constexpr uint32_t CONS = ST_CONSUMERS;
     constexpr uint32_t R = CONS / LPR;
     constexpr uint32_t PTRS = R + 4;           // pointer slots per stage: R + 1 needed, whole 16-byte units
@@ -597,6 +612,7 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
         uint32_t s = 0, phase = 0;
         uint32_t edge = __ldg(xlo0 + blockIdx.x);                 // x below this is somebody else's first touch
         uint32_t lo = __ldg(t_lo);
+        const uint64_t pol = l2_policy_evict_first();
         for (uint32_t k = 0; k < ntiles; ++k) {
             const uint32_t hi = __ldg(t_lo + k + 1), x1 = __ldg(t_xhi + k);     // consecutive words: L1 hits
             if (k >= stages) mbar_wait(empty + s, phase ^ 1u);     // the consumers are done with this stage
@@ -607,7 +623,10 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
             const uint32_t np = left < PTRS ? left : PTRS;
             mbar_expect_tx(full + s, cnt * (uint32_t)(sizeof(uint32_t) + sizeof(T)) + np * (uint32_t)sizeof(uint32_t));
             tma_bulk_g2s(s_ptr + (size_t)s * PTRS, ptr + r0, np * (uint32_t)sizeof(uint32_t), full + s);
-            if (cnt) {
+            if (cnt && l2_hint) {
+                tma_bulk_g2s_hint(s_ind + (size_t)s * cap, ind + za, cnt * (uint32_t)sizeof(uint32_t), full + s, pol);
+                tma_bulk_g2s_hint(s_val + (size_t)s * cap, val + za, cnt * (uint32_t)sizeof(T), full + s, pol);
+            } else if (cnt) {
                 tma_bulk_g2s(s_ind + (size_t)s * cap, ind + za, cnt * (uint32_t)sizeof(uint32_t), full + s);
                 tma_bulk_g2s(s_val + (size_t)s * cap, val + za, cnt * (uint32_t)sizeof(T), full + s);
             }
@@ -765,7 +784,8 @@ void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *
                                 static_cast<const T *>(a->val), xg, y, (const uint32_t *)a->stream_cta_rows,
                                 (const uint32_t *)a->stream_tile_lo, (const uint32_t *)a->stream_xhi,
                                 (const uint32_t *)a->stream_xlo0, a->stream_max_tiles, a->stream_cap, stages,
-                                ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols));
+                                ((uintptr_t)x_edge & 15u) ? (const T *)nullptr : x_edge, a->ncols,
+                                env_int("SPL_STREAM_L2HINT", 1)));
     check_launch(ctx, "spmv_stream");
     ctx->pdl_chain = true;
 }
@@ -774,7 +794,7 @@ template <typename T, int LPR, typename XG>
 void spmv_stream_u(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
     // entries per lane and trip: one trip for the short rows of stencils and bands
     const bool wide = (a->max_row_len + LPR - 1) / LPR > 4;
-    const bool tight = env_int("SPL_STREAM_TIGHT", 0) != 0;
+    const bool tight = env_int("SPL_STREAM_TIGHT", 1) != 0;      // four CTAs of 56 registers: measured best on C1, C2
     if (wide) {
         if (tight) launch_stream<T, LPR, 8, true>(ctx, a, xg, y, x_edge);
         else launch_stream<T, LPR, 8, false>(ctx, a, xg, y, x_edge);
@@ -1242,8 +1262,79 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     a->plan_ready.store(1, std::memory_order_release);
 }
 
+// ------------------------------------------------------------------ CSC operands
+// `&A * &X` with A a CscMatrix (src/csc/ops/mul.rs:5-61) accumulates every y[i] over ascending k, the
+// same order as the row-wise product.  The CSC arrays are the CSR arrays of the transpose, so the
+// row kernels cannot run on them; the first product on a CSC matrix builds its CSR form (one
+// histogram + scan + scatter, recompress.cu) and keeps it with the matrix.  SPL_SPMV_SCATTER is the
+// copy-free alternative: a lane group per column scatters val * x[col] into y with atomic adds
+// (order of the adds not fixed: results vary in the last bits from run to run; tolerance parity only).
+const spl_mat *csr_form(spl_ctx *ctx, const spl_mat *a) {
+    if (a->format == SPL_CSR) return a;
+    spl_mat *m = const_cast<spl_mat *>(a);
+    if (spl_mat *t = m->twin.load(std::memory_order_acquire)) return t;
+    std::lock_guard<std::mutex> lock(m->plan_mu);
+    if (spl_mat *t = m->twin.load(std::memory_order_relaxed)) return t;
+    spl_mat *t = new_mat(ctx, SPL_CSR, a->dtype, a->nrows, a->ncols, a->nnz);
+    try {
+        recompress(ctx, a->dtype, a->nmajor(), a->nminor(), a->nnz, a->ptr, a->ind, a->val, t->ptr, t->ind, t->val);
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));          // visible to any other stream from here on
+    } catch (...) {
+        free_mat(ctx, t);
+        throw;
+    }
+    m->twin.store(t, std::memory_order_release);
+    return t;
+}
+
+void drop_value_copies(spl_ctx *ctx, spl_mat *m) {
+    std::lock_guard<std::mutex> lock(m->plan_mu);
+    free_mat(ctx, m->twin.exchange(nullptr));
+    dfree(ctx, m->slice_ptr); dfree(ctx, m->slice_ind); dfree(ctx, m->slice_val);
+    m->slice_ptr = m->slice_ind = nullptr;
+    m->slice_val = nullptr;
+    m->slice_entries = 0;
+    m->slice_state.store(0, std::memory_order_release);
+}
+
+namespace {
+template <typename T, int LPC>
+__global__ void __launch_bounds__(256)
+spmv_csc_scatter_kernel(uint32_t ncols, const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind,
+                        const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y) {
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t col = gtid / LPC;
+    if (col >= ncols) return;
+    const T xc = __ldg(x + col);
+    const uint32_t e = __ldg(ptr + col + 1);
+    for (uint32_t p = __ldg(ptr + col) + (uint32_t)(gtid % LPC); p < e; p += LPC)
+        atomicAdd(y + __ldg(ind + p), __ldg(val + p) * xc);
+}
+
+template <typename T>
+void spmv_csc_scatter(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
+    SPL_CUDA(cudaMemsetAsync(y, 0, sizeof(T) * (size_t)a->nrows, ctx->stream));
+    if (a->nnz == 0) return;
+    const double mean = (double)a->nnz / a->ncols;
+    const T *v = static_cast<const T *>(a->val);
+    if (mean <= 6.0)
+        spmv_csc_scatter_kernel<T, 1><<<div_up(a->ncols, 256), 256, 0, ctx->stream>>>(a->ncols, a->ptr, a->ind, v, x, y);
+    else if (mean <= 48.0)
+        spmv_csc_scatter_kernel<T, 4><<<div_up((uint64_t)a->ncols * 4, 256), 256, 0, ctx->stream>>>(a->ncols, a->ptr, a->ind, v, x, y);
+    else
+        spmv_csc_scatter_kernel<T, 32><<<div_up((uint64_t)a->ncols * 32, 256), 256, 0, ctx->stream>>>(a->ncols, a->ptr, a->ind, v, x, y);
+    check_launch(ctx, "spmv_csc_scatter");
+}
+}  // namespace
+
 void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes) {
-    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
+    if (kernel == SPL_SPMV_SCATTER) {
+        SPL_REQUIRE(a->format == SPL_CSC, SPL_ERR_UNSUPPORTED, "SPL_SPMV_SCATTER is the column kernel: it needs a CSC matrix");
+        if (a->dtype == SPL_F32) spmv_csc_scatter<float>(ctx, a, (const float *)x, (float *)y);
+        else spmv_csc_scatter<double>(ctx, a, (const double *)x, (double *)y);
+        return;
+    }
+    a = csr_form(ctx, a);
     if (kernel == SPL_SPMV_AUTO) {
         spmv_plan(ctx, const_cast<spl_mat *>(a));
         kernel = a->plan_kernel;
@@ -1395,7 +1486,7 @@ void plan_pipeline(spl_ctx *ctx, spl_mat *a) {
 bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host, void *x_dev,
                          void *y_dev) {
     constexpr int K = spl_ctx::kPipeChunks;
-    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv needs a CSR matrix");
+    a = csr_form(ctx, a);
     const size_t vs = a->vsize();
     if ((size_t)a->nrows * vs < (1u << 20) || a->nnz == 0) return false;      // small: one copy each way
     {   // pageable host memory makes every cudaMemcpyAsync block the host: nothing would overlap

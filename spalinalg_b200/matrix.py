@@ -705,24 +705,10 @@ class _Compressed:
         return type(self)._wrap(self._ctx, h)
 
 
-class CsrMatrix(_Compressed):
-    """Compressed sparse row matrix in HBM (reference: src/csr.rs:65-72)."""
-    _FORMAT = capi.SPL_CSR
-
-    def rowptr(self): return self._download()[0]
-    def colind(self): return self._download()[1]
-
-    @classmethod
-    def from_csc(cls, csc: "CscMatrix"):
-        """From<&CscMatrix<T>> for CsrMatrix<T> (src/csr/conv/csc.rs:3-53)."""
-        return csc._convert(cls)
-
-    def to_csc(self) -> "CscMatrix":
-        return self._convert(CscMatrix)
-
     def matvec(self, x: np.ndarray) -> np.ndarray:
         """y = A x with host vectors (extension; reference route is `&A * &X`, X n x 1,
-        src/csr/ops/mul.rs:5-60).  Uploads x, runs the SpMV kernel, downloads y."""
+        src/csr/ops/mul.rs:5-60, src/csc/ops/mul.rs:5-61).  Uploads x, runs the SpMV kernel, downloads y.
+        On a CscMatrix the first product builds (and keeps) the CSR form on the device."""
         x = np.ascontiguousarray(x, dtype=self._dtype)
         if len(x) != self._ncols:
             raise Panic("assertion `left == right` failed: self.ncols() == rhs.nrows()")
@@ -739,6 +725,23 @@ class CsrMatrix(_Compressed):
         k, l = C.c_int(), C.c_int()
         self._ctx.check(self._ctx._lib.spl_spmv_choice(self._ctx._h, self._h, C.byref(k), C.byref(l)))
         return k.value, l.value
+
+
+class CsrMatrix(_Compressed):
+    """Compressed sparse row matrix in HBM (reference: src/csr.rs:65-72)."""
+    _FORMAT = capi.SPL_CSR
+
+    def rowptr(self): return self._download()[0]
+    def colind(self): return self._download()[1]
+
+    @classmethod
+    def from_csc(cls, csc: "CscMatrix"):
+        """From<&CscMatrix<T>> for CsrMatrix<T> (src/csr/conv/csc.rs:3-53)."""
+        return csc._convert(cls)
+
+    def to_csc(self) -> "CscMatrix":
+        return self._convert(CscMatrix)
+
 
 
 class CscMatrix(_Compressed):

@@ -495,6 +495,49 @@ def test_to_coo_random_matches_the_oracle(dtype, n, m, density):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,density", [(1, 1, 1.0), (700, 450, 0.02), (30000, 41000, 0.0004)])
+def test_spmv_on_csc_matrix(dtype, n, m, density):
+    """`&A * &X` with A a CscMatrix (src/csc/ops/mul.rs:5-61; X n x 1): y[i] accumulates over ascending k
+    like the row-wise product.  spl_spmv on a CSC matrix runs on its cached CSR form; the scatter
+    kernel is the copy-free variant (atomic adds, tolerance only); the CSC view of a CSR matrix B
+    (same arrays, dims swapped) gives y = B^T x; values_mut drops the cached form."""
+    import torch
+    rng = np.random.default_rng(n + 3 * m)
+    a = _rand_csr(rng, n, m, density, dtype)
+    x = rng.standard_normal(m).astype(dtype)
+    A = sp.CsrMatrix.new(n, m, *a)
+    Cm = A.to_csc()
+    want = orc.csr_spmv(n, *a, x)
+    scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x))
+    rtol = SPMV_RTOL[np.dtype(dtype)]
+    tiny = np.finfo(dtype).tiny
+    y = Cm.matvec(x)
+    assert y.tobytes() == A.matvec(x).tobytes()                 # same kernel on the same CSR arrays
+    assert np.all(np.abs(y - want) <= rtol * np.maximum(scale, tiny))
+    assert Cm.spmv_choice() == A.spmv_choice()
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.full((n,), 7.0, dtype=xd.dtype, device="cuda")
+    torch.cuda.synchronize()
+    Cm.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=6)      # SPL_SPMV_SCATTER
+    sp.default_context().sync()
+    assert np.all(np.abs(yd.cpu().numpy() - want) <= 4 * rtol * np.maximum(scale, tiny))
+    with pytest.raises(sp.DeviceError):
+        A.spmv_device(xd.data_ptr(), yd.data_ptr(), kernel=6)   # the column kernel needs a CSC matrix
+    # y = B^T z through the CSC view of B's own arrays
+    z = rng.standard_normal(n).astype(dtype)
+    Bt = sp.CscMatrix.new(m, n, *a)                             # m x n matrix whose columns are B's rows
+    t = orc.recompress(n, m, *a)                                # CSR arrays of B^T
+    wt = orc.csr_spmv(m, *t, z)
+    st = orc.csr_spmv(m, t[0], t[1], np.abs(t[2]), np.abs(z))
+    assert np.all(np.abs(Bt.matvec(z) - wt) <= rtol * np.maximum(st, tiny))
+    # values_mut: the cached CSR form follows the new values
+    if len(a[2]):
+        v2 = (2.0 * a[2]).astype(dtype)
+        Bt.set_values(v2)
+        assert np.all(np.abs(Bt.matvec(z) - 2.0 * wt) <= 2 * rtol * np.maximum(2 * st, tiny))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", ["laplace", "band9", "stencil27", "ragged"])
 def test_spmv_stream_kernel(dtype, shape):
     """The persistent TMA-pipelined kernel (SPL_SPMV_STREAM): row counts that are not a multiple of the
