@@ -3,26 +3,27 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A step is one SpMV y = A x over the workload.  N = 1: config 2 of BASELINE.json (27-point stencil
-128^3, f64, 2.1 M rows, 55.7 M nnz; footprint 702 MB > L2, so no flush is needed).  N > 1: config
-5 (banded 9, n = 1e8, f64), row-sharded over the ranks — fixed total work, strong scaling.  The
-exchange of x is part of every step: `peer` (default for banded/stencil shards) leaves x in its
-owners' peer-visible memory and gathers it inside the SpMV kernel over NVLink, ordered by a
-device-side flag barrier; `halo` sends boundary slices with NCCL send/recv; `allgather` is the
-NCCL all-gather general matrices need.  `value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V,
-SURVEY.md 8d) of the whole job per second of the slowest rank, device-timed.  `e2e` = the same
-metric through the reference-facing call `&A * &x` with HOST vectors: A is a constructed
-CsrMatrix (device resident, as the reference's is host resident), every step copies x from pinned
-host memory to the device, runs the SpMV and copies y back (spl_spmv_host at N = 1; upload into
-the peer slice + barrier + spl_spmv_peer + download at N > 1).  `e2e_cold` adds the construction
-of A from the reference-layout host arrays (usize indices, validating CsrMatrix::new) to every
-step.  The line also carries the secondary metrics of the path (COO->CSR assembly on config 1,
-CSR->CSC on config 2, config 5 on one GPU as the strong-scaling base; sharded add and sharded
-assembly at N > 1), `roofline`, `cpu_baseline` (oracle port of the reference's only SpMV route,
-`&A * &X` with X n x 1, on a bounded sample) and `clocks`.
+ONE workload at every N: config 5 of BASELINE.json (banded, offsets -4..+4, n = 1e8, 9e8 stored
+entries, f64; 12.4 GB algorithmic per product, inputs far larger than L2, so no flush is needed).
+N = 1 runs it on one GPU; N > 1 row-shards the SAME matrix over the ranks (fixed total work: strong
+scaling).  A step is one SpMV y = A x over the whole matrix.  At N > 1 x stays in its owners'
+peer-visible memory and is gathered inside the SpMV kernel over NVLink; the step includes the
+device-side barrier that orders an iteration's writes of x before the peers' reads.
+`value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V) of the whole job per second
+of the slowest rank, device-timed.  `e2e` = the same metric through the reference-facing call
+`&A * &x` with HOST vectors: A is a constructed CsrMatrix (device resident, as the reference's is
+host resident), every step moves x from pinned host memory to the device, runs the product and moves
+y back (spl_spmv_host at N = 1, spl_spmv_peer_host on every rank at N > 1).
+`parity_check`: before anything is timed, a small problem sharded over the same N ranks is compared
+with the CPU oracle (assembly and add bit-exact, SpMV within 1e-12, and a 50-step iteration whose x
+changes every step with one rank delayed).  The line also carries, as named extras, configs 1-4
+(SpMV, assembly, conversions) and the add of config 5 at N = 1, the sharded forms at N > 1,
+`roofline`, `cpu_baseline` and `clocks`.
 
---impl reference times that CPU route alone (the reference is Rust; no rustc here, so the
-oracle's line-by-line port stands in: cpu_baseline.kind = "port").
+--impl reference times the reference's only SpMV route (`&A * &X`, X n x 1: three counting-sort
+transposes + Gustavson) on the host: the oracle's line-by-line port (the reference is Rust; no rustc
+in this image: cpu_baseline.kind = "port"), one core because the reference is single-threaded, on a
+bounded sample of the same workload (the same banded matrix at n = 1e7).
 """
 from __future__ import annotations
 
@@ -43,9 +44,36 @@ sys.path.insert(0, ROOT)
 
 I_BYTES = 4   # device index width used for the algorithmic byte count
 
+WORKLOADS = {
+    # name: (family, size, cpu sample size)
+    "banded9_1e8_f64": ("banded", 10 ** 8, 10 ** 7),
+    "banded9_1e7_f64": ("banded", 10 ** 7, 10 ** 7),
+    "stencil27_128_f64": ("stencil27", 128, 64),
+    "laplace2d_1024_f64": ("laplace2d", 1024, 1024),
+}
+DEFAULT_WORKLOAD = "banded9_1e8_f64"
+
 
 def spmv_bytes(nnz, nrows, ncols, v):
     return nnz * (I_BYTES + v) + (ncols + nrows) * v
+
+
+def workload_shape(wl):
+    """(nrows, nnz) of a workload without building it."""
+    fam, size, _ = WORKLOADS[wl]
+    if fam == "banded":
+        return size, 9 * size - 20
+    if fam == "stencil27":
+        return size ** 3, (3 * size - 2) ** 3
+    return size * size, 5 * size * size - 4 * size
+
+
+def config_of(wl):
+    """The `config` object, identical in both arms (the reference arm samples it: cpu_baseline.sample)."""
+    n, nnz = workload_shape(wl)
+    b = spmv_bytes(nnz, n, n, 8)
+    return {"workload": wl, "nrows": n, "nnz": nnz, "algorithmic_bytes": b,
+            "l2": "inputs larger than L2 (no flush)" if b > 2 * 126e6 else "rotating copies of (A, x, y) larger than L2"}
 
 
 def peaks():
@@ -57,14 +85,29 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------- CPU side
-def cpu_sample(kind="stencil", m=64):
-    """Bounded sample of the bench workload for the CPU legs: the same stencil at m^3."""
+def cpu_sample(wl):
+    """Bounded sample of the workload for the CPU legs: same family, reference layout (usize indices)."""
     from spalinalg_b200 import synthetic as syn
-    r, c, v = syn.stencil_27(m)
-    n = m ** 3
+    fam, _, m = WORKLOADS[wl]
+    if fam == "banded":
+        n = m
+        r, c, v = syn.banded(n, range(-4, 5))
+        x = np.sin(np.arange(n) * 1e-3)
+        what = f"banded9 n={n}"
+    elif fam == "stencil27":
+        n = m ** 3
+        r, c, v = syn.stencil_27(m)
+        x = 1.0 / (1.0 + (np.arange(n) % 97))
+        what = f"27-point stencil {m}^3"
+    else:
+        n = m * m
+        r, c, v = syn.laplacian_2d(m)
+        order = np.lexsort((c, r))
+        r, c, v = r[order], c[order], v[order]
+        x = 1.0 / (1.0 + (np.arange(n) % 97))
+        what = f"2-D Laplacian {m}^2"
     ptr, ind, val = syn.csr_from_sorted_triplets(n, r, c, v)
-    x = 1.0 / (1.0 + (np.arange(n) % 97))
-    return n, ptr, ind, val, x
+    return n, ptr, ind, val, x, f"{what} (n={n}, nnz={len(val)}), f64, X n x 1"
 
 
 def cpu_reference_step(n, ptr, ind, val, x):
@@ -115,34 +158,30 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    m = 64
-    n, ptr, ind, val, x = cpu_sample(m=m)
-    nnz = len(val)
-    b = spmv_bytes(nnz, n, n, 8)
+    wl = workload_name(args)
+    n, ptr, ind, val, x, sample = cpu_sample(wl)
+    b = spmv_bytes(len(val), n, n, 8)
     for _ in range(args.warmup):
         cpu_reference_step(n, ptr, ind, val, x)
     t = [cpu_reference_step(n, ptr, ind, val, x) for _ in range(args.steps)]
     per = sum(t) / len(t)
     value = b / per / 1e9
-    sample = f"27-point stencil {m}^3 (n={n}, nnz={nnz}), f64, X n x 1"
-    asm = cpu_assembly_baseline()
     line = {
         "impl": "reference", "metric": "spmv_algorithmic_bandwidth", "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(wl),
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count(), "assembly": asm, "mul": cpu_mul_baseline()},
+                         "host_cores": os.cpu_count(),
+                         "what": "oracle port of the reference's `&A * &X` route; a rate, so the sample's GB/s stands "
+                                 "for the workload's; one core: the reference is single-threaded"},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_name(args):
-    if args.workload != "auto":
-        return args.workload
-    return "stencil27_128_f64" if args.gpus == 1 else "banded9_1e8_f64"
+    return DEFAULT_WORKLOAD if args.workload == "auto" else args.workload
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -196,18 +235,128 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None}
 
 
+KERNEL_NAMES = {1: "vector", 2: "merge", 3: "split", 4: "sliced", 5: "stream", 6: "scatter"}
+
+
 # ------------------------------------------------------------------------------- our arm
+def build_workload(torch, sp, ctx, wl, rank, world):
+    """Rows [r0, r1) of the workload on this rank's device (global column indices)."""
+    from spalinalg_b200 import sharding
+    from spalinalg_b200.synthetic_device import banded_device, stencil_device
+    f64 = torch.float64
+    fam, size, _ = WORKLOADS[wl]
+    if fam == "banded":
+        n = size
+        r0, r1 = sharding.row_partition(n, world, rank)
+        rowptr, colind, values = banded_device(torch, n, r0, r1, range(-4, 5), f64)
+        halo = 4
+    else:
+        if fam == "stencil27":
+            offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+            n, rowptr, colind, values = stencil_device(torch, offs, size, 26.0, -1.0, f64)
+            halo = size * size + size + 1
+        else:
+            offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
+            n, rowptr, colind, values = stencil_device(torch, offs, size, 4.0, -1.0, f64)
+            halo = size
+        r0, r1 = sharding.row_partition(n, world, rank)
+        if world > 1:                       # keep this rank's rows of the stencil
+            lo, hi = int(rowptr[r0].item()), int(rowptr[r1].item())
+            rowptr = (rowptr[r0:r1 + 1] - rowptr[r0]).contiguous()
+            colind, values = colind[lo:hi].contiguous(), values[lo:hi].contiguous()
+    A = sp.CsrMatrix.from_device_arrays(r1 - r0, n, int(colind.numel()), rowptr.data_ptr(), colind.data_ptr(),
+                                        values.data_ptr(), np.float64, validate=True, ctx=ctx)
+    return A, n, r0, r1, halo
+
+
+def x_values(torch, wl, lo, hi):
+    idx = torch.arange(lo, hi, device="cuda", dtype=torch.int64)
+    if wl.startswith("banded"):
+        return torch.sin(idx.to(torch.float64) * 1e-3)
+    return (1.0 / (1.0 + (idx % 97))).to(torch.float64)
+
+
+def parity_check(torch, dist, sp, spd, ctx, rank, world):
+    """A small problem sharded over the SAME ranks, against the CPU oracle (the checker, never the thing
+    measured): sharded assembly bit-exact, sharded SpMV within 1e-12, sharded add bit-exact, and the
+    changing-x iteration over peer memory (one rank delayed every step) bit-exact."""
+    import oracle as orc
+    from tests.test_dist import make_coo, shard_of, syn_block
+    from tests.test_multi_gpu import iterate_against_oracle
+    from spalinalg_b200.synthetic_device import device_view
+    out = {"world": world}
+    n = 20011
+    r, c, v = make_coo(n, n, 400000, 123)
+    full = orc.compress_from_coo(n, n, orc.make_triplets(r, c, v), "row")
+    a, b = syn_block(len(v), world, rank)
+    dev = lambda arr, dt: torch.from_numpy(np.ascontiguousarray(arr).astype(dt)).cuda()
+    rd, cd, vd = dev(r[a:b], np.int32), dev(c[a:b], np.int32), dev(v[a:b], np.float64)
+    if world > 1:
+        ex = spd.PeerExchange(ctx, dist)
+        D = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, n, n, rd, cd, vd, ex)
+        ex.check()
+        ex.close()
+        starts = D.starts
+        L = D.local
+    else:
+        L = sp.CsrMatrix.from_device_triplets(n, n, len(v), rd.data_ptr(), cd.data_ptr(), vd.data_ptr(), np.float64, ctx=ctx)
+        starts = [0, n]
+        D = spd.DistCsrMatrix(L, starts, 0, n, n)
+    want = shard_of(full, starts, rank)
+    ok_asm = bool(np.array_equal(L.rowptr(), want[0]) and np.array_equal(L.colind(), want[1])
+                  and L.values().tobytes() == want[2].tobytes())
+    # SpMV on the shard: x in its owners' memory (peer gather) / one buffer at N = 1
+    x = np.random.default_rng(9).standard_normal(n)
+    yw = orc.csr_spmv(n, *full, x)
+    sc = orc.csr_spmv(n, full[0], full[1], np.abs(full[2]), np.abs(x))
+    r0, r1 = starts[rank], starts[rank + 1]
+    y = torch.zeros(r1 - r0, dtype=torch.float64, device="cuda")
+    if world > 1:
+        xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+        device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(x[r0:r1]))
+        xv.publish()
+        D.spmv_peer(xv, y.data_ptr())
+        torch.cuda.synchronize()
+        xv.check()
+        xv.close(dist)
+    else:
+        xd = torch.from_numpy(x).cuda()
+        torch.cuda.synchronize()
+        L.spmv_device(xd.data_ptr(), y.data_ptr())
+        torch.cuda.synchronize()
+    err = np.abs(y.cpu().numpy() - yw[r0:r1])
+    ok_spmv = bool(np.all(err <= 1e-12 * sc[r0:r1] + 1e-300))
+    # add on the shared partition
+    S = D + D
+    w = shard_of(orc.addsub(0, n, n, full, full), starts, rank)
+    ok_add = bool(np.array_equal(S.local.rowptr(), w[0]) and np.array_equal(S.local.colind(), w[1])
+                  and S.local.values().tobytes() == w[2].tobytes())
+    ok_iter = None
+    if world > 1:
+        ok_iter = iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50)
+    flags = [ok_asm, ok_spmv, ok_add] + ([ok_iter] if ok_iter is not None else [])
+    t = torch.tensor([1 if all(flags) else 0] + [1 if f else 0 for f in flags], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    res = [bool(int(q)) for q in t.tolist()]
+    out.update({"ok": res[0], "assembly_bit_exact": res[1], "spmv_within_1e-12": res[2], "add_bit_exact": res[3],
+                "problem": f"random {n} x {n}, {len(v)} triplets with duplicates and cancellations, f64"})
+    if ok_iter is not None:
+        out["changing_x_iteration_bit_exact"] = res[4]
+        out["iteration"] = "x_{t+1} = A x_t, 50 steps, banded n=300007, y written into the unpublished peer buffer, " \
+                           "one rank delayed by a spin kernel every step"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto",
-                    choices=["auto", "stencil27_128_f64", "laplace2d_1024_f64", "banded9_1e8_f64", "banded9_1e7_f64"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "halo", "allgather"])
-    ap.add_argument("--kernel", default="auto")       # auto | vectorN | merge
-    ap.add_argument("--no-extras", action="store_true", help="skip secondary metrics / cpu baseline")
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--kernel", default="auto")       # auto | vectorN | stream | merge  (N = 1 only)
+    ap.add_argument("--no-extras", action="store_true", help="skip secondary metrics / cpu baseline / parity check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -218,9 +367,9 @@ def main():
     import torch
     import torch.distributed as dist
     import spalinalg_b200 as sp
-    from spalinalg_b200 import _capi as capi, sharding
+    from spalinalg_b200 import _capi as capi
+    from spalinalg_b200 import dist as spd
     from spalinalg_b200 import synthetic_device
-    from spalinalg_b200.synthetic_device import banded_device, stencil_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -244,98 +393,74 @@ def main():
     f64 = torch.float64
     V = 8
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity first: the sharded path against the oracle on this many ranks -----------------
+    parity = None
+    if not args.no_extras:
+        parity = parity_check(torch, dist, sp, spd, ctx, rank, world)
+        assert parity["ok"], f"parity check against the oracle failed: {parity}"
+
     # ---- build the workload on the device -------------------------------------------------
-    halo = 0
-    if wl.startswith("stencil27"):
-        offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
-        n, rowptr, colind, values = stencil_device(torch, offs, 128, 26.0, -1.0, f64)
-        r0, r1 = 0, n
-    elif wl.startswith("laplace2d"):
-        offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
-        n, rowptr, colind, values = stencil_device(torch, offs, 1024, 4.0, -1.0, f64)
-        r0, r1 = 0, n
-    else:
-        n = 10 ** 8 if "1e8" in wl else 10 ** 7
-        r0, r1 = sharding.row_partition(n, ngpu, rank)
-        rowptr, colind, values = banded_device(torch, n, r0, r1, range(-4, 5), f64)
-        halo = 4
+    A, n, r0, r1, halo = build_workload(torch, sp, ctx, wl, rank, world)
     nloc = r1 - r0
-    nnz_loc = int(colind.numel())
-    A = sp.CsrMatrix.from_device_arrays(nloc, n, nnz_loc, rowptr.data_ptr(), colind.data_ptr(),
-                                        values.data_ptr(), np.float64, validate=True, ctx=ctx)
+    nnz_loc = A.nnz()
+    cfg = config_of(wl)
     nnz_t = torch.tensor([nnz_loc], device="cuda", dtype=torch.int64)
     if world > 1:
         dist.all_reduce(nnz_t)
-    nnz_total = int(nnz_t.item())
-    bytes_total = spmv_bytes(nnz_total, n, n, V)
-    bytes_local = spmv_bytes(nnz_loc, nloc, n if ngpu == 1 else nloc + 2 * halo, V)
-
-    # x: `peer` keeps only the owned slice (peer-visible memory, mapped by every rank); the NCCL
-    # exchanges use a global-length buffer per rank of which the rank owns [r0, r1)
-    from spalinalg_b200 import dist as spd
-    exchange = "none"
-    if world > 1:
-        exchange = args.exchange if args.exchange != "auto" else ("peer" if halo else "allgather")
-
-    def x_values(lo, hi):
-        idx = torch.arange(lo, hi, device="cuda", dtype=torch.int64)
-        if wl.startswith("banded"):
-            return torch.sin(idx.to(f64) * 1e-3)
-        return (1.0 / (1.0 + (idx % 97))).to(f64)
-
-    xv = None
-    if exchange == "peer":
-        starts = spd.partition_starts(n, world)
-        xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
-        x_loc = synthetic_device.device_view(torch, xv.local_ptr, nloc, f64)
-        x_loc.copy_(x_values(r0, r1))
-        x_full = None
-        dA = spd.DistCsrMatrix(A, starts, rank, n, n)
-    else:
-        x_full = x_values(0, n)
-        x_loc = x_full[r0:r1]
-    y = torch.zeros(nloc, device="cuda", dtype=f64)
+    assert int(nnz_t.item()) == cfg["nnz"] and n == cfg["nrows"]
+    bytes_total = cfg["algorithmic_bytes"]
+    bytes_local = spmv_bytes(nnz_loc, nloc, n if ngpu == 1 else nloc + 2 * min(halo, nloc), V)
 
     kern, lanes = capi.SPL_SPMV_AUTO, 0
     if args.kernel.startswith("vector"):
         kern, lanes = capi.SPL_SPMV_VECTOR, int(args.kernel[6:] or 0)
     elif args.kernel == "merge":
         kern = capi.SPL_SPMV_MERGE
+    elif args.kernel == "stream":
+        kern = capi.SPL_SPMV_STREAM
+
+    # x: at N > 1 every rank keeps only its slice, in peer-visible memory mapped by every rank
+    xv = dA = x_full = None
+    if world > 1:
+        starts = spd.partition_starts(n, world)
+        xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+        for _ in range(2):                            # both halves of the double buffer hold x: the timed
+            synthetic_device.device_view(torch, xv.local_ptr, nloc, f64).copy_(x_values(torch, wl, r0, r1))
+            xv.publish()                              # steps re-read an unchanged x (barrier, no swap)
+        dA = spd.DistCsrMatrix(A, starts, rank, n, n)
+    else:
+        x_full = x_values(torch, wl, 0, n)
+    y = torch.zeros(nloc, device="cuda", dtype=f64)
 
     def local_spmv():
-        if exchange == "peer":
+        if world > 1:
             dA.spmv_peer(xv, y.data_ptr())
         else:
             A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
 
     def step():
-        if exchange == "peer":
+        if world > 1:
             xv.barrier()                      # device-side: peers' slices are final before the gathers
-        elif exchange == "allgather":
-            sharding.exchange_allgather(dist, x_full, r0, r1, world, n % world == 0)
-        elif exchange == "halo":
-            sharding.exchange_halo(dist, x_full, r0, r1, halo, rank, world)
         local_spmv()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- correctness spot check before timing: analytic row sums are checked by the tests; here
-    # the sharded result must equal the single-buffer kernel's on the same rows ----------------
+    # ---- sanity before timing: the step's result equals the single-buffer vector kernel's --------
     step()
     torch.cuda.synchronize()
-    if exchange == "peer":
+    lo, hi = max(0, r0 - halo), min(n, r1 + halo)
+    x_chk = torch.zeros(n, device="cuda", dtype=f64)
+    x_chk[lo:hi] = x_values(torch, wl, lo, hi)
+    y_chk = torch.empty_like(y)
+    A.spmv_device(x_chk.data_ptr(), y_chk.data_ptr(), capi.SPL_SPMV_VECTOR, 0)
+    torch.cuda.synchronize()
+    if xv is not None:
         xv.check()
-        lo, hi = max(0, r0 - halo), min(n, r1 + halo)
-        x_chk = torch.zeros(n if n <= 2 * 10 ** 8 else 1, device="cuda", dtype=f64)
-        x_chk[lo:hi] = x_values(lo, hi)
-        y_chk = torch.empty_like(y)
-        A.spmv_device(x_chk.data_ptr(), y_chk.data_ptr(), kern, lanes)
-        torch.cuda.synchronize()
-        assert torch.equal(y, y_chk), "peer-gather SpMV differs from the single-buffer kernel"
-        del x_chk, y_chk
+    assert torch.equal(y, y_chk), "the step's SpMV differs from the single-buffer vector kernel"
+    del x_chk, y_chk
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -375,20 +500,22 @@ def main():
     peak, peak_src = peaks()
     achieved = bytes_local / (kern_ms * 1e-3) / 1e9
     choice = A.spmv_choice()
-    kname = "vector" if exchange == "peer" else {1: "vector", 2: "merge"}.get(kern or choice[0], "?")
-    traffic = None
-    try:                                   # per-launch DRAM bytes from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+    kname = KERNEL_NAMES.get(kern or choice[0], "?")
+    traffic, traffic_src = None, None
+    try:     # per-launch DRAM bytes of this kernel on this workload from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t_ = json.load(f)[wl]["spmv_" + kname]
-            traffic = t_["dram_read_bytes"] + t_["dram_write_bytes"]
+            if ngpu == 1:
+                traffic = t_["dram_read_bytes"] + t_["dram_write_bytes"]
+                traffic_src = t_.get("source")
     except Exception:
         pass
 
     # ---- e2e through the reference-facing call with HOST vectors ------------------------------
     # A is a constructed CsrMatrix (device resident; the reference's lives in host memory); a step
     # is `&A * &x`: x from pinned host memory, SpMV, y back to pinned host memory.
-    e2e_steps = max(3, min(args.steps, 20))
-    h_x = x_loc.cpu().pin_memory() if world > 1 else x_full.cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    h_x = x_values(torch, wl, r0, r1).cpu().pin_memory() if world > 1 else x_full.cpu().pin_memory()
     h_y = torch.empty(nloc, dtype=f64).pin_memory()
     h2d = h_x.numel() * 8
     d2h = h_y.numel() * 8
@@ -396,14 +523,12 @@ def main():
     def e2e_step():
         if world == 1:
             ctx.check(lib.spl_spmv_host(ctx._h, A._h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
-            return
-        x_loc.copy_(h_x, non_blocking=True)           # this rank's slice of the new x
-        step()                                        # exchange + SpMV
-        h_y.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        else:
+            dA.matvec_host(xv, h_x.data_ptr(), h_y.data_ptr())
 
     e2e_step()
     assert torch.equal(h_y, y.cpu()), "e2e result differs from the device-resident result"
+    e2e_step()
     barrier()
     e2e_l0 = ctx.launch_count()
     t0 = time.perf_counter()
@@ -415,43 +540,20 @@ def main():
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = bytes_total / float(t.item()) / 1e9
-
-    # cold variant: construction of A from the reference-layout host arrays inside every step
-    cold = None
-    if world == 1 and not args.no_extras:
-        h_ptr = rowptr.to(torch.int64).cpu().pin_memory()
-        h_ind = colind.to(torch.int64).cpu().pin_memory()
-        h_val = values.cpu().pin_memory()
-
-        def cold_step():
-            h = C.c_void_p()
-            ctx.check(lib.spl_mat_from_compressed(ctx._h, capi.SPL_CSR, capi.SPL_F64, nloc, n,
-                                                  h_ptr.numel(), C.c_void_p(h_ptr.data_ptr()),
-                                                  h_ind.numel(), C.c_void_p(h_ind.data_ptr()),
-                                                  h_val.numel(), C.c_void_p(h_val.data_ptr()), C.byref(h)))
-            ctx.check(lib.spl_spmv_host(ctx._h, h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
-            ctx.check(lib.spl_mat_free(ctx._h, h))
-
-        cold_step()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            cold_step()
-        torch.cuda.synchronize()
-        cs = (time.perf_counter() - t0) / 3
-        cold = {"value": bytes_total / cs / 1e9, "unit": "GB/s", "ms_per_step": cs * 1e3,
-                "h2d_bytes_per_step": (h_ptr.numel() + h_ind.numel() + h_val.numel()) * 8 + h2d,
-                "what": "CsrMatrix::new from host usize arrays (validating) + &A * &x, every step"}
-        del h_ptr, h_ind, h_val
+    e2e_s = float(t.item())
+    e2e_value = bytes_total / e2e_s / 1e9
+    del h_x, h_y
 
     # keep the device busy long enough for a few clock samples if the timed region was short
+    clk = None
     if rank == 0:
         t_end = time.perf_counter() + max(0.0, 0.6 - ms_total * 2e-3)
         while time.perf_counter() < t_end:
-            for _ in range(50):
+            for _ in range(10):
                 local_spmv()
             torch.cuda.synchronize()
         clk = clocks.stop()
+    barrier()
 
     # ---- secondary metrics of the path ------------------------------------------------------
     extras = {}
@@ -459,48 +561,48 @@ def main():
     if ngpu > 1 and not args.no_extras:
         extras = sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world)
     if rank == 0 and ngpu == 1 and not args.no_extras:
+        x_full = None
         extras = secondary_metrics(torch, sp, ctx, A, wl)
-        m = 64
-        sn, sptr, sind, sval, sx = cpu_sample(m=m)
+        sn, sptr, sind, sval, sx, sample = cpu_sample(wl)
         sb = spmv_bytes(len(sval), sn, sn, 8)
         cpu_reference_step(sn, sptr, sind, sval, sx)
         ts = [cpu_reference_step(sn, sptr, sind, sval, sx) for _ in range(3)]
         import oracle as orc
         t0 = time.perf_counter()
-        for _ in range(5):
+        for _ in range(3):
             orc.csr_spmv(sn, sptr, sind, sval, sx)
-        rowdot = (time.perf_counter() - t0) / 5
+        rowdot = (time.perf_counter() - t0) / 3
         cpu = {"value": sb / statistics.median(ts) / 1e9, "unit": "GB/s", "cores": 1,
                "assembly": cpu_assembly_baseline(), "mul": cpu_mul_baseline(),
                "kind": "port", "host_cores": os.cpu_count(),
-               "sample": f"27-point stencil {m}^3 (n={sn}, nnz={len(sval)}), f64; reference route "
-                         f"&A * &X (3 transposes + Gustavson), 3 reps median",
+               "sample": sample + "; reference route &A * &X (3 transposes + Gustavson), 3 reps median",
                "rowdot_value": sb / rowdot / 1e9}
 
     if rank == 0:
         line = {
             "metric": "spmv_algorithmic_bandwidth", "value": value, "unit": "GB/s", "n_gpus": ngpu,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong" if ngpu > 1 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl, "nrows": n, "nnz": nnz_total, "algorithmic_bytes": bytes_total,
-                       "l2": "inputs larger than L2 (no flush)" if bytes_local > 2 * 126e6 else
-                             "footprint below 2x L2: L2-resident number",
-                       "exchange": exchange, "spmv_kernel": kname,
-                       "lanes_per_row": choice[1] if lanes == 0 else lanes,
-                       "pct_of_8TBps_nominal": 100.0 * achieved / 8000.0},
+            "config": cfg,
+            "detail": {"exchange": "peer memory: x gathered from its owners' slices inside the SpMV kernel (NVLink), "
+                                   "device-side flag barrier per step" if ngpu > 1 else "none",
+                       "spmv_kernel": kname, "lanes_per_row": choice[1] if lanes == 0 else lanes,
+                       "rows_per_rank": nloc, "pct_of_8TBps_nominal_per_gpu": 100.0 * achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d * ngpu, "d2h_bytes_per_step": d2h * ngpu,
-                    "steps": e2e_steps, "launches_per_step": e2e_launches,
+                    "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "launches_per_step": e2e_launches,
                     "what": "&A * &x on a constructed (device-resident) CsrMatrix with pinned host x, y: "
-                            + ("spl_spmv_host" if ngpu == 1 else f"slice upload + {exchange} exchange + SpMV + download, all ranks")},
+                            + ("spl_spmv_host" if ngpu == 1 else "spl_spmv_peer_host on every rank (slice upload, barrier, "
+                                                                 "chunked product with the download behind it)")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "spmv", "kernel_ms": kern_ms, "bytes_per_launch": bytes_local},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "kernel": "spmv_" + kname, "kernel_ms": kern_ms,
+                         "bytes_per_launch": bytes_local},
             "clocks": clk,
         }
-        if cold:
-            line["e2e_cold"] = cold
+        if parity:
+            line["parity_check"] = parity
         if cpu:
             line["cpu_baseline"] = cpu
         line.update(extras)
@@ -510,11 +612,16 @@ def main():
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------- N > 1 extras
 def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
-    """Row-sharded add (config 5: A + B, B = offsets {-8,-2,0,2,8}; no exchange) and row-sharded
-    COO->CSR assembly (config-3 style random triplets, block-distributed by entry index, routed by
-    one all-to-all).  Times are the slowest rank's; rates are whole-job."""
-    from spalinalg_b200.synthetic_device import banded_device, random_uniform_coo_device
+    """Secondary sharded metrics on FIXED global inputs (the same problem at every N): the add of
+    config 5 (A + B, B = offsets {-8,-2,0,2,8}; no exchange), COO->CSR assembly of config 3's triplet
+    list block-distributed by entry index (NCCL all-to-all, and routing fused with the exchange over
+    peer memory), the general (random-column) SpMV with x all-gathered, and config 4 (R-MAT) with an
+    nnz-balanced row partition.  Times are the slowest rank's; rates are whole-job."""
+    from spalinalg_b200 import sharding
+    from spalinalg_b200.synthetic_device import banded_device, device_view, random_uniform_coo_device, rmat_coo_device
+    from tests.test_dist import syn_block
     out = {}
 
     def timed_all(fn, reps=3, warm=1):
@@ -531,11 +638,12 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
             ts.append(float(t.item()))
         return statistics.median(ts)
 
-    def total(v):
+    def total(v, op=None):
         t = torch.tensor([v], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
+        dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
         return int(t.item())
 
+    # ---- config 5: A + B, rows sharded, no exchange
     bp, bc, bv = banded_device(torch, n, r0, r1, (-8, -2, 0, 2, 8), torch.float64)
     B = sp.CsrMatrix.from_device_arrays(r1 - r0, n, bc.numel(), bp.data_ptr(), bc.data_ptr(), bv.data_ptr(),
                                         np.float64, validate=False, ctx=ctx)
@@ -551,18 +659,20 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
                           "ms": ms, "nnz_out": nc, "mnnz_per_s": (na + nb) / ms / 1e3,
                           "gbps_algorithmic": b_add / ms / 1e6}
     del keep["C"], B
+    torch.cuda.empty_cache()
 
+    # ---- config 3: the SAME 168 M triplets at every N, rank g holds entries [g*len/N, (g+1)*len/N)
     nr = 10_000_000
-    per = nr // world                      # each rank emits the triplets of `per` rows' worth of entries
-    r_, c_, v_ = random_uniform_coo_device(torch, per, 16, per * 16 // 20, torch.float32, seed=100 + rank)
-    # spread the rows over the whole matrix so that ~ (world-1)/world of the entries change rank
-    r_ = ((r_.to(torch.int64) * world + rank) % nr).to(torch.int32)
-    c_ = ((c_.to(torch.int64) * world + (rank * 7) % world) % nr).to(torch.int32)
+    gr, gc, gv = random_uniform_coo_device(torch, nr, 16, 8_000_000, torch.float32, seed=1)
+    ln = int(gv.numel())
+    a_, b_ = syn_block(ln, world, rank)
+    r_, c_, v_ = gr[a_:b_].clone(), gc[a_:b_].clone(), gv[a_:b_].clone()
+    del gr, gc, gv
+    torch.cuda.empty_cache()
 
     def asm():
         keep["D"] = spd.DistCsrMatrix.from_device_triplets(dist, torch, nr, nr, r_, c_, v_, ctx=ctx)
     ms = timed_all(asm)
-    ln = total(int(v_.numel()))
     ex = spd.PeerExchange(ctx, dist)
 
     def asm_peer():
@@ -571,34 +681,30 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     ex.check()
     assert keep["P"].local.nnz() == keep["D"].local.nnz()
     del keep["P"]
-    ex.close()
-    out["sharded_assembly_peer"] = {"workload": "same triplets; routing and exchange fused: the partition pass writes "
-                                                "into the owners' buffers over NVLink (peer memory), no all-to-all",
-                                    "len": total(int(v_.numel())), "ms": ms_p,
-                                    "mnnz_per_s": total(int(v_.numel())) / ms_p / 1e3}
     D = keep["D"]
     nnz_d = total(D.local.nnz())
-    out["sharded_assembly"] = {"workload": "random 1e7 x 1e7, 16/row + 5% duplicates, f32, triplets block-"
-                                           "distributed by entry index, one all-to-all",
+    out["sharded_assembly"] = {"workload": "config 3: random 1e7 x 1e7, 16/row + 5% duplicates, f32, the same 168 M "
+                                           "triplets at every N, block-distributed by entry index, one NCCL all-to-all",
                                "len": ln, "nnz_out": nnz_d, "ms": ms, "mnnz_per_s": ln / ms / 1e3}
+    out["sharded_assembly_peer"] = {"workload": "same triplets; routing and exchange fused: the partition pass writes "
+                                                "into the owners' buffers over NVLink (peer memory), no all-to-all",
+                                    "len": ln, "nnz_out": nnz_d, "ms": ms_p, "mnnz_per_s": ln / ms_p / 1e3}
     del r_, c_, v_
 
-    # general (random-column) matrix: x exchanged by NCCL all-gather, then the local SpMV
+    # general (random-column) matrix: x exchanged (NCCL all-gather / pull over peer memory), then the local SpMV
     d0, d1 = D.local_rows()
     xg = torch.rand(nr, device="cuda", dtype=torch.float32) - 0.5
     yg = torch.empty(d1 - d0, device="cuda", dtype=torch.float32)
     even = nr % world == 0
 
     def spmv_ag():
-        from spalinalg_b200 import sharding
         sharding.exchange_allgather(dist, xg, d0, d1, world, even)
         D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
     ms = timed_all(spmv_ag, reps=7, warm=3)
     b_ag = nnz_d * 8 + 2 * nr * 4
-    # the same exchange done by pulling the peers' slices over NVLink (peer memory) instead of NCCL
-    from spalinalg_b200.synthetic_device import device_view
     xs = spd.PeerVector(ctx, dist, nr, np.float32, D.starts)
     device_view(torch, xs.local_ptr, d1 - d0, torch.float32).copy_(xg[d0:d1])
+    xs.publish()
     torch.cuda.synchronize()
 
     def spmv_pull():
@@ -609,21 +715,71 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     ms_pull = timed_all(spmv_pull, reps=7, warm=3)
     xs.check()
     assert torch.equal(y_ag, yg), "pulled all-gather gives a different y"
+    out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
+                                                 "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
+                                     "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
     out["sharded_spmv_peer_pull"] = {"workload": "same matrix; x all-gathered by one pull kernel over peer memory "
                                                  "(device barrier + 128-bit NVLink reads), then the local SpMV",
                                      "ms": ms_pull, "gbps_algorithmic": b_ag / ms_pull / 1e6}
     xs.close(dist)
-    out["sharded_spmv_allgather"] = {"workload": "the matrix assembled above (random 16/row, f32), x all-gathered "
-                                                 "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
-                                     "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
+    del D, keep["D"], xg, yg, y_ag
+    torch.cuda.empty_cache()
+
+    # ---- config 4: R-MAT 2^24, the SAME 2^29 edges at every N, nnz-balanced row partition
+    scale = 24
+    n4 = 1 << scale
+    gr, gc, gv = rmat_coo_device(torch, scale, 32, torch.float32, seed=3)
+    ln4 = int(gv.numel())
+    a_, b_ = syn_block(ln4, world, rank)
+    r_, c_, v_ = gr[a_:b_].clone(), gc[a_:b_].clone(), gv[a_:b_].clone()
+    del gr, gc, gv
+    torch.cuda.empty_cache()
+    res4 = {}
+    for balance in ("nnz", None):
+        def asm4():
+            keep["R"] = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, n4, n4, r_, c_, v_, ex, balance=balance)
+        ms_a = timed_all(asm4, reps=2, warm=1)
+        R = keep["R"]
+        q0, q1 = R.local_rows()
+        nnz_max, nnz_sum = total(R.local.nnz(), dist.ReduceOp.MAX), total(R.local.nnz())
+        x4 = torch.rand(n4, device="cuda", dtype=torch.float32) - 0.5
+        y4 = torch.empty(q1 - q0, device="cuda", dtype=torch.float32)
+        xs4 = spd.PeerVector(ctx, dist, n4, np.float32, R.starts)
+        device_view(torch, xs4.local_ptr, q1 - q0, torch.float32).copy_(x4[q0:q1])
+        xs4.publish()
+
+        def spmv4():
+            xs4.barrier()
+            xs4.pull(x4.data_ptr())
+            R.local.spmv_device(x4.data_ptr(), y4.data_ptr())
+        ms_s = timed_all(spmv4, reps=7, warm=3)
+        xs4.check()
+        b4 = nnz_sum * 8 + 2 * n4 * 4
+        res4["nnz_balanced" if balance else "equal_rows"] = {
+            "assembly_ms": ms_a, "assembly_mnnz_per_s": ln4 / ms_a / 1e3, "nnz": nnz_sum,
+            "max_rank_share_of_nnz": nnz_max / nnz_sum, "spmv_ms": ms_s, "spmv_gbps_algorithmic": b4 / ms_s / 1e6,
+            "rows_of_rank0": R.starts[1]}
+        xs4.close(dist)
+        del R, keep["R"], x4, y4
+        torch.cuda.empty_cache()
+    res4["workload"] = ("config 4: R-MAT scale 24, 2^29 edges (the same list at every N, block-distributed by entry index), "
+                        "f32; assembly fused with the exchange over peer memory; SpMV = barrier + pulled all-gather of x "
+                        "+ the nnz-split kernel on the shard")
+    out["sharded_rmat"] = res4
+    ex.close()
     return out if rank == 0 else {}
 
 
-def secondary_metrics(torch, sp, ctx, A, wl):
-    """COO->CSR assembly on config 1 (shuffled and row-ordered), CSR->CSC on the bench matrix, and
-    SpMV on config 5 (one GPU: the base of the N > 1 strong-scaling runs) and config 1."""
-    from spalinalg_b200.synthetic_device import banded_device, stencil_device
+# ------------------------------------------------------------------------------- N = 1 extras
+def secondary_metrics(torch, sp, ctx, A5, wl):
+    """Configs 1-4 on one GPU and the add of config 5: SpMV (ms, algorithmic GB/s, fraction of the
+    measured HBM peak, kernel chosen), COO->CSR assembly, CSR->CSC / transpose — each with its own
+    algorithmic bytes — plus the reference's general Mul on config 1."""
+    from spalinalg_b200 import _capi as capi
+    from spalinalg_b200.synthetic_device import (banded_device, random_uniform_coo_device, rmat_coo_device,
+                                                 stencil_device)
     out = {}
+    peak, _ = peaks()
 
     def timed(fn, reps=5, warm=2):
         for _ in range(warm):
@@ -636,81 +792,6 @@ def secondary_metrics(torch, sp, ctx, A, wl):
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
-
-    # CSR -> CSC / transpose of the bench matrix
-    nnz = A.nnz()
-    ms = timed(lambda: A.to_csc())
-    b_tr = 2 * nnz * (4 + 8) + (A.nrows() + 1) * 4 + (A.ncols() + 1) * 4
-    out["csr_to_csc"] = {"workload": wl, "ms": ms, "mnnz_per_s": nnz / ms / 1e3, "gbps_algorithmic": b_tr / ms / 1e6}
-
-    # assembly: config 1, shuffled COO, device-resident SoA in -> device CSR out
-    offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
-    n, rowptr, colind, values = stencil_device(torch, offs, 1024, 4.0, -1.0, torch.float64)
-    rows = torch.repeat_interleave(torch.arange(n, device="cuda", dtype=torch.int32),
-                                   (rowptr[1:] - rowptr[:-1]).to(torch.int64))
-    g = torch.Generator(device="cuda"); g.manual_seed(42)
-    perm = torch.randperm(rows.numel(), device="cuda", generator=g)
-    out_host_triplets = (rows[perm].contiguous(), colind[perm].contiguous(), values[perm].contiguous())
-    for name, (r_, c_, v_) in {"shuffled": out_host_triplets,
-                               "row_ordered": (rows, colind, values)}.items():
-        ln = r_.numel()
-        ms = timed(lambda: sp.CsrMatrix.from_device_triplets(n, n, ln, r_.data_ptr(), c_.data_ptr(),
-                                                             v_.data_ptr(), np.float64, ctx=ctx))
-        b_asm = ln * (8 + 8) + ln * (4 + 8) + (n + 1) * 4
-        out[f"assembly_{name}"] = {"workload": "laplace2d_1024_f64 COO->CSR", "len": ln, "ms": ms,
-                                   "mnnz_per_s": ln / ms / 1e3, "gbps_algorithmic": b_asm / ms / 1e6}
-
-    # the same assembly through the reference-facing call: host usize (u64) row/col + f64 values in
-    # pinned memory -> spl_mat_from_coo (upload, narrow, sort, sum) -> CsrMatrix
-    sr, sc_, sv = out_host_triplets
-    coo_h = [t.cpu().pin_memory() for t in (sr.to(torch.int64), sc_.to(torch.int64), sv)]
-    lib = ctx._lib
-    import ctypes as C
-    from spalinalg_b200 import _capi as capi
-
-    def asm_host():
-        h = C.c_void_p()
-        ctx.check(lib.spl_mat_from_coo(ctx._h, capi.SPL_CSR, capi.SPL_F64, n, n, coo_h[2].numel(),
-                                       C.c_void_p(coo_h[0].data_ptr()), C.c_void_p(coo_h[1].data_ptr()),
-                                       C.c_void_p(coo_h[2].data_ptr()), 1, 1, C.byref(h)))
-        ctx.check(lib.spl_mat_free(ctx._h, h))
-    asm_host(); asm_host()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        asm_host()
-    torch.cuda.synchronize()
-    hs = (time.perf_counter() - t0) / 5
-    out["assembly_shuffled_e2e"] = {"workload": "laplace2d_1024_f64 COO->CSR from pinned host usize triplets",
-                                    "len": int(coo_h[2].numel()), "ms": hs * 1e3,
-                                    "mnnz_per_s": coo_h[2].numel() / hs / 1e6,
-                                    "h2d_bytes": int(coo_h[2].numel()) * 24}
-
-    # the same triplets through the streaming CooMatrix storage (spl_coo): the fill
-    # (extend from the host arrays, chunks sent while the rest is copied in) and the conversion
-    # (flush of the last partial chunk + device assembly) timed separately and together
-    np_trip = [t.numpy() for t in coo_h]
-    np_trip = (np_trip[0].view(np.uint64), np_trip[1].view(np.uint64), np_trip[2])
-    ln = int(np_trip[2].shape[0])
-    fill_s, conv_s = [], []
-    for it in range(6):
-        pc = sp.PinnedCooMatrix.with_capacity(n, n, ln, np.float64, ctx=ctx)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pc.extend_triplets(*np_trip)
-        t1 = time.perf_counter()
-        M_ = sp.CsrMatrix.from_coo(pc, ctx=ctx)
-        ctx.sync()
-        t2 = time.perf_counter()
-        if it:
-            fill_s.append(t1 - t0); conv_s.append(t2 - t1)
-        del M_, pc
-    fill_ms, conv_ms = 1e3 * float(np.median(fill_s)), 1e3 * float(np.median(conv_s))
-    out["assembly_shuffled_streamed"] = {
-        "workload": "laplace2d_1024_f64: PinnedCooMatrix filled from host usize triplets, then CsrMatrix::from(&coo)",
-        "len": ln, "fill_ms": fill_ms, "convert_ms": conv_ms, "total_ms": fill_ms + conv_ms,
-        "convert_mnnz_per_s": ln / conv_ms / 1e3, "total_mnnz_per_s": ln / (fill_ms + conv_ms) / 1e3}
-    del coo_h, np_trip
 
     def spmv_rate(M, x, y, copies=1, reps=100):
         """Back-to-back launches; `copies` > 1 rotates over independent (A, x, y) sets whose total
@@ -726,44 +807,182 @@ def secondary_metrics(torch, sp, ctx, A, wl):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    # the reference's Mul on a general right-hand side: A * A on the config-1 matrix
-    A1m = sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(),
-                                          values.data_ptr(), np.float64, validate=False, ctx=ctx)
+    def spmv_entry(M, V, tdt, copies=1, reps=100, note=None):
+        Ms = M if isinstance(M, list) else [M]
+        n_, m_, nnz_ = Ms[0].nrows(), Ms[0].ncols(), Ms[0].nnz()
+        xs = [torch.rand(m_, device="cuda", dtype=tdt) - 0.5 for _ in Ms]
+        ys = [torch.empty(n_, device="cuda", dtype=tdt) for _ in Ms]
+        b = spmv_bytes(nnz_, n_, m_, V)
+        ms = spmv_rate(Ms, xs, ys, copies=len(Ms), reps=reps)
+        k, l = Ms[0].spmv_choice()
+        e = {"ms": ms, "gbps": b / ms / 1e6, "frac_measured_peak": b / ms / 1e6 / peak, "frac_8TBps": b / ms / 1e6 / 8000.0,
+             "kernel": KERNEL_NAMES.get(k, "?"), "lanes_per_row": l, "algorithmic_bytes": b, "nrows": n_, "nnz": nnz_}
+        if note:
+            e["l2"] = note
+        return e
+
+    def tr_entry(fn, M, V):
+        ms = timed(fn, reps=5, warm=1)
+        b = 2 * M.nnz() * (4 + V) + (M.nrows() + 1) * 4 + (M.ncols() + 1) * 4
+        return {"ms": ms, "mnnz_per_s": M.nnz() / ms / 1e3, "gbps_algorithmic": b / ms / 1e6,
+                "frac_measured_peak": b / ms / 1e6 / peak}
+
+    def asm_entry(nr, nc, r_, c_, v_, npdt, V, reps=5):
+        keep = {}
+        ln = int(r_.numel())
+
+        def run():
+            keep["A"] = sp.CsrMatrix.from_device_triplets(nr, nc, ln, r_.data_ptr(), c_.data_ptr(), v_.data_ptr(), npdt, ctx=ctx)
+        ms = timed(run, reps=reps, warm=1)
+        M = keep["A"]
+        b = ln * (8 + V) + M.nnz() * (4 + V) + (nr + 1) * 4
+        return M, {"len": ln, "nnz_out": M.nnz(), "ms": ms, "mnnz_per_s": ln / ms / 1e3,
+                   "gbps_algorithmic": b / ms / 1e6, "frac_measured_peak": b / ms / 1e6 / peak}
+
+    # ---- config 5: A + B (the bench matrix is A)
+    n5 = A5.nrows()
+    if wl.startswith("banded"):
+        bp, bc, bv = banded_device(torch, n5, 0, n5, (-8, -2, 0, 2, 8), torch.float64)
+        B = sp.CsrMatrix.from_device_arrays(n5, n5, bc.numel(), bp.data_ptr(), bc.data_ptr(), bv.data_ptr(), np.float64,
+                                            validate=False, ctx=ctx)
+        del bp, bc, bv
+        keep = {}
+
+        def add():
+            keep["C"] = A5 + B
+        ms = timed(add, reps=3, warm=1)
+        Cm = keep["C"]
+        b = (A5.nnz() + B.nnz() + Cm.nnz()) * 12 + 3 * (n5 + 1) * 4
+        out["c5_add"] = {"workload": "banded9 + banded{-8,-2,0,2,8}, n=%d, f64" % n5, "ms": ms, "nnz_out": Cm.nnz(),
+                         "mnnz_per_s": (A5.nnz() + B.nnz()) / ms / 1e3, "gbps_algorithmic": b / ms / 1e6,
+                         "frac_measured_peak": b / ms / 1e6 / peak}
+        del keep, Cm, B
+        torch.cuda.empty_cache()
+
+    # ---- config 1: 2-D Laplacian 1024^2, f64
+    offs = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1)]
+    n, rowptr, colind, values = stencil_device(torch, offs, 1024, 4.0, -1.0, torch.float64)
+    rows = torch.repeat_interleave(torch.arange(n, device="cuda", dtype=torch.int32),
+                                   (rowptr[1:] - rowptr[:-1]).to(torch.int64))
+    g = torch.Generator(device="cuda"); g.manual_seed(42)
+    perm = torch.randperm(rows.numel(), device="cuda", generator=g)
+    shuffled = (rows[perm].contiguous(), colind[perm].contiguous(), values[perm].contiguous())
+    _, out["c1_assembly_shuffled"] = asm_entry(n, n, *shuffled, np.float64, 8)
+    _, out["c1_assembly_row_ordered"] = asm_entry(n, n, rows, colind, values, np.float64, 8)
+    for k_ in ("c1_assembly_shuffled", "c1_assembly_row_ordered"):
+        out[k_]["workload"] = "laplace2d_1024_f64 COO->CSR, device-resident SoA triplets in, device CSR out"
+
+    # the same assembly through the reference-facing call: host usize (u64) row/col + f64 values in
+    # pinned memory -> spl_mat_from_coo (upload, narrow, sort, sum) -> CsrMatrix
+    sr, sc_, sv = shuffled
+    coo_h = [t.cpu().pin_memory() for t in (sr.to(torch.int64), sc_.to(torch.int64), sv)]
+    lib = ctx._lib
+
+    def asm_host():
+        h = C.c_void_p()
+        ctx.check(lib.spl_mat_from_coo(ctx._h, capi.SPL_CSR, capi.SPL_F64, n, n, coo_h[2].numel(),
+                                       C.c_void_p(coo_h[0].data_ptr()), C.c_void_p(coo_h[1].data_ptr()),
+                                       C.c_void_p(coo_h[2].data_ptr()), 1, 1, C.byref(h)))
+        ctx.check(lib.spl_mat_free(ctx._h, h))
+    asm_host(); asm_host()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        asm_host()
+    torch.cuda.synchronize()
+    hs = (time.perf_counter() - t0) / 5
+    out["c1_assembly_shuffled_e2e"] = {"workload": "laplace2d_1024_f64 COO->CSR from pinned host usize triplets",
+                                       "len": int(coo_h[2].numel()), "ms": hs * 1e3,
+                                       "mnnz_per_s": coo_h[2].numel() / hs / 1e6,
+                                       "h2d_bytes": int(coo_h[2].numel()) * 24}
+    # the same triplets through the streaming CooMatrix storage (spl_coo)
+    np_trip = [t.numpy() for t in coo_h]
+    np_trip = (np_trip[0].view(np.uint64), np_trip[1].view(np.uint64), np_trip[2])
+    ln = int(np_trip[2].shape[0])
+    fill_s, conv_s = [], []
+    for it in range(5):
+        pc = sp.PinnedCooMatrix.with_capacity(n, n, ln, np.float64, ctx=ctx)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pc.extend_triplets(*np_trip)
+        t1 = time.perf_counter()
+        M_ = sp.CsrMatrix.from_coo(pc, ctx=ctx)
+        ctx.sync()
+        t2 = time.perf_counter()
+        if it:
+            fill_s.append(t1 - t0); conv_s.append(t2 - t1)
+        del M_, pc
+    fill_ms, conv_ms = 1e3 * float(np.median(fill_s)), 1e3 * float(np.median(conv_s))
+    out["c1_assembly_shuffled_streamed"] = {
+        "workload": "laplace2d_1024_f64: PinnedCooMatrix filled from host usize triplets, then CsrMatrix::from(&coo)",
+        "len": ln, "fill_ms": fill_ms, "convert_ms": conv_ms, "total_ms": fill_ms + conv_ms,
+        "convert_mnnz_per_s": ln / conv_ms / 1e3, "total_mnnz_per_s": ln / (fill_ms + conv_ms) / 1e3}
+    del coo_h, np_trip, shuffled, perm, rows
+
+    mk1 = lambda: sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(),
+                                                  values.data_ptr(), np.float64, validate=False, ctx=ctx)
+    A1 = [mk1() for _ in range(4)]
+    out["c1_spmv"] = spmv_entry(A1, 8, torch.float64, reps=400, note="4 rotating copies of (A, x, y), 320 MB > L2")
+    out["c1_spmv_l2_resident"] = spmv_entry(A1[0], 8, torch.float64, reps=400, note="one copy, 80 MB: L2-resident")
+    out["c1_csr_to_csc"] = tr_entry(lambda: A1[0].to_csc(), A1[0], 8)
     keepm = {}
 
     def mul():
-        keepm["C"] = A1m * A1m
+        keepm["C"] = A1[0] * A1[0]
     ms = timed(mul, reps=5, warm=2)
-    out["mul_laplace2d_1024_f64"] = {"workload": "A * A, 2-D Laplacian 1024^2 (impl Mul for &CsrMatrix)", "ms": ms,
-                                     "nnz_out": keepm["C"].nnz(), "mnnz_out_per_s": keepm["C"].nnz() / ms / 1e3}
-    del A1m, keepm
+    out["c1_mul"] = {"workload": "A * A, 2-D Laplacian 1024^2 (impl Mul for &CsrMatrix)", "ms": ms,
+                     "nnz_out": keepm["C"].nnz(), "mnnz_out_per_s": keepm["C"].nnz() / ms / 1e3}
+    del A1, keepm, rowptr, colind, values
+    torch.cuda.empty_cache()
 
-    peak, _ = peaks()
-    # config 1 SpMV, 4 rotating copies (4 x 80 MB > L2)
-    A1 = [sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(),
-                                          values.data_ptr(), np.float64, validate=False, ctx=ctx) for _ in range(4)]
-    x1 = [torch.rand(n, device="cuda", dtype=torch.float64) for _ in range(4)]
-    y1 = [torch.empty(n, device="cuda", dtype=torch.float64) for _ in range(4)]
-    b1 = spmv_bytes(int(colind.numel()), n, n, 8)
-    ms = spmv_rate(A1, x1, y1, copies=4, reps=200)
-    out["spmv_laplace2d_1024_f64"] = {"ms": ms, "gbps": b1 / ms / 1e6, "frac_measured_peak": b1 / ms / 1e6 / peak,
-                                      "l2": "4 rotating copies of (A, x, y), 320 MB > L2"}
-    ms = spmv_rate(A1[:1], x1[:1], y1[:1], reps=200)
-    out["spmv_laplace2d_1024_f64_l2_resident"] = {"ms": ms, "gbps": b1 / ms / 1e6}
-    del A1, x1, y1, rows, perm, out_host_triplets
-    # config 5 on one GPU
-    n5 = 10 ** 8
-    p5, c5, v5 = banded_device(torch, n5, 0, n5, range(-4, 5), torch.float64)
-    A5 = sp.CsrMatrix.from_device_arrays(n5, n5, c5.numel(), p5.data_ptr(), c5.data_ptr(), v5.data_ptr(),
+    # ---- config 2: 27-point stencil 128^3, f64
+    offs = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    n, rowptr, colind, values = stencil_device(torch, offs, 128, 26.0, -1.0, torch.float64)
+    A2 = sp.CsrMatrix.from_device_arrays(n, n, colind.numel(), rowptr.data_ptr(), colind.data_ptr(), values.data_ptr(),
                                          np.float64, validate=False, ctx=ctx)
-    nnz5 = int(c5.numel())
-    del p5, c5, v5
-    x5 = torch.rand(n5, device="cuda", dtype=torch.float64)
-    y5 = torch.empty(n5, device="cuda", dtype=torch.float64)
-    b5 = spmv_bytes(nnz5, n5, n5, 8)
-    ms = spmv_rate([A5], [x5], [y5], reps=20)
-    out["spmv_banded9_1e8_f64_1gpu"] = {"ms": ms, "gbps": b5 / ms / 1e6, "frac_measured_peak": b5 / ms / 1e6 / peak,
-                                        "note": "same workload as the N > 1 runs: base of their strong scaling"}
+    del rowptr, colind, values
+    out["c2_spmv"] = spmv_entry(A2, 8, torch.float64, reps=100)
+    out["c2_csr_to_csc"] = tr_entry(lambda: A2.to_csc(), A2, 8)
+    out["c2_transpose"] = tr_entry(lambda: A2.transpose(), A2, 8)
+    # the host-vector product on this matrix, pipelined (16.8 MB each way), and with the matrix built from the
+    # reference-layout host arrays inside every step
+    h_x = torch.rand(n, dtype=torch.float64).pin_memory()
+    h_y = torch.empty(n, dtype=torch.float64).pin_memory()
+    b2 = spmv_bytes(A2.nnz(), n, n, 8)
+
+    def host_step():
+        ctx.check(lib.spl_spmv_host(ctx._h, A2._h, C.c_void_p(h_x.data_ptr()), C.c_void_p(h_y.data_ptr())))
+    host_step(); host_step()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        host_step()
+    hs = (time.perf_counter() - t0) / 10
+    out["c2_spmv_host_vectors"] = {"ms": hs * 1e3, "gbps": b2 / hs / 1e9, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8,
+                                   "what": "spl_spmv_host: x up in prefixes, row chunks, y down behind them (3 streams)"}
+    del A2, h_x, h_y
+    torch.cuda.empty_cache()
+
+    # ---- config 3: random 1e7 x 1e7, 16/row + 5 % duplicates, f32
+    n = 10_000_000
+    r_, c_, v_ = random_uniform_coo_device(torch, n, 16, 8_000_000, torch.float32, seed=1)
+    A3, out["c3_assembly"] = asm_entry(n, n, r_, c_, v_, np.float32, 4, reps=3)
+    del r_, c_, v_
+    torch.cuda.empty_cache()
+    out["c3_spmv"] = spmv_entry(A3, 4, torch.float32, reps=30)
+    out["c3_csr_to_csc"] = tr_entry(lambda: A3.to_csc(), A3, 4)
+    del A3
+    torch.cuda.empty_cache()
+
+    # ---- config 4: R-MAT 2^24, 2^29 edges, f32
+    n = 1 << 24
+    r_, c_, v_ = rmat_coo_device(torch, 24, 32, torch.float32, seed=3)
+    A4, out["c4_assembly"] = asm_entry(n, n, r_, c_, v_, np.float32, 4, reps=3)
+    del r_, c_, v_
+    torch.cuda.empty_cache()
+    out["c4_spmv"] = spmv_entry(A4, 4, torch.float32, reps=20)
+    out["c4_transpose"] = tr_entry(lambda: A4.transpose(), A4, 4)
+    del A4
+    torch.cuda.empty_cache()
     return out
 
 

@@ -210,6 +210,16 @@ int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32
 /* From<&CsrMatrix>/<&CscMatrix> for CooMatrix (src/coo.rs:629-705): expand to
  * host triplets in storage order.  Arrays need nnz slots.  Synchronises. */
 int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val);
+/* The same conversion with the result left in device memory (uint32 SoA triplets, nnz slots each):
+ * the input format of spl_mat_from_coo_dev / spl_coo_route_dev, so results flow back into the builder
+ * format without visiting the host.  Asynchronous on the context's stream. */
+int spl_mat_to_coo_dev(spl_ctx *ctx, const spl_mat *m, uint32_t *row_dev, uint32_t *col_dev, void *val_dev);
+/* iter() / into_iter() on a device-resident matrix (src/csr.rs:303-316, 409-440; src/csc.rs same
+ * lines): the stored entries [start, start + count) in storage order as host triplets.  An iterator
+ * reads the matrix chunk by chunk through this call instead of materialising nnz tuples at once; the
+ * row (column) of an entry is found from the pointer array on the device.  Synchronises. */
+int spl_mat_read_entries(spl_ctx *ctx, const spl_mat *m, uint64_t start, uint64_t count, uint64_t *row,
+                         uint64_t *col, void *val);
 int spl_mat_free(spl_ctx *ctx, spl_mat *m);
 
 /* ---- row sharding across GPUs (one process per GPU) ----------------
@@ -283,6 +293,18 @@ int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *
  * of `&A * &X`, src/csr/ops/mul.rs:5-60).  A_local is CSR with global column indices. */
 int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
                   const uint64_t *col_starts, const void *const *x_slices, void *y_dev);
+
+/* The reference-facing `&A * &x` on one rank of a row-sharded matrix, with HOST vectors:
+ * x_host_local is this rank's slice of x (col_starts[rank+1] - col_starts[rank] values),
+ * y_host_local receives its rows of y.  The slice is uploaded into x_slices[rank] (this rank's
+ * peer-visible buffer: pass the set of buffers being written, e.g. the unpublished half of a
+ * double-buffered vector), the device barrier (flag_ptrs / epoch / timeout_ms as in
+ * spl_peer_barrier) publishes it, and the product runs in row chunks on the compute stream while
+ * finished chunks of y travel back on a second stream.  Synchronises; a timed-out barrier is
+ * reported here (SPL_ERR_CUDA) and y holds NaN.  Pinned host vectors make the copies overlap. */
+int spl_spmv_peer_host(spl_ctx *ctx, const spl_mat *a_local, int world, int rank, const uint64_t *col_starts,
+                       void *const *x_slices, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
+                       const void *x_host_local, void *y_host_local);
 
 #ifdef __cplusplus
 }

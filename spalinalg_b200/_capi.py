@@ -50,6 +50,8 @@ SIGNATURES = {
     "spl_mat_set_values": (_i, [_vp, _vp, _vp]),
     "spl_mat_device_ptrs": (_i, [_vp, _pp, _pp, _pp]),
     "spl_mat_to_coo": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "spl_mat_to_coo_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "spl_mat_read_entries": (_i, [_vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     "spl_mat_free": (_i, [_vp, _vp]),
     "spl_coo_route_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "spl_coo_route_count_dev": (_i, [_vp, _i, _u64, _u64, _u64, _vp, _vp, _i, _vp, _vp]),
@@ -63,6 +65,7 @@ SIGNATURES = {
     "spl_peer_pull": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
     "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "spl_spmv_peer_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "spl_coo_create": (_i, [_vp, _i, _u64, _u64, _u64, _pp]),
     "spl_coo_free": (_i, [_vp]),
     "spl_coo_last_error": (C.c_char_p, [_vp]),

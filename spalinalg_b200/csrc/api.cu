@@ -482,6 +482,37 @@ int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col,
     API_END(ctx)
 }
 
+int spl_mat_to_coo_dev(spl_ctx *ctx, const spl_mat *m, uint32_t *row_dev, uint32_t *col_dev, void *val_dev) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
+    if (m->nnz) {
+        SPL_REQUIRE(row_dev && col_dev && val_dev, SPL_ERR_ARG, "NULL array");
+        expand_major(ctx, m->nmajor(), m->nnz, m->ptr, m->format == SPL_CSR ? row_dev : col_dev);
+        SPL_CUDA(cudaMemcpyAsync(m->format == SPL_CSR ? col_dev : row_dev, m->ind, (size_t)m->nnz * 4,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(val_dev, m->val, (size_t)m->nnz * m->vsize(), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int spl_mat_read_entries(spl_ctx *ctx, const spl_mat *m, uint64_t start, uint64_t count, uint64_t *row,
+                         uint64_t *col, void *val) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
+    SPL_REQUIRE(start <= m->nnz && count <= m->nnz - start, SPL_ERR_ARG, "entry range outside the matrix");
+    if (count) {
+        SPL_REQUIRE(row && col && val, SPL_ERR_ARG, "NULL array");
+        Tmp<uint64_t> major(ctx, count), minor(ctx, count);
+        entry_range(ctx, m, (uint32_t)start, (uint32_t)count, major, minor);
+        SPL_CUDA(cudaMemcpyAsync(m->format == SPL_CSR ? row : col, major, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->format == SPL_CSR ? col : row, minor, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(val, static_cast<const unsigned char *>(m->val) + start * m->vsize(), count * m->vsize(),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
 int spl_mat_free(spl_ctx *ctx, spl_mat *m) {
     API_BEGIN(ctx)
     free_mat(ctx, m);
@@ -640,6 +671,35 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
         px.slice[g] = x_slices[g];
     }
     spmv_peer(ctx, a_local, px, y_dev);
+    API_END(ctx)
+}
+
+int spl_spmv_peer_host(spl_ctx *ctx, const spl_mat *a_local, int world, int rank, const uint64_t *col_starts,
+                       void *const *x_slices, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
+                       const void *x_host_local, void *y_host_local) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(a_local && col_starts && x_slices && flag_ptrs && y_host_local, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
+                "world must be 1..8 and rank inside it");
+    SPL_REQUIRE(col_starts[0] == 0 && col_starts[world] == a_local->ncols, SPL_ERR_SHAPE,
+                "col_starts must run from 0 to A.ncols()");
+    PeerX px{};
+    px.world = world;
+    px.rank = rank;
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) px.start[g] = (uint32_t)col_starts[g < world ? g : world];
+    for (int g = 0; g < world; ++g) {
+        SPL_REQUIRE(col_starts[g] <= col_starts[g + 1], SPL_ERR_ARG, "col_starts must be non-decreasing");
+        SPL_REQUIRE(x_slices[g] || col_starts[g] == col_starts[g + 1], SPL_ERR_ARG, "NULL x slice");
+        px.slice[g] = x_slices[g];
+    }
+    SPL_REQUIRE(x_host_local || col_starts[rank] == col_starts[rank + 1], SPL_ERR_ARG, "NULL x");
+    Tmp<unsigned char> y(ctx, (size_t)a_local->nrows * a_local->vsize());
+    spmv_peer_host(ctx, a_local, px, flag_ptrs, epoch, timeout_ms, x_host_local, y_host_local, y);
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t failed = 0;
+    read_back(ctx, ctx->d_scratch + 32, &failed, 1);
+    if (failed) SPL_CUDA(cudaMemsetAsync(ctx->d_scratch + 32, 0, sizeof(uint32_t), ctx->stream));
+    SPL_REQUIRE(failed == 0, SPL_ERR_CUDA, "spl_spmv_peer_host: the barrier timed out waiting for a peer (y holds NaN)");
     API_END(ctx)
 }
 

@@ -62,6 +62,10 @@ struct PeerX {
     int rank;
 };
 void spmv_peer(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *y);
+// the same with this rank's slices of x and y in host memory: upload into the rank's peer slice,
+// barrier, product in row chunks with the download of each chunk behind it (does not synchronise)
+void spmv_peer_host(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *const *flag_ptrs, uint32_t epoch,
+                    uint32_t timeout_ms, const void *x_host_local, void *y_host_local, void *y_dev);
 
 // peer.cu — CUDA IPC buffers and the flag barrier over peer memory
 void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
@@ -88,6 +92,9 @@ void widen_u32(spl_ctx *ctx, const uint32_t *src, uint64_t *dst, size_t n);
 void fill_eye(spl_ctx *ctx, int dtype, uint32_t size, uint32_t *ptr, uint32_t *ind, void *val);
 // major index of every stored entry (rowptr expansion, src/csr.rs:303-316)
 void expand_major(spl_ctx *ctx, uint32_t nmajor, uint32_t nnz, const uint32_t *ptr, uint32_t *out);
+// (major, minor) of the stored entries [start, start + count) as uint64 (the chunks of iter())
+void entry_range(spl_ctx *ctx, const spl_mat *m, uint32_t start, uint32_t count, uint64_t *major_out,
+                 uint64_t *minor_out);
 // ptr[q] = first position p with sorted_major[p] >= q, for q in [0, nmajor]
 void fill_ptr(spl_ctx *ctx, const uint32_t *sorted_major, uint32_t nnz, uint32_t nmajor,
               uint32_t *ptr);

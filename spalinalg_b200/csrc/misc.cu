@@ -94,6 +94,18 @@ expand_major_kernel(const uint32_t *__restrict__ ptr, uint32_t nmajor, uint32_t 
     for (uint32_t p = __ldg(ptr + m) + (uint32_t)(gtid % LPR); p < e; p += LPR) out[p] = (uint32_t)m;
 }
 
+// major index and widened minor index of the stored entries [start, start + count): one search of the
+// pointer array per entry (chunks of an iterator are small; the whole-matrix form uses expand_major)
+__global__ void __launch_bounds__(256)
+entry_range_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, uint32_t nmajor, uint32_t start,
+                   uint32_t count, uint64_t *__restrict__ major_out, uint64_t *__restrict__ minor_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t p = start + i;
+    major_out[i] = upper_bound_u32(ptr, 0u, nmajor + 1u, p) - 1u;      // ptr[m] <= p < ptr[m + 1]
+    minor_out[i] = ind[p];
+}
+
 inline unsigned stream_grid(spl_ctx *ctx, size_t n) {
     unsigned g = div_up(n ? n : 1, 256 * 4);
     unsigned cap = (unsigned)ctx->num_sms * 16u;
@@ -167,6 +179,14 @@ void expand_major(spl_ctx *ctx, uint32_t nmajor, uint32_t nnz, const uint32_t *p
     else
         expand_major_kernel<32><<<div_up((uint64_t)nmajor * 32, 256), 256, 0, ctx->stream>>>(ptr, nmajor, out);
     check_launch(ctx, "expand_major");
+}
+
+void entry_range(spl_ctx *ctx, const spl_mat *m, uint32_t start, uint32_t count, uint64_t *major_out,
+                 uint64_t *minor_out) {
+    if (count == 0) return;
+    entry_range_kernel<<<div_up(count, 256), 256, 0, ctx->stream>>>(m->ptr, m->ind, m->nmajor(), start, count, major_out,
+                                                                   minor_out);
+    check_launch(ctx, "entry_range");
 }
 
 spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t nnz) {

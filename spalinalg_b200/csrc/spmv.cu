@@ -125,20 +125,6 @@ void spmv_vector(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, int lanes) 
     }
 }
 
-template <typename T>
-void spmv_peer_t(spl_ctx *ctx, const spl_mat *a, const PeerX &px, T *y, int lanes) {
-    XPeer<T> xg;
-    xg.world = px.world;
-    for (int g = 0; g < SPL_MAX_PEERS; ++g) xg.slice[g] = static_cast<const T *>(px.slice[g]);
-    for (int g = 0; g <= SPL_MAX_PEERS; ++g) xg.start[g] = px.start[g];
-    xg.mine = xg.slice[px.rank];
-    xg.my_start = px.start[px.rank];
-    xg.my_len = px.start[px.rank + 1] - px.start[px.rank];
-    xg.barrier_failed = ctx->d_scratch + 32;
-    spmv_vector<T>(ctx, a, xg, y, lanes);
-}
-
-
 // ------------------------------------------------------------------ sliced kernel
 // The vector kernel with more than one lane per row spends its L1 bandwidth on partial sectors (a
 // warp's load touches 32/LPR rows, 16-32 useful bytes of each line) and its rows pay a shuffle
@@ -677,7 +663,7 @@ spmv_stream_kernel(uint32_t nrows, const uint32_t *__restrict__ ptr, const uint3
         if (lane_id() == 0) mbar_arrive(empty + s);
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (sub == 0 && r < re) y[r] = acc;
+        if (sub == 0 && r < re) y[r] = xg.poisoned() ? (T)NAN : acc;
         if (++s == stages) { s = 0; phase ^= 1u; }
     }
 }
@@ -707,8 +693,8 @@ void stream_capacity(spl_ctx *ctx, spl_mat *a, uint32_t rows_per_tile) {
     uint32_t max_window = 0;
     read_back(ctx, ctx->d_scratch + 1, &max_window, 1);
     const uint32_t cap = (max_window + 6u + 3u) & ~3u;            // the 16-byte aligned superset of the largest slice
-    // two stages of it (with the pointer slices) must fit beside the barriers
-    if (2 * ((size_t)cap * (4 + a->vsize()) + ((size_t)rows_per_tile + 4) * 4) + 64 <= 226 * 1024) a->stream_cap = cap;
+    // three stages of it (with the pointer slices) must fit beside the barriers
+    if (3 * ((size_t)cap * (4 + a->vsize()) + ((size_t)rows_per_tile + 4) * 4) + 64 <= 226 * 1024) a->stream_cap = cap;
 }
 
 // Row range per CTA and the x edges per tile for a grid of `grid` CTAs.  Cached; rebuilt when the grid changes.
@@ -745,10 +731,10 @@ template <typename T, int LPR, int U, bool TIGHT, typename XG>
 void launch_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
     auto k = spmv_stream_kernel<T, LPR, U, TIGHT, XG>;
     constexpr int CONS = ST_CONSUMERS;
-    // shape: two stages are enough once the CTAs overlap each other, and more CTAs beat deeper rings
-    // (measured: profiles/r2_spmv_notes.md)
+    // shape (measured, profiles/r2_spmv_notes.md): three stages, three CTAs of 64 registers per SM; a
+    // deeper ring or a fourth, register-starved CTA does not pay
     const size_t stage_bytes = stream_stage_bytes(a);
-    const uint32_t stages = (uint32_t)std::max(2, env_int("SPL_STREAM_STAGES", 2));
+    const uint32_t stages = (uint32_t)std::max(2, env_int("SPL_STREAM_STAGES", 3));
     const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
     SPL_REQUIRE(smem <= 227 * 1024, SPL_ERR_UNSUPPORTED, "stream SpMV: the stages do not fit in shared memory");
     static std::atomic<size_t> smem_set{0};                       // per instantiation
@@ -794,7 +780,7 @@ template <typename T, int LPR, typename XG>
 void spmv_stream_u(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_edge) {
     // entries per lane and trip: one trip for the short rows of stencils and bands
     const bool wide = (a->max_row_len + LPR - 1) / LPR > 4;
-    const bool tight = env_int("SPL_STREAM_TIGHT", 1) != 0;      // four CTAs of 56 registers: measured best on C1, C2
+    const bool tight = env_int("SPL_STREAM_TIGHT", 0) != 0;      // four CTAs of 56 registers: measured, not better
     if (wide) {
         if (tight) launch_stream<T, LPR, 8, true>(ctx, a, xg, y, x_edge);
         else launch_stream<T, LPR, 8, false>(ctx, a, xg, y, x_edge);
@@ -814,6 +800,26 @@ void spmv_stream(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, const T *x_
         case 16: spmv_stream_u<T, 16>(ctx, a, xg, y, x_edge); break;
         default: spmv_stream_u<T, 32>(ctx, a, xg, y, x_edge); break;
     }
+}
+
+template <typename T>
+XPeer<T> make_xpeer(spl_ctx *ctx, const PeerX &px) {
+    XPeer<T> xg;
+    xg.world = px.world;
+    for (int g = 0; g < SPL_MAX_PEERS; ++g) xg.slice[g] = static_cast<const T *>(px.slice[g]);
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) xg.start[g] = px.start[g];
+    xg.mine = xg.slice[px.rank];
+    xg.my_start = px.start[px.rank];
+    xg.my_len = px.start[px.rank + 1] - px.start[px.rank];
+    xg.barrier_failed = ctx->d_scratch + 32;
+    return xg;
+}
+
+template <typename T>
+void spmv_peer_t(spl_ctx *ctx, const spl_mat *a, const PeerX &px, T *y, int lanes) {
+    const XPeer<T> xg = make_xpeer<T>(ctx, px);
+    if (a->plan_kernel == SPL_SPMV_STREAM && !std::getenv("SPL_PEER_VECTOR")) spmv_stream<T>(ctx, a, xg, y, (const T *)nullptr);
+    else spmv_vector<T>(ctx, a, xg, y, lanes);
 }
 
 // ------------------------------------------------------------------ nnz-split kernel
@@ -1257,6 +1263,10 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     // skewed rows (power law) -> balanced nnz-split kernel; regular rows -> vector
     const bool skewed = mean > 0 && (double)mx > 8.0 * mean + 64.0;
     a->plan_kernel = skewed ? SPL_SPMV_SPLIT : SPL_SPMV_VECTOR;
+    // regular rows, a tile fits in shared memory and there is at least a tile per resident CTA: the
+    // persistent stream kernel (same bits as the vector kernel: same lanes, same order)
+    if (!skewed && a->stream_cap && (uint64_t)a->nrows * lanes >= (uint64_t)ctx->num_sms * 3u * ST_CONSUMERS)
+        a->plan_kernel = SPL_SPMV_STREAM;
     // the plan arrays were written on this context's stream: make them visible to any other stream
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));
     a->plan_ready.store(1, std::memory_order_release);
@@ -1442,23 +1452,23 @@ __global__ void chunk_need_kernel(const uint32_t *__restrict__ ptr, const uint32
     if (lane_id() == 0 && m && r < nrows) atomicMax(need + (uint32_t)(r / rows_per_chunk), m);
 }
 
-template <typename T, int LPR>
-void launch_vector_rows(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, uint32_t r0, uint32_t r1) {
+template <typename T, int LPR, typename XG>
+void launch_vector_rows(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, uint32_t r0, uint32_t r1) {
     const uint64_t threads = (uint64_t)(r1 - r0) * LPR;
-    spmv_vector_kernel<T, LPR, XLocal<T>><<<div_up(threads, 256), 256, 0, ctx->stream>>>(
-        r1 - r0, a->ptr + r0, a->ind, static_cast<const T *>(a->val), XLocal<T>{x}, y + r0);
+    spmv_vector_kernel<T, LPR, XG><<<div_up(threads, 256), 256, 0, ctx->stream>>>(
+        r1 - r0, a->ptr + r0, a->ind, static_cast<const T *>(a->val), xg, y + r0);
     check_launch(ctx, "spmv_vector");
 }
 
-template <typename T>
-void spmv_vector_rows(spl_ctx *ctx, const spl_mat *a, const T *x, T *y, int lanes, uint32_t r0, uint32_t r1) {
+template <typename T, typename XG>
+void spmv_vector_rows(spl_ctx *ctx, const spl_mat *a, const XG &xg, T *y, int lanes, uint32_t r0, uint32_t r1) {
     switch (lanes) {
-        case 1: launch_vector_rows<T, 1>(ctx, a, x, y, r0, r1); break;
-        case 2: launch_vector_rows<T, 2>(ctx, a, x, y, r0, r1); break;
-        case 4: launch_vector_rows<T, 4>(ctx, a, x, y, r0, r1); break;
-        case 8: launch_vector_rows<T, 8>(ctx, a, x, y, r0, r1); break;
-        case 16: launch_vector_rows<T, 16>(ctx, a, x, y, r0, r1); break;
-        default: launch_vector_rows<T, 32>(ctx, a, x, y, r0, r1); break;
+        case 1: launch_vector_rows<T, 1>(ctx, a, xg, y, r0, r1); break;
+        case 2: launch_vector_rows<T, 2>(ctx, a, xg, y, r0, r1); break;
+        case 4: launch_vector_rows<T, 4>(ctx, a, xg, y, r0, r1); break;
+        case 8: launch_vector_rows<T, 8>(ctx, a, xg, y, r0, r1); break;
+        case 16: launch_vector_rows<T, 16>(ctx, a, xg, y, r0, r1); break;
+        default: launch_vector_rows<T, 32>(ctx, a, xg, y, r0, r1); break;
     }
 }
 
@@ -1527,9 +1537,9 @@ bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, voi
         SPL_CUDA(cudaEventRecord(up_ev[c], ctx->up_stream));
         SPL_CUDA(cudaStreamWaitEvent(ctx->stream, up_ev[c], 0));
         if (a->dtype == SPL_F32)
-            spmv_vector_rows<float>(ctx, a, (const float *)x_dev, (float *)y_dev, a->plan_lanes, r0, r1);
+            spmv_vector_rows<float>(ctx, a, XLocal<float>{(const float *)x_dev}, (float *)y_dev, a->plan_lanes, r0, r1);
         else
-            spmv_vector_rows<double>(ctx, a, (const double *)x_dev, (double *)y_dev, a->plan_lanes, r0, r1);
+            spmv_vector_rows<double>(ctx, a, XLocal<double>{(const double *)x_dev}, (double *)y_dev, a->plan_lanes, r0, r1);
         SPL_CUDA(cudaEventRecord(run_ev[c], ctx->stream));
         SPL_CUDA(cudaStreamWaitEvent(ctx->down_stream, run_ev[c], 0));
         SPL_CUDA(cudaMemcpyAsync(yh + (size_t)r0 * vs, yd + (size_t)r0 * vs, (size_t)(r1 - r0) * vs,
@@ -1540,6 +1550,62 @@ bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, voi
     SPL_CUDA(cudaEventRecord(end_ev, ctx->down_stream));
     SPL_CUDA(cudaStreamWaitEvent(ctx->stream, end_ev, 0));
     return true;
+}
+
+// The row-sharded `&A * &x` with HOST vectors (the reference-facing call on one rank of a sharded
+// matrix): this rank's slice of x goes up in chunks on the upload stream into its peer-visible slice,
+// the device barrier publishes it, then the product runs row chunk by row chunk on the compute stream
+// with each chunk of y going down on the download stream while the next chunk runs.  The barrier is
+// a real dependence (peers gather from the slice), so upload and product do not overlap inside one
+// step; product and download do.
+void spmv_peer_host(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *const *flag_ptrs, uint32_t epoch,
+                    uint32_t timeout_ms, const void *x_host_local, void *y_host_local, void *y_dev) {
+    constexpr int K = spl_ctx::kPipeChunks;
+    SPL_REQUIRE(a->format == SPL_CSR, SPL_ERR_UNSUPPORTED, "spl_spmv_peer_host needs a CSR matrix");
+    spl_mat *m = const_cast<spl_mat *>(a);
+    spmv_plan(ctx, m);
+    const size_t vs = a->vsize();
+    const uint32_t my_len = px.start[px.rank + 1] - px.start[px.rank];
+    unsigned char *x_slice = static_cast<unsigned char *>(const_cast<void *>(px.slice[px.rank]));
+    if (!ctx->up_stream) {
+        SPL_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+        SPL_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : ctx->pipe_ev) SPL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t *run_ev = ctx->pipe_ev + K;
+    cudaEvent_t start_ev = ctx->pipe_ev[2 * K], end_ev = ctx->pipe_ev[2 * K + 1], up_ev = ctx->pipe_ev[0];
+    // upload behind whatever the compute stream did to the slice before (a previous product may still gather from
+    // the OTHER buffer; this one is free: see PeerVector)
+    SPL_CUDA(cudaEventRecord(start_ev, ctx->stream));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->up_stream, start_ev, 0));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->down_stream, start_ev, 0));
+    if (my_len)
+        SPL_CUDA(cudaMemcpyAsync(x_slice, x_host_local, (size_t)my_len * vs, cudaMemcpyHostToDevice, ctx->up_stream));
+    SPL_CUDA(cudaEventRecord(up_ev, ctx->up_stream));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->stream, up_ev, 0));
+    peer_barrier(ctx, px.world, px.rank, flag_ptrs, epoch, timeout_ms);
+    const bool pinned = [&] {
+        cudaPointerAttributes ay{};
+        const bool ok = cudaPointerGetAttributes(&ay, y_host_local) == cudaSuccess && ay.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return ok;
+    }();
+    const int chunks = (pinned && (size_t)a->nrows * vs >= (1u << 20)) ? K : 1;
+    const uint32_t per = (uint32_t)((((uint64_t)a->nrows + chunks - 1) / chunks + 255) / 256 * 256);
+    unsigned char *yd = static_cast<unsigned char *>(y_dev), *yh = static_cast<unsigned char *>(y_host_local);
+    for (int c = 0; c < chunks; ++c) {
+        const uint32_t r0 = (uint32_t)std::min<uint64_t>((uint64_t)c * per, a->nrows);
+        const uint32_t r1 = (uint32_t)std::min<uint64_t>((uint64_t)(c + 1) * per, a->nrows);
+        if (r1 <= r0) continue;
+        if (a->dtype == SPL_F32) spmv_vector_rows<float>(ctx, a, make_xpeer<float>(ctx, px), (float *)y_dev, a->plan_lanes, r0, r1);
+        else spmv_vector_rows<double>(ctx, a, make_xpeer<double>(ctx, px), (double *)y_dev, a->plan_lanes, r0, r1);
+        SPL_CUDA(cudaEventRecord(run_ev[c], ctx->stream));
+        SPL_CUDA(cudaStreamWaitEvent(ctx->down_stream, run_ev[c], 0));
+        SPL_CUDA(cudaMemcpyAsync(yh + (size_t)r0 * vs, yd + (size_t)r0 * vs, (size_t)(r1 - r0) * vs,
+                                 cudaMemcpyDeviceToHost, ctx->down_stream));
+    }
+    SPL_CUDA(cudaEventRecord(end_ev, ctx->down_stream));
+    SPL_CUDA(cudaStreamWaitEvent(ctx->stream, end_ev, 0));
 }
 
 // Row-sharded SpMV with x left in its owners' memory: the vector kernel with the

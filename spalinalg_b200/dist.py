@@ -38,6 +38,36 @@ def partition_starts(n: int, world: int) -> List[int]:
     return [row_partition(n, world, g)[0] for g in range(world)] + [n]
 
 
+def balanced_starts(bin_counts: Sequence[int], rows_per_bin: int, n: int, world: int) -> List[int]:
+    """Row partition balanced on stored entries ("boundaries chosen to balance nnz ...
+    matters for C4"): bin_counts[b] = entries whose row lies in [b * rows_per_bin, (b+1) * rows_per_bin).
+    starts[g] is the bin boundary closest to the g/world quantile of the entries (contiguous blocks,
+    every rank non-empty when there are at least `world` bins)."""
+    counts = np.asarray(bin_counts, dtype=np.float64)
+    nb = len(counts)
+    # balance rows + entries, as the single-GPU kernels do: empty stretches still cost pointer traffic
+    w = counts + np.minimum(rows_per_bin, np.maximum(n - np.arange(nb) * rows_per_bin, 0))
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    starts = [0]
+    for g in range(1, world):
+        b = int(np.searchsorted(cum, cum[-1] * g / world, side="left"))
+        b = min(max(b, starts[-1] // rows_per_bin + 1), nb - (world - g))     # strictly increasing, room for the rest
+        starts.append(min(b * rows_per_bin, n))
+    return starts + [n]
+
+
+def balanced_starts_from_rows(dist, torch, rows, n: int, world: int, bins: int = 1 << 16, group=None) -> List[int]:
+    """balanced_starts from this rank's int32 (uint32 bit pattern) row indices on the device: a coarse
+    histogram per rank, one all-reduce, the boundaries computed identically on every rank."""
+    rows_per_bin = max(1, -(-n // bins))
+    nb = -(-n // rows_per_bin)
+    r = rows.long() & 0xFFFFFFFF
+    h = torch.bincount(torch.div(r, rows_per_bin, rounding_mode="floor"), minlength=nb).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(h, group=group)
+    return balanced_starts(h.cpu().numpy(), rows_per_bin, n, world)
+
+
 def bits_for(count: int) -> int:
     """Bits needed for values in [0, count) — the packing rule of spl_coo_route_dev."""
     return 0 if count <= 1 else int(count - 1).bit_length()
@@ -85,14 +115,15 @@ def route_device(ctx: Context, torch, fmt: int, nrows: int, ncols: int, row, col
     return keys, vals, [int(c) for c in cnt]
 
 
-def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col, val, exchange, dedup, dropzero):
+def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col, val, exchange, dedup, dropzero,
+                         starts=None):
     """Route this rank's triplets to the owners of their major index (rows for CSR, columns for CSC)
     through peer memory and assemble the own shard.  Returns (spl_mat handle, major partition)."""
     ctx, group = exchange.ctx, exchange.group
     world, rank = exchange.world, exchange.rank
     _torch_to_ctx(torch)                      # row/col/val were produced on torch's stream
     nmajor = nrows if fmt == capi.SPL_CSR else ncols
-    starts = partition_starts(nmajor, world)
+    starts = list(starts) if starts is not None else partition_starts(nmajor, world)
     n = int(val.numel())
     dtype = np.float32 if val.dtype == torch.float32 else np.float64
     st = (C.c_uint64 * (world + 1))(*starts)
@@ -142,18 +173,22 @@ class DistCsrMatrix:
 
     @classmethod
     def from_device_triplets_peer(cls, dist, torch, nrows: int, ncols: int, row, col, val, exchange: "PeerExchange",
-                                  dedup=True, dropzero=True):
+                                  dedup=True, dropzero=True, starts=None, balance: Optional[str] = None):
         """Sharded From<&CooMatrix<T>> for CsrMatrix<T> with routing and exchange fused: the partition
         pass writes every triplet straight into its owner's receive buffer over NVLink (peer memory),
         bracketed by two device-side barriers; the only collective is the all-gather of world*world
-        counts that lays the buffers out.  Same result, bit for bit, as from_device_triplets."""
+        counts that lays the buffers out.  Same result, bit for bit, as from_device_triplets.
+        `balance="nnz"` cuts the rows so that every rank gets about the same number of triplets."""
+        if starts is None and balance == "nnz":
+            starts = balanced_starts_from_rows(dist, torch, row, nrows, exchange.world, group=exchange.group)
         h, starts = _assemble_over_peers(dist, torch, capi.SPL_CSR, nrows, ncols, row, col, val, exchange,
-                                         dedup, dropzero)
+                                         dedup, dropzero, starts)
         return cls(CsrMatrix._wrap(exchange.ctx, h), starts, exchange.rank, nrows, ncols)
 
     @classmethod
     def from_device_triplets(cls, dist, torch, nrows: int, ncols: int, row, col, val,
-                             ctx: Optional[Context] = None, dedup=True, dropzero=True, group=None):
+                             ctx: Optional[Context] = None, dedup=True, dropzero=True, group=None, starts=None,
+                             balance: Optional[str] = None):
         """Sharded From<&CooMatrix<T>> for CsrMatrix<T> (src/csr/conv/coo.rs:3-116).  row/col are
         this rank's int32 (uint32 bit pattern) device tensors, val f32/f64; entries are
         block-distributed by entry index (rank 0 holds the first entries of the COO list)."""
@@ -161,7 +196,9 @@ class DistCsrMatrix:
         import time
         ctx = ctx or default_context()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        starts = partition_starts(nrows, world)
+        if starts is None and balance == "nnz":
+            starts = balanced_starts_from_rows(dist, torch, row, nrows, world, group=group)
+        starts = list(starts) if starts is not None else partition_starts(nrows, world)
         timing = os.environ.get("SPL_DIST_TIMING") and rank == 0
         _torch_to_ctx(torch)                  # row/col/val were produced on torch's stream
         t0 = time.perf_counter()
@@ -258,6 +295,24 @@ class DistCsrMatrix:
         sl = (C.c_void_p * self.world)(*x.ptrs)
         ctx.check(ctx._lib.spl_spmv_peer(ctx._h, self.local._h, self.world, self.rank,
                                          C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(y_dev)))
+
+
+    def matvec_host(self, x: "PeerVector", x_host_local, y_host_local, timeout_ms: int = 2000):
+        """`&A * &x` with this rank's slices of x and y in host memory (numpy arrays or raw host
+        addresses; pinned memory lets the copies overlap): spl_spmv_peer_host.  The slice is uploaded
+        into the unpublished half of `x`, published by the barrier inside the call, and gathered from."""
+        ctx = self.local._ctx
+        nxt = x._data[(x._cur + 1) % len(x._data)]
+        st = (C.c_uint64 * (self.world + 1))(*x.starts)
+        sl = (C.c_void_p * self.world)(*nxt.ptrs)
+        fl = (C.c_void_p * self.world)(*x._flags.ptrs)
+        x._epoch += 1
+        xp = x_host_local if isinstance(x_host_local, int) else x_host_local.ctypes.data
+        yp = y_host_local if isinstance(y_host_local, int) else y_host_local.ctypes.data
+        ctx.check(ctx._lib.spl_spmv_peer_host(ctx._h, self.local._h, self.world, self.rank, C.cast(st, C.c_void_p),
+                                              C.cast(sl, C.c_void_p), C.cast(fl, C.c_void_p), x._epoch, int(timeout_ms),
+                                              C.c_void_p(xp), C.c_void_p(yp)))
+        x._cur = (x._cur + 1) % len(x._data)
 
 
 class DistCscMatrix:

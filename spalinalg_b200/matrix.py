@@ -675,10 +675,30 @@ class _Compressed:
         self._ctx.check(self._ctx._lib.spl_mat_to_coo(self._ctx._h, self._h, _ptr(r), _ptr(c), _ptr(v)))
         return CooMatrix.with_triplets(self._nrows, self._ncols, r, c, v)
 
+    ITER_CHUNK = 1 << 16
+
     def iter(self):
-        return self.to_coo().iter()
+        """iter() (src/csr.rs:303-316 / src/csc.rs:303-316): (row, col, value) in storage order, read
+        from the device in chunks of ITER_CHUNK entries (spl_mat_read_entries): the host never holds
+        more than one chunk, whatever nnz is."""
+        n = self._nnz
+        cap = min(self.ITER_CHUNK, max(n, 1))
+        r = np.empty(cap, np.uint64)
+        c = np.empty(cap, np.uint64)
+        v = np.empty(cap, self._dtype)
+        for start in range(0, n, cap):
+            cnt = min(cap, n - start)
+            self._ctx.check(self._ctx._lib.spl_mat_read_entries(self._ctx._h, self._h, start, cnt, _ptr(r), _ptr(c),
+                                                                _ptr(v)))
+            yield from zip(r[:cnt].tolist(), c[:cnt].tolist(), v[:cnt].tolist())
 
     __iter__ = iter
+
+    def to_coo_device(self, row_dev: int, col_dev: int, val_dev: int):
+        """From<&CsrMatrix>/<&CscMatrix> for CooMatrix with the triplets left on the device (raw device
+        addresses of uint32 row/col and T value arrays with nnz slots): spl_mat_to_coo_dev."""
+        self._ctx.check(self._ctx._lib.spl_mat_to_coo_dev(self._ctx._h, self._h, C.c_void_p(row_dev), C.c_void_p(col_dev),
+                                                          C.c_void_p(val_dev)))
 
     # -- hot-path operators
     def transpose(self):

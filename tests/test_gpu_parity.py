@@ -489,6 +489,29 @@ def test_to_coo_random_matches_the_oracle(dtype, n, m, density):
         assert r.dtype == np.uint64 and c.dtype == np.uint64 and len(v) == M.nnz()
         assert np.array_equal(r, want["row"]) and np.array_equal(c, want["col"]), major
         assert v.tobytes() == want["val"].tobytes(), major
+        # iter(): the same entries, read chunk by chunk from the device
+        M.ITER_CHUNK = 1000                                   # several chunks, a ragged last one
+        got = list(M.iter())
+        assert len(got) == M.nnz()
+        if got:
+            gr, gc, gv = (np.array(t) for t in zip(*got))
+            assert np.array_equal(gr.astype(np.uint64), want["row"]) and np.array_equal(gc.astype(np.uint64), want["col"])
+            assert gv.astype(dtype).tobytes() == want["val"].tobytes()
+        # the device-side form: uint32 SoA triplets left in HBM, fed straight back into the assembly
+        import torch
+        nz = max(M.nnz(), 1)
+        rd = torch.empty(nz, dtype=torch.int32, device="cuda")
+        cd = torch.empty(nz, dtype=torch.int32, device="cuda")
+        vd = torch.empty(nz, dtype=torch.float32 if dtype == np.float32 else torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        M.to_coo_device(rd.data_ptr(), cd.data_ptr(), vd.data_ptr())
+        sp.default_context().sync()
+        k = M.nnz()
+        assert np.array_equal(rd.cpu().numpy()[:k].astype(np.uint64), want["row"])
+        assert np.array_equal(cd.cpu().numpy()[:k].astype(np.uint64), want["col"])
+        assert vd.cpu().numpy()[:k].tobytes() == want["val"].tobytes()
+        again = type(M).from_device_triplets(n, m, k, rd.data_ptr(), cd.data_ptr(), vd.data_ptr(), dtype)
+        same(arrays(again), arr, f"device round trip through COO ({major})")
         # and back: CooMatrix -> the same compressed matrix (round trip through the builder format)
         back = type(M).from_coo(M.to_coo())
         same(arrays(back), arr, f"round trip through COO ({major})")       # values are non-zero: nothing is dropped

@@ -74,3 +74,22 @@ def test_sharded_spmv_world2_gloo(mode, n):
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) == 1
+
+
+def test_balanced_starts_follow_the_entries():
+    """nnz-balanced row partition: contiguous, strictly increasing, every rank gets about
+    total / world entries on a power-law row distribution; uniform rows reduce to equal blocks."""
+    from spalinalg_b200 import dist as spd
+    rng = np.random.default_rng(0)
+    counts = (rng.pareto(1.2, 4096) * 100).astype(np.int64)
+    rows_per_bin, n = 16, 4096 * 16
+    for world in (2, 3, 8):
+        st = spd.balanced_starts(counts, rows_per_bin, n, world)
+        assert st[0] == 0 and st[-1] == n and all(b > a for a, b in zip(st, st[1:]))
+        cum = np.concatenate([[0], np.cumsum(counts + rows_per_bin)])
+        share = [cum[st[g + 1] // rows_per_bin] - cum[st[g] // rows_per_bin] for g in range(world)]
+        assert max(share) <= 1.15 * cum[-1] / world
+    assert spd.balanced_starts([7] * 8, 10, 80, 4) == [0, 20, 40, 60, 80]
+    # more ranks than non-empty bins: still a valid partition
+    st = spd.balanced_starts([5, 0, 0, 0], 4, 16, 4)
+    assert st[0] == 0 and st[-1] == 16 and all(b > a for a, b in zip(st, st[1:]))
