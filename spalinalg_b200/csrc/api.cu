@@ -2,6 +2,7 @@
 // status codes out; nothing unwinds across it.  No CPU fallback: every entry point needs a
 // live CUDA context.
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "kernels.cuh"
@@ -52,6 +53,29 @@ void check_dims(spl_ctx *ctx, uint64_t nrows, uint64_t ncols) {
                 "dimensions must be below 2^32 (device indices are 32 bit)");
 }
 
+// One private memory pool per device for the whole library.  Freed blocks stay in it (release
+// threshold raised on THIS pool only), so the temporaries of the next call are reused without a
+// synchronisation; the device's default pool, which torch and others allocate from, is left alone.
+cudaMemPool_t library_pool(int device) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    SPL_REQUIRE(device >= 0 && device < 64, SPL_ERR_ARG, "device ordinal out of range");
+    if (!pools[device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        SPL_CUDA(cudaMemPoolCreate(&pool, &props));
+        uint64_t threshold = UINT64_MAX;
+        SPL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        pools[device] = pool;
+    }
+    return pools[device];
+}
+
 [[noreturn]] void invalid(spl_ctx *ctx, int reason, const char *text) {
     ctx->invalid_reason = reason;
     throw Error{SPL_ERR_INVALID, text};
@@ -97,11 +121,7 @@ int spl_ctx_create(int device, void *stream, spl_ctx **out) {
         int sms = 0;
         SPL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         ctx->num_sms = sms > 0 ? sms : kNumSmFallback;
-        // keep freed blocks in the pool: temporaries of the next call reuse them without a sync
-        cudaMemPool_t pool;
-        SPL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t threshold = UINT64_MAX;
-        SPL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        ctx->pool = library_pool(device);
         SPL_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(uint32_t)));
         SPL_CUDA(cudaMalloc(&ctx->d_scratch, 64 * sizeof(uint32_t)));
         SPL_CUDA(cudaMemset(ctx->d_scratch, 0, 64 * sizeof(uint32_t)));
@@ -153,6 +173,7 @@ int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, ui
     SPL_REQUIRE(len == 0 || (row_dev && col_dev && val_dev), SPL_ERR_ARG, "NULL COO array");
     *out = assemble_from_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
                                  row_dev, col_dev, val_dev, dedup, dropzero);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -181,6 +202,7 @@ int spl_mat_from_coo(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64
     // bounds (CooMatrix::push, src/coo.rs:432-433) are re-checked on the narrowed arrays
     *out = assemble_from_coo_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
                                  r32, c32, v, dedup, dropzero);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -219,6 +241,7 @@ int spl_mat_from_compressed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nr
         throw;
     }
     *out = m;
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -268,6 +291,7 @@ int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
         throw;
     }
     *out = m;
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -285,6 +309,7 @@ int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **ou
         throw;
     }
     *out = m;
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -304,6 +329,7 @@ static spl_mat *regroup(spl_ctx *ctx, const spl_mat *in, int out_format, uint32_
 
 int spl_mat_convert(spl_ctx *ctx, const spl_mat *in, int format, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_in(ctx, in);
     SPL_REQUIRE(in && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     check_enums(format, in->dtype);
@@ -316,46 +342,60 @@ int spl_mat_convert(spl_ctx *ctx, const spl_mat *in, int format, spl_mat **out) 
         SPL_CUDA(cudaMemcpyAsync(m->val, in->val, (size_t)in->nnz * in->vsize(),
                                  cudaMemcpyDeviceToDevice, ctx->stream));
         *out = m;
+        publish_mat(ctx, *out);
     } else {
-        *out = regroup(ctx, in, format, in->nrows, in->ncols);   // same matrix, other format
+        *out = regroup(ctx, in, format, in->nrows, in->ncols);
+        publish_mat(ctx, *out);   // same matrix, other format
     }
     API_END(ctx)
 }
 
 int spl_mat_transpose(spl_ctx *ctx, const spl_mat *in, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_in(ctx, in);
     SPL_REQUIRE(in && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
-    *out = regroup(ctx, in, in->format, in->ncols, in->nrows);   // same format, dims swapped
+    *out = regroup(ctx, in, in->format, in->ncols, in->nrows);
+    publish_mat(ctx, *out);   // same format, dims swapped
     API_END(ctx)
 }
 
 int spl_mat_add(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
+    MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     *out = addsub(ctx, a, b, 0);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
 int spl_mat_sub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
+    MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     *out = addsub(ctx, a, b, 1);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
 int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
+    MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     *out = spgemm(ctx, a, b);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
 int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
     SPL_REQUIRE(a && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     spl_mat *m = new_mat(ctx, a->format, a->dtype, a->nrows, a->ncols, a->nnz);
@@ -370,11 +410,13 @@ int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out) {
         throw;
     }
     *out = m;
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
 int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, int kernel) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
     SPL_REQUIRE(a && x_dev && y_dev, SPL_ERR_ARG, "NULL argument");
     spmv(ctx, a, x_dev, y_dev, kernel & 0xff, (kernel >> 8) & 0xff);
     API_END(ctx)
@@ -386,6 +428,7 @@ int spl_spmv(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev) {
 
 int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_host) {
     API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
     SPL_REQUIRE(a && x_host && y_host, SPL_ERR_ARG, "NULL argument");
     const size_t vs = a->vsize();
     Tmp<unsigned char> x(ctx, (size_t)a->ncols * vs), y(ctx, (size_t)a->nrows * vs);
@@ -421,6 +464,7 @@ int spl_mat_info(const spl_mat *m, int *format, int *dtype, uint64_t *nrows, uin
 
 int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *ind, void *val) {
     API_BEGIN(ctx)
+    MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     const size_t np = (size_t)m->nmajor() + 1;
     Tmp<uint64_t> wide(ctx, np > m->nnz ? np : m->nnz);
@@ -441,6 +485,7 @@ int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *in
 
 int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val) {
     API_BEGIN(ctx)
+    MatUse use_m(ctx, m);
     SPL_REQUIRE(m && (val || m->nnz == 0), SPL_ERR_ARG, "NULL argument");
     if (m->nnz) {
         SPL_CUDA(cudaMemcpyAsync(m->val, val, (size_t)m->nnz * m->vsize(), cudaMemcpyHostToDevice, ctx->stream));
@@ -461,6 +506,7 @@ int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32
 
 int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val) {
     API_BEGIN(ctx)
+    MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     if (m->nnz) {
         SPL_REQUIRE(row && col && val, SPL_ERR_ARG, "NULL array");
@@ -484,6 +530,7 @@ int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col,
 
 int spl_mat_to_coo_dev(spl_ctx *ctx, const spl_mat *m, uint32_t *row_dev, uint32_t *col_dev, void *val_dev) {
     API_BEGIN(ctx)
+    MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     if (m->nnz) {
         SPL_REQUIRE(row_dev && col_dev && val_dev, SPL_ERR_ARG, "NULL array");
@@ -498,6 +545,7 @@ int spl_mat_to_coo_dev(spl_ctx *ctx, const spl_mat *m, uint32_t *row_dev, uint32
 int spl_mat_read_entries(spl_ctx *ctx, const spl_mat *m, uint64_t start, uint64_t count, uint64_t *row,
                          uint64_t *col, void *val) {
     API_BEGIN(ctx)
+    MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     SPL_REQUIRE(start <= m->nnz && count <= m->nnz - start, SPL_ERR_ARG, "entry range outside the matrix");
     if (count) {
@@ -577,6 +625,7 @@ int spl_mat_from_packed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
     SPL_REQUIRE(len == 0 || (keys_dev && vals_dev), SPL_ERR_ARG, "NULL COO array");
     *out = assemble_from_packed_dev(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)len,
                                     keys_dev, vals_dev, dedup, dropzero);
+    publish_mat(ctx, *out);
     API_END(ctx)
 }
 
@@ -656,6 +705,7 @@ int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out) {
 int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
                   const uint64_t *col_starts, const void *const *x_slices, void *y_dev) {
     API_BEGIN(ctx)
+    MatUse use_a_local(ctx, a_local);
     SPL_REQUIRE(a_local && col_starts && x_slices && y_dev, SPL_ERR_ARG, "NULL argument");
     SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
                 "world must be 1..8 and rank inside it");
@@ -678,6 +728,7 @@ int spl_spmv_peer_host(spl_ctx *ctx, const spl_mat *a_local, int world, int rank
                        void *const *x_slices, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
                        const void *x_host_local, void *y_host_local) {
     API_BEGIN(ctx)
+    MatUse use_a_local(ctx, a_local);
     SPL_REQUIRE(a_local && col_starts && x_slices && flag_ptrs && y_host_local, SPL_ERR_ARG, "NULL argument");
     SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
                 "world must be 1..8 and rank inside it");

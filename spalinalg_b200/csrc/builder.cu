@@ -16,6 +16,7 @@
 // never written by push).  pop()/clear() below `sent` wait for the copy stream and lower `sent`, so
 // the positions are sent again when they are refilled.
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "kernels.cuh"
@@ -39,6 +40,10 @@ struct spl_coo {
     uint64_t *d_wide = nullptr;                    // staging: 2 * kChunk wide indices
     cudaEvent_t landed = nullptr;
     uint64_t counted_launches = 0;                 // launches of `copy` already credited to a caller
+    // From<&CooMatrix> takes the builder by shared reference, and the reference's CooMatrix is Sync:
+    // two threads may convert the same builder at once.  The conversion's flush of the last partial
+    // chunk (send, sent, the staging pair, the landed event) is therefore serialised here.
+    std::mutex convert_mu;
     size_t vsize() const { return dtype == SPL_F32 ? 4 : 8; }
 };
 
@@ -203,6 +208,15 @@ int spl_coo_free(spl_coo *b) {
 const char *spl_coo_last_error(const spl_coo *b) { return b && b->copy ? b->copy->last_error.c_str() : "null builder"; }
 
 int spl_coo_push(spl_coo *b, uint64_t row, uint64_t col, const void *value) {
+    if (!b || !b->copy) return SPL_ERR_ARG;
+    // the common case touches no CUDA state: bounds, three stores, a counter
+    if (value && row < b->nrows && col < b->ncols && b->len < b->cap && b->len + 1 - b->sent < kChunk) {
+        b->h_row[b->len] = row;
+        b->h_col[b->len] = col;
+        std::memcpy(b->h_val + b->len * b->vsize(), value, b->vsize());
+        ++b->len;
+        return SPL_OK;
+    }
     COO_BEGIN(b)
     SPL_REQUIRE(value, SPL_ERR_ARG, "value is NULL");
     SPL_REQUIRE(row < b->nrows, SPL_ERR_ARG, "assertion failed: row < self.nrows (src/coo.rs:432)");
@@ -278,13 +292,18 @@ int spl_mat_from_coo_builder(spl_ctx *ctx, spl_coo *b, int format, int dedup, in
         SPL_REQUIRE(format == SPL_CSR || format == SPL_CSC, SPL_ERR_ARG, "unknown format");
         SPL_REQUIRE(ctx->device == b->copy->device, SPL_ERR_ARG, "builder lives on another device");
         SPL_CUDA(cudaSetDevice(ctx->device));
-        send(b, b->len);   // the partial last chunk
-        SPL_CUDA(cudaEventRecord(b->landed, b->copy->stream));
-        SPL_CUDA(cudaStreamWaitEvent(ctx->stream, b->landed, 0));
-        ctx->launches += b->copy->launches - b->counted_launches;
-        b->counted_launches = b->copy->launches;
+        ctx->pdl_chain = false;
+        {
+            std::lock_guard<std::mutex> lock(b->convert_mu);
+            send(b, b->len);   // the partial last chunk
+            SPL_CUDA(cudaEventRecord(b->landed, b->copy->stream));
+            SPL_CUDA(cudaStreamWaitEvent(ctx->stream, b->landed, 0));
+            ctx->launches += b->copy->launches - b->counted_launches;
+            b->counted_launches = b->copy->launches;
+        }
         *out = assemble_from_coo_dev(ctx, format, b->dtype, (uint32_t)b->nrows, (uint32_t)b->ncols,
                                      (uint32_t)b->len, b->d_row, b->d_col, b->d_val, dedup, dropzero);
+        publish_mat(ctx, *out);
     } catch (const spl::Error &e) {
         ctx->last_error = e.msg;
         return e.status;

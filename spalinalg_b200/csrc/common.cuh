@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "../../include/spl.h"
 
@@ -60,6 +61,10 @@ struct spl_ctx {
     // programmatic dependent launch: true while the last thing this context put on its stream was a
     // stream-kernel SpMV (whose CTAs signal launch_dependents); the next one may then start its
     // matrix prefetch under the tail of that product.  Any other entry point clears it.
+    // the library's own stream-ordered memory pool on this device (shared by all contexts of the
+    // process): freed blocks stay in it for the next call without touching the device's default
+    // pool, which other libraries in the process (torch) allocate from
+    cudaMemPool_t pool = nullptr;
     bool pdl_chain = false;
     bool pdl_prev = false;     // pdl_chain as the current entry point found it
 };
@@ -118,6 +123,16 @@ struct spl_mat {
     // and kept: products on a CscMatrix then run the row kernels at full speed and in the reference's
     // summation order.  Owned by this matrix; dropped when the values change.
     std::atomic<spl_mat *> twin{nullptr};
+    // Sharing across contexts (spl.h: a matrix may be used read-only by several host threads, each
+    // with its own context and stream).  `home` is the stream the matrix was created on and `ready`
+    // the event recorded there behind the last kernel that wrote it: a context on another stream
+    // waits on it before its first use.  Every use from another stream leaves an event in `foreign`
+    // (one slot per stream), so that whoever frees the matrix waits for those readers first.
+    cudaStream_t home = nullptr;
+    cudaEvent_t ready = nullptr;
+    std::mutex use_mu;
+    struct ForeignUse { cudaStream_t stream; cudaEvent_t done; };
+    std::vector<ForeignUse> foreign;
 
     uint32_t nmajor() const { return format == SPL_CSR ? nrows : ncols; }
     uint32_t nminor() const { return format == SPL_CSR ? ncols : nrows; }
@@ -131,12 +146,12 @@ template <typename T>
 inline T *dalloc(spl_ctx *ctx, size_t count) {
     void *p = nullptr;
     size_t bytes = (count ? count : 1) * sizeof(T);
-    SPL_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
+    SPL_CUDA(cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream));
     return static_cast<T *>(p);
 }
 inline void *dalloc_bytes(spl_ctx *ctx, size_t bytes) {
     void *p = nullptr;
-    SPL_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, ctx->stream));
+    SPL_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, ctx->pool, ctx->stream));
     return p;
 }
 inline void dfree(spl_ctx *ctx, void *p) {
@@ -254,6 +269,39 @@ __device__ __forceinline__ double ld_stream(const double *p) {
 }
 
 struct NoPayload {};
+
+// Marks a freshly created matrix complete on the creating context's stream.
+inline void publish_mat(spl_ctx *ctx, spl_mat *m) {
+    if (!m) return;
+    m->home = ctx->stream;
+    if (!m->ready) SPL_CUDA(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+    SPL_CUDA(cudaEventRecord(m->ready, ctx->stream));
+}
+
+// Scope of one use of a matrix by a context: a context on the matrix's home stream is ordered by
+// the stream itself; any other context waits for `ready` first and leaves an event behind.
+struct MatUse {
+    spl_ctx *ctx;
+    spl_mat *m;
+    bool foreign = false;
+    MatUse(spl_ctx *c, const spl_mat *mat) : ctx(c), m(const_cast<spl_mat *>(mat)) {
+        if (!m || !m->ready || m->home == ctx->stream) return;
+        foreign = true;
+        SPL_CUDA(cudaStreamWaitEvent(ctx->stream, m->ready, 0));
+    }
+    ~MatUse() {
+        if (!foreign) return;
+        std::lock_guard<std::mutex> lock(m->use_mu);
+        for (auto &f : m->foreign)
+            if (f.stream == ctx->stream) { cudaEventRecord(f.done, ctx->stream); return; }
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+        cudaEventRecord(e, ctx->stream);
+        m->foreign.push_back({ctx->stream, e});
+    }
+    MatUse(const MatUse &) = delete;
+    MatUse &operator=(const MatUse &) = delete;
+};
 
 // Rust's unary minus on floats is a sign-bit flip for every input, NaN included (the GPU's FNEG
 // path may canonicalise NaN), so negate on the integer view.

@@ -211,6 +211,19 @@ spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t n
 
 void free_mat(spl_ctx *ctx, spl_mat *m) {
     if (!m) return;
+    // readers on other streams first: the blocks go back to the pool in this context's stream order
+    if (m->ready && m->home != ctx->stream) {
+        // freed by a context other than its creator: the creator's stream may still hold queued readers
+        // this context cannot name; rare, so settle it the blunt way
+        cudaDeviceSynchronize();
+    } else {
+        std::lock_guard<std::mutex> lock(m->use_mu);
+        for (auto &f : m->foreign) cudaStreamWaitEvent(ctx->stream, f.done, 0);
+    }
+    for (auto &f : m->foreign) cudaEventDestroy(f.done);
+    m->foreign.clear();
+    if (m->ready) cudaEventDestroy(m->ready);
+    m->ready = nullptr;
     free_mat(ctx, m->twin.exchange(nullptr));
     dfree(ctx, m->ptr);
     dfree(ctx, m->ind);

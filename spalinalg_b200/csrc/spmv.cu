@@ -214,8 +214,8 @@ bool build_slices(spl_ctx *ctx, spl_mat *a, double max_ratio) {
     if ((double)padded > max_ratio * (double)a->nnz + 4096.0) return false;
     uint32_t *si = nullptr;
     T *sv = nullptr;
-    if (cudaMallocAsync((void **)&si, padded * sizeof(uint32_t), ctx->stream) != cudaSuccess ||
-        cudaMallocAsync((void **)&sv, padded * sizeof(T), ctx->stream) != cudaSuccess) {
+    if (cudaMallocFromPoolAsync((void **)&si, padded * sizeof(uint32_t), ctx->pool, ctx->stream) != cudaSuccess ||
+        cudaMallocFromPoolAsync((void **)&sv, padded * sizeof(T), ctx->pool, ctx->stream) != cudaSuccess) {
         cudaGetLastError();                      // no room for a second copy: stay with CSR
         if (si) cudaFreeAsync(si, ctx->stream);
         return false;
@@ -1288,6 +1288,7 @@ const spl_mat *csr_form(spl_ctx *ctx, const spl_mat *a) {
     spl_mat *t = new_mat(ctx, SPL_CSR, a->dtype, a->nrows, a->ncols, a->nnz);
     try {
         recompress(ctx, a->dtype, a->nmajor(), a->nminor(), a->nnz, a->ptr, a->ind, a->val, t->ptr, t->ind, t->val);
+        publish_mat(ctx, t);
         SPL_CUDA(cudaStreamSynchronize(ctx->stream));          // visible to any other stream from here on
     } catch (...) {
         free_mat(ctx, t);
