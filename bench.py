@@ -715,6 +715,22 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     ms_pull = timed_all(spmv_pull, reps=7, warm=3)
     xs.check()
     assert torch.equal(y_ag, yg), "pulled all-gather gives a different y"
+    # the all-gather fused into the product: one persistent kernel, copy CTAs pull the slices over NVLink while the
+    # compute CTAs work through the owner blocks
+    D.prepare_gather(torch)
+
+    def spmv_fused():
+        xs.barrier()
+        D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr())
+    ms_fused = timed_all(spmv_fused, reps=7, warm=3)
+    xs.check()
+    err = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+    assert err < 1e-5, f"fused gather SpMV differs from the all-gather product: {err}"
+    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: copy CTAs pull the peers' slices of x over "
+                                                    "NVLink while compute CTAs multiply the shard block by block "
+                                                    "(blocked by column owner, ring order)",
+                                        "ms": ms_fused, "gbps_algorithmic": b_ag / ms_fused / 1e6,
+                                        "max_rel_diff_vs_allgather": err}
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}

@@ -294,6 +294,22 @@ int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *
 int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
                   const uint64_t *col_starts, const void *const *x_slices, void *y_dev);
 
+/* Row-sharded y_local = A_local * x for GENERAL shards (random / unstructured columns; the sharded
+ * form of `&A * &X`, src/csr/ops/mul.rs:5-60), the all-gather of x fused into the product: ONE
+ * persistent kernel whose copy CTAs pull the peers' slices of x over NVLink (x_slices as in
+ * spl_spmv_peer) into x_full_dev, slice by slice in ring order (rank+1, rank+2, ...), while its
+ * compute CTAs multiply the shard block by block in the same order — block 0 (columns of the own
+ * slice) at once, block k as soon as slice k has landed — and write y once.  The shard is passed
+ * blocked by column owner in that ring order: block_ptr_dev holds world row-pointer arrays of
+ * nrows_local+1 entries each (absolute positions into block_ind_dev / block_val_dev, global column
+ * indices).  ready_dev: uint32[SPL_MAX_PEERS], zeroed once by the caller; epoch = 1, 2, 3, ... per
+ * call on this buffer.  Order it after the peers' writes of x with spl_peer_barrier.  x_full_dev
+ * (ncols values) is scratch: afterwards it holds the peers' slices (not the own one). */
+int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
+                          const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
+                          const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
+                          uint32_t *ready_dev, uint32_t epoch);
+
 /* The reference-facing `&A * &x` on one rank of a row-sharded matrix, with HOST vectors:
  * x_host_local is this rank's slice of x (col_starts[rank+1] - col_starts[rank] values),
  * y_host_local receives its rows of y.  The slice is uploaded into x_slices[rank] (this rank's

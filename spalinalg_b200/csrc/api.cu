@@ -724,6 +724,27 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
     API_END(ctx)
 }
 
+int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
+                          const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
+                          const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
+                          uint32_t *ready_dev, uint32_t epoch) {
+    API_BEGIN(ctx)
+    check_enums(SPL_CSR, dtype);
+    SPL_REQUIRE(col_starts && x_slices && block_ptr_dev && x_full_dev && y_dev && ready_dev, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
+                "world must be 1..8 and rank inside it");
+    SPL_REQUIRE(nrows_local > 0 && nrows_local < (1ull << 32) && col_starts[world] < (1ull << 32), SPL_ERR_UNSUPPORTED,
+                "dimensions must be below 2^32");
+    SPL_REQUIRE(epoch > 0, SPL_ERR_ARG, "epoch counts from 1 and grows by one per call");
+    for (int g = 0; g < world; ++g) {
+        SPL_REQUIRE(col_starts[g] <= col_starts[g + 1], SPL_ERR_ARG, "col_starts must be non-decreasing");
+        SPL_REQUIRE(x_slices[g] || col_starts[g] == col_starts[g + 1], SPL_ERR_ARG, "NULL x slice");
+    }
+    spmv_gather_fused(ctx, dtype, (uint32_t)nrows_local, world, rank, col_starts, x_slices, block_ptr_dev, block_ind_dev,
+                      block_val_dev, x_full_dev, y_dev, ready_dev, epoch);
+    API_END(ctx)
+}
+
 int spl_spmv_peer_host(spl_ctx *ctx, const spl_mat *a_local, int world, int rank, const uint64_t *col_starts,
                        void *const *x_slices, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
                        const void *x_host_local, void *y_host_local) {

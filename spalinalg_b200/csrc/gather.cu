@@ -1,0 +1,195 @@
+// gather.cu — row-sharded y = A x for GENERAL shards (random / unstructured columns), the
+// all-gather of x fused into the product ("Collective (general)").
+//
+// A banded or stencil shard gathers its few halo columns straight from the owners' memory inside
+// the SpMV kernel (spmv.cu, XPeer).  A shard with random columns cannot: every remote gather would
+// be a 4-byte NVLink transaction.  It needs the whole of x locally, and done as "all-gather, then
+// SpMV" the exchange (35 MB per rank at 8 GPUs on config 3) costs more than the product and nothing
+// overlaps.  Here ONE persistent kernel does both:
+//   * the shard is stored blocked by column owner, own block first, then the peers in ring order
+//     (rank+1, rank+2, ...): block k holds, row by row, the entries whose column lives on that rank;
+//   * a few COPY CTAs pull the peers' slices of x over NVLink (128-bit loads from the CUDA-IPC
+//     mappings, 8 in flight per thread) into the local full-length x, slice by slice in the same
+//     ring order, and bump a per-slice counter (release) when their share of a slice has landed;
+//   * the COMPUTE CTAs own a fixed range of rows each, keep the row sums in shared memory, and walk
+//     the blocks in order: block 0 needs only the rank's own slice and runs while the first slices
+//     are in flight; before block k they wait (acquire) for slice k's counter.  Transfer and math
+//     overlap block by block, and y is written once.
+// All CTAs are resident at once (grid = what fits), so the waits cannot deadlock.  Row sums add the
+// blocks in ring order, not in ascending column order: tolerance parity (1e-12 / 1e-5), like every
+// multi-lane kernel.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace spl {
+
+namespace {
+
+struct GatherPeers {
+    const void *slice[SPL_MAX_PEERS];
+    uint32_t start[SPL_MAX_PEERS + 1];
+    int world, rank;
+};
+
+constexpr int GF_THREADS = 256;
+constexpr int GF_ROWS = 4;        // rows in flight per thread
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GF_THREADS)
+spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const uint32_t *__restrict__ bind,
+                         const T *__restrict__ bval, GatherPeers gp, T *x_full, T *__restrict__ y, uint32_t ncopy,
+                         uint32_t *ready, uint32_t target, uint32_t rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char gf_raw[];
+    const int G = gp.world;
+    if (blockIdx.x < ncopy) {
+        // ---- copy role: slices of the peers, ring order, this CTA's 1/ncopy share of each ----
+        for (int k = 1; k < G; ++k) {
+            const int g = (gp.rank + k) % G;
+            const unsigned char *src = static_cast<const unsigned char *>(gp.slice[g]);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(x_full + gp.start[g]);
+            const unsigned long long bytes = (unsigned long long)(gp.start[g + 1] - gp.start[g]) * sizeof(T);
+            // whole 16-byte units when both ends are aligned (IPC blocks are; slice starts of f32 vectors may not be)
+            const bool wide = ((((unsigned long long)(uintptr_t)src) | ((unsigned long long)(uintptr_t)dst)) & 15ull) == 0;
+            const unsigned long long n16 = wide ? bytes / 16 : 0;
+            const unsigned long long per = (n16 + ncopy - 1) / ncopy;
+            const unsigned long long lo = (unsigned long long)blockIdx.x * per;
+            const unsigned long long hi = lo + per < n16 ? lo + per : n16;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+            unsigned long long i = lo + threadIdx.x;
+            for (; i + 7ull * GF_THREADS < hi; i += 8ull * GF_THREADS) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(s4 + i + (unsigned long long)u * GF_THREADS);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) d4[i + (unsigned long long)u * GF_THREADS] = v[u];
+            }
+            for (; i < hi; i += GF_THREADS) d4[i] = __ldcg(s4 + i);
+            // the unaligned / trailing bytes: element by element, by the first copy CTA
+            if (blockIdx.x == 0) {
+                const T *se = reinterpret_cast<const T *>(src);
+                T *de = reinterpret_cast<T *>(dst);
+                const unsigned long long n = bytes / sizeof(T);
+                for (unsigned long long e = n16 * (16 / sizeof(T)) + threadIdx.x; e < n; e += GF_THREADS) de[e] = __ldcg(se + e);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();                       // this CTA's stores of the slice, before the count
+                atomicAdd(ready + k, 1u);
+            }
+        }
+        return;
+    }
+
+    // ---- compute role: rows [rs, re), sums in shared memory, blocks in ring order ----
+    T *acc = reinterpret_cast<T *>(gf_raw);
+    const uint32_t c = blockIdx.x - ncopy;
+    const uint64_t rs64 = (uint64_t)c * rows_per_cta;
+    if (rs64 >= nloc) return;
+    const uint32_t rs = (uint32_t)rs64;
+    const uint32_t re = rs + rows_per_cta < nloc ? rs + rows_per_cta : nloc;
+    for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) acc[i] = (T)0;
+    // (every thread only ever touches its own slots of acc: no barrier needed for them)
+    const T *own = static_cast<const T *>(gp.slice[gp.rank]) - gp.start[gp.rank];
+    for (int k = 0; k < G; ++k) {
+        const T *xb = k == 0 ? own : x_full;
+        if (k > 0) {
+            if (threadIdx.x == 0)
+                while ((int32_t)(ld_acquire_gpu(ready + k) - target) < 0) __nanosleep(64);
+            __syncthreads();
+        }
+        const uint32_t *p = bptr + (size_t)k * (nloc + 1);
+        for (uint32_t base = rs + threadIdx.x; base < re; base += GF_THREADS * GF_ROWS) {
+            uint32_t a[GF_ROWS], b[GF_ROWS];
+            T s[GF_ROWS];
+#pragma unroll
+            for (int q = 0; q < GF_ROWS; ++q) {
+                const uint32_t r = base + q * GF_THREADS;
+                a[q] = b[q] = 0;
+                s[q] = (T)0;
+                if (r < re) { a[q] = __ldg(p + r); b[q] = __ldg(p + r + 1); }
+            }
+            for (;;) {
+                uint32_t col[GF_ROWS];
+                T v[GF_ROWS], xv[GF_ROWS];
+                bool any = false;
+#pragma unroll
+                for (int q = 0; q < GF_ROWS; ++q) {
+                    const bool ok = a[q] < b[q];
+                    col[q] = ok ? ld_stream(bind + a[q]) : 0xffffffffu;
+                    v[q] = ok ? ld_stream(bval + a[q]) : (T)0;
+                    any |= ok;
+                }
+                if (!any) break;
+#pragma unroll
+                for (int q = 0; q < GF_ROWS; ++q) xv[q] = col[q] != 0xffffffffu ? __ldcg(xb + col[q]) : (T)0;   // L2: x_full changes under L1
+#pragma unroll
+                for (int q = 0; q < GF_ROWS; ++q) {
+                    if (col[q] != 0xffffffffu) { s[q] += v[q] * xv[q]; ++a[q]; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < GF_ROWS; ++q) {
+                const uint32_t r = base + q * GF_THREADS;
+                if (r < re) acc[r - rs] += s[q];
+            }
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) y[rs + i] = acc[i];
+}
+
+}  // namespace
+
+// Launch shape: `ncopy` copy CTAs plus as many compute CTAs as stay resident beside them; the row range
+// of a compute CTA (its shared-memory sums) shrinks as the CTAs per SM grow, so the two are found together.
+template <typename T>
+void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, const uint32_t *bind, const T *bval,
+                         const GatherPeers &gp, T *x_full, T *y, uint32_t *ready, uint32_t epoch) {
+    auto k = spmv_gather_fused_kernel<T>;
+    const uint32_t ncopy = gp.world > 1 ? std::min<uint32_t>(48u, (uint32_t)ctx->num_sms / 3u) : 0u;
+    uint32_t ncompute = 0, rows_per_cta = 0;
+    size_t smem = 0;
+    for (int want = 6; want >= 1; --want) {
+        const uint32_t total = (uint32_t)ctx->num_sms * (uint32_t)want;
+        if (total <= ncopy) continue;
+        ncompute = total - ncopy;
+        rows_per_cta = (uint32_t)(((uint64_t)nloc + ncompute - 1) / ncompute);
+        rows_per_cta = (rows_per_cta + 31u) & ~31u;
+        smem = (size_t)rows_per_cta * sizeof(T);
+        if (smem > 200 * 1024) continue;
+        if (smem > 48 * 1024) SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int resident = 0;
+        SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k, GF_THREADS, smem));
+        if (resident >= want) break;
+        ncompute = 0;
+    }
+    SPL_REQUIRE(ncompute > 0, SPL_ERR_UNSUPPORTED,
+                "fused gather SpMV: the shard's rows do not fit in the shared-memory sums of one resident grid");
+    k<<<ncopy + ncompute, GF_THREADS, smem, ctx->stream>>>(nloc, bptr, bind, bval, gp, x_full, y, ncopy, ready,
+                                                          epoch * ncopy, rows_per_cta);
+    check_launch(ctx, "spmv_gather_fused");
+}
+
+void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int rank, const uint64_t *col_starts,
+                       const void *const *x_slices, const uint32_t *bptr, const uint32_t *bind, const void *bval,
+                       void *x_full, void *y, uint32_t *ready, uint32_t epoch) {
+    GatherPeers gp{};
+    gp.world = world;
+    gp.rank = rank;
+    for (int g = 0; g <= SPL_MAX_PEERS; ++g) gp.start[g] = (uint32_t)col_starts[g < world ? g : world];
+    for (int g = 0; g < world; ++g) gp.slice[g] = x_slices[g];
+    if (dtype == SPL_F32)
+        spmv_gather_fused_t<float>(ctx, nloc, bptr, bind, (const float *)bval, gp, (float *)x_full, (float *)y, ready, epoch);
+    else
+        spmv_gather_fused_t<double>(ctx, nloc, bptr, bind, (const double *)bval, gp, (double *)x_full, (double *)y, ready,
+                                    epoch);
+}
+
+}  // namespace spl

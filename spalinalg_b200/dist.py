@@ -297,6 +297,53 @@ class DistCsrMatrix:
                                          C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(y_dev)))
 
 
+    def prepare_gather(self, torch):
+        """One-time layout for spmv_gather: the shard's entries blocked by the rank that owns their column,
+        own block first, then the peers in ring order (rank+1, rank+2, ...), row order kept inside a
+        block; one row-pointer array per block.  Device-side plumbing (a stable sort by block id and
+        one row histogram per block); the arrays stay with the matrix."""
+        from .synthetic_device import device_view
+        ctx = self.local._ctx
+        ctx.sync()
+        r0, r1 = self.local_rows()
+        nloc, nnz, G = r1 - r0, self.local.nnz(), self.world
+        tdt = torch.float32 if self.local.dtype == np.float32 else torch.float64
+        p_ptr, p_ind, p_val = self.local.device_ptrs()
+        ptr = device_view(torch, p_ptr, nloc + 1, torch.int32).long()
+        col = device_view(torch, p_ind, max(nnz, 1), torch.int32)[:nnz]
+        val = device_view(torch, p_val, max(nnz, 1), tdt)[:nnz]
+        rows = torch.repeat_interleave(torch.arange(nloc, device=col.device), ptr[1:] - ptr[:-1])
+        bounds = torch.tensor(self.starts[1:-1], device=col.device, dtype=torch.int64)
+        owner = torch.searchsorted(bounds, col.long() & 0xFFFFFFFF, right=True)
+        block = ((owner - self.rank) % G).to(torch.int16)
+        order = torch.sort(block, stable=True).indices
+        bind = col[order].contiguous()
+        bval = val[order].contiguous()
+        key = block[order].long() * nloc + rows[order]
+        counts = torch.bincount(key, minlength=G * nloc).view(G, nloc)
+        base = torch.cumsum(counts.sum(1), 0) - counts.sum(1)                 # first position of every block
+        bptr = torch.zeros((G, nloc + 1), dtype=torch.int64, device=col.device)
+        bptr[:, 1:] = torch.cumsum(counts, 1)
+        bptr += base[:, None]
+        self._gather = {"bptr": bptr.to(torch.int32).contiguous(), "bind": bind, "bval": bval,
+                        "ready": torch.zeros(capi.SPL_MAX_PEERS, dtype=torch.int32, device=col.device), "epoch": 0}
+        torch.cuda.current_stream().synchronize()
+
+    def spmv_gather(self, x: "PeerVector", x_full_dev: int, y_dev: int):
+        """y_local = A_local x for a general shard with the all-gather of x fused into the product
+        (spl_spmv_gather_fused): call prepare_gather once, publish x, then this per product."""
+        g = self._gather
+        g["epoch"] += 1
+        ctx = self.local._ctx
+        st = (C.c_uint64 * (self.world + 1))(*x.starts)
+        sl = (C.c_void_p * self.world)(*x.ptrs)
+        r0, r1 = self.local_rows()
+        ctx.check(ctx._lib.spl_spmv_gather_fused(
+            ctx._h, _dtype_code(self.local.dtype), r1 - r0, self.world, self.rank, C.cast(st, C.c_void_p),
+            C.cast(sl, C.c_void_p), C.c_void_p(g["bptr"].data_ptr()), C.c_void_p(g["bind"].data_ptr()),
+            C.c_void_p(g["bval"].data_ptr()), C.c_void_p(x_full_dev), C.c_void_p(y_dev),
+            C.c_void_p(g["ready"].data_ptr()), g["epoch"]))
+
     def matvec_host(self, x: "PeerVector", x_host_local, y_host_local, timeout_ms: int = 2000):
         """`&A * &x` with this rank's slices of x and y in host memory (numpy arrays or raw host
         addresses; pinned memory lets the copies overlap): spl_spmv_peer_host.  The slice is uploaded
@@ -326,6 +373,33 @@ class DistCscMatrix:
     def nrows(self): return self._nrows
     def ncols(self): return self._ncols
     def local_cols(self): return self.starts[self.rank], self.starts[self.rank + 1]
+
+    def spmv(self, dist, torch, x_local, group=None):
+        """y = A x with A column-sharded (this rank holds columns [c0, c1) as a CscMatrix with global row
+        indices) and x sharded like the columns: the sharded form of `&A * &X` for a CscMatrix
+        (src/csc/ops/mul.rs:5-61) — with A the CSC view of a row-sharded CSR matrix B it is y = B^T x.
+        Every rank multiplies its column block by its slice of x (spl_spmv on the CSC block: the row
+        kernels on its cached CSR form) into a full-length partial y; the partials are summed by one
+        reduce-scatter, which leaves rank g with rows [rstarts[g], rstarts[g+1]) of y.  This path has
+        a real exchange step (the sum over column blocks), so it uses the collective (NCCL on GPUs).
+        Returns (y_rows tensor, rstarts)."""
+        world, rank = self.world, self.rank
+        c0, c1 = self.local_cols()
+        assert x_local.numel() == c1 - c0
+        rstarts = partition_starts(self._nrows, world)
+        chunk = -(-self._nrows // world)
+        part = torch.zeros(chunk * world, dtype=x_local.dtype, device=x_local.device)
+        _torch_to_ctx(torch)
+        if c1 > c0:
+            self.local.spmv_device(x_local.data_ptr(), part.data_ptr())        # rows [0, nrows) of the partial
+        self.local._ctx.sync()
+        if world == 1:
+            return part[:self._nrows], rstarts
+        # equal chunks for the collective: rank g's rows are re-cut at g * chunk afterwards
+        out = torch.empty(chunk, dtype=x_local.dtype, device=x_local.device)
+        dist.reduce_scatter_tensor(out, part, group=group)
+        lo, hi = rank * chunk, min((rank + 1) * chunk, self._nrows)
+        return out[:max(hi - lo, 0)], [min(g * chunk, self._nrows) for g in range(world)] + [self._nrows]
 
 
 # ------------------------------------------------------------------------- peer memory

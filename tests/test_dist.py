@@ -317,6 +317,14 @@ def test_sharded_front_end_world1_nccl():
         yw = orc.csr_spmv(n, *full, x)
         sc = orc.csr_spmv(n, full[0], full[1], np.abs(full[2]), np.abs(x))
         assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
+        # the fused gather kernel with a world of one: no copy CTAs, the own block only
+        D.prepare_gather(torch)
+        xf = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+        y.fill_(7.0)
+        torch.cuda.synchronize()
+        D.spmv_gather(xv, xf.data_ptr(), y.data_ptr())
+        ctx.sync()
+        assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
         # y_t -> x_{t+1} without a copy: the product writes the next x into the unpublished buffer
         A1 = 0.05 * np.asarray(full[2])
         D1 = spd.DistCsrMatrix(type(D.local).new(n, n, full[0], full[1], A1, ctx=ctx), D.starts, 0, n, n)
@@ -338,6 +346,8 @@ def test_sharded_front_end_world1_nccl():
         for T in (D.to_csc(dist, torch), D.to_csc(dist, torch, exchange=ex2)):
             assert np.array_equal(T.local.colptr(), wc[0]) and np.array_equal(T.local.rowind(), wc[1])
             assert T.local.values().tobytes() == wc[2].tobytes()
+        yt, rst = T.spmv(dist, torch, torch.from_numpy(x).cuda())          # column-sharded y = A x (world 1)
+        assert rst == [0, n] and np.all(np.abs(yt.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
         ex2.close()
         xv.close(dist)
     finally:

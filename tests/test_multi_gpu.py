@@ -98,6 +98,21 @@ def _worker(rank, world, port, out):
         ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
         assert ok, "pulled all-gather SpMV differs from the oracle"
 
+        # general shards: the all-gather fused into the product (copy CTAs pull the slices over NVLink while
+        # the compute CTAs work through the owner blocks); two products on one set of flags, x changed between
+        D.prepare_gather(torch)
+        for scale_x in (1.0, -0.5):
+            device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(scale_x * x[r0:r1]))
+            xv.publish()
+            x_full.fill_(float("nan"))
+            y.fill_(7.0)
+            torch.cuda.synchronize()
+            D.spmv_gather(xv, x_full.data_ptr(), y.data_ptr())
+            torch.cuda.synchronize()
+            ok &= bool(np.all(np.abs(y.cpu().numpy() - scale_x * yw[r0:r1]) <= 4e-12 * sc[r0:r1] + 1e-300))
+        xv.check()
+        assert ok, "fused gather SpMV differs from the oracle"
+
         # an iteration whose x changes every step: y_t is written straight into the unpublished buffer
         # and published as x_{t+1} (one barrier per step).  One rank is held back by a spin kernel at a
         # different point of every step, so the fast rank runs ahead as far as the barrier lets it; with
@@ -132,6 +147,13 @@ def _worker(rank, world, port, out):
         ex2.check()
         ex2.close()
         assert ok, "peer-memory sharded CSR -> CSC differs from the oracle"
+        # y = A x on the column-sharded CSC form (x sharded like the columns; partials summed by reduce-scatter)
+        c0, c1 = T.local_cols()
+        yt, rst = T.spmv(dist, torch, torch.from_numpy(x[c0:c1]).cuda())
+        torch.cuda.synchronize()
+        a0, a1 = rst[rank], rst[rank + 1]
+        ok &= bool(np.all(np.abs(yt.cpu().numpy() - yw[a0:a1]) <= 4e-12 * sc[a0:a1] + 1e-300))
+        assert ok, "column-sharded CSC SpMV differs from the oracle"
         xv.close(dist)
     finally:
         flag = torch.tensor([1 if ok else 0], device="cuda")
