@@ -303,12 +303,13 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
  * blocked by column owner in that ring order: block_ptr_dev holds world row-pointer arrays of
  * nrows_local+1 entries each (absolute positions into block_ind_dev / block_val_dev, global column
  * indices).  ready_dev: uint32[SPL_MAX_PEERS], zeroed once by the caller; epoch = 1, 2, 3, ... per
- * call on this buffer.  Order it after the peers' writes of x with spl_peer_barrier.  x_full_dev
+ * call on this buffer; nnz_local = stored entries of the shard (picks the lanes per row).  Order
+ * it after the peers' writes of x with spl_peer_barrier.  x_full_dev
  * (ncols values) is scratch: afterwards it holds the peers' slices (not the own one). */
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
                           const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
                           const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
-                          uint32_t *ready_dev, uint32_t epoch);
+                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local);
 
 /* The reference-facing `&A * &x` on one rank of a row-sharded matrix, with HOST vectors:
  * x_host_local is this rank's slice of x (col_starts[rank+1] - col_starts[rank] values),

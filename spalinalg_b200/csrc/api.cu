@@ -727,7 +727,7 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
                           const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
                           const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
-                          uint32_t *ready_dev, uint32_t epoch) {
+                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local) {
     API_BEGIN(ctx)
     check_enums(SPL_CSR, dtype);
     SPL_REQUIRE(col_starts && x_slices && block_ptr_dev && x_full_dev && y_dev && ready_dev, SPL_ERR_ARG, "NULL argument");
@@ -741,7 +741,8 @@ int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int wor
         SPL_REQUIRE(x_slices[g] || col_starts[g] == col_starts[g + 1], SPL_ERR_ARG, "NULL x slice");
     }
     spmv_gather_fused(ctx, dtype, (uint32_t)nrows_local, world, rank, col_starts, x_slices, block_ptr_dev, block_ind_dev,
-                      block_val_dev, x_full_dev, y_dev, ready_dev, epoch);
+                      block_val_dev, x_full_dev, y_dev, ready_dev, epoch,
+                      (double)nnz_local / (double)nrows_local / (double)world);
     API_END(ctx)
 }
 

@@ -33,7 +33,7 @@ struct GatherPeers {
 };
 
 constexpr int GF_THREADS = 256;
-constexpr int GF_ROWS = 4;        // rows in flight per thread
+constexpr int GF_ROWS = 8;        // rows in flight per lane group: a block holds only nnz / world entries of a row
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
     uint32_t v;
@@ -41,7 +41,7 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
     return v;
 }
 
-template <typename T>
+template <typename T, int LPR>
 __global__ void __launch_bounds__(GF_THREADS)
 spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const uint32_t *__restrict__ bind,
                          const T *__restrict__ bval, GatherPeers gp, T *x_full, T *__restrict__ y, uint32_t ncopy,
@@ -96,7 +96,7 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
     const uint32_t rs = (uint32_t)rs64;
     const uint32_t re = rs + rows_per_cta < nloc ? rs + rows_per_cta : nloc;
     for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) acc[i] = (T)0;
-    // (every thread only ever touches its own slots of acc: no barrier needed for them)
+    __syncthreads();
     const T *own = static_cast<const T *>(gp.slice[gp.rank]) - gp.start[gp.rank];
     for (int k = 0; k < G; ++k) {
         const T *xb = k == 0 ? own : x_full;
@@ -106,15 +106,18 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
             __syncthreads();
         }
         const uint32_t *p = bptr + (size_t)k * (nloc + 1);
-        for (uint32_t base = rs + threadIdx.x; base < re; base += GF_THREADS * GF_ROWS) {
+        constexpr uint32_t RL = GF_THREADS / LPR;          // rows a CTA covers per step of one q
+        const uint32_t sub = threadIdx.x % LPR;
+        for (uint32_t base0 = rs; base0 < re; base0 += RL * GF_ROWS) {       // uniform trip count: shuffles below
+            const uint32_t base = base0 + threadIdx.x / LPR;
             uint32_t a[GF_ROWS], b[GF_ROWS];
             T s[GF_ROWS];
 #pragma unroll
             for (int q = 0; q < GF_ROWS; ++q) {
-                const uint32_t r = base + q * GF_THREADS;
+                const uint32_t r = base + q * RL;
                 a[q] = b[q] = 0;
                 s[q] = (T)0;
-                if (r < re) { a[q] = __ldg(p + r); b[q] = __ldg(p + r + 1); }
+                if (r < re) { a[q] = __ldg(p + r) + sub; b[q] = __ldg(p + r + 1); }
             }
             for (;;) {
                 uint32_t col[GF_ROWS];
@@ -132,16 +135,19 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
                 for (int q = 0; q < GF_ROWS; ++q) xv[q] = col[q] != 0xffffffffu ? __ldcg(xb + col[q]) : (T)0;   // L2: x_full changes under L1
 #pragma unroll
                 for (int q = 0; q < GF_ROWS; ++q) {
-                    if (col[q] != 0xffffffffu) { s[q] += v[q] * xv[q]; ++a[q]; }
+                    if (col[q] != 0xffffffffu) { s[q] += v[q] * xv[q]; a[q] += LPR; }
                 }
             }
 #pragma unroll
             for (int q = 0; q < GF_ROWS; ++q) {
-                const uint32_t r = base + q * GF_THREADS;
-                if (r < re) acc[r - rs] += s[q];
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+                const uint32_t r = base + q * RL;
+                if (sub == 0 && r < re) acc[r - rs] += s[q];      // one owner per row for the whole kernel: no race
             }
         }
     }
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) y[rs + i] = acc[i];
 }
 
@@ -149,14 +155,14 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
 
 // Launch shape: `ncopy` copy CTAs plus as many compute CTAs as stay resident beside them; the row range
 // of a compute CTA (its shared-memory sums) shrinks as the CTAs per SM grow, so the two are found together.
-template <typename T>
+template <typename T, int LPR>
 void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, const uint32_t *bind, const T *bval,
                          const GatherPeers &gp, T *x_full, T *y, uint32_t *ready, uint32_t epoch) {
-    auto k = spmv_gather_fused_kernel<T>;
+    auto k = spmv_gather_fused_kernel<T, LPR>;
     const uint32_t ncopy = gp.world > 1 ? std::min<uint32_t>(48u, (uint32_t)ctx->num_sms / 3u) : 0u;
     uint32_t ncompute = 0, rows_per_cta = 0;
     size_t smem = 0;
-    for (int want = 6; want >= 1; --want) {
+    for (int want = 8; want >= 1; --want) {
         const uint32_t total = (uint32_t)ctx->num_sms * (uint32_t)want;
         if (total <= ncopy) continue;
         ncompute = total - ncopy;
@@ -179,17 +185,27 @@ void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, cons
 
 void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int rank, const uint64_t *col_starts,
                        const void *const *x_slices, const uint32_t *bptr, const uint32_t *bind, const void *bval,
-                       void *x_full, void *y, uint32_t *ready, uint32_t epoch) {
+                       void *x_full, void *y, uint32_t *ready, uint32_t epoch, double entries_per_row_block) {
     GatherPeers gp{};
     gp.world = world;
     gp.rank = rank;
     for (int g = 0; g <= SPL_MAX_PEERS; ++g) gp.start[g] = (uint32_t)col_starts[g < world ? g : world];
     for (int g = 0; g < world; ++g) gp.slice[g] = x_slices[g];
-    if (dtype == SPL_F32)
-        spmv_gather_fused_t<float>(ctx, nloc, bptr, bind, (const float *)bval, gp, (float *)x_full, (float *)y, ready, epoch);
-    else
-        spmv_gather_fused_t<double>(ctx, nloc, bptr, bind, (const double *)bval, gp, (double *)x_full, (double *)y, ready,
-                                    epoch);
+    // lanes per row from the entries a row holds in ONE block (nnz / rows / world)
+    const int lanes = entries_per_row_block <= 3.0 ? 1 : entries_per_row_block <= 12.0 ? 2 : 4;
+    auto go = [&](auto tag, auto lpr) {
+        using T = decltype(tag);
+        spmv_gather_fused_t<T, decltype(lpr)::value>(ctx, nloc, bptr, bind, (const T *)bval, gp, (T *)x_full, (T *)y, ready, epoch);
+    };
+    if (dtype == SPL_F32) {
+        if (lanes == 1) go(float{}, std::integral_constant<int, 1>{});
+        else if (lanes == 2) go(float{}, std::integral_constant<int, 2>{});
+        else go(float{}, std::integral_constant<int, 4>{});
+    } else {
+        if (lanes == 1) go(double{}, std::integral_constant<int, 1>{});
+        else if (lanes == 2) go(double{}, std::integral_constant<int, 2>{});
+        else go(double{}, std::integral_constant<int, 4>{});
+    }
 }
 
 }  // namespace spl

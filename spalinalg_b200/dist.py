@@ -342,7 +342,7 @@ class DistCsrMatrix:
             ctx._h, _dtype_code(self.local.dtype), r1 - r0, self.world, self.rank, C.cast(st, C.c_void_p),
             C.cast(sl, C.c_void_p), C.c_void_p(g["bptr"].data_ptr()), C.c_void_p(g["bind"].data_ptr()),
             C.c_void_p(g["bval"].data_ptr()), C.c_void_p(x_full_dev), C.c_void_p(y_dev),
-            C.c_void_p(g["ready"].data_ptr()), g["epoch"]))
+            C.c_void_p(g["ready"].data_ptr()), g["epoch"], self.local.nnz()))
 
     def matvec_host(self, x: "PeerVector", x_host_local, y_host_local, timeout_ms: int = 2000):
         """`&A * &x` with this rank's slices of x and y in host memory (numpy arrays or raw host
