@@ -120,6 +120,9 @@ int spl_mat_from_coo_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, ui
  *   spl_coo_len / _capacity                            src/coo.rs:349-351, 366-368
  *   spl_coo_host_ptrs get / iter (borrowed, valid until the next push/extend/reserve)
  *                                                      src/coo.rs:386-390, 491-495
+ *   spl_coo_invalidate get_mut / iter_mut                src/coo.rs:408-412, 514-518: the caller is about to
+ *                     write values through the host pointers from entry `first` on; what the copy
+ *                     stream already took from there is sent again at the next conversion
  *   spl_mat_from_coo_builder   From<&CooMatrix> for CsrMatrix / CscMatrix (as spl_mat_from_coo);
  *                     the builder stays valid and can be pushed to and converted again. */
 typedef struct spl_coo spl_coo;
@@ -135,6 +138,7 @@ uint64_t spl_coo_len(const spl_coo *coo);
 uint64_t spl_coo_capacity(const spl_coo *coo);
 /* Entries already handed to the copy stream (diagnostic). */
 uint64_t spl_coo_streamed(const spl_coo *coo);
+int spl_coo_invalidate(spl_coo *coo, uint64_t first);
 int spl_coo_host_ptrs(const spl_coo *coo, const uint64_t **row, const uint64_t **col, const void **val);
 int spl_mat_from_coo_builder(spl_ctx *ctx, spl_coo *coo, int format, int dedup, int dropzero,
                              spl_mat **out);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "spl_coo_len": (_u64, [_vp]),
     "spl_coo_capacity": (_u64, [_vp]),
     "spl_coo_streamed": (_u64, [_vp]),
+    "spl_coo_invalidate": (_i, [_vp, _u64]),
     "spl_coo_host_ptrs": (_i, [_vp, _pp, _pp, _pp]),
     "spl_mat_from_coo_builder": (_i, [_vp, _vp, _i, _i, _i, _pp]),
 }

@@ -277,6 +277,15 @@ int spl_coo_truncate(spl_coo *b, uint64_t len) {
     COO_END
 }
 
+int spl_coo_invalidate(spl_coo *b, uint64_t first) {
+    COO_BEGIN(b)
+    if (first < b->sent) {   // entries from `first` on were already handed to the copy stream: send them again
+        SPL_CUDA(cudaStreamSynchronize(b->copy->stream));
+        b->sent = first;
+    }
+    COO_END
+}
+
 int spl_coo_host_ptrs(const spl_coo *b, const uint64_t **row, const uint64_t **col, const void **val) {
     if (!b) return SPL_ERR_ARG;
     if (row) *row = b->h_row;

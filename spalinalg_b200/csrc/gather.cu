@@ -33,7 +33,8 @@ struct GatherPeers {
 };
 
 constexpr int GF_THREADS = 256;
-constexpr int GF_ROWS = 8;        // rows in flight per lane group: a block holds only nnz / world entries of a row
+constexpr int GF_INFLIGHT = 8;    // entries in flight per thread = rows in flight x entries per row and trip: a block
+                                  // holds only nnz / world entries of a row, so short rows need many rows in flight
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
     uint32_t v;
@@ -41,7 +42,7 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
     return v;
 }
 
-template <typename T, int LPR>
+template <typename T, int LPR, int U>
 __global__ void __launch_bounds__(GF_THREADS)
 spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const uint32_t *__restrict__ bind,
                          const T *__restrict__ bval, GatherPeers gp, T *x_full, T *__restrict__ y, uint32_t ncopy,
@@ -107,39 +108,49 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
         }
         const uint32_t *p = bptr + (size_t)k * (nloc + 1);
         constexpr uint32_t RL = GF_THREADS / LPR;          // rows a CTA covers per step of one q
+        constexpr int ROWS = GF_INFLIGHT / U;
         const uint32_t sub = threadIdx.x % LPR;
-        for (uint32_t base0 = rs; base0 < re; base0 += RL * GF_ROWS) {       // uniform trip count: shuffles below
+        for (uint32_t base0 = rs; base0 < re; base0 += RL * ROWS) {       // uniform trip count: shuffles below
             const uint32_t base = base0 + threadIdx.x / LPR;
-            uint32_t a[GF_ROWS], b[GF_ROWS];
-            T s[GF_ROWS];
+            uint32_t a[ROWS], b[ROWS];
+            T s[ROWS];
 #pragma unroll
-            for (int q = 0; q < GF_ROWS; ++q) {
+            for (int q = 0; q < ROWS; ++q) {
                 const uint32_t r = base + q * RL;
                 a[q] = b[q] = 0;
                 s[q] = (T)0;
                 if (r < re) { a[q] = __ldg(p + r) + sub; b[q] = __ldg(p + r + 1); }
             }
             for (;;) {
-                uint32_t col[GF_ROWS];
-                T v[GF_ROWS], xv[GF_ROWS];
+                uint32_t col[ROWS][U];
+                T v[ROWS][U], xv[ROWS][U];
                 bool any = false;
 #pragma unroll
-                for (int q = 0; q < GF_ROWS; ++q) {
-                    const bool ok = a[q] < b[q];
-                    col[q] = ok ? ld_stream(bind + a[q]) : 0xffffffffu;
-                    v[q] = ok ? ld_stream(bval + a[q]) : (T)0;
-                    any |= ok;
-                }
+                for (int q = 0; q < ROWS; ++q)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t j = a[q] + u * LPR;
+                        const bool ok = j < b[q];
+                        col[q][u] = ok ? ld_stream(bind + j) : 0xffffffffu;
+                        v[q][u] = ok ? ld_stream(bval + j) : (T)0;
+                        any |= ok;
+                    }
                 if (!any) break;
 #pragma unroll
-                for (int q = 0; q < GF_ROWS; ++q) xv[q] = col[q] != 0xffffffffu ? __ldcg(xb + col[q]) : (T)0;   // L2: x_full changes under L1
+                for (int q = 0; q < ROWS; ++q)
 #pragma unroll
-                for (int q = 0; q < GF_ROWS; ++q) {
-                    if (col[q] != 0xffffffffu) { s[q] += v[q] * xv[q]; a[q] += LPR; }
+                    for (int u = 0; u < U; ++u)
+                        xv[q][u] = col[q][u] != 0xffffffffu ? __ldcg(xb + col[q][u]) : (T)0;     // L2: x_full changes under L1
+#pragma unroll
+                for (int q = 0; q < ROWS; ++q) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (col[q][u] != 0xffffffffu) s[q] += v[q][u] * xv[q][u];
+                    a[q] += U * LPR;
                 }
             }
 #pragma unroll
-            for (int q = 0; q < GF_ROWS; ++q) {
+            for (int q = 0; q < ROWS; ++q) {
 #pragma unroll
                 for (int o = LPR / 2; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
                 const uint32_t r = base + q * RL;
@@ -155,10 +166,10 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
 
 // Launch shape: `ncopy` copy CTAs plus as many compute CTAs as stay resident beside them; the row range
 // of a compute CTA (its shared-memory sums) shrinks as the CTAs per SM grow, so the two are found together.
-template <typename T, int LPR>
+template <typename T, int LPR, int U>
 void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, const uint32_t *bind, const T *bval,
                          const GatherPeers &gp, T *x_full, T *y, uint32_t *ready, uint32_t epoch) {
-    auto k = spmv_gather_fused_kernel<T, LPR>;
+    auto k = spmv_gather_fused_kernel<T, LPR, U>;
     const uint32_t ncopy = gp.world > 1 ? std::min<uint32_t>(48u, (uint32_t)ctx->num_sms / 3u) : 0u;
     uint32_t ncompute = 0, rows_per_cta = 0;
     size_t smem = 0;
@@ -191,21 +202,26 @@ void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int ra
     gp.rank = rank;
     for (int g = 0; g <= SPL_MAX_PEERS; ++g) gp.start[g] = (uint32_t)col_starts[g < world ? g : world];
     for (int g = 0; g < world; ++g) gp.slice[g] = x_slices[g];
-    // lanes per row from the entries a row holds in ONE block (nnz / rows / world)
-    const int lanes = entries_per_row_block <= 3.0 ? 1 : entries_per_row_block <= 12.0 ? 2 : 4;
-    auto go = [&](auto tag, auto lpr) {
+    // lanes per row x entries per lane and trip from the entries a row holds in ONE block (nnz / rows / world):
+    // one trip for a typical row
+    const double e = entries_per_row_block;
+    auto go = [&](auto tag, auto lpr, auto u) {
         using T = decltype(tag);
-        spmv_gather_fused_t<T, decltype(lpr)::value>(ctx, nloc, bptr, bind, (const T *)bval, gp, (T *)x_full, (T *)y, ready, epoch);
+        spmv_gather_fused_t<T, decltype(lpr)::value, decltype(u)::value>(ctx, nloc, bptr, bind, (const T *)bval, gp, (T *)x_full,
+                                                                        (T *)y, ready, epoch);
     };
-    if (dtype == SPL_F32) {
-        if (lanes == 1) go(float{}, std::integral_constant<int, 1>{});
-        else if (lanes == 2) go(float{}, std::integral_constant<int, 2>{});
-        else go(float{}, std::integral_constant<int, 4>{});
-    } else {
-        if (lanes == 1) go(double{}, std::integral_constant<int, 1>{});
-        else if (lanes == 2) go(double{}, std::integral_constant<int, 2>{});
-        else go(double{}, std::integral_constant<int, 4>{});
-    }
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I4 = std::integral_constant<int, 4>;
+    auto pick = [&](auto tag) {
+        if (e <= 1.5) go(tag, I1{}, I1{});
+        else if (e <= 3.0) go(tag, I1{}, I2{});
+        else if (e <= 6.0) go(tag, I2{}, I2{});
+        else if (e <= 12.0) go(tag, I2{}, I4{});
+        else go(tag, I4{}, I4{});
+    };
+    if (dtype == SPL_F32) pick(float{});
+    else pick(double{});
 }
 
 }  // namespace spl
