@@ -7,8 +7,9 @@ ONE workload at every N: config 5 of BASELINE.json (banded, offsets -4..+4, n = 
 entries, f64; 12.4 GB algorithmic per product, inputs far larger than L2, so no flush is needed).
 N = 1 runs it on one GPU; N > 1 row-shards the SAME matrix over the ranks (fixed total work: strong
 scaling).  A step is one SpMV y = A x over the whole matrix.  At N > 1 x stays in its owners'
-peer-visible memory and is gathered inside the SpMV kernel over NVLink; the step includes the
-device-side barrier that orders an iteration's writes of x before the peers' reads.
+peer-visible memory; every step runs ONE small kernel that is the device-side barrier (it orders an
+iteration's writes of x before the peers' reads) and then copies the few halo values a shard needs
+from its neighbours over NVLink next to the own slice, and the SpMV reads one local array.
 `value` = algorithmic bytes (nnz*(4+V) + (ncols+nrows)*V) of the whole job per second
 of the slowest rank, device-timed.  `e2e` = the same metric through the reference-facing call
 `&A * &x` with HOST vectors: A is a constructed CsrMatrix (device resident, as the reference's is
@@ -428,24 +429,25 @@ def main():
     xv = dA = x_full = None
     if world > 1:
         starts = spd.partition_starts(n, world)
-        xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+        dA = spd.DistCsrMatrix(A, starts, rank, n, n)
+        widths = dA.halo_widths(dist, torch)          # how far the shards' columns reach into the neighbours
+        xv = spd.PeerVector(ctx, dist, n, np.float64, starts, halo=widths)
         for _ in range(2):                            # both halves of the double buffer hold x: the timed
             synthetic_device.device_view(torch, xv.local_ptr, nloc, f64).copy_(x_values(torch, wl, r0, r1))
-            xv.publish()                              # steps re-read an unchanged x (barrier, no swap)
-        dA = spd.DistCsrMatrix(A, starts, rank, n, n)
+            xv.publish(halo=True)                     # steps re-read an unchanged x (barrier + halo, no swap)
     else:
         x_full = x_values(torch, wl, 0, n)
     y = torch.zeros(nloc, device="cuda", dtype=f64)
 
     def local_spmv():
         if world > 1:
-            dA.spmv_peer(xv, y.data_ptr())
+            dA.spmv_halo(xv, y.data_ptr())    # own slice + halo: one local array, the unsharded kernels
         else:
             A.spmv_device(x_full.data_ptr(), y.data_ptr(), kern, lanes)
 
     def step():
         if world > 1:
-            xv.barrier()                      # device-side: peers' slices are final before the gathers
+            xv.barrier_halo()                 # device-side: peers' slices are final, then the halo comes over NVLink
         local_spmv()
 
     # ---- sanity before timing: the step's result equals the single-buffer vector kernel's --------
@@ -585,8 +587,9 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": cfg,
-            "detail": {"exchange": "peer memory: x gathered from its owners' slices inside the SpMV kernel (NVLink), "
-                                   "device-side flag barrier per step" if ngpu > 1 else "none",
+            "detail": {"exchange": "peer memory: one kernel per step runs the device-side flag barrier and copies the halo "
+                                   "(the columns a shard reaches into its neighbours' slices of x) over NVLink next to "
+                                   "the own slice; the product then reads one local array" if ngpu > 1 else "none",
                        "spmv_kernel": kname, "lanes_per_row": choice[1] if lanes == 0 else lanes,
                        "rows_per_rank": nloc, "pct_of_8TBps_nominal_per_gpu": 100.0 * achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d * ngpu, "d2h_bytes_per_step": d2h * ngpu,

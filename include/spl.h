@@ -283,6 +283,23 @@ int spl_peer_free(spl_ctx *ctx, void *dev_ptr);
 int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
                      uint32_t timeout_ms);
 int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out);
+/* Barrier + halo for banded / stencil shards whose slices are allocated with padding: after the
+ * barrier (same protocol and arguments as spl_peer_barrier), the halo_left columns before and the
+ * halo_right columns after this rank's own slice are copied from their owners' slices x_slices[g]
+ * (= &x[starts[g]]) into the memory just before / after x_slices[rank], which the caller allocated
+ * with that much room (halo_left * V bytes before the slice, halo_right * V after).  One launch; the
+ * product that follows (spl_spmv_window) reads one local array. */
+int spl_peer_barrier_halo(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
+                          uint32_t timeout_ms, int dtype, const uint64_t *starts, void *const *x_slices,
+                          uint64_t halo_left, uint64_t halo_right);
+/* y = A*x where only the columns [window_start, window_start + window_len) of x are present, at
+ * x_window_dev (x_window_dev[0] = x[window_start]).  Every stored column of A must lie in the window
+ * (SPL_ERR_SHAPE otherwise): the row shard of a banded / stencil matrix beside its halo.  Same
+ * kernels and results as spl_spmv. */
+int spl_spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window_dev, uint64_t window_start,
+                    uint64_t window_len, void *y_dev);
+/* Smallest and largest stored column of A (0, 0 for an empty matrix): sizes the halo. */
+int spl_spmv_footprint(spl_ctx *ctx, const spl_mat *a, uint64_t *col_min, uint64_t *col_max);
 /* All-gather of x by pulling over peer memory, for general (random / power-law) shards whose
  * gathers would be 4-byte NVLink transactions: one kernel copies every peer's slice
  * (slices[g] = x[starts[g] .. starts[g+1]), mapped with spl_peer_open) into the local full-length

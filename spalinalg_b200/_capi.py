@@ -62,6 +62,9 @@ SIGNATURES = {
     "spl_peer_close": (_i, [_vp, _vp]),
     "spl_peer_free": (_i, [_vp, _vp]),
     "spl_peer_barrier": (_i, [_vp, _i, _i, _vp, C.c_uint32, C.c_uint32]),
+    "spl_peer_barrier_halo": (_i, [_vp, _i, _i, _vp, C.c_uint32, C.c_uint32, _i, _vp, _vp, _u64, _u64]),
+    "spl_spmv_window": (_i, [_vp, _vp, _vp, _u64, _u64, _vp]),
+    "spl_spmv_footprint": (_i, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "spl_peer_pull": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
     "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -683,6 +683,38 @@ int spl_peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, 
     API_END(ctx)
 }
 
+int spl_peer_barrier_halo(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,
+                          uint32_t timeout_ms, int dtype, const uint64_t *starts, void *const *x_slices,
+                          uint64_t halo_left, uint64_t halo_right) {
+    API_BEGIN(ctx)
+    check_enums(SPL_CSR, dtype);
+    SPL_REQUIRE(flag_ptrs && starts && x_slices, SPL_ERR_ARG, "NULL argument");
+    SPL_REQUIRE(halo_left < (1ull << 31) && halo_right < (1ull << 31), SPL_ERR_UNSUPPORTED, "halo too wide");
+    peer_barrier_halo(ctx, world, rank, flag_ptrs, epoch, timeout_ms, dtype == SPL_F32 ? 4 : 8, starts, x_slices,
+                      (uint32_t)halo_left, (uint32_t)halo_right);
+    API_END(ctx)
+}
+
+int spl_spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window_dev, uint64_t window_start,
+                    uint64_t window_len, void *y_dev) {
+    API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
+    SPL_REQUIRE(a && x_window_dev && y_dev, SPL_ERR_ARG, "NULL argument");
+    spmv_window(ctx, a, x_window_dev, window_start, window_len, y_dev);
+    API_END(ctx)
+}
+
+int spl_spmv_footprint(spl_ctx *ctx, const spl_mat *a, uint64_t *col_min, uint64_t *col_max) {
+    API_BEGIN(ctx)
+    MatUse use_a(ctx, a);
+    SPL_REQUIRE(a, SPL_ERR_ARG, "NULL handle");
+    a = csr_form(ctx, a);
+    spmv_plan(ctx, const_cast<spl_mat *>(a));
+    if (col_min) *col_min = a->nnz ? a->col_min : 0;
+    if (col_max) *col_max = a->nnz ? a->col_max : 0;
+    API_END(ctx)
+}
+
 int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *starts,
                   const void *const *slices, void *x_full_dev) {
     API_BEGIN(ctx)

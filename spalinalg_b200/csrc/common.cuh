@@ -84,6 +84,7 @@ struct spl_mat {
     int plan_kernel = 0;       // SPL_SPMV_VECTOR / SPL_SPMV_MERGE
     int plan_lanes = 0;        // lanes per row of the vector kernel
     uint32_t max_row_len = 0;
+    uint32_t col_min = 0, col_max = 0;   // smallest / largest stored column (plan; meaningless when nnz == 0)
     uint32_t *merge_rows = nullptr;   // merge-path tile start rows (merge_tiles + 1)
     uint32_t merge_tiles = 0;
     uint32_t *split_rows = nullptr;   // nnz-split kernel: row holding the first entry of each chunk

@@ -45,7 +45,11 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a);
 const spl_mat *csr_form(spl_ctx *ctx, const spl_mat *a);
 // forget everything derived from the values (after values_mut): CSR twin, sliced copy
 void drop_value_copies(spl_ctx *ctx, spl_mat *m);
-void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes);
+void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes, uint32_t x_lo = 0,
+          uint32_t x_hi = 0);
+// y = A x where x_window holds only the columns [start, start + len) of x (the matrix's column footprint
+// must lie inside): the product of a row shard next to its halo
+void spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window, uint64_t start, uint64_t len, void *y);
 // `&A * &x` with host vectors, pipelined: x goes up in prefixes, row chunks run as soon as the prefix
 // they need is there, their part of y goes down while the next chunk runs (PCIe both ways at once).
 // x_dev / y_dev are device buffers of ncols / nrows values.  Returns false (nothing done) when the
@@ -77,6 +81,10 @@ void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uin
                   uint32_t timeout_ms);
 void peer_pull(spl_ctx *ctx, int world, int rank, size_t vsize, const uint64_t *starts,
                const void *const *slices, void *x_full);
+// the barrier, then this rank's halo: the halo_left columns before and the halo_right columns after its own
+// slice are copied from their owners' slices into the padding around slices[rank] (one small kernel)
+void peer_barrier_halo(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
+                       size_t vsize, const uint64_t *starts, void *const *slices, uint32_t halo_left, uint32_t halo_right);
 
 // addsub.cu — C = A +/- B on compressed arrays of equal format (a-7)
 spl_mat *addsub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, int subtract);

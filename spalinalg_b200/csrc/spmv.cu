@@ -1223,14 +1223,31 @@ void plan_hot_columns(spl_ctx *ctx, spl_mat *a) {
 }
 
 // ------------------------------------------------------------------ row statistics (plan)
-__global__ void max_row_len_kernel(const uint32_t *__restrict__ ptr, uint32_t nrows, uint32_t *out) {
-    uint32_t m = 0;
+// out[0] = longest row, out[1] = largest column, out[2] = ~smallest column (rows are column-sorted: the
+// first and last entry of every row bound its columns)
+__global__ void max_row_len_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restrict__ ind, uint32_t nrows,
+                                   uint32_t *out) {
+    uint32_t m = 0, cmax = 0, cmin_inv = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
-         r += (uint64_t)gridDim.x * blockDim.x)
-        m = max(m, ptr[r + 1] - ptr[r]);
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t lo = ptr[r], hi = ptr[r + 1];
+        m = max(m, hi - lo);
+        if (hi > lo) {
+            cmax = max(cmax, ind[hi - 1]);
+            cmin_inv = max(cmin_inv, ~ind[lo]);
+        }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane_id() == 0 && m) atomicMax(out, m);
+    for (int o = 16; o > 0; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        cmin_inv = max(cmin_inv, __shfl_xor_sync(0xffffffffu, cmin_inv, o));
+    }
+    if (lane_id() == 0 && m) {
+        atomicMax(out, m);
+        atomicMax(out + 1, cmax);
+        atomicMax(out + 2, cmin_inv);
+    }
 }
 
 }  // namespace
@@ -1241,11 +1258,15 @@ void spmv_plan(spl_ctx *ctx, spl_mat *a) {
     if (a->plan_ready.load(std::memory_order_relaxed)) return;
     uint32_t mx = 0;
     if (a->nnz) {
-        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+        SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 3 * sizeof(uint32_t), ctx->stream));
         unsigned grid = min(div_up(a->nrows, 256), (unsigned)ctx->num_sms * 8u);
-        max_row_len_kernel<<<grid, 256, 0, ctx->stream>>>(a->ptr, a->nrows, ctx->d_scratch);
+        max_row_len_kernel<<<grid, 256, 0, ctx->stream>>>(a->ptr, a->ind, a->nrows, ctx->d_scratch);
         check_launch(ctx, "max_row_len");
-        read_back(ctx, ctx->d_scratch, &mx, 1);
+        uint32_t w[3] = {0, 0, 0};
+        read_back(ctx, ctx->d_scratch, w, 3);
+        mx = w[0];
+        a->col_max = w[1];
+        a->col_min = ~w[2];
     }
     a->max_row_len = mx;
     const double mean = a->nrows ? (double)a->nnz / a->nrows : 0.0;
@@ -1356,7 +1377,10 @@ void spmv_csc_scatter(spl_ctx *ctx, const spl_mat *a, const T *x, T *y) {
 }
 }  // namespace
 
-void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes) {
+// x_lo / x_hi: the columns [x_lo, x_hi) of x that `x` (indexed by column) really holds; the whole vector
+// unless the caller passed a window (spmv_window)
+void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, int lanes, uint32_t x_lo, uint32_t x_hi) {
+    if (x_hi == 0) x_hi = a->ncols;
     if (kernel == SPL_SPMV_SCATTER) {
         SPL_REQUIRE(a->format == SPL_CSC, SPL_ERR_UNSUPPORTED, "SPL_SPMV_SCATTER is the column kernel: it needs a CSC matrix");
         if (a->dtype == SPL_F32) spmv_csc_scatter<float>(ctx, a, (const float *)x, (float *)y);
@@ -1391,8 +1415,8 @@ void spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y, int kernel, in
             SPL_CUDA(cudaMemsetAsync(y, 0, a->vsize() * (size_t)a->nrows, ctx->stream));
             return;
         }
-        if (a->dtype == SPL_F32) spmv_stream<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y, (const float *)x, 0u, a->ncols);
-        else spmv_stream<double>(ctx, a, XLocal<double>{(const double *)x}, (double *)y, (const double *)x, 0u, a->ncols);
+        if (a->dtype == SPL_F32) spmv_stream<float>(ctx, a, XLocal<float>{(const float *)x}, (float *)y, (const float *)x, x_lo, x_hi);
+        else spmv_stream<double>(ctx, a, XLocal<double>{(const double *)x}, (double *)y, (const double *)x, x_lo, x_hi);
         return;
     }
     if (kernel == SPL_SPMV_VECTOR && lanes == 0) {
@@ -1569,6 +1593,20 @@ bool spmv_host_pipelined(spl_ctx *ctx, const spl_mat *a, const void *x_host, voi
     SPL_CUDA(cudaEventRecord(end_ev, ctx->down_stream));
     SPL_CUDA(cudaStreamWaitEvent(ctx->stream, end_ev, 0));
     return true;
+}
+
+// y = A x with only a WINDOW of x present: x_window holds the columns [start, start + len).  The matrix's
+// column footprint (plan: smallest and largest stored column) must lie inside it.  This is the product
+// of a row shard whose halo has been copied next to the rank's own slice (peer_barrier_halo): the
+// kernels run with a plain local gather, at the speed of the unsharded product.
+void spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window, uint64_t start, uint64_t len, void *y) {
+    a = csr_form(ctx, a);
+    spmv_plan(ctx, const_cast<spl_mat *>(a));
+    SPL_REQUIRE(start + len <= a->ncols && len > 0, SPL_ERR_ARG, "window outside the columns of A");
+    SPL_REQUIRE(a->nnz == 0 || (a->col_min >= start && (uint64_t)a->col_max < start + len), SPL_ERR_SHAPE,
+                "the matrix has stored columns outside the window of x");
+    const unsigned char *base = static_cast<const unsigned char *>(x_window) - start * a->vsize();
+    spmv(ctx, a, base, y, SPL_SPMV_AUTO, 0, (uint32_t)start, (uint32_t)(start + len));
 }
 
 // The row-sharded `&A * &x` with HOST vectors (the reference-facing call on one rank of a sharded

@@ -297,6 +297,31 @@ class DistCsrMatrix:
                                          C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), C.c_void_p(y_dev)))
 
 
+    def halo_widths(self, dist, torch, group=None):
+        """(left, right): how far the shards' stored columns reach outside their owners' slices, maximised
+        over the ranks (spl_spmv_footprint + one all-reduce): the `halo` a PeerVector needs for spmv_halo."""
+        ctx = self.local._ctx
+        lo, hi = C.c_uint64(), C.c_uint64()
+        ctx.check(ctx._lib.spl_spmv_footprint(ctx._h, self.local._h, C.byref(lo), C.byref(hi)))
+        r0, r1 = self.local_rows()                    # square partition: the slice of x has the rows' bounds
+        left = max(0, r0 - lo.value) if self.local.nnz() else 0
+        right = max(0, hi.value + 1 - r1) if self.local.nnz() else 0
+        t = torch.tensor([left, right], dtype=torch.int64, device="cuda" if torch.cuda.is_available() else "cpu")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return int(t[0].item()), int(t[1].item())
+
+    def spmv_halo(self, x: "PeerVector", y_dev: int):
+        """y_local = A_local x against the rank's own slice of the published x plus its halo (filled by
+        x.publish(halo=True) / x.barrier_halo()): one local array, the plain kernels (spl_spmv_window)."""
+        ctx = self.local._ctx
+        r0, r1 = x.starts[self.rank], x.starts[self.rank + 1]
+        w0 = max(0, r0 - x.halo[0])
+        w1 = min(x.n, r1 + x.halo[1])
+        item = x.dtype.itemsize
+        ctx.check(ctx._lib.spl_spmv_window(ctx._h, self.local._h, C.c_void_p(x.published_ptr - (r0 - w0) * item),
+                                           w0, w1 - w0, C.c_void_p(y_dev)))
+
     def prepare_gather(self, torch):
         """One-time layout for spmv_gather: the shard's entries blocked by the rank that owns their column,
         own block first, then the peers in ring order (rank+1, rank+2, ...), row order kept inside a
@@ -349,9 +374,9 @@ class DistCsrMatrix:
         addresses; pinned memory lets the copies overlap): spl_spmv_peer_host.  The slice is uploaded
         into the unpublished half of `x`, published by the barrier inside the call, and gathered from."""
         ctx = self.local._ctx
-        nxt = x._data[(x._cur + 1) % len(x._data)]
+        nxt_slices = x._slices[(x._cur + 1) % len(x._data)]
         st = (C.c_uint64 * (self.world + 1))(*x.starts)
-        sl = (C.c_void_p * self.world)(*nxt.ptrs)
+        sl = (C.c_void_p * self.world)(*nxt_slices)
         fl = (C.c_void_p * self.world)(*x._flags.ptrs)
         x._epoch += 1
         xp = x_host_local if isinstance(x_host_local, int) else x_host_local.ctypes.data
@@ -498,14 +523,22 @@ class PeerVector:
     `barrier()` is the same barrier without the swap, for products that re-read an unchanged x."""
 
     def __init__(self, ctx: Context, dist, n: int, dtype, starts: Optional[Sequence[int]] = None, group=None,
-                 buffers: int = 2):
+                 buffers: int = 2, halo: Sequence[int] = (0, 0)):
+        """halo = (left, right): room for that many values before and after every rank's slice (same on all
+        ranks), filled by publish(halo=True) / barrier_halo() from the neighbouring slices, so that a banded or
+        stencil shard multiplies against ONE local array (DistCsrMatrix.spmv_halo)."""
         self.ctx, self.dtype = ctx, np.dtype(dtype)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.starts = list(starts) if starts is not None else partition_starts(n, self.world)
         self.n = int(n)
+        self.halo = (int(halo[0]), int(halo[1]))
         longest = max(self.starts[g + 1] - self.starts[g] for g in range(self.world))
         assert buffers in (1, 2)
-        self._data = [PeerBuffer(ctx, dist, max(longest, 1) * self.dtype.itemsize, group) for _ in range(buffers)]
+        item = self.dtype.itemsize
+        pad = -(-self.halo[0] * item // 256) * 256             # keeps the slices 256-byte aligned
+        self._pad = pad
+        self._data = [PeerBuffer(ctx, dist, pad + (max(longest, 1) + self.halo[1]) * item, group) for _ in range(buffers)]
+        self._slices = [[p + pad for p in d.ptrs] for d in self._data]       # &x[starts[g]] on every rank
         self._flags = PeerBuffer(ctx, dist, 4 * capi.SPL_MAX_PEERS, group)
         self._cur = 0                          # the published buffer
         self.local_len = self.starts[self.rank + 1] - self.starts[self.rank]
@@ -515,16 +548,16 @@ class PeerVector:
     @property
     def ptrs(self) -> List[int]:
         """Every rank's slice of the published x (own slice included): what the products read."""
-        return self._data[self._cur].ptrs
+        return self._slices[self._cur]
 
     @property
     def published_ptr(self) -> int:
-        return self._data[self._cur].local
+        return self._slices[self._cur][self.rank]
 
     @property
     def local_ptr(self) -> int:
         """This rank's slice of the NEXT x: write here, then publish()."""
-        return self._data[(self._cur + 1) % len(self._data)].local
+        return self._slices[(self._cur + 1) % len(self._data)][self.rank]
 
     def barrier(self, timeout_ms: int = 2000):
         """Device-side barrier on the context's stream (no host synchronisation), no swap."""
@@ -533,10 +566,28 @@ class PeerVector:
         self.ctx.check(self.ctx._lib.spl_peer_barrier(self.ctx._h, self.world, self.rank,
                                                       C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms)))
 
-    def publish(self, timeout_ms: int = 2000):
-        """The slice at `local_ptr` is final: barrier, then it becomes the published buffer."""
-        self.barrier(timeout_ms)
-        self._cur = (self._cur + 1) % len(self._data)
+    def publish(self, timeout_ms: int = 2000, halo: bool = False):
+        """The slice at `local_ptr` is final: barrier, then it becomes the published buffer.  halo=True also
+        fills the padding around it from the neighbouring ranks' new slices (same launch as the barrier)."""
+        nxt = (self._cur + 1) % len(self._data)
+        if halo:
+            self._barrier_halo(nxt, timeout_ms)
+        else:
+            self.barrier(timeout_ms)
+        self._cur = nxt
+
+    def barrier_halo(self, timeout_ms: int = 2000):
+        """Barrier + halo refresh of the published buffer, no swap."""
+        self._barrier_halo(self._cur, timeout_ms)
+
+    def _barrier_halo(self, which: int, timeout_ms: int):
+        self._epoch += 1
+        fl = (C.c_void_p * self.world)(*self._flags.ptrs)
+        st = (C.c_uint64 * (self.world + 1))(*self.starts)
+        sl = (C.c_void_p * self.world)(*self._slices[which])
+        self.ctx.check(self.ctx._lib.spl_peer_barrier_halo(
+            self.ctx._h, self.world, self.rank, C.cast(fl, C.c_void_p), self._epoch, int(timeout_ms),
+            _dtype_code(self.dtype), C.cast(st, C.c_void_p), C.cast(sl, C.c_void_p), self.halo[0], self.halo[1]))
 
     def pull(self, x_full_dev: int):
         """All-gather by pulling: copies every peer's slice of the published x into the local

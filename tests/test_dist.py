@@ -317,6 +317,15 @@ def test_sharded_front_end_world1_nccl():
         yw = orc.csr_spmv(n, *full, x)
         sc = orc.csr_spmv(n, full[0], full[1], np.abs(full[2]), np.abs(x))
         assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
+        # the windowed product (halo path) with a world of one: the window is the whole of x
+        assert D.halo_widths(dist, torch) == (0, 0)
+        y.fill_(7.0)
+        torch.cuda.synchronize()
+        xv.barrier_halo()
+        D.spmv_halo(xv, y.data_ptr())
+        ctx.sync()
+        xv.check()
+        assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
         # the fused gather kernel with a world of one: no copy CTAs, the own block only
         D.prepare_gather(torch)
         xf = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")

@@ -121,6 +121,8 @@ def _worker(rank, world, port, out):
         # bit for bit.
         ok &= iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50)
         assert ok, "changing-x iteration over peer memory differs from the oracle's sequential iteration"
+        ok &= iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50, halo=True)
+        assert ok, "changing-x iteration with the halo copied by the barrier kernel differs from the oracle"
 
         # add / sub / neg on the shared partition
         r2, c2, v2 = make_coo(n, n, 300000, 321)
@@ -163,7 +165,7 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50, n=300_007, delay_cycles=3_000_000):
+def iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50, n=300_007, delay_cycles=3_000_000, halo=False):
     """x_{t+1} = A x_t over a PeerVector, `iters` steps, against the oracle's sequential iteration.
     Returns True when this rank's slice of the last x equals the oracle's bit for bit."""
     from spalinalg_b200.synthetic_device import device_view
@@ -180,17 +182,25 @@ def iterate_against_oracle(orc, spd, sp, ctx, rank, world, iters=50, n=300_007, 
     A = sp.CsrMatrix.new(r1 - r0, n, (ptr[r0:r1 + 1] - ptr[r0]).astype(np.uint64), cols[lo:hi].astype(np.uint64),
                          val[lo:hi], ctx=ctx)
     dA = spd.DistCsrMatrix(A, starts, rank, n, n)
-    xv = spd.PeerVector(ctx, dist, n, np.float64, starts)
+    # halo=True: the halo is copied next to the own slice by the barrier kernel and the product reads one
+    # local array (spmv_halo); halo=False: the product gathers from the owners' slices itself (spmv_peer)
+    widths = dA.halo_widths(dist, torch) if halo else (0, 0)
+    if halo:
+        assert widths == (4, 4), widths
+    xv = spd.PeerVector(ctx, dist, n, np.float64, starts, halo=widths)
     device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(x0[r0:r1]))
-    xv.publish()
+    xv.publish(halo=halo)
     for t in range(iters):
         slow = (t % world) == rank                    # the late rank changes every step
         if slow and t % 2 == 0:
             torch.cuda._sleep(delay_cycles)           # late before its product: peers wait at the barrier
-        dA.spmv_peer(xv, xv.local_ptr)                # y_t -> the unpublished buffer
+        if halo:
+            dA.spmv_halo(xv, xv.local_ptr)            # y_t -> the unpublished buffer
+        else:
+            dA.spmv_peer(xv, xv.local_ptr)
         if slow and t % 2 == 1:
             torch.cuda._sleep(delay_cycles)           # late after its product, before the barrier
-        xv.publish()
+        xv.publish(halo=halo)
     torch.cuda.synchronize()
     xv.check()
     got = device_view(torch, xv.published_ptr, r1 - r0, torch.float64).cpu().numpy()
