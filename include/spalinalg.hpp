@@ -16,6 +16,7 @@
 #ifndef SPALINALG_HPP
 #define SPALINALG_HPP
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <memory>
@@ -126,6 +127,48 @@ public:
         if (index >= vals_.size()) return std::nullopt;
         return std::make_tuple(rows_[index], cols_[index], vals_[index]);
     }
+    // get_mut (coo.rs:408-412): the indices stay const, the value is writable
+    std::optional<std::tuple<std::size_t, std::size_t, T *>> get_mut(std::size_t index) {
+        if (index >= vals_.size()) return std::nullopt;
+        return std::make_tuple(rows_[index], cols_[index], &vals_[index]);
+    }
+    std::size_t capacity() const { return vals_.capacity(); }                             // coo.rs:366-368
+    // iter / iter_mut / into_iter (coo.rs:491-518, 576-627): entries in insertion order
+    template <typename F> void for_each(F &&f) const {
+        for (std::size_t i = 0; i < vals_.size(); ++i) f(rows_[i], cols_[i], vals_[i]);
+    }
+    template <typename F> void for_each_mut(F &&f) {
+        for (std::size_t i = 0; i < vals_.size(); ++i) f(rows_[i], cols_[i], vals_[i]);
+    }
+    std::vector<std::tuple<std::size_t, std::size_t, T>> into_entries() const {
+        std::vector<std::tuple<std::size_t, std::size_t, T>> out;
+        out.reserve(vals_.size());
+        for_each([&](std::size_t r, std::size_t c, const T &v) { out.emplace_back(r, c, v); });
+        return out;
+    }
+    // Extend (coo.rs:548-574): every entry asserted before any is stored
+    void extend(const std::vector<std::tuple<std::size_t, std::size_t, T>> &entries) {
+        for (const auto &e : entries) {
+            if (!(std::get<0>(e) < nrows_)) throw Panic("assertion failed: *row < self.nrows");
+            if (!(std::get<1>(e) < ncols_)) throw Panic("assertion failed: *col < self.ncols");
+        }
+        for (const auto &e : entries) push(std::get<0>(e), std::get<1>(e), std::get<2>(e));
+    }
+    // Add / Sub / Neg for &CooMatrix (coo.rs:751-804): concatenation, duplicates summed at conversion
+    friend CooMatrix operator+(const CooMatrix &a, const CooMatrix &b) {
+        if (a.nrows_ != b.nrows_ || a.ncols_ != b.ncols_) throw Panic("assertion `left == right` failed (shape)");
+        CooMatrix m = a;
+        m.rows_.insert(m.rows_.end(), b.rows_.begin(), b.rows_.end());
+        m.cols_.insert(m.cols_.end(), b.cols_.begin(), b.cols_.end());
+        m.vals_.insert(m.vals_.end(), b.vals_.begin(), b.vals_.end());
+        return m;
+    }
+    friend CooMatrix operator-(const CooMatrix &a, const CooMatrix &b) { return a + (-b); }
+    friend CooMatrix operator-(const CooMatrix &a) {
+        CooMatrix m = a;
+        for (T &v : m.vals_) v = -v;
+        return m;
+    }
     void clear() { rows_.clear(); cols_.clear(); vals_.clear(); }
     CooMatrix transpose() const {                                                         // coo.rs:538-545
         CooMatrix m(ncols_, nrows_);
@@ -235,6 +278,60 @@ public:
         return it == map_.end() ? std::nullopt : std::optional<T>(it->second);
     }
     const Map &entries() const { return map_; }
+    static DokMatrix with_capacity(std::size_t nrows, std::size_t ncols, std::size_t capacity) {   // dok.rs:163-171
+        DokMatrix m(nrows, ncols);
+        m.map_.reserve(capacity);
+        return m;
+    }
+    static DokMatrix eye(std::size_t size) {                                              // dok.rs:128-135
+        if (!(size > 0)) throw Panic("assertion failed: size > 0");
+        DokMatrix m(size, size);
+        for (std::size_t i = 0; i < size; ++i) m.map_[{i, i}] = T(1);
+        return m;
+    }
+    static DokMatrix with_entries(std::size_t nrows, std::size_t ncols,
+                                  const std::vector<std::tuple<std::size_t, std::size_t, T>> &entries) {   // dok.rs:205-221
+        DokMatrix m(nrows, ncols);
+        m.extend(entries);
+        return m;
+    }
+    void extend(const std::vector<std::tuple<std::size_t, std::size_t, T>> &entries) {    // dok.rs:561-587
+        for (const auto &e : entries) {
+            if (!(std::get<0>(e) < nrows_)) throw Panic("assertion failed: *row < self.nrows");
+            if (!(std::get<1>(e) < ncols_)) throw Panic("assertion failed: *col < self.ncols");
+        }
+        for (const auto &e : entries) map_[{std::get<0>(e), std::get<1>(e)}] = std::get<2>(e);
+    }
+    T *get_mut(std::size_t row, std::size_t col) {                                        // dok.rs:439-441
+        auto it = map_.find({row, col});
+        return it == map_.end() ? nullptr : &it->second;
+    }
+    void clear() { map_.clear(); }                                                        // dok.rs:484-486
+    DokMatrix transpose() const {                                                         // dok.rs:547-558
+        DokMatrix m(ncols_, nrows_);
+        for (const auto &kv : map_) m.map_[{kv.first.second, kv.first.first}] = kv.second;
+        return m;
+    }
+    template <typename F> void for_each(F &&f) const { for (const auto &kv : map_) f(kv.first.first, kv.first.second, kv.second); }
+    template <typename F> void for_each_mut(F &&f) { for (auto &kv : map_) f(kv.first.first, kv.first.second, kv.second); }
+    // Add / Sub / Neg for &DokMatrix (dok.rs:722-769): lhs entries, then or_default() += / -= rhs
+    friend DokMatrix operator+(const DokMatrix &a, const DokMatrix &b) {
+        DokMatrix m = a;
+        for (const auto &kv : b.map_) m.map_[kv.first] += kv.second;
+        return m;
+    }
+    friend DokMatrix operator-(const DokMatrix &a, const DokMatrix &b) {
+        DokMatrix m = a;
+        for (const auto &kv : b.map_) m.map_[kv.first] -= kv.second;
+        return m;
+    }
+    friend DokMatrix operator-(const DokMatrix &a) {
+        DokMatrix m = a;
+        for (auto &kv : m.map_) kv.second = -kv.second;
+        return m;
+    }
+    static DokMatrix from(const CsrMatrix<T> &m);                                         // dok.rs:702-720
+    static DokMatrix from(const CscMatrix<T> &m);                                         // dok.rs:676-693
     static DokMatrix from(const CooMatrix<T> &coo) {                                      // dok.rs:640-668
         DokMatrix m(coo.nrows(), coo.ncols());
         for (std::size_t i = 0; i < coo.length(); ++i)
@@ -277,6 +374,38 @@ public:
         if (v.size() != nnz_) throw Panic("values_mut: the number of values must not change");
         ctx().check(spl_mat_set_values(ctx().raw(), raw(), v.data()));
         if (host_) host_->val = v;
+    }
+    // iter() / into_iter() (csr.rs:303-316, 409-440): (row, col, value) in storage order, read from the
+    // device in chunks (spl_mat_read_entries): the host never holds more than one chunk
+    template <typename F>
+    void for_each(F &&f, std::size_t chunk = std::size_t(1) << 16) const {
+        std::vector<std::uint64_t> r(std::min(chunk, nnz_)), c(r.size());
+        std::vector<T> v(r.size());
+        for (std::size_t start = 0; start < nnz_; start += chunk) {
+            const std::size_t cnt = std::min(chunk, nnz_ - start);
+            ctx().check(spl_mat_read_entries(ctx().raw(), raw(), start, cnt, r.data(), c.data(), v.data()));
+            for (std::size_t i = 0; i < cnt; ++i) f(std::size_t(r[i]), std::size_t(c[i]), v[i]);
+        }
+    }
+    // iter_mut (csr.rs:330-343): f may change the values; they are stored back afterwards
+    template <typename F>
+    void for_each_mut(F &&f) {
+        download();
+        const std::size_t nmajor = FORMAT == SPL_CSR ? nrows_ : ncols_;
+        std::vector<T> v = host_->val;
+        for (std::size_t m = 0; m < nmajor; ++m)
+            for (std::size_t p = host_->ptr[m]; p < host_->ptr[m + 1]; ++p)
+                FORMAT == SPL_CSR ? f(m, host_->ind[p], v[p]) : f(host_->ind[p], m, v[p]);
+        ctx().check(spl_mat_set_values(ctx().raw(), raw(), v.data()));
+        host_->val = v;
+    }
+    // y = A x with host vectors: the dense form of `&A * &X`, X n x 1 (src/csr/ops/mul.rs:5-60,
+    // src/csc/ops/mul.rs:5-61); a CSC matrix multiplies through its cached CSR form on the device
+    std::vector<T> matvec(const std::vector<T> &x) const {
+        if (x.size() != ncols_) throw Panic("assertion `left == right` failed: self.ncols() == rhs.nrows()");
+        std::vector<T> y(nrows_);
+        ctx().check(spl_spmv_host(ctx().raw(), raw(), x.data(), y.data()));
+        return y;
     }
     CooMatrix<T> to_coo() const {                                                         // coo.rs:629-705
         std::vector<std::uint64_t> r(nnz_), c(nnz_);
@@ -363,13 +492,6 @@ public:
         Base::ctx().check(spl_mat_transpose(Base::ctx().raw(), this->raw(), &m));
         return CsrMatrix(m);
     }
-    // y = A x with host vectors: the dense form of `&A * &X`, X n x 1 (src/csr/ops/mul.rs:5-60)
-    std::vector<T> matvec(const std::vector<T> &x) const {
-        if (x.size() != this->ncols()) throw Panic("assertion `left == right` failed: self.ncols() == rhs.nrows()");
-        std::vector<T> y(this->nrows());
-        Base::ctx().check(spl_spmv_host(Base::ctx().raw(), this->raw(), x.data(), y.data()));
-        return y;
-    }
     friend CsrMatrix operator+(const CsrMatrix &a, const CsrMatrix &b) { return binary(spl_mat_add, a, b); }   // csr/ops/add.rs:5-75
     friend CsrMatrix operator-(const CsrMatrix &a, const CsrMatrix &b) { return binary(spl_mat_sub, a, b); }   // csr/ops/sub.rs:5-75
     friend CsrMatrix operator*(const CsrMatrix &a, const CsrMatrix &b) { return binary(spl_mat_mul, a, b); }   // csr/ops/mul.rs:5-60
@@ -450,6 +572,19 @@ CsrMatrix<T> CsrMatrix<T>::from(const CscMatrix<T> &csc) {
     spl_mat *m = nullptr;
     Base::ctx().check(spl_mat_convert(Base::ctx().raw(), csc.raw(), SPL_CSR, &m));
     return CsrMatrix(m);
+}
+
+template <typename T>
+DokMatrix<T> DokMatrix<T>::from(const CsrMatrix<T> &m) {
+    DokMatrix d(m.nrows(), m.ncols());
+    m.for_each([&](std::size_t r, std::size_t c, const T &v) { d.map_[{r, c}] = v; });
+    return d;
+}
+template <typename T>
+DokMatrix<T> DokMatrix<T>::from(const CscMatrix<T> &m) {
+    DokMatrix d(m.nrows(), m.ncols());
+    m.for_each([&](std::size_t r, std::size_t c, const T &v) { d.map_[{r, c}] = v; });
+    return d;
 }
 
 }  // namespace spalinalg

@@ -1,9 +1,10 @@
 //! What `CsrMatrix` and `CscMatrix` share: the device handle (`spl_mat`, immutable after creation,
 //! freed on drop) and the lazily downloaded host mirror behind `rowptr()` / `colind()` / `values()`
 //! (exactly sized `Vec`s with `usize` indices, as the reference's tests assert on `capacity()`).
-use std::cell::{Cell, OnceCell};
 use std::marker::PhantomData;
 use std::os::raw::{c_int, c_void};
+use std::sync::atomic::{AtomicBool, Ordering};
+use std::sync::OnceLock;
 
 use crate::coo::CooMatrix;
 use crate::ctx::with_ctx;
@@ -23,15 +24,19 @@ pub(crate) struct Compressed<T: Scalar> {
     pub nnz: usize,
     format: c_int,
     raw: *mut spl_mat,
-    host: OnceCell<Host<T>>,
-    dirty: Cell<bool>,           // values_mut() was handed out: store the values back before device work
+    host: OnceLock<Host<T>>,
+    dirty: AtomicBool,           // values_mut() was handed out: store the values back before device work
     _t: PhantomData<T>,
 }
 
-// spl_mat is immutable after creation and may be shared read-only (spl.h); the host mirror is
-// filled once behind a OnceCell, so the type is Send; Sync would need a sync::OnceLock — the
-// reference's types are Sync, use OnceLock if that matters to the application.
+// The reference's CsrMatrix / CscMatrix are plain Vecs: Send + Sync, and `&`-operations from several
+// threads on one matrix are legal.  They stay legal here: the device handle is immutable after creation,
+// every thread works through its own context (stream), and the library orders those streams against
+// the matrix itself (a `ready` event recorded at creation, one event per foreign stream that used it,
+// waited for before the blocks are freed: include/spl.h, "sharing across contexts").  The host mirror
+// is filled once behind a OnceLock; the write-back flag is atomic and only set through `&mut self`.
 unsafe impl<T: Scalar> Send for Compressed<T> {}
+unsafe impl<T: Scalar> Sync for Compressed<T> {}
 
 impl<T: Scalar> Compressed<T> {
     /// Takes ownership of a handle returned by the library.
@@ -41,7 +46,7 @@ impl<T: Scalar> Compressed<T> {
         unsafe { spl_mat_info(raw, &mut format, &mut dtype, &mut nrows, &mut ncols, &mut nnz) };
         debug_assert_eq!(dtype, T::DTYPE);
         Compressed { nrows: nrows as usize, ncols: ncols as usize, nnz: nnz as usize, format, raw,
-                     host: OnceCell::new(), dirty: Cell::new(false), _t: PhantomData }
+                     host: OnceLock::new(), dirty: AtomicBool::new(false), _t: PhantomData }
     }
 
     /// `CsrMatrix::new` / `CscMatrix::new` (src/csr.rs:137-164, src/csc.rs:137-164): validating;
@@ -90,7 +95,7 @@ impl<T: Scalar> Compressed<T> {
     }
 
     fn flush(&self) {
-        if self.dirty.replace(false) {
+        if self.dirty.swap(false, Ordering::AcqRel) {
             let h = self.host.get().expect("values_mut implies a host mirror");
             with_ctx(|c| c.check(unsafe { spl_mat_set_values(c.raw(), self.raw, h.val.as_ptr() as *const c_void) }));
         }
@@ -114,8 +119,15 @@ impl<T: Scalar> Compressed<T> {
     /// `values_mut()` (src/csr.rs:270-272): structure kept, values written back lazily.
     pub fn values_mut(&mut self) -> &mut [T] {
         self.host();
-        self.dirty.set(true);
+        self.dirty.store(true, Ordering::Release);
         &mut self.host.get_mut().unwrap().val
+    }
+
+    /// Pointer and index arrays shared, values mutable: what `iter_mut` walks.
+    pub fn host_parts_mut(&mut self) -> (&[usize], &[usize], &mut [T]) {
+        self.host();
+        let h = self.host.get_mut().unwrap();
+        (&h.ptr, &h.ind, &mut h.val)
     }
 
     pub fn unary(&self, f: unsafe extern "C" fn(*mut spl_ctx, *const spl_mat, *mut *mut spl_mat) -> c_int) -> Self {
@@ -147,7 +159,25 @@ impl<T: Scalar> Compressed<T> {
         (rows, cols, vals)
     }
 
-    /// y = A x with host vectors: the dense form of `&A * &X`, X n x 1 (CSR only).
+    /// Stored entries [start, start + count) in storage order, read from the device (`spl_mat_read_entries`):
+    /// the chunk an iterator holds instead of a host copy of the whole matrix.
+    pub fn read_entries(&self, start: usize, count: usize) -> (Vec<usize>, Vec<usize>, Vec<T>) {
+        let (mut rows, mut cols, mut vals) = (vec![0usize; count], vec![0usize; count], vec![T::zero(); count]);
+        with_ctx(|c| c.check(unsafe {
+            spl_mat_read_entries(c.raw(), self.raw(), start as u64, count as u64, rows.as_mut_ptr() as *mut u64,
+                                 cols.as_mut_ptr() as *mut u64, vals.as_mut_ptr() as *mut c_void)
+        }));
+        (rows, cols, vals)
+    }
+
+    /// Row (CSR) or column (CSC) of the stored entry at position `p`, from the host mirror's pointer array.
+    pub fn major_of(ptr: &[usize], p: usize) -> usize {
+        ptr.partition_point(|&q| q <= p) - 1
+    }
+
+    /// y = A x with host vectors: the dense form of `&A * &X`, X n x 1.  On a CSC matrix the first product
+    /// builds (and keeps) the CSR form on the device.  Pageable slices take the driver's staged copies;
+    /// vectors allocated with `spl_host_alloc` (pinned) are pipelined chunk by chunk.
     pub fn matvec(&self, x: &[T]) -> Vec<T> {
         assert_eq!(self.ncols, x.len());
         let mut y = vec![T::zero(); self.nrows];
@@ -155,6 +185,18 @@ impl<T: Scalar> Compressed<T> {
             spl_spmv_host(c.raw(), self.raw(), x.as_ptr() as *const c_void, y.as_mut_ptr() as *mut c_void)
         }));
         y
+    }
+}
+
+impl<T: Scalar> std::fmt::Debug for Compressed<T> {
+    /// `#[derive(Debug)]` in the reference (src/csr.rs:65): dims and the three arrays.
+    fn fmt(&self, f: &mut std::fmt::Formatter<'_>) -> std::fmt::Result {
+        let h = self.host();
+        f.debug_struct(if self.format == SPL_CSR { "CsrMatrix" } else { "CscMatrix" })
+            .field("nrows", &self.nrows).field("ncols", &self.ncols)
+            .field(if self.format == SPL_CSR { "rowptr" } else { "colptr" }, &h.ptr)
+            .field(if self.format == SPL_CSR { "colind" } else { "rowind" }, &h.ind)
+            .field("values", &h.val).finish()
     }
 }
 

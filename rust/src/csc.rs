@@ -9,7 +9,39 @@ use crate::dok::DokMatrix;
 use crate::ffi::*;
 use crate::scalar::Scalar;
 
+#[derive(Debug)]
 pub struct CscMatrix<T: Scalar>(Compressed<T>);
+
+/// Immutable entries iterator created by [`CscMatrix::iter`] (src/csc.rs:81-85, 442-448): storage order.
+#[derive(Clone, Debug)]
+pub struct Iter<'iter, T> {
+    ptr: &'iter [usize],
+    ind: &'iter [usize],
+    val: &'iter [T],
+    major: usize,
+    pos: usize,
+}
+
+/// Mutable entries iterator created by [`CscMatrix::iter_mut`] (src/csc.rs:87-91, 450-456).
+#[derive(Debug)]
+pub struct IterMut<'iter, T> {
+    ptr: &'iter [usize],
+    ind: &'iter [usize],
+    val: std::slice::IterMut<'iter, T>,
+    major: usize,
+    pos: usize,
+}
+
+/// Move entries iterator created by `CscMatrix::into_iter` (src/csc.rs:93-96, 458-464): the matrix is read
+/// from the device chunk by chunk (`spl_mat_read_entries`), never as one host copy of nnz tuples.
+#[derive(Debug)]
+pub struct IntoIter<T: Scalar> {
+    matrix: CscMatrix<T>,
+    next: usize,
+    chunk: std::vec::IntoIter<(usize, usize, T)>,
+}
+
+const ITER_CHUNK: usize = 1 << 16;
 
 impl<T: Scalar> CscMatrix<T> {
     /// src/csc.rs:137-164 — panics like the reference on the first failing assertion
@@ -31,14 +63,27 @@ impl<T: Scalar> CscMatrix<T> {
     /// src/csc.rs:270-272
     pub fn values_mut(&mut self) -> &mut [T] { self.0.values_mut() }
 
-    /// src/csc.rs:303-316: (row, col, value) in storage order (column by column)
-    pub fn iter(&self) -> impl Iterator<Item = (usize, usize, &T)> + '_ {
+    /// src/csc.rs:303-316: (row, col, value) in storage order
+    pub fn iter(&self) -> Iter<T> {
         let h = self.0.host();
-        (0..self.0.ncols).flat_map(move |c| (h.ptr[c]..h.ptr[c + 1]).map(move |p| (h.ind[p], c, &h.val[p])))
+        Iter { ptr: &h.ptr, ind: &h.ind, val: &h.val, major: 0, pos: 0 }
+    }
+
+    /// src/csc.rs:330-343 (the reference loops over the wrong dimension on non-square matrices,
+    /// SURVEY.md appendix A; this walks every stored entry).  The values are written back to the device
+    /// before the next device operation, like `values_mut`.
+    pub fn iter_mut(&mut self) -> IterMut<T> {
+        self.0.values_mut();                                   // marks the mirror dirty, downloads it if needed
+        let (ptr, ind, val) = self.0.host_parts_mut();
+        IterMut { ptr, ind, val: val.iter_mut(), major: 0, pos: 0 }
     }
 
     /// src/csc.rs:358-406
     pub fn transpose(&self) -> Self { CscMatrix(self.0.unary(spl_mat_transpose)) }
+
+    /// Extension: y = A x with dense host vectors (`&A * &X`, X n x 1, src/csc/ops/mul.rs:5-61); the first
+    /// product builds the CSR form of the matrix on the device and keeps it.
+    pub fn matvec(&self, x: &[T]) -> Vec<T> { self.0.matvec(x) }
 
     pub(crate) fn inner(&self) -> &Compressed<T> { &self.0 }
     pub(crate) fn wrap(c: Compressed<T>) -> Self { CscMatrix(c) }
@@ -85,4 +130,60 @@ impl<T: Scalar> Mul for &CscMatrix<T> {
 impl<T: Scalar> Neg for &CscMatrix<T> {
     type Output = CscMatrix<T>;
     fn neg(self) -> Self::Output { CscMatrix(self.0.unary(spl_mat_neg)) }
+}
+
+/// src/csc.rs:409-440
+impl<T: Scalar> IntoIterator for CscMatrix<T> {
+    type Item = (usize, usize, T);
+    type IntoIter = IntoIter<T>;
+    fn into_iter(self) -> Self::IntoIter {
+        IntoIter { matrix: self, next: 0, chunk: Vec::new().into_iter() }
+    }
+}
+
+impl<'iter, T> Iterator for Iter<'iter, T> {
+    type Item = (usize, usize, &'iter T);
+    fn next(&mut self) -> Option<Self::Item> {
+        if self.pos >= self.val.len() {
+            return None;
+        }
+        while self.ptr[self.major + 1] <= self.pos {
+            self.major += 1;                                   // skips empty cols
+        }
+        let p = self.pos;
+        self.pos += 1;
+        let (ind, val) = (self.ind, self.val);                 // the slices outlive the iterator borrow
+        Some((ind[p], self.major, &val[p]))
+    }
+}
+
+impl<'iter, T> Iterator for IterMut<'iter, T> {
+    type Item = (usize, usize, &'iter mut T);
+    fn next(&mut self) -> Option<Self::Item> {
+        let v = self.val.next()?;
+        while self.ptr[self.major + 1] <= self.pos {
+            self.major += 1;
+        }
+        let p = self.pos;
+        self.pos += 1;
+        Some((self.ind[p], self.major, v))
+    }
+}
+
+impl<T: Scalar> Iterator for IntoIter<T> {
+    type Item = (usize, usize, T);
+    fn next(&mut self) -> Option<Self::Item> {
+        if let Some(e) = self.chunk.next() {
+            return Some(e);
+        }
+        let nnz = self.matrix.nnz();
+        if self.next >= nnz {
+            return None;
+        }
+        let count = ITER_CHUNK.min(nnz - self.next);
+        let (rows, cols, vals) = self.matrix.inner().read_entries(self.next, count);
+        self.next += count;
+        self.chunk = rows.into_iter().zip(cols).zip(vals).map(|((r, c), v)| (r, c, v)).collect::<Vec<_>>().into_iter();
+        self.chunk.next()
+    }
 }

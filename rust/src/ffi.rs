@@ -11,6 +11,7 @@ pub const SPL_CSR: c_int = 0; pub const SPL_CSC: c_int = 1;
 pub const SPL_F32: c_int = 0; pub const SPL_F64: c_int = 1;
 pub const SPL_SPMV_AUTO: c_int = 0; pub const SPL_SPMV_VECTOR: c_int = 1; pub const SPL_SPMV_MERGE: c_int = 2;
 pub const SPL_SPMV_SPLIT: c_int = 3; pub const SPL_SPMV_SLICED: c_int = 4;   // spl_spmv_ex: kernel | lanes << 8
+pub const SPL_SPMV_STREAM: c_int = 5; pub const SPL_SPMV_SCATTER: c_int = 6;
 
 extern "C" {
     pub fn spl_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut spl_ctx) -> c_int;
@@ -48,6 +49,9 @@ extern "C" {
     pub fn spl_mat_set_values(ctx: *mut spl_ctx, m: *mut spl_mat, val: *const c_void) -> c_int;
     pub fn spl_mat_device_ptrs(m: *const spl_mat, ptr: *mut *const u32, ind: *mut *const u32, val: *mut *const c_void) -> c_int;
     pub fn spl_mat_to_coo(ctx: *mut spl_ctx, m: *const spl_mat, row: *mut u64, col: *mut u64, val: *mut c_void) -> c_int;
+    pub fn spl_mat_to_coo_dev(ctx: *mut spl_ctx, m: *const spl_mat, row: *mut u32, col: *mut u32, val: *mut c_void) -> c_int;
+    pub fn spl_mat_read_entries(ctx: *mut spl_ctx, m: *const spl_mat, start: u64, count: u64,
+        row: *mut u64, col: *mut u64, val: *mut c_void) -> c_int;
     pub fn spl_mat_free(ctx: *mut spl_ctx, m: *mut spl_mat) -> c_int;
     // CooMatrix storage streamed to the device while it is filled, section 4
     pub fn spl_coo_create(ctx: *mut spl_ctx, dtype: c_int, nrows: u64, ncols: u64, capacity: u64,
@@ -61,6 +65,7 @@ extern "C" {
     pub fn spl_coo_len(coo: *const spl_coo) -> u64;
     pub fn spl_coo_capacity(coo: *const spl_coo) -> u64;
     pub fn spl_coo_streamed(coo: *const spl_coo) -> u64;
+    pub fn spl_coo_invalidate(coo: *mut spl_coo, first: u64) -> c_int;
     pub fn spl_coo_host_ptrs(coo: *const spl_coo, row: *mut *const u64, col: *mut *const u64,
         val: *mut *const c_void) -> c_int;
     pub fn spl_mat_from_coo_builder(ctx: *mut spl_ctx, coo: *mut spl_coo, format: c_int, dedup: c_int,
@@ -89,4 +94,17 @@ extern "C" {
         slices: *const *const c_void, x_full_dev: *mut c_void) -> c_int;
     pub fn spl_spmv_peer(ctx: *mut spl_ctx, a_local: *const spl_mat, world: c_int, rank: c_int,
         col_starts: *const u64, x_slices: *const *const c_void, y_dev: *mut c_void) -> c_int;
+    pub fn spl_peer_barrier_halo(ctx: *mut spl_ctx, world: c_int, rank: c_int, flag_ptrs: *const *mut c_void,
+        epoch: u32, timeout_ms: u32, dtype: c_int, starts: *const u64, x_slices: *const *mut c_void,
+        halo_left: u64, halo_right: u64) -> c_int;
+    pub fn spl_spmv_window(ctx: *mut spl_ctx, a: *const spl_mat, x_window_dev: *const c_void, window_start: u64,
+        window_len: u64, y_dev: *mut c_void) -> c_int;
+    pub fn spl_spmv_footprint(ctx: *mut spl_ctx, a: *const spl_mat, col_min: *mut u64, col_max: *mut u64) -> c_int;
+    pub fn spl_spmv_gather_fused(ctx: *mut spl_ctx, dtype: c_int, nrows_local: u64, world: c_int, rank: c_int,
+        col_starts: *const u64, x_slices: *const *const c_void, block_ptr: *const u32, block_ind: *const u32,
+        block_val: *const c_void, x_full_dev: *mut c_void, y_dev: *mut c_void, ready_dev: *mut u32, epoch: u32,
+        nnz_local: u64) -> c_int;
+    pub fn spl_spmv_peer_host(ctx: *mut spl_ctx, a_local: *const spl_mat, world: c_int, rank: c_int,
+        col_starts: *const u64, x_slices: *const *mut c_void, flag_ptrs: *const *mut c_void, epoch: u32,
+        timeout_ms: u32, x_host_local: *const c_void, y_host_local: *mut c_void) -> c_int;
 }

@@ -145,6 +145,77 @@ static int run() {
         CHECK(coo.transpose().rowind() == (V{1}) && coo.pop().has_value() && coo.length() == 0);
         CHECK(panics([] { CooMatrix<float>(0, 1); }) && panics([] { DokMatrix<float>(1, 0); }));
     }
+    {   // CooMatrix builder surface: src/coo.rs tests get_mut :986-991, iter :1031-1039, iter_mut :1042-1050,
+        // extend :1053-1063, into_iter :1066-1074, add :1077-1091, sub :1094-1108, neg :1111-1119
+        using E = std::vector<std::tuple<std::size_t, std::size_t, double>>;
+        const E entries{{0, 0, 1.0}, {1, 0, 2.0}, {0, 2, 3.0}};
+        auto m = CooMatrix<double>::with_entries(2, 3, entries);
+        CHECK(m.length() == 3 && m.capacity() >= 3);
+        auto g = m.get_mut(0);
+        CHECK(g.has_value() && std::get<0>(*g) == 0 && std::get<1>(*g) == 0 && *std::get<2>(*g) == 1.0 && !m.get_mut(3).has_value());
+        *std::get<2>(*g) = 1.5;
+        CHECK(std::get<2>(*m.get(0)) == 1.5);
+        *std::get<2>(*m.get_mut(0)) = 1.0;
+        E seen;
+        m.for_each([&](std::size_t r, std::size_t c, const double &v) { seen.emplace_back(r, c, v); });
+        CHECK(seen == entries && m.into_entries() == entries);
+        m.for_each_mut([](std::size_t, std::size_t, double &v) { v *= 2; });
+        CHECK(m.values() == (D{2, 4, 6}));
+        CooMatrix<double> ext(2, 3);
+        ext.extend(entries);
+        CHECK(ext.length() == 3 && ext.into_entries() == entries);
+        CHECK(panics([&] { ext.extend(E{{0, 0, 1.0}, {2, 0, 1.0}}); }) && ext.length() == 3);      // asserted before any is stored
+        auto lhs = CooMatrix<double>::with_entries(2, 3, entries);
+        auto rhs = CooMatrix<double>::with_entries(2, 3, E{{0, 0, 2.0}, {1, 1, 4.0}, {1, 2, 6.0}});
+        CHECK((lhs + rhs).into_entries() == (E{{0, 0, 1.0}, {1, 0, 2.0}, {0, 2, 3.0}, {0, 0, 2.0}, {1, 1, 4.0}, {1, 2, 6.0}}));
+        CHECK((lhs - rhs).into_entries() == (E{{0, 0, 1.0}, {1, 0, 2.0}, {0, 2, 3.0}, {0, 0, -2.0}, {1, 1, -4.0}, {1, 2, -6.0}}));
+        CHECK((-lhs).into_entries() == (E{{0, 0, -1.0}, {1, 0, -2.0}, {0, 2, -3.0}}));
+        CHECK(panics([&] { (void)(lhs + CooMatrix<double>(3, 3)); }));
+        // the sum converts to the device formats with its duplicates added in insertion order (1.0 + 2.0)
+        auto sum = CsrMatrix<double>::from(lhs + rhs);
+        CHECK(sum.rowptr() == (V{0, 2, 5}) && sum.colind() == (V{0, 2, 0, 1, 2}) && sum.values() == (D{3, 3, 2, 4, 6}));
+    }
+    {   // DokMatrix builder surface (src/dok.rs:105-769) and the conversions back from the device formats
+        using E = std::vector<std::tuple<std::size_t, std::size_t, double>>;
+        auto eye = DokMatrix<double>::eye(2);
+        CHECK(eye.length() == 2 && eye.contains(1, 1) && !eye.contains(0, 1) && *eye.get(0, 0) == 1.0);
+        auto d = DokMatrix<double>::with_entries(2, 3, E{{0, 0, 1.0}, {1, 0, 2.0}, {0, 2, 3.0}});
+        *d.get_mut(1, 0) = 2.5;
+        CHECK(*d.get(1, 0) == 2.5 && d.get_mut(1, 1) == nullptr);
+        auto t = d.transpose();
+        CHECK(t.nrows() == 3 && t.ncols() == 2 && *t.get(2, 0) == 3.0 && *t.get(0, 1) == 2.5);
+        auto s2 = d + d;
+        CHECK(*s2.get(0, 2) == 6.0 && s2.length() == 3);
+        auto z = d - d;
+        CHECK(*z.get(0, 0) == 0.0 && z.length() == 3);                                     // explicit zeros stay
+        CHECK(*(-d).get(0, 0) == -1.0);
+        CHECK(panics([&] { d.extend(E{{5, 0, 1.0}}); }));
+        auto csr = CsrMatrix<double>::from(d);                                             // DOK -> CSR on the device ...
+        auto back = DokMatrix<double>::from(csr);                                          // ... and back, read in chunks
+        CHECK(back.length() == 3 && *back.get(1, 0) == 2.5 && *back.get(0, 2) == 3.0);
+        auto backc = DokMatrix<double>::from(CscMatrix<double>::from(csr));
+        CHECK(backc.length() == 3 && *backc.get(0, 0) == 1.0);
+        d.clear();
+        CHECK(d.length() == 0);
+    }
+    {   // iter / iter_mut / into_iter on the device formats (src/csr.rs:303-343, 409-464; the CSC twins), Aᵀ x through
+        // the CSC view, SpMV on a CscMatrix (src/csc/ops/mul.rs:5-61)
+        using E = std::vector<std::tuple<std::size_t, std::size_t, double>>;
+        CsrMatrix<double> a(3, 4, V{0, 2, 2, 5}, V{0, 3, 0, 1, 2}, D{1, 2, 3, 4, 5});
+        E seen;
+        a.for_each([&](std::size_t r, std::size_t c, const double &v) { seen.emplace_back(r, c, v); }, 2);   // chunks of 2
+        CHECK(seen == (E{{0, 0, 1.0}, {0, 3, 2.0}, {2, 0, 3.0}, {2, 1, 4.0}, {2, 2, 5.0}}));
+        auto c = CscMatrix<double>::from(a);
+        seen.clear();
+        c.for_each([&](std::size_t r, std::size_t cc, const double &v) { seen.emplace_back(r, cc, v); });
+        CHECK(seen == (E{{0, 0, 1.0}, {2, 0, 3.0}, {2, 1, 4.0}, {2, 2, 5.0}, {0, 3, 2.0}}));
+        CHECK(c.matvec(D{1, 10, 100, 1000}) == a.matvec(D{1, 10, 100, 1000}) && a.matvec(D{1, 10, 100, 1000}) == (D{2001, 0, 543}));
+        a.for_each_mut([](std::size_t r, std::size_t, double &v) { if (r == 2) v = -v; });
+        CHECK(a.values() == (D{1, 2, -3, -4, -5}) && a.matvec(D{1, 10, 100, 1000}) == (D{2001, 0, -543}));
+        // y = A^T z: the CSC matrix with A's arrays and swapped dims
+        CscMatrix<double> at(4, 3, V{0, 2, 2, 5}, V{0, 3, 0, 1, 2}, D{1, 2, 3, 4, 5});
+        CHECK(at.matvec(D{1, 10, 100}) == (D{301, 400, 500, 2}));
+    }
     if (failures == 0) std::printf("cpp mirror: all reference tests passed\n");
     return failures == 0 ? 0 : 1;
 }
