@@ -723,17 +723,26 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     D.prepare_gather(torch)
 
     def spmv_fused():
-        xs.barrier()
-        D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr())
+        D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True)      # the barrier is part of the kernel
     ms_fused = timed_all(spmv_fused, reps=7, warm=3)
     xs.check()
     err = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
     assert err < 1e-5, f"fused gather SpMV differs from the all-gather product: {err}"
-    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: copy CTAs pull the peers' slices of x over "
-                                                    "NVLink while compute CTAs multiply the shard block by block "
-                                                    "(blocked by column owner, ring order)",
+    # where the time of one fused product goes: %globaltimer stamps from the kernel (first compute CTA)
+    tl = torch.zeros(1 + 3 * world, dtype=torch.int64, device="cuda")
+    dist.barrier(); torch.cuda.synchronize()
+    D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())
+    torch.cuda.synchronize()
+    t = tl.cpu().tolist()
+    t0 = min(v for v in t if v > 0)
+    stamps = [{"block": k, "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3, "slice_landed_us": (t[2 + 3 * k] - t0) / 1e3,
+               "block_done_us": (t[3 + 3 * k] - t0) / 1e3} for k in range(world)]
+    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: the device barrier, copy warps pulling the peers' "
+                                                    "slices of x over NVLink, and compute CTAs multiplying the shard block by "
+                                                    "block (blocked by column owner, ring order) as the slices land",
                                         "ms": ms_fused, "gbps_algorithmic": b_ag / ms_fused / 1e6,
-                                        "max_rel_diff_vs_allgather": err}
+                                        "max_rel_diff_vs_allgather": err,
+                                        "timeline_rank0_first_compute_cta": stamps}
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}

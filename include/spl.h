@@ -324,13 +324,19 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
  * blocked by column owner in that ring order: block_ptr_dev holds world row-pointer arrays of
  * nrows_local+1 entries each (absolute positions into block_ind_dev / block_val_dev, global column
  * indices).  ready_dev: uint32[SPL_MAX_PEERS], zeroed once by the caller; epoch = 1, 2, 3, ... per
- * call on this buffer; nnz_local = stored entries of the shard (picks the lanes per row).  Order
- * it after the peers' writes of x with spl_peer_barrier.  x_full_dev
- * (ncols values) is scratch: afterwards it holds the peers' slices (not the own one). */
+ * call on this buffer; nnz_local = stored entries of the shard (picks the lanes per row).  The
+ * barrier that orders the peers' writes of x before the pulls is part of the kernel when flag_ptrs
+ * is given (flag blocks / barrier_epoch / timeout_ms exactly as spl_peer_barrier takes them: the
+ * kernel announces this rank's slice, and each slice is pulled as soon as ITS owner has arrived);
+ * with flag_ptrs NULL run spl_peer_barrier first.  x_full_dev (ncols values) is scratch: afterwards
+ * it holds the peers' slices (not the own one).  timeline_dev: NULL, or 1 + 3*world uint64 that
+ * receive %globaltimer stamps (kernel start; per block: wait begins, slice landed, block done on the
+ * first compute CTA) — the evidence behind profiles/r2_gather_timeline.txt. */
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
                           const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
                           const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
-                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local);
+                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local, void *const *flag_ptrs,
+                          uint32_t barrier_epoch, uint32_t timeout_ms, uint64_t *timeline_dev);
 
 /* The reference-facing `&A * &x` on one rank of a row-sharded matrix, with HOST vectors:
  * x_host_local is this rank's slice of x (col_starts[rank+1] - col_starts[rank] values),

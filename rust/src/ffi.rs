@@ -103,7 +103,8 @@ extern "C" {
     pub fn spl_spmv_gather_fused(ctx: *mut spl_ctx, dtype: c_int, nrows_local: u64, world: c_int, rank: c_int,
         col_starts: *const u64, x_slices: *const *const c_void, block_ptr: *const u32, block_ind: *const u32,
         block_val: *const c_void, x_full_dev: *mut c_void, y_dev: *mut c_void, ready_dev: *mut u32, epoch: u32,
-        nnz_local: u64) -> c_int;
+        nnz_local: u64, flag_ptrs: *const *mut c_void, barrier_epoch: u32, timeout_ms: u32,
+        timeline_dev: *mut u64) -> c_int;
     pub fn spl_spmv_peer_host(ctx: *mut spl_ctx, a_local: *const spl_mat, world: c_int, rank: c_int,
         col_starts: *const u64, x_slices: *const *mut c_void, flag_ptrs: *const *mut c_void, epoch: u32,
         timeout_ms: u32, x_host_local: *const c_void, y_host_local: *mut c_void) -> c_int;

@@ -759,7 +759,8 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
                           const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
                           const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
-                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local) {
+                          uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local, void *const *flag_ptrs,
+                          uint32_t barrier_epoch, uint32_t timeout_ms, uint64_t *timeline_dev) {
     API_BEGIN(ctx)
     check_enums(SPL_CSR, dtype);
     SPL_REQUIRE(col_starts && x_slices && block_ptr_dev && x_full_dev && y_dev && ready_dev, SPL_ERR_ARG, "NULL argument");
@@ -774,7 +775,8 @@ int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int wor
     }
     spmv_gather_fused(ctx, dtype, (uint32_t)nrows_local, world, rank, col_starts, x_slices, block_ptr_dev, block_ind_dev,
                       block_val_dev, x_full_dev, y_dev, ready_dev, epoch,
-                      (double)nnz_local / (double)nrows_local / (double)world);
+                      (double)nnz_local / (double)nrows_local / (double)world, flag_ptrs, barrier_epoch, timeout_ms,
+                      reinterpret_cast<unsigned long long *>(timeline_dev));
     API_END(ctx)
 }
 

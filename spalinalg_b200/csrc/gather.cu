@@ -19,6 +19,7 @@
 // blocks in ring order, not in ascending column order: tolerance parity (1e-12 / 1e-5), like every
 // multi-lane kernel.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -31,6 +32,22 @@ struct GatherPeers {
     uint32_t start[SPL_MAX_PEERS + 1];
     int world, rank;
 };
+
+// The device-side barrier of spl_peer_barrier, folded into the kernel: flags[g] = rank g's flag block
+// (peer memory), flags_mine = this rank's own block (NULL: the caller ran the barrier itself)
+struct GatherBarrier {
+    uint32_t *flags[SPL_MAX_PEERS];
+    const uint32_t *flags_mine;
+    uint32_t epoch;
+    unsigned long long timeout_ns;
+    uint32_t *failed;
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int GF_THREADS = 256;
 constexpr int GF_INFLIGHT = 8;    // entries in flight per thread = rows in flight x entries per row and trip: a block
@@ -46,43 +63,67 @@ template <typename T, int LPR, int U>
 __global__ void __launch_bounds__(GF_THREADS)
 spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const uint32_t *__restrict__ bind,
                          const T *__restrict__ bval, GatherPeers gp, T *x_full, T *__restrict__ y, uint32_t ncopy,
-                         uint32_t *ready, uint32_t target, uint32_t rows_per_cta) {
+                         uint32_t *ready, uint32_t target, uint32_t rows_per_cta, GatherBarrier gb,
+                         unsigned long long *timeline) {
     extern __shared__ __align__(16) unsigned char gf_raw[];
     const int G = gp.world;
     if (blockIdx.x < ncopy) {
-        // ---- copy role: slices of the peers, ring order, this CTA's 1/ncopy share of each ----
+        // ---- copy role: every WARP owns a contiguous 1/(8 ncopy) share of each peer slice, slices in ring order;
+        // warps run independently (no CTA barrier), 8 x 16 bytes in flight per lane ----
+        const unsigned lane = lane_id();
+        const unsigned long long w = (unsigned long long)blockIdx.x * (GF_THREADS / 32) + (threadIdx.x >> 5);
+        const unsigned long long nwarps = (unsigned long long)ncopy * (GF_THREADS / 32);
+        if (gb.flags_mine && w == 0 && (int)lane < G && (int)lane != gp.rank) {
+            // fused barrier, arrival: this rank's published slice is final (stream order put its writers before us)
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gb.flags[lane] + gp.rank), "r"(gb.epoch) : "memory");
+        }
+        if (timeline && w == 0 && lane == 0) timeline[0] = global_timer_ns();
         for (int k = 1; k < G; ++k) {
             const int g = (gp.rank + k) % G;
+            if (gb.flags_mine) {         // fused barrier, wait: rank g's slice is final once its epoch shows up here
+                if (lane == 0) {
+                    const uint64_t t0 = global_timer_ns();
+                    for (;;) {
+                        uint32_t v;
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.flags_mine + g) : "memory");
+                        if ((int32_t)(v - gb.epoch) >= 0) break;
+                        if (global_timer_ns() - t0 > gb.timeout_ns) { atomicExch(gb.failed, 1u); break; }
+                        __nanosleep(100);
+                    }
+                }
+                __syncwarp();
+            }
             const unsigned char *src = static_cast<const unsigned char *>(gp.slice[g]);
             unsigned char *dst = reinterpret_cast<unsigned char *>(x_full + gp.start[g]);
             const unsigned long long bytes = (unsigned long long)(gp.start[g + 1] - gp.start[g]) * sizeof(T);
             // whole 16-byte units when both ends are aligned (IPC blocks are; slice starts of f32 vectors may not be)
             const bool wide = ((((unsigned long long)(uintptr_t)src) | ((unsigned long long)(uintptr_t)dst)) & 15ull) == 0;
             const unsigned long long n16 = wide ? bytes / 16 : 0;
-            const unsigned long long per = (n16 + ncopy - 1) / ncopy;
-            const unsigned long long lo = (unsigned long long)blockIdx.x * per;
+            const unsigned long long per = (n16 + nwarps - 1) / nwarps;
+            const unsigned long long lo = w * per;
             const unsigned long long hi = lo + per < n16 ? lo + per : n16;
             const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
             uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-            unsigned long long i = lo + threadIdx.x;
-            for (; i + 7ull * GF_THREADS < hi; i += 8ull * GF_THREADS) {
+            unsigned long long i = lo + lane;
+            for (; i + 7ull * 32 < hi; i += 8ull * 32) {
                 uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldcg(s4 + i + (unsigned long long)u * GF_THREADS);
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(s4 + i + (unsigned long long)u * 32);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) d4[i + (unsigned long long)u * GF_THREADS] = v[u];
+                for (int u = 0; u < 8; ++u) d4[i + (unsigned long long)u * 32] = v[u];
             }
-            for (; i < hi; i += GF_THREADS) d4[i] = __ldcg(s4 + i);
-            // the unaligned / trailing bytes: element by element, by the first copy CTA
-            if (blockIdx.x == 0) {
+            for (; i < hi; i += 32) d4[i] = __ldcg(s4 + i);
+            // the unaligned / trailing bytes: element by element, by the first copy warp
+            if (w == 0) {
                 const T *se = reinterpret_cast<const T *>(src);
                 T *de = reinterpret_cast<T *>(dst);
                 const unsigned long long n = bytes / sizeof(T);
-                for (unsigned long long e = n16 * (16 / sizeof(T)) + threadIdx.x; e < n; e += GF_THREADS) de[e] = __ldcg(se + e);
+                for (unsigned long long e = n16 * (16 / sizeof(T)) + lane; e < n; e += 32) de[e] = __ldcg(se + e);
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();                       // this CTA's stores of the slice, before the count
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();                       // this warp's stores of the slice, before the count
                 atomicAdd(ready + k, 1u);
             }
         }
@@ -101,11 +142,13 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
     const T *own = static_cast<const T *>(gp.slice[gp.rank]) - gp.start[gp.rank];
     for (int k = 0; k < G; ++k) {
         const T *xb = k == 0 ? own : x_full;
+        if (timeline && c == 0 && threadIdx.x == 0) timeline[1 + 3 * k] = global_timer_ns();          // block k: wait begins
         if (k > 0) {
             if (threadIdx.x == 0)
                 while ((int32_t)(ld_acquire_gpu(ready + k) - target) < 0) __nanosleep(64);
             __syncthreads();
         }
+        if (timeline && c == 0 && threadIdx.x == 0) timeline[2 + 3 * k] = global_timer_ns();          // slice k has landed
         const uint32_t *p = bptr + (size_t)k * (nloc + 1);
         constexpr uint32_t RL = GF_THREADS / LPR;          // rows a CTA covers per step of one q
         constexpr int ROWS = GF_INFLIGHT / U;
@@ -157,9 +200,12 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
                 if (sub == 0 && r < re) acc[r - rs] += s[q];      // one owner per row for the whole kernel: no race
             }
         }
+        if (timeline && c == 0 && threadIdx.x == 0) timeline[3 + 3 * k] = global_timer_ns();          // block k done (this CTA)
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) y[rs + i] = acc[i];
+    // a fused barrier that gave up: NaN instead of sums over a half-written x (the status call reports it)
+    const bool poisoned = gb.failed && *reinterpret_cast<const volatile uint32_t *>(gb.failed) != 0u;
+    for (uint32_t i = threadIdx.x; i < re - rs; i += GF_THREADS) y[rs + i] = poisoned ? (T)NAN : acc[i];
 }
 
 }  // namespace
@@ -168,9 +214,11 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, const
 // of a compute CTA (its shared-memory sums) shrinks as the CTAs per SM grow, so the two are found together.
 template <typename T, int LPR, int U>
 void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, const uint32_t *bind, const T *bval,
-                         const GatherPeers &gp, T *x_full, T *y, uint32_t *ready, uint32_t epoch) {
+                         const GatherPeers &gp, T *x_full, T *y, uint32_t *ready, uint32_t epoch, const GatherBarrier &gb,
+                         unsigned long long *timeline) {
     auto k = spmv_gather_fused_kernel<T, LPR, U>;
-    const uint32_t ncopy = gp.world > 1 ? std::min<uint32_t>(48u, (uint32_t)ctx->num_sms / 3u) : 0u;
+    const char *nc = std::getenv("SPL_GATHER_COPY_CTAS");            // measurement knob
+    const uint32_t ncopy = gp.world > 1 ? (nc ? (uint32_t)std::atoi(nc) : std::min<uint32_t>(64u, (uint32_t)ctx->num_sms / 2u)) : 0u;
     uint32_t ncompute = 0, rows_per_cta = 0;
     size_t smem = 0;
     for (int want = 8; want >= 1; --want) {
@@ -190,13 +238,22 @@ void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, cons
     SPL_REQUIRE(ncompute > 0, SPL_ERR_UNSUPPORTED,
                 "fused gather SpMV: the shard's rows do not fit in the shared-memory sums of one resident grid");
     k<<<ncopy + ncompute, GF_THREADS, smem, ctx->stream>>>(nloc, bptr, bind, bval, gp, x_full, y, ncopy, ready,
-                                                          epoch * ncopy, rows_per_cta);
+                                                          epoch * ncopy * (GF_THREADS / 32), rows_per_cta, gb, timeline);
     check_launch(ctx, "spmv_gather_fused");
 }
 
 void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int rank, const uint64_t *col_starts,
                        const void *const *x_slices, const uint32_t *bptr, const uint32_t *bind, const void *bval,
-                       void *x_full, void *y, uint32_t *ready, uint32_t epoch, double entries_per_row_block) {
+                       void *x_full, void *y, uint32_t *ready, uint32_t epoch, double entries_per_row_block,
+                       void *const *flag_ptrs, uint32_t barrier_epoch, uint32_t timeout_ms, unsigned long long *timeline) {
+    GatherBarrier gb{};
+    if (flag_ptrs && world > 1) {
+        for (int g = 0; g < world; ++g) gb.flags[g] = static_cast<uint32_t *>(flag_ptrs[g]);
+        gb.flags_mine = gb.flags[rank];
+        gb.epoch = barrier_epoch;
+        gb.timeout_ns = (unsigned long long)(timeout_ms ? timeout_ms : 2000) * 1000000ull;
+    }
+    gb.failed = ctx->d_scratch + 32;
     GatherPeers gp{};
     gp.world = world;
     gp.rank = rank;
@@ -208,7 +265,7 @@ void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int ra
     auto go = [&](auto tag, auto lpr, auto u) {
         using T = decltype(tag);
         spmv_gather_fused_t<T, decltype(lpr)::value, decltype(u)::value>(ctx, nloc, bptr, bind, (const T *)bval, gp, (T *)x_full,
-                                                                        (T *)y, ready, epoch);
+                                                                        (T *)y, ready, epoch, gb, timeline);
     };
     using I1 = std::integral_constant<int, 1>;
     using I2 = std::integral_constant<int, 2>;

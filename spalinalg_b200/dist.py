@@ -354,11 +354,18 @@ class DistCsrMatrix:
                         "ready": torch.zeros(capi.SPL_MAX_PEERS, dtype=torch.int32, device=col.device), "epoch": 0}
         torch.cuda.current_stream().synchronize()
 
-    def spmv_gather(self, x: "PeerVector", x_full_dev: int, y_dev: int):
+    def spmv_gather(self, x: "PeerVector", x_full_dev: int, y_dev: int, barrier: bool = False, timeline_dev: int = 0,
+                    timeout_ms: int = 2000):
         """y_local = A_local x for a general shard with the all-gather of x fused into the product
-        (spl_spmv_gather_fused): call prepare_gather once, publish x, then this per product."""
+        (spl_spmv_gather_fused): call prepare_gather once, then per product publish x and call this.
+        barrier=True folds x's device-side barrier into the kernel (then do NOT call x.barrier() /
+        x.publish() for this product; swap the buffers with x.swap() when the slice was rewritten)."""
         g = self._gather
         g["epoch"] += 1
+        fl = None
+        if barrier:
+            x._epoch += 1
+            fl = C.cast((C.c_void_p * self.world)(*x._flags.ptrs), C.c_void_p)
         ctx = self.local._ctx
         st = (C.c_uint64 * (self.world + 1))(*x.starts)
         sl = (C.c_void_p * self.world)(*x.ptrs)
@@ -367,7 +374,8 @@ class DistCsrMatrix:
             ctx._h, _dtype_code(self.local.dtype), r1 - r0, self.world, self.rank, C.cast(st, C.c_void_p),
             C.cast(sl, C.c_void_p), C.c_void_p(g["bptr"].data_ptr()), C.c_void_p(g["bind"].data_ptr()),
             C.c_void_p(g["bval"].data_ptr()), C.c_void_p(x_full_dev), C.c_void_p(y_dev),
-            C.c_void_p(g["ready"].data_ptr()), g["epoch"], self.local.nnz()))
+            C.c_void_p(g["ready"].data_ptr()), g["epoch"], self.local.nnz(), fl, x._epoch if barrier else 0,
+            int(timeout_ms), C.c_void_p(timeline_dev) if timeline_dev else None))
 
     def matvec_host(self, x: "PeerVector", x_host_local, y_host_local, timeout_ms: int = 2000):
         """`&A * &x` with this rank's slices of x and y in host memory (numpy arrays or raw host
@@ -575,6 +583,11 @@ class PeerVector:
         else:
             self.barrier(timeout_ms)
         self._cur = nxt
+
+    def swap(self):
+        """Make the buffer at `local_ptr` the published one WITHOUT a barrier of its own: for products that carry
+        the barrier themselves (DistCsrMatrix.spmv_gather(barrier=True))."""
+        self._cur = (self._cur + 1) % len(self._data)
 
     def barrier_halo(self, timeout_ms: int = 2000):
         """Barrier + halo refresh of the published buffer, no swap."""

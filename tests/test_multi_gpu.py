@@ -112,6 +112,18 @@ def _worker(rank, world, port, out):
             ok &= bool(np.all(np.abs(y.cpu().numpy() - scale_x * yw[r0:r1]) <= 4e-12 * sc[r0:r1] + 1e-300))
         xv.check()
         assert ok, "fused gather SpMV differs from the oracle"
+        # the same with the barrier folded into the kernel: write the next slice, swap, one launch
+        for scale_x in (2.0, -1.0):
+            device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(scale_x * x[r0:r1]))
+            xv.swap()
+            x_full.fill_(float("nan"))
+            y.fill_(7.0)
+            torch.cuda.synchronize()
+            D.spmv_gather(xv, x_full.data_ptr(), y.data_ptr(), barrier=True)
+            torch.cuda.synchronize()
+            ok &= bool(np.all(np.abs(y.cpu().numpy() - scale_x * yw[r0:r1]) <= 4e-12 * sc[r0:r1] + 1e-300))
+        xv.check()
+        assert ok, "fused gather SpMV with its own barrier differs from the oracle"
 
         # an iteration whose x changes every step: y_t is written straight into the unpublished buffer
         # and published as x_{t+1} (one barrier per step).  One rank is held back by a spin kernel at a
