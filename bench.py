@@ -646,6 +646,32 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
         return int(t.item())
 
+    # ---- what the host link gives every rank when all ranks copy at once (explains e2e: the slices of x and y
+    # are 2 x (n / N) x 8 bytes of pinned traffic per rank and step)
+    probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+
+    def h2d():
+        probe_d.copy_(probe_h, non_blocking=True)
+
+    def d2h():
+        probe_h.copy_(probe_d, non_blocking=True)
+
+    def both():
+        probe_d.copy_(probe_h, non_blocking=True)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            probe_h2.copy_(probe_d2, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+    probe_h2 = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    probe_d2 = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    gb = (64 << 20) / 1e6
+    out["host_link_probe"] = {"what": "64 MiB pinned copies on every rank at the same time; GB/s per rank (slowest rank)",
+                              "h2d_gbps": gb / timed_all(h2d, reps=5, warm=2), "d2h_gbps": gb / timed_all(d2h, reps=5, warm=2),
+                              "both_directions_gbps_each": gb / timed_all(both, reps=5, warm=2)}
+    del probe_h, probe_d, probe_h2, probe_d2
+
     # ---- config 5: A + B, rows sharded, no exchange
     bp, bc, bv = banded_device(torch, n, r0, r1, (-8, -2, 0, 2, 8), torch.float64)
     B = sp.CsrMatrix.from_device_arrays(r1 - r0, n, bc.numel(), bp.data_ptr(), bc.data_ptr(), bv.data_ptr(),

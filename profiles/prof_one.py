@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Builds one config's matrix on the device and launches one SpMV kernel variant a few times
-(target of ncu captures).  Usage: python profiles/prof_one.py c3|c4|c2|c1 merge|vectorN [launches]"""
+(target of ncu captures).  Usage: python profiles/prof_one.py c3|c4|c2|c1 auto|stream|merge|split|vectorN [launches]"""
 import os
 import sys
 
@@ -41,7 +41,7 @@ else:
     tdt = torch.float64
 x = torch.rand(n, device="cuda", dtype=tdt) - 0.5
 y = torch.empty(n, device="cuda", dtype=tdt)
-k, l = (2, 0) if kern == "merge" else (3, 0) if kern == "split" else (1, int(kern[6:]))
+k, l = (0, 0) if kern == "auto" else (5, 0) if kern == "stream" else (2, 0) if kern == "merge" else (3, 0) if kern == "split" else (1, int(kern[6:]))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 A.spmv_device(x.data_ptr(), y.data_ptr(), k, l)
 e0.record()
