@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --gpus 1 --steps 2 --warmup 3 --no-extras"
 $CMD > gpurun_out/r2_ncu_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:spl:: -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:spmv_stream_kernel -s 3 -c 2 -f -o gpurun_out/r2_spmv_stream_c5 $CMD > gpurun_out/r2_ncu_full.log 2>&1
 # the same kernel on config 1 (the 80 MB Laplacian) and the hot-column kernel on config 4
 python profiles/prof_one.py c1 auto 8 > gpurun_out/r2_prof_c1_plain.log 2>&1 &&
