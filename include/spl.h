@@ -18,8 +18,11 @@
  *  - One spl_ctx per host thread (it owns a stream and the last-error text).
  *    spl_mat objects are immutable after creation and may be shared read-only.
  *  - There is no CPU fallback: without a CUDA device spl_ctx_create fails.
- *  - Limits: dims below 2^32, nnz / COO length / intermediate products below
- *    2^32 - 65536 (device indices and positions are 32 bit), else SPL_ERR_UNSUPPORTED.
+ *  - Limits: dims below 2^32 (device indices are 32 bit).  Positions are 32 bit on the fast
+ *    paths; a CsrMatrix / CscMatrix with 2^32 - 65536 stored entries or more ("wide") keeps a 64-bit
+ *    pointer array on the device and supports construction + validation, SpMV, transpose, CSR<->CSC,
+ *    download and chunked iteration; COO assembly, add/sub/mul/neg and the sharded calls answer
+ *    SPL_ERR_UNSUPPORTED for it (COO length and intermediate products stay below 2^32 - 65536).
  */
 #ifndef SPL_H
 #define SPL_H
@@ -153,6 +156,12 @@ int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
 int spl_mat_from_compressed_dev(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
                                 uint64_t nnz, const uint32_t *ptr_dev, const uint32_t *ind_dev,
                                 const void *val_dev, int validate, spl_mat **out);
+/* The same with a 64-bit device pointer array (usize, src/csr.rs:66-72): the constructor for matrices
+ * with 2^32 - 65536 stored entries or more, which stay "wide" (64-bit positions) on the device; smaller
+ * ones are narrowed to the usual form. */
+int spl_mat_from_compressed_dev64(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                                  uint64_t nnz, const uint64_t *ptr_dev, const uint32_t *ind_dev,
+                                  const void *val_dev, int validate, spl_mat **out);
 /* CsrMatrix::eye (src/csr.rs:179-188) / CscMatrix::eye (src/csc.rs:179-188). */
 int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **out);
 
@@ -211,6 +220,9 @@ int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val);
 /* Borrow the device arrays (uint32 ptr[nmajor+1], uint32 ind[nnz], T val[nnz]). */
 int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32_t **ind_dev,
                         const void **val_dev);
+/* The 64-bit pointer array of a wide matrix (NULL for the usual ones, whose spl_mat_device_ptrs ptr is
+ * then valid instead). */
+int spl_mat_device_ptr64(const spl_mat *m, const uint64_t **ptr64_dev);
 /* From<&CsrMatrix>/<&CscMatrix> for CooMatrix (src/coo.rs:629-705): expand to
  * host triplets in storage order.  Arrays need nnz slots.  Synchronises. */
 int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val);

@@ -32,6 +32,10 @@ extern "C" {
     pub fn spl_mat_from_compressed_dev(ctx: *mut spl_ctx, format: c_int, dtype: c_int, nrows: u64,
         ncols: u64, nnz: u64, ptr: *const u32, ind: *const u32, val: *const c_void,
         validate: c_int, out: *mut *mut spl_mat) -> c_int;
+    pub fn spl_mat_from_compressed_dev64(ctx: *mut spl_ctx, format: c_int, dtype: c_int, nrows: u64,
+        ncols: u64, nnz: u64, ptr: *const u64, ind: *const u32, val: *const c_void,
+        validate: c_int, out: *mut *mut spl_mat) -> c_int;
+    pub fn spl_mat_device_ptr64(m: *const spl_mat, ptr64: *mut *const u64) -> c_int;
     pub fn spl_mat_eye(ctx: *mut spl_ctx, format: c_int, dtype: c_int, size: u64, out: *mut *mut spl_mat) -> c_int;
     pub fn spl_mat_convert(ctx: *mut spl_ctx, m: *const spl_mat, format: c_int, out: *mut *mut spl_mat) -> c_int;
     pub fn spl_mat_transpose(ctx: *mut spl_ctx, m: *const spl_mat, out: *mut *mut spl_mat) -> c_int;

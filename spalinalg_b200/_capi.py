@@ -33,6 +33,8 @@ SIGNATURES = {
     "spl_mat_from_coo_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _i, _pp]),
     "spl_mat_from_compressed": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _u64, _vp, _u64, _vp, _pp]),
     "spl_mat_from_compressed_dev": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _pp]),
+    "spl_mat_from_compressed_dev64": (_i, [_vp, _i, _i, _u64, _u64, _u64, _vp, _vp, _vp, _i, _pp]),
+    "spl_mat_device_ptr64": (_i, [_vp, _pp]),
     "spl_mat_eye": (_i, [_vp, _i, _i, _u64, _pp]),
     "spl_mat_convert": (_i, [_vp, _vp, _i, _pp]),
     "spl_mat_transpose": (_i, [_vp, _vp, _pp]),

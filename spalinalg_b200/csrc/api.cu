@@ -1,9 +1,11 @@
 // api.cu — the extern "C" boundary declared in include/spl.h.  Plain pointers and sizes in,
 // status codes out; nothing unwinds across it.  No CPU fallback: every entry point needs a
 // live CUDA context.
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
 
 #include "kernels.cuh"
 
@@ -79,6 +81,12 @@ cudaMemPool_t library_pool(int device) {
 [[noreturn]] void invalid(spl_ctx *ctx, int reason, const char *text) {
     ctx->invalid_reason = reason;
     throw Error{SPL_ERR_INVALID, text};
+}
+
+void require_narrow(const spl_mat *m, const char *what) {
+    if (m && m->wide())
+        throw Error{SPL_ERR_UNSUPPORTED, std::string(what) + ": operand has 2^32 - 65536 stored entries or more (64-bit "
+                    "positions); supported on such matrices: new / validation, SpMV, transpose, CSR<->CSC, download, iter"};
 }
 
 const char *kReasonText[10] = {
@@ -261,8 +269,33 @@ int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
     if (ind_len != ptr[nmajor]) invalid(ctx, 5, kReasonText[5]);
     if (val_len != ptr[nmajor]) invalid(ctx, 6, kReasonText[6]);
     const uint64_t nnz = ind_len;
-    SPL_REQUIRE(nnz < kMaxEntries, SPL_ERR_UNSUPPORTED, "nnz must be below 2^32 - 65536");
     SPL_REQUIRE(nnz == 0 || (ind && val), SPL_ERR_ARG, "NULL array");
+    if (nnz >= kMaxEntries) {              // 64-bit positions: the pointers go up as they are, the indices narrow in chunks
+        spl_mat *w = new_wide_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, nnz);
+        try {
+            SPL_CUDA(cudaMemcpyAsync(w->ptr64, ptr, (nmajor + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            constexpr uint64_t kChunk = 1ull << 26;
+            Tmp<uint64_t> stage(ctx, kChunk);
+            SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 2 * sizeof(uint32_t), ctx->stream));
+            for (uint64_t at = 0; at < nnz; at += kChunk) {
+                const uint64_t cnt = std::min(kChunk, nnz - at);
+                SPL_CUDA(cudaMemcpyAsync(stage, ind + at, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+                narrow_u64(ctx, stage, w->ind + at, cnt, nminor, ctx->d_scratch + 1);
+            }
+            SPL_CUDA(cudaMemcpyAsync(w->val, val, nnz * w->vsize(), cudaMemcpyHostToDevice, ctx->stream));
+            uint32_t flags[2] = {0, 0};
+            read_back(ctx, ctx->d_scratch, flags, 2);
+            int why = wide_validate(ctx, w);
+            if (why == 0 && flags[1]) why = 8;
+            if (why) invalid(ctx, why, kReasonText[why]);
+        } catch (...) {
+            free_mat(ctx, w);
+            throw;
+        }
+        *out = w;
+        publish_mat(ctx, *out);
+        return SPL_OK;
+    }
 
     spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)nnz);
     try {
@@ -295,6 +328,65 @@ int spl_mat_from_compressed(spl_ctx *ctx, int format, int dtype, uint64_t nrows,
     API_END(ctx)
 }
 
+int spl_mat_from_compressed_dev64(spl_ctx *ctx, int format, int dtype, uint64_t nrows, uint64_t ncols,
+                                  uint64_t nnz, const uint64_t *ptr_dev, const uint32_t *ind_dev,
+                                  const void *val_dev, int validate, spl_mat **out) {
+    API_BEGIN(ctx)
+    SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    check_enums(format, dtype);
+    check_dims(ctx, nrows, ncols);
+    SPL_REQUIRE(ptr_dev && (nnz == 0 || (ind_dev && val_dev)), SPL_ERR_ARG, "NULL array");
+    const uint32_t nmajor = (uint32_t)(format == SPL_CSR ? nrows : ncols);
+    const uint32_t nminor = (uint32_t)(format == SPL_CSR ? ncols : nrows);
+    uint32_t ends[4] = {0, 0, 0, 0};                     // ptr[0] and ptr[n] as two 32-bit words each
+    if (validate) {
+        read_back(ctx, reinterpret_cast<const uint32_t *>(ptr_dev), ends, 2);
+        read_back(ctx, reinterpret_cast<const uint32_t *>(ptr_dev + nmajor), ends + 2, 2);
+        if (ends[0] != 0 || ends[1] != 0) invalid(ctx, 4, kReasonText[4]);
+        if ((((uint64_t)ends[3] << 32) | ends[2]) != nnz) invalid(ctx, 5, kReasonText[5]);
+    }
+    if (nnz < kMaxEntries) {                             // fits 32-bit positions: the usual matrix
+        spl_mat *m = new_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, (uint32_t)nnz);
+        try {
+            SPL_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(uint32_t), ctx->stream));
+            narrow_u64(ctx, ptr_dev, m->ptr, (size_t)nmajor + 1, nnz + 1, ctx->d_scratch);
+            if (nnz) {
+                SPL_CUDA(cudaMemcpyAsync(m->ind, ind_dev, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                SPL_CUDA(cudaMemcpyAsync(m->val, val_dev, nnz * m->vsize(), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            if (validate) {
+                uint32_t over = 0;
+                read_back(ctx, ctx->d_scratch, &over, 1);
+                if (over) invalid(ctx, 7, kReasonText[7]);
+                int why = validate_compressed(ctx, nmajor, nminor, (uint32_t)nnz, m->ptr, m->ind);
+                if (why) invalid(ctx, why, kReasonText[why]);
+            }
+        } catch (...) {
+            free_mat(ctx, m);
+            throw;
+        }
+        *out = m;
+    } else {
+        spl_mat *m = new_wide_mat(ctx, format, dtype, (uint32_t)nrows, (uint32_t)ncols, nnz);
+        try {
+            SPL_CUDA(cudaMemcpyAsync(m->ptr64, ptr_dev, ((size_t)nmajor + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            SPL_CUDA(cudaMemcpyAsync(m->ind, ind_dev, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            SPL_CUDA(cudaMemcpyAsync(m->val, val_dev, nnz * m->vsize(), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (validate) {
+                int why = wide_validate(ctx, m);
+                if (why) invalid(ctx, why, kReasonText[why]);
+            }
+        } catch (...) {
+            free_mat(ctx, m);
+            throw;
+        }
+        *out = m;
+    }
+    publish_mat(ctx, *out);
+    API_END(ctx)
+}
+
 int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **out) {
     API_BEGIN(ctx)
     SPL_REQUIRE(out, SPL_ERR_ARG, "out is NULL");
@@ -315,6 +407,7 @@ int spl_mat_eye(spl_ctx *ctx, int format, int dtype, uint64_t size, spl_mat **ou
 
 static spl_mat *regroup(spl_ctx *ctx, const spl_mat *in, int out_format, uint32_t out_rows,
                         uint32_t out_cols) {
+    if (in->wide()) return wide_regroup(ctx, in, out_format, out_rows, out_cols);
     // out's major axis is in's minor axis
     spl_mat *m = new_mat(ctx, out_format, in->dtype, out_rows, out_cols, in->nnz);
     try {
@@ -333,7 +426,14 @@ int spl_mat_convert(spl_ctx *ctx, const spl_mat *in, int format, spl_mat **out) 
     SPL_REQUIRE(in && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
     check_enums(format, in->dtype);
-    if (format == in->format) {
+    if (format == in->format && in->wide()) {
+        spl_mat *m = new_wide_mat(ctx, in->format, in->dtype, in->nrows, in->ncols, in->nnz64);
+        SPL_CUDA(cudaMemcpyAsync(m->ptr64, in->ptr64, ((size_t)in->nmajor() + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->ind, in->ind, (size_t)in->nnz64 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        SPL_CUDA(cudaMemcpyAsync(m->val, in->val, (size_t)in->nnz64 * in->vsize(), cudaMemcpyDeviceToDevice, ctx->stream));
+        *out = m;
+        publish_mat(ctx, *out);
+    } else if (format == in->format) {
         spl_mat *m = new_mat(ctx, in->format, in->dtype, in->nrows, in->ncols, in->nnz);
         SPL_CUDA(cudaMemcpyAsync(m->ptr, in->ptr, ((size_t)in->nmajor() + 1) * 4,
                                  cudaMemcpyDeviceToDevice, ctx->stream));
@@ -362,6 +462,8 @@ int spl_mat_transpose(spl_ctx *ctx, const spl_mat *in, spl_mat **out) {
 
 int spl_mat_add(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_mat_add");
+    require_narrow(b, "spl_mat_add");
     MatUse use_a(ctx, a);
     MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
@@ -373,6 +475,8 @@ int spl_mat_add(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out)
 
 int spl_mat_sub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_mat_sub");
+    require_narrow(b, "spl_mat_sub");
     MatUse use_a(ctx, a);
     MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
@@ -384,6 +488,8 @@ int spl_mat_sub(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out)
 
 int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_mat_mul");
+    require_narrow(b, "spl_mat_mul");
     MatUse use_a(ctx, a);
     MatUse use_b(ctx, b);
     SPL_REQUIRE(a && b && out, SPL_ERR_ARG, "NULL handle");
@@ -395,6 +501,7 @@ int spl_mat_mul(spl_ctx *ctx, const spl_mat *a, const spl_mat *b, spl_mat **out)
 
 int spl_mat_neg(spl_ctx *ctx, const spl_mat *a, spl_mat **out) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_mat_neg");
     MatUse use_a(ctx, a);
     SPL_REQUIRE(a && out, SPL_ERR_ARG, "NULL handle");
     *out = nullptr;
@@ -418,7 +525,8 @@ int spl_spmv_ex(spl_ctx *ctx, const spl_mat *a, const void *x_dev, void *y_dev, 
     API_BEGIN(ctx)
     MatUse use_a(ctx, a);
     SPL_REQUIRE(a && x_dev && y_dev, SPL_ERR_ARG, "NULL argument");
-    spmv(ctx, a, x_dev, y_dev, kernel & 0xff, (kernel >> 8) & 0xff);
+    if (a->wide()) wide_spmv(ctx, a, x_dev, y_dev);          // 64-bit positions: the vector kernel of wide.cu
+    else spmv(ctx, a, x_dev, y_dev, kernel & 0xff, (kernel >> 8) & 0xff);
     API_END(ctx)
 }
 
@@ -432,9 +540,10 @@ int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_ho
     SPL_REQUIRE(a && x_host && y_host, SPL_ERR_ARG, "NULL argument");
     const size_t vs = a->vsize();
     Tmp<unsigned char> x(ctx, (size_t)a->ncols * vs), y(ctx, (size_t)a->nrows * vs);
-    if (!spmv_host_pipelined(ctx, a, x_host, y_host, x, y)) {
+    if (a->wide() || !spmv_host_pipelined(ctx, a, x_host, y_host, x, y)) {
         SPL_CUDA(cudaMemcpyAsync(x, x_host, (size_t)a->ncols * vs, cudaMemcpyHostToDevice, ctx->stream));
-        spmv(ctx, a, x, y, SPL_SPMV_AUTO, 0);
+        if (a->wide()) wide_spmv(ctx, a, x, y);
+        else spmv(ctx, a, x, y, SPL_SPMV_AUTO, 0);
         SPL_CUDA(cudaMemcpyAsync(y_host, y, (size_t)a->nrows * vs, cudaMemcpyDeviceToHost, ctx->stream));
     }
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -444,6 +553,11 @@ int spl_spmv_host(spl_ctx *ctx, const spl_mat *a, const void *x_host, void *y_ho
 int spl_spmv_choice(spl_ctx *ctx, const spl_mat *a, int *kernel, int *lanes_per_row) {
     API_BEGIN(ctx)
     SPL_REQUIRE(a, SPL_ERR_ARG, "NULL handle");
+    if (a->wide()) {                      // 64-bit positions: the vector kernel, lanes from the mean row length
+        if (kernel) *kernel = SPL_SPMV_VECTOR;
+        if (lanes_per_row) *lanes_per_row = 0;
+        return SPL_OK;
+    }
     a = csr_form(ctx, a);                 // a CSC matrix is planned on its CSR form
     spmv_plan(ctx, const_cast<spl_mat *>(a));
     if (kernel) *kernel = a->plan_kernel;
@@ -458,7 +572,7 @@ int spl_mat_info(const spl_mat *m, int *format, int *dtype, uint64_t *nrows, uin
     if (dtype) *dtype = m->dtype;
     if (nrows) *nrows = m->nrows;
     if (ncols) *ncols = m->ncols;
-    if (nnz) *nnz = m->nnz;
+    if (nnz) *nnz = m->entries();
     return SPL_OK;
 }
 
@@ -467,6 +581,21 @@ int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *in
     MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     const size_t np = (size_t)m->nmajor() + 1;
+    if (m->wide()) {                      // pointers are already uint64; indices widen in chunks
+        if (ptr) SPL_CUDA(cudaMemcpyAsync(ptr, m->ptr64, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ind) {
+            constexpr uint64_t kChunk = 1ull << 26;
+            Tmp<uint64_t> stage(ctx, kChunk);
+            for (uint64_t at = 0; at < m->nnz64; at += kChunk) {
+                const uint64_t cnt = std::min(kChunk, m->nnz64 - at);
+                widen_u32(ctx, m->ind + at, stage, cnt);
+                SPL_CUDA(cudaMemcpyAsync(ind + at, stage, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
+        if (val) SPL_CUDA(cudaMemcpyAsync(val, m->val, (size_t)m->nnz64 * m->vsize(), cudaMemcpyDeviceToHost, ctx->stream));
+        SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SPL_OK;
+    }
     Tmp<uint64_t> wide(ctx, np > m->nnz ? np : m->nnz);
     if (ptr) {
         widen_u32(ctx, m->ptr, wide, np);
@@ -485,6 +614,7 @@ int spl_mat_download(spl_ctx *ctx, const spl_mat *m, uint64_t *ptr, uint64_t *in
 
 int spl_mat_set_values(spl_ctx *ctx, spl_mat *m, const void *val) {
     API_BEGIN(ctx)
+    require_narrow(m, "spl_mat_set_values");
     MatUse use_m(ctx, m);
     SPL_REQUIRE(m && (val || m->nnz == 0), SPL_ERR_ARG, "NULL argument");
     if (m->nnz) {
@@ -504,8 +634,15 @@ int spl_mat_device_ptrs(const spl_mat *m, const uint32_t **ptr_dev, const uint32
     return SPL_OK;
 }
 
+int spl_mat_device_ptr64(const spl_mat *m, const uint64_t **ptr64_dev) {
+    if (!m || !ptr64_dev) return SPL_ERR_ARG;
+    *ptr64_dev = m->ptr64;
+    return SPL_OK;
+}
+
 int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col, void *val) {
     API_BEGIN(ctx)
+    require_narrow(m, "spl_mat_to_coo");
     MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     if (m->nnz) {
@@ -530,6 +667,7 @@ int spl_mat_to_coo(spl_ctx *ctx, const spl_mat *m, uint64_t *row, uint64_t *col,
 
 int spl_mat_to_coo_dev(spl_ctx *ctx, const spl_mat *m, uint32_t *row_dev, uint32_t *col_dev, void *val_dev) {
     API_BEGIN(ctx)
+    require_narrow(m, "spl_mat_to_coo_dev");
     MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
     if (m->nnz) {
@@ -547,11 +685,13 @@ int spl_mat_read_entries(spl_ctx *ctx, const spl_mat *m, uint64_t start, uint64_
     API_BEGIN(ctx)
     MatUse use_m(ctx, m);
     SPL_REQUIRE(m, SPL_ERR_ARG, "NULL handle");
-    SPL_REQUIRE(start <= m->nnz && count <= m->nnz - start, SPL_ERR_ARG, "entry range outside the matrix");
+    SPL_REQUIRE(start <= m->entries() && count <= m->entries() - start, SPL_ERR_ARG, "entry range outside the matrix");
+    SPL_REQUIRE(count < kMaxEntries, SPL_ERR_ARG, "one chunk holds fewer than 2^32 - 65536 entries");
     if (count) {
         SPL_REQUIRE(row && col && val, SPL_ERR_ARG, "NULL array");
         Tmp<uint64_t> major(ctx, count), minor(ctx, count);
-        entry_range(ctx, m, (uint32_t)start, (uint32_t)count, major, minor);
+        if (m->wide()) wide_entry_range(ctx, m, start, (uint32_t)count, major, minor);
+        else entry_range(ctx, m, (uint32_t)start, (uint32_t)count, major, minor);
         SPL_CUDA(cudaMemcpyAsync(m->format == SPL_CSR ? row : col, major, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SPL_CUDA(cudaMemcpyAsync(m->format == SPL_CSR ? col : row, minor, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SPL_CUDA(cudaMemcpyAsync(val, static_cast<const unsigned char *>(m->val) + start * m->vsize(), count * m->vsize(),
@@ -698,6 +838,7 @@ int spl_peer_barrier_halo(spl_ctx *ctx, int world, int rank, void *const *flag_p
 int spl_spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window_dev, uint64_t window_start,
                     uint64_t window_len, void *y_dev) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_spmv_window");
     MatUse use_a(ctx, a);
     SPL_REQUIRE(a && x_window_dev && y_dev, SPL_ERR_ARG, "NULL argument");
     spmv_window(ctx, a, x_window_dev, window_start, window_len, y_dev);
@@ -706,6 +847,7 @@ int spl_spmv_window(spl_ctx *ctx, const spl_mat *a, const void *x_window_dev, ui
 
 int spl_spmv_footprint(spl_ctx *ctx, const spl_mat *a, uint64_t *col_min, uint64_t *col_max) {
     API_BEGIN(ctx)
+    require_narrow(a, "spl_spmv_footprint");
     MatUse use_a(ctx, a);
     SPL_REQUIRE(a, SPL_ERR_ARG, "NULL handle");
     a = csr_form(ctx, a);
@@ -737,6 +879,7 @@ int spl_peer_barrier_status(spl_ctx *ctx, int *timed_out) {
 int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
                   const uint64_t *col_starts, const void *const *x_slices, void *y_dev) {
     API_BEGIN(ctx)
+    require_narrow(a_local, "spl_spmv_peer");
     MatUse use_a_local(ctx, a_local);
     SPL_REQUIRE(a_local && col_starts && x_slices && y_dev, SPL_ERR_ARG, "NULL argument");
     SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,
@@ -784,6 +927,7 @@ int spl_spmv_peer_host(spl_ctx *ctx, const spl_mat *a_local, int world, int rank
                        void *const *x_slices, void *const *flag_ptrs, uint32_t epoch, uint32_t timeout_ms,
                        const void *x_host_local, void *y_host_local) {
     API_BEGIN(ctx)
+    require_narrow(a_local, "spl_spmv_peer_host");
     MatUse use_a_local(ctx, a_local);
     SPL_REQUIRE(a_local && col_starts && x_slices && flag_ptrs && y_host_local, SPL_ERR_ARG, "NULL argument");
     SPL_REQUIRE(world >= 1 && world <= SPL_MAX_PEERS && rank >= 0 && rank < world, SPL_ERR_ARG,

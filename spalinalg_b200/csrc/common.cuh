@@ -76,6 +76,13 @@ struct spl_mat {
     uint32_t *ptr = nullptr;   // nmajor + 1
     uint32_t *ind = nullptr;   // nnz
     void *val = nullptr;       // nnz * sizeof(T)
+    // "wide" matrices (2^32 - 65536 stored entries or more): 64-bit positions.  ptr64 replaces ptr (which
+    // stays NULL), nnz64 holds the count and nnz is pinned to 0xffffffff; only the kernels in wide.cu
+    // (validation, SpMV, transpose / convert, download, entry chunks) take them.
+    uint64_t *ptr64 = nullptr;
+    uint64_t nnz64 = 0;
+    bool wide() const { return ptr64 != nullptr; }
+    uint64_t entries() const { return ptr64 ? nnz64 : (uint64_t)nnz; }
     // SpMV plan (filled lazily by the first spl_spmv on this matrix; read-only afterwards).
     // A matrix may be shared read-only by several host threads / contexts (spl.h): the first
     // caller plans under plan_mu, everybody else sees plan_ready (acquire) and only reads.

@@ -114,6 +114,14 @@ void fill_ptr(spl_ctx *ctx, const uint32_t *sorted_major, uint32_t nnz, uint32_t
               uint32_t *ptr);
 
 spl_mat *new_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint32_t nnz);
+
+// wide.cu — matrices with 2^32 - 65536 stored entries or more (64-bit positions, spl_mat::ptr64)
+spl_mat *new_wide_mat(spl_ctx *ctx, int format, int dtype, uint32_t nrows, uint32_t ncols, uint64_t nnz);
+int wide_validate(spl_ctx *ctx, const spl_mat *m);      // 0, or the failing assertion of CsrMatrix::new (7, 8, 9)
+void wide_spmv(spl_ctx *ctx, const spl_mat *a, const void *x, void *y);
+spl_mat *wide_regroup(spl_ctx *ctx, const spl_mat *in, int out_format, uint32_t out_rows, uint32_t out_cols);
+void wide_entry_range(spl_ctx *ctx, const spl_mat *m, uint64_t start, uint32_t count, uint64_t *major_out,
+                      uint64_t *minor_out);
 void free_mat(spl_ctx *ctx, spl_mat *m);
 
 }  // namespace spl

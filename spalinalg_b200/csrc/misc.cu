@@ -226,6 +226,7 @@ void free_mat(spl_ctx *ctx, spl_mat *m) {
     m->ready = nullptr;
     free_mat(ctx, m->twin.exchange(nullptr));
     dfree(ctx, m->ptr);
+    dfree(ctx, m->ptr64);
     dfree(ctx, m->ind);
     dfree(ctx, m->val);
     dfree(ctx, m->merge_rows);

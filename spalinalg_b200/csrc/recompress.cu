@@ -75,12 +75,31 @@ minor_scatter_kernel(const uint32_t *__restrict__ ptr, const uint32_t *__restric
     const uint64_t m = gtid / LPR;
     if (m >= nmajor) return;
     const uint32_t e = __ldg(ptr + m + 1);
-    for (uint32_t p = __ldg(ptr + m) + (uint32_t)(gtid % LPR); p < e; p += LPR) {
-        const uint32_t c = __ldg(ind + p);
-        const VB v = __ldg(val + p);
-        const uint32_t slot = __ldg(out_ptr + c) + atomicSub(remaining + c, 1u) - 1u;
-        out_ind[slot] = (uint32_t)m;
-        out_val[slot] = v;
+    // four entries in flight per lane: the chain index -> output pointer -> atomic slot -> stores is three
+    // dependent round trips, and one entry at a time left the kernel latency-bound (config 2: 725 us)
+    constexpr int U = 4;
+    for (uint32_t p = __ldg(ptr + m) + (uint32_t)(gtid % LPR); p < e; p += U * LPR) {
+        uint32_t c[U], slot[U];
+        VB v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t q = p + u * LPR;
+            const bool ok = q < e;
+            c[u] = ok ? __ldg(ind + q) : 0xffffffffu;
+            if (ok) v[u] = __ldg(val + q);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] != 0xffffffffu) slot[u] = __ldg(out_ptr + c[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] != 0xffffffffu) slot[u] += atomicSub(remaining + c[u], 1u) - 1u;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (c[u] != 0xffffffffu) {
+                out_ind[slot[u]] = (uint32_t)m;
+                out_val[slot[u]] = v[u];
+            }
     }
 }
 

@@ -609,6 +609,33 @@ class _Compressed:
             C.c_void_p(ind_dev), C.c_void_p(val_dev), int(validate), C.byref(h)))
         return cls._wrap(ctx, h)
 
+    @classmethod
+    def from_device_arrays64(cls, nrows, ncols, nnz, ptr64_dev: int, ind_dev: int, val_dev: int, dtype,
+                             validate=True, ctx=None):
+        """CsrMatrix::new on device-resident arrays with a 64-bit pointer array (usize, src/csr.rs:66-72): the
+        constructor for matrices with 2^32 - 65536 stored entries or more (spl_mat_from_compressed_dev64)."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        ctx.check(ctx._lib.spl_mat_from_compressed_dev64(
+            ctx._h, cls._FORMAT, _dtype_code(dtype), nrows, ncols, nnz, C.c_void_p(ptr64_dev),
+            C.c_void_p(ind_dev), C.c_void_p(val_dev), int(validate), C.byref(h)))
+        return cls._wrap(ctx, h)
+
+    def device_ptr64(self):
+        """Device address of the 64-bit pointer array of a wide matrix (None for the usual 32-bit ones)."""
+        p = C.c_void_p()
+        self._ctx._lib.spl_mat_device_ptr64(self._h, C.byref(p))
+        return p.value
+
+    def read_entries(self, start: int, count: int):
+        """Stored entries [start, start + count) in storage order as (rows, cols, values) host arrays."""
+        r = np.empty(count, np.uint64)
+        c = np.empty(count, np.uint64)
+        v = np.empty(count, self._dtype)
+        self._ctx.check(self._ctx._lib.spl_mat_read_entries(self._ctx._h, self._h, int(start), int(count), _ptr(r), _ptr(c),
+                                                            _ptr(v)))
+        return r, c, v
+
     def _convert(self, target_cls):
         h = C.c_void_p()
         self._ctx.check(self._ctx._lib.spl_mat_convert(self._ctx._h, self._h, target_cls._FORMAT,

@@ -276,3 +276,98 @@ def test_c5_full_size_spmv_and_add():
     D = C - B                                                                # pattern of C, values of A (+0.0 on +-8)
     yd = spmv(D, x)
     assert bool(((yd - ya).abs() <= 1e-12 * 20).all())
+
+
+# ------------------------------------------------------------------ beyond 2^32 stored entries
+def test_wide_matrix_beyond_2_pow_32_entries():
+    """A CsrMatrix with more than 2^32 stored entries (the reference indexes with usize, src/csr.rs:66-72;
+    the device keeps a 64-bit pointer array for such matrices): CsrMatrix::new validation, SpMV against the
+    analytic band, transpose against the analytic transposed band, transpose twice = the matrix bit for bit,
+    entry chunks past position 2^32, and the strictly-increasing assertion on an entry beyond 2^32.
+    f32, 65 diagonals, n = 2^26: 4.36 G entries, 35 GB per copy."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150 * 2 ** 30:
+        pytest.skip(f"needs ~150 GB of free device memory, {free / 2 ** 30:.0f} GB available")
+    sd = gen()
+    n, half = 1 << 26, 32
+    offs = torch.arange(-half, half + 1, device="cuda", dtype=torch.int64)
+    nnz = sum(n - abs(d) for d in range(-half, half + 1))
+    assert nnz > 2 ** 32
+    ind = torch.empty(nnz, dtype=torch.int32, device="cuda")
+    val = torch.empty(nnz, dtype=torch.float32, device="cuda")
+    cnt = torch.empty(n, dtype=torch.int64, device="cuda")
+    pos, chunk = 0, 1 << 21
+
+    def band_values(i, d):                                   # A[i, i+d], f32
+        return (1.0 / (1.0 + d.abs().double()) + (i % 7).double() * 1e-3).float()
+
+    for s in range(0, n, chunk):
+        i = torch.arange(s, min(n, s + chunk), device="cuda", dtype=torch.int64)
+        cols = i[:, None] + offs[None, :]
+        mask = (cols >= 0) & (cols < n)
+        k = int(mask.sum().item())
+        ind[pos:pos + k] = cols[mask].to(torch.int32)
+        val[pos:pos + k] = band_values(i[:, None].expand_as(cols)[mask], offs[None, :].expand_as(cols)[mask])
+        cnt[s:s + i.numel()] = mask.sum(1)
+        pos += k
+        del cols, mask, i
+    assert pos == nnz
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    ptr[1:] = torch.cumsum(cnt, 0)
+    del cnt
+    torch.cuda.synchronize()
+    A = sp.CsrMatrix.from_device_arrays64(n, n, nnz, ptr.data_ptr(), ind.data_ptr(), val.data_ptr(), np.float32, validate=True)
+    assert A.nnz() == nnz and A.spmv_choice()[0] == capi.SPL_SPMV_VECTOR
+    # the strictly-increasing assertion (src/csr.rs:152-156) on an entry beyond position 2^32
+    last = int(ptr[n - 5].item())
+    assert last > 2 ** 32
+    ind[last], ind[last + 1] = ind[last + 1].clone(), ind[last].clone()
+    torch.cuda.synchronize()
+    with pytest.raises(sp.Panic):
+        sp.CsrMatrix.from_device_arrays64(n, n, nnz, ptr.data_ptr(), ind.data_ptr(), val.data_ptr(), np.float32, validate=True)
+    assert sp.default_context().invalid_reason() == 9
+    ind[last], ind[last + 1] = ind[last + 1].clone(), ind[last].clone()
+    # entry chunks behind position 2^32: storage order, rows found from the 64-bit pointers
+    r, c, v = A.read_entries(nnz - 70, 70)
+    assert np.array_equal(c, ind[nnz - 70:].cpu().numpy().astype(np.uint64)) and v.tobytes() == val[nnz - 70:].cpu().numpy().tobytes()
+    assert r[-1] == n - 1 and r[0] == n - 3 and np.all(np.diff(r.astype(np.int64)) >= 0)
+    del ind, val
+    torch.cuda.empty_cache()
+
+    def check_product(M, transposed):
+        x = torch.sin(torch.arange(n, device="cuda", dtype=torch.float64) * 1e-3).float()
+        y = spmv(M, x)
+        for lo in (0, n // 2 - 3, n - 200_000):               # first rows, the middle, rows whose entries lie beyond 2^32
+            i = torch.arange(lo, min(n, lo + 200_000), device="cuda", dtype=torch.int64)
+            want = torch.zeros(i.numel(), device="cuda", dtype=torch.float64)
+            scale = torch.zeros_like(want)
+            for d in range(-half, half + 1):
+                j = i + d
+                ok = (j >= 0) & (j < n)
+                jj = j.clamp(0, n - 1)
+                dd = torch.full_like(i, d)
+                a = band_values(jj, -dd) if transposed else band_values(i, dd)      # A^T[i, j] = A[j, i] = band(j, i - j)
+                term = torch.where(ok, a.double() * x[jj].double(), torch.zeros_like(want))
+                want += term
+                scale += term.abs()
+            assert bool(((y[i].double() - want).abs() <= 1e-5 * scale + 1e-30).all()), (transposed, lo)
+
+    check_product(A, False)
+    T = A.transpose()                                          # histogram + 64-bit scan + scatter + repair (wide.cu)
+    assert T.nnz() == nnz
+    check_product(T, True)
+    TT = T.transpose()
+    del T
+    torch.cuda.empty_cache()
+    p64 = sd.device_view(torch, TT.device_ptr64(), n + 1, torch.int64)
+    assert torch.equal(p64, ptr)
+    _, ti, tv = TT.device_ptrs()
+    _, ai, av = A.device_ptrs()
+    step = 1 << 28                                             # compare in slices: no 35 GB temporaries
+    for s in range(0, nnz, step):
+        k = min(step, nnz - s)
+        assert torch.equal(sd.device_view(torch, ti + 4 * s, k, torch.int32), sd.device_view(torch, ai + 4 * s, k, torch.int32))
+        assert torch.equal(sd.device_view(torch, tv + 4 * s, k, torch.int32), sd.device_view(torch, av + 4 * s, k, torch.int32))
+    # the 32-bit paths refuse a wide operand instead of truncating its positions
+    with pytest.raises(sp.DeviceError):
+        A + TT
