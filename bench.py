@@ -754,6 +754,16 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     xs.check()
     err = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
     assert err < 1e-5, f"fused gather SpMV differs from the all-gather product: {err}"
+    # copy CTAs: how many of the resident CTAs pull slices (the rest multiply); measured per run, the library's
+    # default stands in the headline number above
+    sweep = {}
+    for nc in (32, 96, 128, 192):
+        os.environ["SPL_GATHER_COPY_CTAS"] = str(nc)
+        try:
+            sweep[str(nc)] = timed_all(spmv_fused, reps=5, warm=2)
+        except Exception as e:                                           # noqa: BLE001
+            sweep[str(nc)] = str(e)[:60]
+    os.environ.pop("SPL_GATHER_COPY_CTAS", None)
     # where the time of one fused product goes: %globaltimer stamps from the kernel (first compute CTA)
     tl = torch.zeros(1 + 3 * world, dtype=torch.int64, device="cuda")
     dist.barrier(); torch.cuda.synchronize()
@@ -767,7 +777,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
                                                     "slices of x over NVLink, and compute CTAs multiplying the shard block by "
                                                     "block (blocked by column owner, ring order) as the slices land",
                                         "ms": ms_fused, "gbps_algorithmic": b_ag / ms_fused / 1e6,
-                                        "max_rel_diff_vs_allgather": err,
+                                        "max_rel_diff_vs_allgather": err, "ms_by_copy_ctas": sweep,
                                         "timeline_rank0_first_compute_cta": stamps}
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
