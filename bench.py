@@ -627,16 +627,21 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     from tests.test_dist import syn_block
     out = {}
 
-    def timed_all(fn, reps=3, warm=1):
+    def timed_all(fn, reps=3, warm=1, batch=1):
+        """ms per call, max over ranks, median of `reps`.  batch > 1: that many calls back to back between the events
+        (a product of ~0.1 ms timed alone would mostly measure how far apart the ranks' hosts left the barrier)."""
         for _ in range(warm):
             fn()
         ts = []
         for _ in range(reps):
             dist.barrier(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
+            a.record()
+            for _ in range(batch):
+                fn()
+            b.record()
             torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            t = torch.tensor([a.elapsed_time(b) / batch], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ts.append(float(t.item()))
         return statistics.median(ts)
@@ -729,7 +734,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     def spmv_ag():
         sharding.exchange_allgather(dist, xg, d0, d1, world, even)
         D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
-    ms = timed_all(spmv_ag, reps=7, warm=3)
+    ms = timed_all(spmv_ag, reps=7, warm=3, batch=10)
     b_ag = nnz_d * 8 + 2 * nr * 4
     xs = spd.PeerVector(ctx, dist, nr, np.float32, D.starts)
     device_view(torch, xs.local_ptr, d1 - d0, torch.float32).copy_(xg[d0:d1])
@@ -741,44 +746,69 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         xs.pull(xg.data_ptr())
         D.local.spmv_device(xg.data_ptr(), yg.data_ptr())
     y_ag = yg.clone()
-    ms_pull = timed_all(spmv_pull, reps=7, warm=3)
+    ms_pull = timed_all(spmv_pull, reps=7, warm=3, batch=10)
     xs.check()
     assert torch.equal(y_ag, yg), "pulled all-gather gives a different y"
-    # the all-gather fused into the product: one persistent kernel, copy CTAs pull the slices over NVLink while the
-    # compute CTAs work through the owner blocks
+    # the all-gather fused into the product: one persistent kernel, a copy warp per CTA pulls the slices over NVLink
+    # (TMA bulk copies) while the compute warps work through the owner blocks
     D.prepare_gather(torch)
 
     def spmv_fused():
         D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True)      # the barrier is part of the kernel
-    ms_fused = timed_all(spmv_fused, reps=7, warm=3)
+    ms_fused = timed_all(spmv_fused, reps=7, warm=3, batch=10)
     xs.check()
     err = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
     assert err < 1e-5, f"fused gather SpMV differs from the all-gather product: {err}"
-    # copy CTAs: how many of the resident CTAs pull slices (the rest multiply); measured per run, the library's
-    # default stands in the headline number above
-    sweep = {}
-    for nc in (32, 96, 128, 192):
-        os.environ["SPL_GATHER_COPY_CTAS"] = str(nc)
-        try:
-            sweep[str(nc)] = timed_all(spmv_fused, reps=5, warm=2)
-        except Exception as e:                                           # noqa: BLE001
-            sweep[str(nc)] = str(e)[:60]
-    os.environ.pop("SPL_GATHER_COPY_CTAS", None)
-    # where the time of one fused product goes: %globaltimer stamps from the kernel (first compute CTA)
-    tl = torch.zeros(1 + 3 * world, dtype=torch.int64, device="cuda")
+    # where the time of one fused product goes: %globaltimer stamps from the kernel (first CTA)
+    first = D._gather["first"]
+    nb = len(first) - 1
+    tl = torch.zeros(2 + 3 * nb, dtype=torch.int64, device="cuda")
     dist.barrier(); torch.cuda.synchronize()
     D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())
     torch.cuda.synchronize()
     t = tl.cpu().tolist()
     t0 = min(v for v in t if v > 0)
-    stamps = [{"block": k, "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3, "slice_landed_us": (t[2 + 3 * k] - t0) / 1e3,
-               "block_done_us": (t[3 + 3 * k] - t0) / 1e3} for k in range(world)]
-    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: the device barrier, copy warps pulling the peers' "
-                                                    "slices of x over NVLink, and compute CTAs multiplying the shard block by "
-                                                    "block (blocked by column owner, ring order) as the slices land",
+    stamps = [{"block": k, "ring_offsets": [first[k], first[k + 1]], "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3,
+               "slices_landed_us": (t[2 + 3 * k] - t0) / 1e3, "block_done_us": (t[3 + 3 * k] - t0) / 1e3}
+              for k in range(nb)]
+    stamps.append({"last_cta_done_us": (t[1 + 3 * nb] - t0) / 1e3})
+    # how the shard is blocked (one pass over the rows per block) and how many CTAs stay resident: measured per run,
+    # the library's defaults stand in the headline number above
+    sweep = {}
+    shapes = {"per_rank": list(range(world + 1)), "own|rest": [0, 1, world]}
+    if world >= 8:
+        shapes["1|1|2|4"] = [0, 1, 2, 4, 8]
+        shapes["1|1|1|1|2|2"] = [0, 1, 2, 3, 4, 6, 8]
+    for name, bf in shapes.items():
+        if bf == first or len(set(bf)) != len(bf):
+            continue
+        D.prepare_gather(torch, block_first=bf)
+        try:
+            sweep["blocks " + name] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
+            e2 = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+            assert e2 < 1e-5, f"fused gather SpMV, blocks {name}: differs from the all-gather product: {e2}"
+        except RuntimeError as e:
+            sweep["blocks " + name] = str(e)[:60]
+    for knob, value in (("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_TILE_ROWS", "512"), ("SPL_GATHER_TILE_ROWS", "256"),
+                        ("SPL_GATHER_STAGES", "2")):
+        os.environ[knob] = value
+        D.prepare_gather(torch)                                          # fresh counters: the grid size may change
+        label = f"{knob[11:].lower()} {value}"
+        try:
+            sweep[label] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
+            e2 = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+            assert e2 < 1e-5, f"fused gather SpMV, {label}: differs from the all-gather product: {e2}"
+        except RuntimeError as e:
+            sweep[label] = str(e)[:60]
+        os.environ.pop(knob, None)
+    xs.check()
+    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: the device barrier, one copy warp per CTA pulling "
+                                                    "the peers' slices of x over NVLink with TMA bulk copies, and the compute "
+                                                    "warps multiplying the shard block by block (blocked by column owner, ring "
+                                                    "order) as the slices land",
                                         "ms": ms_fused, "gbps_algorithmic": b_ag / ms_fused / 1e6,
-                                        "max_rel_diff_vs_allgather": err, "ms_by_copy_ctas": sweep,
-                                        "timeline_rank0_first_compute_cta": stamps}
+                                        "max_rel_diff_vs_allgather": err, "block_first": first, "ms_variants": sweep,
+                                        "timeline_rank0_first_cta": stamps}
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
@@ -816,7 +846,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
             xs4.barrier()
             xs4.pull(x4.data_ptr())
             R.local.spmv_device(x4.data_ptr(), y4.data_ptr())
-        ms_s = timed_all(spmv4, reps=7, warm=3)
+        ms_s = timed_all(spmv4, reps=7, warm=3, batch=10)
         xs4.check()
         b4 = nnz_sum * 8 + 2 * n4 * 4
         res4["nnz_balanced" if balance else "equal_rows"] = {

@@ -329,24 +329,35 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
 
 /* Row-sharded y_local = A_local * x for GENERAL shards (random / unstructured columns; the sharded
  * form of `&A * &X`, src/csr/ops/mul.rs:5-60), the all-gather of x fused into the product: ONE
- * persistent kernel whose copy CTAs pull the peers' slices of x over NVLink (x_slices as in
- * spl_spmv_peer) into x_full_dev, slice by slice in ring order (rank+1, rank+2, ...), while its
- * compute CTAs multiply the shard block by block in the same order — block 0 (columns of the own
- * slice) at once, block k as soon as slice k has landed — and write y once.  The shard is passed
- * blocked by column owner in that ring order: block_ptr_dev holds world row-pointer arrays of
- * nrows_local+1 entries each (absolute positions into block_ind_dev / block_val_dev, global column
- * indices).  ready_dev: uint32[SPL_MAX_PEERS], zeroed once by the caller; epoch = 1, 2, 3, ... per
- * call on this buffer; nnz_local = stored entries of the shard (picks the lanes per row).  The
- * barrier that orders the peers' writes of x before the pulls is part of the kernel when flag_ptrs
- * is given (flag blocks / barrier_epoch / timeout_ms exactly as spl_peer_barrier takes them: the
- * kernel announces this rank's slice, and each slice is pulled as soon as ITS owner has arrived);
- * with flag_ptrs NULL run spl_peer_barrier first.  x_full_dev (ncols values) is scratch: afterwards
- * it holds the peers' slices (not the own one).  timeline_dev: NULL, or 1 + 3*world uint64 that
- * receive %globaltimer stamps (kernel start; per block: wait begins, slice landed, block done on the
- * first compute CTA) — the evidence behind profiles/r2_gather_timeline.txt. */
+ * persistent kernel in which one copy warp per CTA pulls the peers' slices of x over NVLink
+ * (x_slices as in spl_spmv_peer) into x_full_dev with TMA bulk copies, in ring order (rank+1,
+ * rank+2, ...), while the compute warps multiply the shard block by block in the same order —
+ * block 0 (columns of the own slice) at once, block b as soon as its slices have landed — and
+ * write y once.  The shard is passed blocked by column owner in that ring order: block b holds the
+ * columns owned by the ring offsets [block_first[b], block_first[b+1]) (host array of nblocks+1
+ * values, 0, 1, ..., world: block 0 is the own slice alone; NULL = one block per rank, nblocks
+ * ignored); block_ptr_dev holds one row-pointer array of nrows_local+1 entries per block, block b's
+ * at block_ptr_dev + b * block_ptr_stride (a multiple of 4 above nrows_local; absolute positions
+ * into block_ind_dev / block_val_dev, global column indices).  The matrix reaches the compute warps
+ * as TMA bulk copies of whole tiles (128 to 1024 consecutive rows of one block, more rows the
+ * shorter they are), so the three arrays are 16-byte aligned, block_ind_dev / block_val_dev are
+ * allocated 4 entries beyond the last stored one, and tile_entries_max[0..4] (host) bound the
+ * entries any 64 / 128 / 256 / 512 / 1024 consecutive rows starting at a multiple of 32 hold in one
+ * block (a tile must fit a shared-memory stage: SPL_ERR_UNSUPPORTED otherwise).  ready_dev:
+ * uint32[SPL_MAX_PEERS], zeroed by the caller before epoch 1; epoch = 1, 2, 3, ... per call on this
+ * buffer; nnz_local = stored entries of the shard (picks the lanes per row).  The barrier that
+ * orders the peers' writes of x before the pulls is part of the kernel when flag_ptrs is given
+ * (flag blocks / barrier_epoch / timeout_ms exactly as spl_peer_barrier takes them); with
+ * flag_ptrs NULL run spl_peer_barrier first.  x_full_dev (ncols values) is scratch: afterwards it
+ * holds the peers' slices (not the own one).  timeline_dev: NULL, or 2 + 3*nblocks zeroed uint64
+ * that receive %globaltimer stamps (first copy warp past the barrier; per block: wait begins, slices
+ * landed, block done on the first warp of the first CTA; the last CTA to finish) — the evidence in
+ * bench.py's `sharded_spmv_gather_fused`.  The launch shape follows from the shard and the device: it is the
+ * same from epoch to epoch on one ready_dev (zero it and restart at epoch 1 if anything changes). */
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
-                          const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
-                          const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
+                          const uint64_t *col_starts, const void *const *x_slices, int nblocks,
+                          const uint32_t *block_first, const uint32_t *block_ptr_dev, uint64_t block_ptr_stride,
+                          const uint32_t *tile_entries_max, const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
                           uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local, void *const *flag_ptrs,
                           uint32_t barrier_epoch, uint32_t timeout_ms, uint64_t *timeline_dev);
 

@@ -105,7 +105,8 @@ extern "C" {
         window_len: u64, y_dev: *mut c_void) -> c_int;
     pub fn spl_spmv_footprint(ctx: *mut spl_ctx, a: *const spl_mat, col_min: *mut u64, col_max: *mut u64) -> c_int;
     pub fn spl_spmv_gather_fused(ctx: *mut spl_ctx, dtype: c_int, nrows_local: u64, world: c_int, rank: c_int,
-        col_starts: *const u64, x_slices: *const *const c_void, block_ptr: *const u32, block_ind: *const u32,
+        col_starts: *const u64, x_slices: *const *const c_void, nblocks: c_int, block_first: *const u32,
+        block_ptr: *const u32, block_ptr_stride: u64, tile_entries_max: *const u32, block_ind: *const u32,
         block_val: *const c_void, x_full_dev: *mut c_void, y_dev: *mut c_void, ready_dev: *mut u32, epoch: u32,
         nnz_local: u64, flag_ptrs: *const *mut c_void, barrier_epoch: u32, timeout_ms: u32,
         timeline_dev: *mut u64) -> c_int;

@@ -70,7 +70,7 @@ SIGNATURES = {
     "spl_peer_pull": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "spl_peer_barrier_status": (_i, [_vp, C.POINTER(_i)]),
     "spl_spmv_peer": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "spl_spmv_gather_fused": (_i, [_vp, _i, _u64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _u64, _vp,
+    "spl_spmv_gather_fused": (_i, [_vp, _i, _u64, _i, _i, _vp, _vp, _i, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, _u64, _vp,
                               C.c_uint32, C.c_uint32, _vp]),
     "spl_spmv_peer_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "spl_coo_create": (_i, [_vp, _i, _u64, _u64, _u64, _pp]),

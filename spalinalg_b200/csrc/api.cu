@@ -900,8 +900,9 @@ int spl_spmv_peer(spl_ctx *ctx, const spl_mat *a_local, int world, int rank,
 }
 
 int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int world, int rank,
-                          const uint64_t *col_starts, const void *const *x_slices, const uint32_t *block_ptr_dev,
-                          const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
+                          const uint64_t *col_starts, const void *const *x_slices, int nblocks,
+                          const uint32_t *block_first, const uint32_t *block_ptr_dev, uint64_t block_ptr_stride,
+                          const uint32_t *tile_entries_max, const uint32_t *block_ind_dev, const void *block_val_dev, void *x_full_dev, void *y_dev,
                           uint32_t *ready_dev, uint32_t epoch, uint64_t nnz_local, void *const *flag_ptrs,
                           uint32_t barrier_epoch, uint32_t timeout_ms, uint64_t *timeline_dev) {
     API_BEGIN(ctx)
@@ -912,13 +913,18 @@ int spl_spmv_gather_fused(spl_ctx *ctx, int dtype, uint64_t nrows_local, int wor
     SPL_REQUIRE(nrows_local > 0 && nrows_local < (1ull << 32) && col_starts[world] < (1ull << 32), SPL_ERR_UNSUPPORTED,
                 "dimensions must be below 2^32");
     SPL_REQUIRE(epoch > 0, SPL_ERR_ARG, "epoch counts from 1 and grows by one per call");
+    SPL_REQUIRE(tile_entries_max, SPL_ERR_ARG, "NULL tile_entries_max");
+    SPL_REQUIRE(block_ptr_stride % 4 == 0 && block_ptr_stride > nrows_local && block_ptr_stride < (1ull << 32), SPL_ERR_ARG,
+                "block_ptr_stride must be a multiple of 4 above nrows_local");
+    SPL_REQUIRE(((uintptr_t)block_ptr_dev | (uintptr_t)block_ind_dev | (uintptr_t)block_val_dev) % 16 == 0, SPL_ERR_ARG,
+                "the block arrays must be 16-byte aligned");
     for (int g = 0; g < world; ++g) {
         SPL_REQUIRE(col_starts[g] <= col_starts[g + 1], SPL_ERR_ARG, "col_starts must be non-decreasing");
         SPL_REQUIRE(x_slices[g] || col_starts[g] == col_starts[g + 1], SPL_ERR_ARG, "NULL x slice");
     }
-    spmv_gather_fused(ctx, dtype, (uint32_t)nrows_local, world, rank, col_starts, x_slices, block_ptr_dev, block_ind_dev,
-                      block_val_dev, x_full_dev, y_dev, ready_dev, epoch,
-                      (double)nnz_local / (double)nrows_local / (double)world, flag_ptrs, barrier_epoch, timeout_ms,
+    spmv_gather_fused(ctx, dtype, (uint32_t)nrows_local, world, rank, col_starts, x_slices, nblocks, block_first,
+                      block_ptr_dev, (uint32_t)block_ptr_stride, tile_entries_max, block_ind_dev, block_val_dev, x_full_dev, y_dev, ready_dev, epoch,
+                      (double)nnz_local / (double)nrows_local, flag_ptrs, barrier_epoch, timeout_ms,
                       reinterpret_cast<unsigned long long *>(timeline_dev));
     API_END(ctx)
 }

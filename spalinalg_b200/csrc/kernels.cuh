@@ -73,9 +73,10 @@ void spmv_peer_host(spl_ctx *ctx, const spl_mat *a, const PeerX &px, void *const
 
 // gather.cu — general shards: the all-gather of x fused into the product (one persistent kernel)
 void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int rank, const uint64_t *col_starts,
-                       const void *const *x_slices, const uint32_t *bptr, const uint32_t *bind, const void *bval,
-                       void *x_full, void *y, uint32_t *ready, uint32_t epoch, double entries_per_row_block,
-                       void *const *flag_ptrs, uint32_t barrier_epoch, uint32_t timeout_ms, unsigned long long *timeline);
+                       const void *const *x_slices, int nblocks, const uint32_t *block_first, const uint32_t *bptr,
+                       uint32_t pstride, const uint32_t *tile_caps, const uint32_t *bind, const void *bval, void *x_full,
+                       void *y, uint32_t *ready, uint32_t epoch, double entries_per_row, void *const *flag_ptrs,
+                       uint32_t barrier_epoch, uint32_t timeout_ms, unsigned long long *timeline);
 
 // peer.cu — CUDA IPC buffers and the flag barrier over peer memory
 void peer_barrier(spl_ctx *ctx, int world, int rank, void *const *flag_ptrs, uint32_t epoch,

@@ -8,6 +8,9 @@
 // a peer's next kernel reads them.  peer_barrier_kernel does that on the device: release-store of
 // the epoch into every peer's flag block, acquire-spin on the own block, bounded by a timeout so
 // a missing peer can never hang the GPU.
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace spl {
@@ -98,35 +101,116 @@ peer_barrier_halo_kernel(FlagBlocks f, int world, int rank, uint32_t epoch, uint
 }
 
 // All-gather of x by pulling: every rank copies its peers' slices (peer memory, NVLink reads) into
-// its own full-length vector with 128-bit coalesced loads.  One launch moves all slices; the grid
-// is split among the source ranks in proportion to their slice lengths.
+// its own full-length vector.  One launch moves all slices.  The bulk of every slice travels as TMA
+// bulk copies driven by ONE thread per CTA — peer memory -> shared-memory ring -> local vector
+// (cp.async.bulk + mbarrier; bulk groups for the stores): an NVLink read takes ~3 us, so the link
+// only fills with megabytes in flight, which a ring of 16 KB chunks holds without a register
+// (profiles/r2_nvlink_copy.txt: 32 such threads reach the copy engines' rate; 128-bit loads need
+// every SM for less).  Slices whose ends are not 16-byte aligned, and tails, go element by element.
 struct PullSlices {
     const unsigned char *src[SPL_MAX_PEERS];
     unsigned long long dst_off[SPL_MAX_PEERS];     // byte offset of slice g in the full vector
     unsigned long long bytes[SPL_MAX_PEERS];
     int world, rank;
+    unsigned int vsize;
 };
 
-__global__ void __launch_bounds__(256) peer_pull_kernel(PullSlices ps, unsigned char *__restrict__ dst) {
-    // blockIdx.y = source rank; blocks of a row stride over that slice
-    const int g = blockIdx.y;
-    if (g >= ps.world || g == ps.rank) return;
-    const unsigned char *src = ps.src[g];
-    unsigned char *out = dst + ps.dst_off[g];
-    const unsigned long long n = ps.bytes[g];
-    const unsigned long long n16 = (((unsigned long long)(uintptr_t)src | (unsigned long long)(uintptr_t)out) & 15ull) ? 0ull : n / 16;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-    uint4 *d4 = reinterpret_cast<uint4 *>(out);
-    for (; i + 3 * stride < n16; i += 4 * stride) {          // four 16-byte loads in flight per thread
-        const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + stride), c = __ldcg(s4 + i + 2 * stride),
-                    d = __ldcg(s4 + i + 3 * stride);
-        d4[i] = a; d4[i + stride] = b; d4[i + 2 * stride] = c; d4[i + 3 * stride] = d;
+constexpr uint32_t PULL_CHUNK = 16384;
+constexpr int PULL_STAGES = 6, PULL_AHEAD = 4;     // loads run 4 chunks in front of the stores (STAGES >= AHEAD + 2)
+constexpr int PULL_THREADS = 128;
+
+__device__ __forceinline__ uint32_t peer_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(PullSlices ps, unsigned char *__restrict__ dst) {
+    extern __shared__ __align__(128) unsigned char pull_ring[];
+    __shared__ __align__(8) uint64_t full[PULL_STAGES];
+    // bulk part of slice k (peers in ring order): whole 16-byte units when both ends are aligned
+    unsigned long long b16[SPL_MAX_PEERS], per[SPL_MAX_PEERS];
+    const unsigned char *src[SPL_MAX_PEERS];
+    unsigned char *out[SPL_MAX_PEERS];
+    int np = 0;
+    unsigned long long most = 0;
+    for (int k = 1; k < ps.world; ++k) {
+        const int g = (ps.rank + k) % ps.world;
+        src[np] = ps.src[g];
+        out[np] = dst + ps.dst_off[g];
+        const bool wide = ((((unsigned long long)(uintptr_t)src[np]) | ((unsigned long long)(uintptr_t)out[np])) & 15ull) == 0;
+        b16[np] = wide ? ps.bytes[g] & ~15ull : 0ull;
+        per[np] = (b16[np] + PULL_CHUNK - 1) / PULL_CHUNK;
+        most = per[np] > most ? per[np] : most;
+        // what the bulk copies leave: this CTA's share, value by value (all threads but the first), four in flight
+        const unsigned long long e0 = b16[np] / ps.vsize, n = ps.bytes[g] / ps.vsize, rest = n - e0;
+        if (rest && threadIdx.x > 0) {
+            const unsigned long long share = (rest + gridDim.x - 1) / gridDim.x, lo = e0 + blockIdx.x * share,
+                                     hi = lo + share < n ? lo + share : n;
+            constexpr unsigned long long W = PULL_THREADS - 1;
+            auto copy = [&](auto tag) {
+                using V = decltype(tag);
+                const V *se = reinterpret_cast<const V *>(src[np]);
+                V *de = reinterpret_cast<V *>(out[np]);
+                unsigned long long e = lo + threadIdx.x - 1;
+                for (; e + 3 * W < hi; e += 4 * W) {
+                    const V a = __ldcg(se + e), b = __ldcg(se + e + W), c = __ldcg(se + e + 2 * W), d = __ldcg(se + e + 3 * W);
+                    de[e] = a; de[e + W] = b; de[e + 2 * W] = c; de[e + 3 * W] = d;
+                }
+                for (; e < hi; e += W) de[e] = __ldcg(se + e);
+            };
+            if (ps.vsize == 8) copy((unsigned long long)0);
+            else copy((unsigned int)0);
+        }
+        ++np;
     }
-    for (; i < n16; i += stride) d4[i] = __ldcg(s4 + i);
-    for (unsigned long long b = n16 * 16 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
-        out[b] = src[b];
+    if (threadIdx.x != 0 || np == 0) return;
+    for (int s = 0; s < PULL_STAGES; ++s)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(peer_smem(full + s)), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // chunk id c = j * np + k: chunk j of peer k, so all peers (all links) move at once; ids past a short slice are skipped
+    const unsigned long long total = most * np;
+    auto locate = [&](unsigned long long c, int &k, unsigned long long &off, uint32_t &len) {
+        k = (int)(c % np);
+        const unsigned long long j = c / np;
+        off = j * PULL_CHUNK;
+        len = j < per[k] ? (uint32_t)(b16[k] - off < PULL_CHUNK ? b16[k] - off : PULL_CHUNK) : 0u;
+    };
+    unsigned long long issued = 0, stored = 0;       // chunks of this CTA that were loaded / stored (skipping empty ids)
+    unsigned long long cl = blockIdx.x, cs = blockIdx.x;
+    for (;;) {
+        // next non-empty chunk to load
+        int k; unsigned long long off; uint32_t len = 0;
+        while (cl < total) { locate(cl, k, off, len); if (len) break; cl += gridDim.x; }
+        const bool more = cl < total;
+        if (more) {
+            const int s = (int)(issued % PULL_STAGES);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(peer_smem(full + s)), "r"(len) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             peer_smem(pull_ring + (size_t)s * PULL_CHUNK)),
+                         "l"(src[k] + off), "r"(len), "r"(peer_smem(full + s))
+                         : "memory");
+            ++issued;
+            cl += gridDim.x;
+        }
+        if (issued - stored > (unsigned long long)PULL_AHEAD || (!more && stored < issued)) {
+            int k2; unsigned long long off2; uint32_t len2 = 0;
+            for (;; cs += gridDim.x) { locate(cs, k2, off2, len2); if (len2) break; }
+            const int s = (int)(stored % PULL_STAGES);
+            const uint32_t parity = (uint32_t)((stored / PULL_STAGES) & 1);
+            asm volatile(
+                "{\n.reg .pred q;\nPLW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n@q bra PLD_%=;\nbra PLW_%=;\nPLD_%=:\n}\n" ::"r"(
+                    peer_smem(full + s)),
+                "r"(parity)
+                : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out[k2] + off2),
+                         "r"(peer_smem(pull_ring + (size_t)s * PULL_CHUNK)), "r"(len2)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every store but the newest has left its slot
+            ++stored;
+            cs += gridDim.x;
+        } else if (!more) {
+            break;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
@@ -146,8 +230,12 @@ void peer_pull(spl_ctx *ctx, int world, int rank, size_t vsize, const uint64_t *
         ps.dst_off[g] = starts[g] * vsize;
         ps.bytes[g] = (starts[g + 1] - starts[g]) * vsize;
     }
-    dim3 grid((unsigned)ctx->num_sms * 2u, (unsigned)world);
-    peer_pull_kernel<<<grid, 256, 0, ctx->stream>>>(ps, static_cast<unsigned char *>(x_full));
+    ps.vsize = (unsigned int)vsize;
+    const size_t smem = (size_t)PULL_CHUNK * PULL_STAGES;
+    SPL_CUDA(cudaFuncSetAttribute(peer_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *pc = std::getenv("SPL_PULL_CTAS");                   // measurement knob
+    const unsigned ctas = pc ? (unsigned)std::max(1, std::atoi(pc)) : 64u;
+    peer_pull_kernel<<<ctas, PULL_THREADS, smem, ctx->stream>>>(ps, static_cast<unsigned char *>(x_full));
     check_launch(ctx, "peer_pull");
 }
 

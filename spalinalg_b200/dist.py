@@ -24,6 +24,7 @@ logic with a numpy stand-in for the two device calls.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -322,9 +323,27 @@ class DistCsrMatrix:
         ctx.check(ctx._lib.spl_spmv_window(ctx._h, self.local._h, C.c_void_p(x.published_ptr - (r0 - w0) * item),
                                            w0, w1 - w0, C.c_void_p(y_dev)))
 
-    def prepare_gather(self, torch):
+    @staticmethod
+    def gather_groups(world: int):
+        """Default blocking of a shard for spmv_gather: ring offsets where blocks begin.  One block per rank (own
+        columns, then rank+1, rank+2, ...): the finest overlap of transfer and product; the kernel keeps eight gathers
+        in flight per lane however short a row's share of a block is.  SPL_GATHER_GROUPS=1,1,2,4 (widths) groups
+        consecutive peers into wider blocks (fewer passes over the rows, coarser overlap)."""
+        env = os.environ.get("SPL_GATHER_GROUPS")
+        widths = [1] * world
+        if env:
+            widths = [int(t) for t in env.split(",")]
+            if widths[0] != 1 or sum(widths) != world or min(widths) < 1:
+                raise ValueError("SPL_GATHER_GROUPS must be widths 1,... that sum to the world size")
+        first = [0]
+        for w in widths:
+            first.append(first[-1] + w)
+        return first
+
+    def prepare_gather(self, torch, block_first=None):
         """One-time layout for spmv_gather: the shard's entries blocked by the rank that owns their column,
-        own block first, then the peers in ring order (rank+1, rank+2, ...), row order kept inside a
+        own block first, then the peers in ring order (rank+1, rank+2, ...) one by one or grouped
+        (block_first: ring offsets where blocks begin, default gather_groups), row order kept inside a
         block; one row-pointer array per block.  Device-side plumbing (a stable sort by block id and
         one row histogram per block); the arrays stay with the matrix."""
         from .synthetic_device import device_view
@@ -332,6 +351,10 @@ class DistCsrMatrix:
         ctx.sync()
         r0, r1 = self.local_rows()
         nloc, nnz, G = r1 - r0, self.local.nnz(), self.world
+        first = list(block_first) if block_first is not None else self.gather_groups(G)
+        if first[0] != 0 or first[-1] != G or (G > 1 and first[1] != 1) or any(a >= b for a, b in zip(first, first[1:])):
+            raise ValueError("block_first must increase from 0 through 1 to the world size")
+        nb = len(first) - 1
         tdt = torch.float32 if self.local.dtype == np.float32 else torch.float64
         p_ptr, p_ind, p_val = self.local.device_ptrs()
         ptr = device_view(torch, p_ptr, nloc + 1, torch.int32).long()
@@ -340,17 +363,28 @@ class DistCsrMatrix:
         rows = torch.repeat_interleave(torch.arange(nloc, device=col.device), ptr[1:] - ptr[:-1])
         bounds = torch.tensor(self.starts[1:-1], device=col.device, dtype=torch.int64)
         owner = torch.searchsorted(bounds, col.long() & 0xFFFFFFFF, right=True)
-        block = ((owner - self.rank) % G).to(torch.int16)
+        offset = (owner - self.rank) % G
+        block_of = torch.searchsorted(torch.tensor(first[1:], device=col.device, dtype=torch.int64), offset, right=True)
+        block = block_of.to(torch.int16)
         order = torch.sort(block, stable=True).indices
         bind = col[order].contiguous()
         bval = val[order].contiguous()
         key = block[order].long() * nloc + rows[order]
-        counts = torch.bincount(key, minlength=G * nloc).view(G, nloc)
+        counts = torch.bincount(key, minlength=nb * nloc).view(nb, nloc)
         base = torch.cumsum(counts.sum(1), 0) - counts.sum(1)                 # first position of every block
-        bptr = torch.zeros((G, nloc + 1), dtype=torch.int64, device=col.device)
-        bptr[:, 1:] = torch.cumsum(counts, 1)
+        # the kernel fetches whole tiles with 16-byte bulk copies: pointer arrays padded to a multiple of 4 entries (the
+        # padding repeats the end position), four entries of slack behind the indices and values
+        stride = (nloc + 1 + 3) // 4 * 4 + 4
+        bptr = torch.zeros((nb, stride), dtype=torch.int64, device=col.device)
+        bptr[:, 1:nloc + 1] = torch.cumsum(counts, 1)
+        bptr[:, nloc + 1:] = bptr[:, nloc:nloc + 1]
         bptr += base[:, None]
-        self._gather = {"bptr": bptr.to(torch.int32).contiguous(), "bind": bind, "bval": bval,
+        pad = lambda t: torch.cat([t, torch.zeros(4, dtype=t.dtype, device=t.device)])
+        # most entries any 64 ... 1024 consecutive rows (from a multiple of 32) hold in one block
+        at = torch.arange(0, max(nloc, 1), 32, device=col.device)
+        caps = [int((bptr[:, torch.clamp(at + w, max=nloc)] - bptr[:, at]).max().item()) for w in (64, 128, 256, 512, 1024)]
+        self._gather = {"bptr": bptr.to(torch.int32).contiguous(), "bind": pad(bind), "bval": pad(bval), "first": first,
+                        "stride": stride, "caps": caps,
                         "ready": torch.zeros(capi.SPL_MAX_PEERS, dtype=torch.int32, device=col.device), "epoch": 0}
         torch.cuda.current_stream().synchronize()
 
@@ -369,10 +403,13 @@ class DistCsrMatrix:
         ctx = self.local._ctx
         st = (C.c_uint64 * (self.world + 1))(*x.starts)
         sl = (C.c_void_p * self.world)(*x.ptrs)
+        first = g["first"]
+        bf = (C.c_uint32 * len(first))(*first)
         r0, r1 = self.local_rows()
         ctx.check(ctx._lib.spl_spmv_gather_fused(
             ctx._h, _dtype_code(self.local.dtype), r1 - r0, self.world, self.rank, C.cast(st, C.c_void_p),
-            C.cast(sl, C.c_void_p), C.c_void_p(g["bptr"].data_ptr()), C.c_void_p(g["bind"].data_ptr()),
+            C.cast(sl, C.c_void_p), len(first) - 1, C.cast(bf, C.c_void_p), C.c_void_p(g["bptr"].data_ptr()),
+            g["stride"], C.cast((C.c_uint32 * 5)(*g["caps"]), C.c_void_p), C.c_void_p(g["bind"].data_ptr()),
             C.c_void_p(g["bval"].data_ptr()), C.c_void_p(x_full_dev), C.c_void_p(y_dev),
             C.c_void_p(g["ready"].data_ptr()), g["epoch"], self.local.nnz(), fl, x._epoch if barrier else 0,
             int(timeout_ms), C.c_void_p(timeline_dev) if timeline_dev else None))

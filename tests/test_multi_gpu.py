@@ -124,6 +124,40 @@ def _worker(rank, world, port, out):
             ok &= bool(np.all(np.abs(y.cpu().numpy() - scale_x * yw[r0:r1]) <= 4e-12 * sc[r0:r1] + 1e-300))
         xv.check()
         assert ok, "fused gather SpMV with its own barrier differs from the oracle"
+        # f32: rank 1's slice starts at an odd column, so its copy into rank 0's x_full is not 16-byte aligned (the copy
+        # warp's element path), and rank 0's slice ends in a tail shorter than 16 bytes behind the bulk copies
+        v32 = v.astype(np.float32)
+        full32 = orc.compress_from_coo(n, n, orc.make_triplets(r, c, v32), "row")
+        D32 = spd.DistCsrMatrix.from_device_triplets(dist, torch, n, n, dev(r[a:b], np.int32), dev(c[a:b], np.int32),
+                                                     dev(v32[a:b], np.float32), ctx=ctx)
+        x32 = x.astype(np.float32)
+        yw32 = orc.csr_spmv(n, *full32, x32).astype(np.float64)
+        sc32 = orc.csr_spmv(n, full32[0], full32[1], np.abs(full32[2]), np.abs(x32)).astype(np.float64)
+        xv32 = spd.PeerVector(ctx, dist, n, np.float32, D32.starts)
+        xf32 = torch.empty(n, dtype=torch.float32, device="cuda")
+        y32 = torch.empty(r1 - r0, dtype=torch.float32, device="cuda")
+        D32.prepare_gather(torch)
+        for scale_x, tile_rows in ((1.0, None), (-3.0, None), (0.5, "64"), (2.0, "128"), (-1.0, "512"), (4.0, "1024")):
+            if tile_rows:                                       # every tile shape of the kernel, not only the one it picks
+                os.environ["SPL_GATHER_TILE_ROWS"] = tile_rows
+                D32.prepare_gather(torch)                       # fresh counters: the shape decides the grid
+            device_view(torch, xv32.local_ptr, r1 - r0, torch.float32).copy_(torch.from_numpy(np.float32(scale_x) * x32[r0:r1]))
+            xv32.swap()
+            xf32.fill_(float("nan"))
+            y32.fill_(7.0)
+            torch.cuda.synchronize()
+            D32.spmv_gather(xv32, xf32.data_ptr(), y32.data_ptr(), barrier=True)
+            torch.cuda.synchronize()
+            got_x = xf32.cpu().numpy()
+            peers = np.ones(n, dtype=bool)
+            peers[r0:r1] = False
+            ok &= bool(np.array_equal(got_x[peers], (np.float32(scale_x) * x32)[peers]))      # the slices, bit for bit
+            ok &= bool(np.all(np.abs(y32.cpu().numpy().astype(np.float64) - scale_x * yw32[r0:r1])
+                              <= 1e-5 * abs(scale_x) * sc32[r0:r1] + 1e-30))
+        os.environ.pop("SPL_GATHER_TILE_ROWS", None)
+        xv32.check()
+        xv32.close(dist)
+        assert ok, "fused gather SpMV (f32, unaligned slice) differs from the oracle"
 
         # an iteration whose x changes every step: y_t is written straight into the unpublished buffer
         # and published as x_{t+1} (one barrier per step).  One rank is held back by a spin kernel at a
