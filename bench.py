@@ -764,14 +764,18 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     nb = len(first) - 1
     tl = torch.zeros(2 + 3 * nb, dtype=torch.int64, device="cuda")
     dist.barrier(); torch.cuda.synchronize()
-    D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())
+    for _ in range(6):                                                   # stamps of a product in the middle of a run of them:
+        spmv_fused()                                                     # a lone launch would mostly show how far apart the
+    D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())     # ranks' hosts are
+    for _ in range(3):
+        spmv_fused()
     torch.cuda.synchronize()
     t = tl.cpu().tolist()
-    t0 = min(v for v in t if v > 0)
+    t0 = t[1]                                                            # the first consumer warp starts
     stamps = [{"block": k, "ring_offsets": [first[k], first[k + 1]], "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3,
                "slices_landed_us": (t[2 + 3 * k] - t0) / 1e3, "block_done_us": (t[3 + 3 * k] - t0) / 1e3}
               for k in range(nb)]
-    stamps.append({"last_cta_done_us": (t[1 + 3 * nb] - t0) / 1e3})
+    stamps.append({"last_cta_done_us": (t[1 + 3 * nb] - t0) / 1e3, "first_peer_arrived_copy_starts_us": (t[0] - t0) / 1e3})
     # how the shard is blocked (one pass over the rows per block) and how many CTAs stay resident: measured per run,
     # the library's defaults stand in the headline number above
     sweep = {}
@@ -789,7 +793,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
             assert e2 < 1e-5, f"fused gather SpMV, blocks {name}: differs from the all-gather product: {e2}"
         except RuntimeError as e:
             sweep["blocks " + name] = str(e)[:60]
-    for knob, value in (("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_TILE_ROWS", "512"), ("SPL_GATHER_TILE_ROWS", "256"),
+    for knob, value in (("SPL_GATHER_CTAS_PER_SM", "4"), ("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_LANES", "2"),
                         ("SPL_GATHER_STAGES", "2")):
         os.environ[knob] = value
         D.prepare_gather(torch)                                          # fresh counters: the grid size may change

@@ -78,6 +78,10 @@ typedef enum { SPL_SPMV_AUTO = 0, SPL_SPMV_VECTOR = 1, SPL_SPMV_MERGE = 2, SPL_S
 int spl_ctx_create(int device, void *stream, spl_ctx **out);
 int spl_ctx_destroy(spl_ctx *ctx);
 int spl_ctx_sync(spl_ctx *ctx);
+/* Synchronises, then returns the freed device memory that the library's own pool keeps for reuse to the
+ * driver (matrices and builders that are alive are untouched).  For callers about to allocate most of
+ * the device themselves. */
+int spl_ctx_trim(spl_ctx *ctx);
 const char *spl_last_error(const spl_ctx *ctx);
 /* After SPL_ERR_INVALID: 1-based ordinal of the failing assertion of
  * CsrMatrix::new (src/csr.rs:144-156) / CscMatrix::new (src/csc.rs:144-156):

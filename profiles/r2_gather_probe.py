@@ -25,7 +25,7 @@ ctx = sp.Context(0, stream.cuda_stream)
 sp.set_default_context(ctx)
 out = {}
 n = 1_250_000
-for per_row in (2, 4, 8, 16):
+for per_row in (2, 4, 16):
     g = torch.Generator(device="cuda").manual_seed(per_row)
     rows = torch.arange(n, device="cuda", dtype=torch.int32).repeat_interleave(per_row)
     cols = torch.randint(0, n, (n * per_row,), device="cuda", generator=g, dtype=torch.int32)
@@ -57,23 +57,24 @@ for per_row in (2, 4, 8, 16):
     res = {"nnz": nnz}
     res["spl_spmv_ms"] = timed(lambda: D.local.spmv_device(x.data_ptr(), y0.data_ptr()))
     res["spl_spmv_choice"] = D.local.spmv_choice() if hasattr(D.local, "spmv_choice") else None
-    for tile_rows in (None, "1024", "512", "256", "128"):
-        for per_sm in (None, "2", "1"):
-            if tile_rows:
-                os.environ["SPL_GATHER_TILE_ROWS"] = tile_rows
+    res["spl_spmv_x_in_peer_buffer_ms"] = timed(lambda: D.local.spmv_device(xv.published_ptr, y0.data_ptr()))
+    for lanes in (None, "1", "2", "4"):
+        for per_sm in (None, "3", "2"):
+            if lanes:
+                os.environ["SPL_GATHER_LANES"] = lanes
             if per_sm:
                 os.environ["SPL_GATHER_CTAS_PER_SM"] = per_sm
             try:
                 D.prepare_gather(torch)
                 ms = timed(lambda: D.spmv_gather(xv, xf.data_ptr(), y.data_ptr()))
                 err = float(((y - y0).abs().max() / (y0.abs().max() + 1e-30)).item())
-                res[f"fused tile_rows={tile_rows} ctas_per_sm={per_sm}"] = {"ms": ms, "rel_diff": err}
+                res[f"fused lanes={lanes} ctas_per_sm={per_sm}"] = {"ms": ms, "rel_diff": err}
             except Exception as e:                                 # noqa: BLE001
-                res[f"fused tile_rows={tile_rows} ctas_per_sm={per_sm}"] = str(e)[:80]
-            os.environ.pop("SPL_GATHER_TILE_ROWS", None)
+                res[f"fused lanes={lanes} ctas_per_sm={per_sm}"] = str(e)[:80]
+            os.environ.pop("SPL_GATHER_LANES", None)
             os.environ.pop("SPL_GATHER_CTAS_PER_SM", None)
     D.prepare_gather(torch)
-    tl = torch.zeros(14 + 3, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(64, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     D.spmv_gather(xv, xf.data_ptr(), y.data_ptr(), timeline_dev=tl.data_ptr())
     torch.cuda.synchronize()

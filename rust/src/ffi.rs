@@ -17,6 +17,7 @@ extern "C" {
     pub fn spl_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut spl_ctx) -> c_int;
     pub fn spl_ctx_destroy(ctx: *mut spl_ctx) -> c_int;
     pub fn spl_ctx_sync(ctx: *mut spl_ctx) -> c_int;
+    pub fn spl_ctx_trim(ctx: *mut spl_ctx) -> c_int;
     pub fn spl_last_error(ctx: *const spl_ctx) -> *const c_char;
     pub fn spl_invalid_reason(ctx: *const spl_ctx) -> c_int;
     pub fn spl_launch_count(ctx: *const spl_ctx) -> u64;

@@ -26,6 +26,7 @@ SIGNATURES = {
     "spl_ctx_create": (_i, [_i, _vp, _pp]),
     "spl_ctx_destroy": (_i, [_vp]),
     "spl_ctx_sync": (_i, [_vp]),
+    "spl_ctx_trim": (_i, [_vp]),
     "spl_last_error": (C.c_char_p, [_vp]),
     "spl_invalid_reason": (_i, [_vp]),
     "spl_launch_count": (_u64, [_vp]),

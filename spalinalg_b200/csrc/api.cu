@@ -165,6 +165,13 @@ int spl_ctx_sync(spl_ctx *ctx) {
     API_END(ctx)
 }
 
+int spl_ctx_trim(spl_ctx *ctx) {
+    API_BEGIN(ctx)
+    SPL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPL_CUDA(cudaMemPoolTrimTo(ctx->pool, 0));          // freed blocks the library's pool still holds go back to the driver
+    API_END(ctx)
+}
+
 const char *spl_last_error(const spl_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 int spl_invalid_reason(const spl_ctx *ctx) { return ctx ? ctx->invalid_reason : 0; }
 uint64_t spl_launch_count(const spl_ctx *ctx) { return ctx ? ctx->launches : 0; }

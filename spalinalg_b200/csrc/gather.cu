@@ -57,10 +57,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 constexpr int GF_THREADS = 256;  // consumer threads of a CTA; one warp more feeds them tiles, another copies x
 constexpr int GF_CTA = GF_THREADS + 64;
-constexpr uint32_t GF_CHUNK = 2048;      // bytes per bulk copy of x
+constexpr uint32_t GF_CHUNK = 4096;      // bytes per bulk copy of x: 5 x 4 KB in flight per CTA, ~9 MB on the chip — beside the
+                                         // product's gathers an NVLink read takes ~15 us, and 4 MB in flight gave 240 GB/s
 constexpr int GF_STAGES = 6;             // x ring slots per CTA
 constexpr int GF_AHEAD = 4;              // loads run this many chunks in front of the stores (STAGES >= AHEAD + 2)
-constexpr int GF_LAG = 3;                // stores whose completion is not waited for before the next chunk moves
 constexpr uint32_t GF_RING = GF_CHUNK * GF_STAGES;
 
 // block b of the shard = the columns owned by ring offsets [first[b], first[b+1]); first[0] = 0, first[1] = 1
@@ -117,19 +117,21 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gb.flags[lane] + gp.rank), "r"(gb.epoch) : "memory");
         }
-        if ((int)lane < G && (int)lane != gp.rank) {       // wait: every peer's slice is final once its epoch shows up here
-            const unsigned long long t0 = global_timer_ns();
-            for (;;) {
-                uint32_t v;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.flags_mine + lane) : "memory");
-                if ((int32_t)(v - gb.epoch) >= 0) break;
-                if (global_timer_ns() - t0 > gb.timeout_ns) { atomicExch(gb.failed, 1u); break; }
-                __nanosleep(100);
-            }
-        }
         __syncwarp();
     }
-    if (timeline && cta == 0 && lane == 0) timeline[0] = global_timer_ns();
+    // fused barrier, wait: rank g's slice is final once its epoch shows up in this rank's flag block; waited for
+    // slice by slice, so a late peer delays only its own slice
+    auto wait_owner = [&](int g) {
+        if (!gb.flags_mine) return;
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.flags_mine + g) : "memory");
+            if ((int32_t)(v - gb.epoch) >= 0) break;
+            if (global_timer_ns() - t0 > gb.timeout_ns) { atomicExch(gb.failed, 1u); break; }
+            __nanosleep(100);
+        }
+    };
     // chunks of the bulk path per slice (ring offset k = 1..G-1): whole 16-byte units of slices whose two ends are
     // 16-byte aligned (IPC blocks are; slice starts of an f32 vector need not be); the rest goes element by element
     unsigned long long cum[SPL_MAX_PEERS + 1];             // cum[k] = chunks in ring offsets 1..k
@@ -145,6 +147,8 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
         // elements outside the bulk path: this CTA's share, all lanes
         const unsigned long long e0 = b16 / sizeof(T), rest = n - e0;
         if (rest) {
+            if (lane == 0) wait_owner(g);
+            __syncwarp();
             const T *se = reinterpret_cast<const T *>(src);
             T *de = reinterpret_cast<T *>(dst);
             const unsigned long long per = (rest + ncta - 1) / ncta, lo = e0 + cta * per,
@@ -159,7 +163,8 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned long long total = cum[G - 1];
         const unsigned long long mine = total > cta ? (total - cta + ncta - 1) / ncta : 0;
-        int kl = 1, ks = 1, ksig = 1;
+        int kl = 1, ks = 1, ksig = 1, kw = 0;
+        for (; ksig < G && cum[ksig] <= cta; ++ksig) atomicAdd(ready + ksig, 1u);      // slices that hold no chunk of this CTA
         auto slice_of = [&](int k, const unsigned char *&src, unsigned char *&dst, unsigned long long &b16) {
             const int g = (gp.rank + k) % G;
             src = static_cast<const unsigned char *>(gp.slice[g]);
@@ -170,6 +175,10 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
             if (i < mine) {
                 const unsigned long long c = cta + i * ncta;
                 while (c >= cum[kl]) ++kl;
+                for (; kw < kl; ++kw) {                                          // owners of the slices up to kl have arrived
+                    wait_owner((gp.rank + kw + 1) % G);
+                    if (timeline && cta == 0 && kw == 0) timeline[0] = global_timer_ns();
+                }
                 const unsigned char *src; unsigned char *dst; unsigned long long b16;
                 slice_of(kl, src, dst, b16);
                 const unsigned long long off = (c - cum[kl - 1]) * GF_CHUNK;
@@ -199,16 +208,15 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
                              "r"(gf_smem(ring + (size_t)s * GF_CHUNK)), "r"(len)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every store but the newest has left its slot
-                asm volatile("cp.async.bulk.wait_group %0;" ::"n"(GF_LAG) : "memory");   // all but the newest LAG are written
-                // slices that lie wholly below this CTA's oldest unwritten chunk hold nothing of it that is still in flight
-                if (j >= (unsigned long long)GF_LAG) {
-                    const unsigned long long cdone = cta + (j - GF_LAG + 1) * ncta;
-                    while (ksig < G && cum[ksig] <= cdone) {
-                        __threadfence();
-                        atomicAdd(ready + ksig, 1u);
-                        ++ksig;
-                    }
+                if (c + ncta >= cum[ks]) {
+                    // this CTA's last chunk of the slice: wait until its stores are WRITTEN (the loads ahead keep flying —
+                    // bulk groups count stores only), then say so.  Slices that lie wholly below the next chunk hold
+                    // nothing of this CTA that is still in flight
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    __threadfence();
+                    for (; ksig < G && cum[ksig] <= c + ncta; ++ksig) atomicAdd(ready + ksig, 1u);
+                } else {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every store but the newest has left its slot
                 }
             }
         }
@@ -218,29 +226,27 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
     }
 }
 
-// Shared memory of a CTA: [tile stages: indices | values | row pointers] [row sums] [x ring] [tile bounds] [barriers]
+// Shared memory of a CTA: [tile stages: indices | values | row pointers] [x ring] [tile bounds] [barriers]
 struct GatherShape {
     uint32_t rows_per_cta;    // multiple of 32
     uint32_t ntiles;          // tiles of R rows per block and CTA
     uint32_t cap;             // entries a tile stage holds (16-byte aligned superset of the largest tile)
     uint32_t stages;          // tile stages
-    uint32_t off_val, off_ptr, off_sum, off_ring, off_tlo, off_bar;      // byte offsets
+    uint32_t off_val, off_ptr, off_ring, off_tlo, off_bar;      // byte offsets
 };
 
-template <typename T, int TR>
-__global__ void __launch_bounds__(GF_CTA, 3)
+template <typename T, int LPR, int U>
+__global__ void __launch_bounds__(GF_CTA, 4)
 spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, uint32_t pstride,
                          const uint32_t *__restrict__ bind, const T *__restrict__ bval, GatherPeers gp, GatherBlocks gk,
                          T *x_full, T *__restrict__ y, uint32_t *ready, uint32_t target, GatherShape sh, GatherBarrier gb,
                          unsigned long long *timeline) {
-    constexpr uint32_t R = TR;                    // rows per tile (chosen so that a tile holds ~2048 entries)
-    constexpr int U = sizeof(T) == 8 ? 4 : 8;     // gathers a lane issues per round (two rounds are in flight: registers)
+    constexpr uint32_t R = GF_THREADS / LPR;      // rows per tile: LPR lanes per row, U gathers per lane and pass
     constexpr uint32_t PTRS = R + 4;              // pointer slots per stage: R + 1 needed, whole 16-byte units
     extern __shared__ __align__(128) unsigned char gf_raw[];
     uint32_t *s_ind = reinterpret_cast<uint32_t *>(gf_raw);
     T *s_val = reinterpret_cast<T *>(gf_raw + sh.off_val);
     uint32_t *s_ptr = reinterpret_cast<uint32_t *>(gf_raw + sh.off_ptr);
-    T *s_sum = reinterpret_cast<T *>(gf_raw + sh.off_sum);
     uint32_t *s_tlo = reinterpret_cast<uint32_t *>(gf_raw + sh.off_tlo);
     uint64_t *full = reinterpret_cast<uint64_t *>(gf_raw + sh.off_bar);
     uint64_t *empty = full + sh.stages;
@@ -301,151 +307,91 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, uint3
         return;
     }
 
-    // ---- consumers.  A tile's rows are dealt to the 8 warps in contiguous runs (so are its entries), and every warp
-    // works through its run on its own, in two steps (pointers, indices and values are in shared memory):
-    //   1. the run's ENTRIES go to the lanes, 32 apart, eight per lane and round: gather x, multiply, put the product
-    //      back in place of the value.  Every lane keeps eight gathers in flight whatever the rows look like;
-    //   2. the run's ROWS go to the lanes: a row's products are summed in column order (one lane, sequentially) and
-    //      added to the row's running sum, which the same lane owns in every block — no atomics, one fixed order.
-    // The two steps are software-pipelined: the gathers of the NEXT tile's run are issued before the sums of the
-    // current one, so the gather latency of a tile hides behind the shared-memory work of its predecessor.  No CTA-wide
-    // barrier: the warps drift apart, which keeps the gathers of an SM flowing instead of arriving in bursts.
-    // Nothing but x comes from global memory ----
+    // ---- consumers: LPR lanes per row, exactly as in the unsharded stream kernel (spmv.cu) — pointers, indices and
+    // values come from shared memory, only x from global memory, and the warps run on their own (no CTA barrier).
+    // A row's running sum lives in y itself: the same lanes own the row in every block, and shared memory spent on
+    // sums would come out of the L1 that holds the gathers in flight.  Measured alternatives (entries dealt to the
+    // lanes with eight gathers each, four rows per lane, products summed in a second pass) kept more gathers in flight
+    // and were all slower: profiles/r2_spmv_notes.md ----
     if (ntiles == 0) return;
     asm volatile("bar.sync 2, %0;" ::"n"(GF_THREADS + 32) : "memory");
     const T *own = static_cast<const T *>(gp.slice[gp.rank]) - gp.start[gp.rank];
-    constexpr uint32_t WR = R / (GF_THREADS / 32);          // rows of a tile per warp
-    const uint32_t lane = threadIdx.x & 31u, w0 = (threadIdx.x >> 5) * WR;
+    const uint32_t lane = threadIdx.x & 31u, rl = threadIdx.x / LPR, sub = threadIdx.x % LPR;
     const bool stamp = timeline && c == 0 && threadIdx.x == 0;
-
-    struct Run { uint32_t s, t, k, r0, r1, j0, j1, za; };    // warp-uniform: stage, tile, block, rows and entries of the run
-    // wait for the stage of tile (k, t), then issue the first round of its gathers
-    auto issue = [&](uint32_t k, uint32_t t, uint32_t s, uint32_t phase, Run &run, T (&xv)[U]) {
-        gf_mbar_wait(full + s, phase);
-        const uint32_t *cp = s_ptr + (size_t)s * PTRS;
-        const uint32_t *ci = s_ind + (size_t)s * sh.cap;
-        const uint32_t rows = re - (rs + t * R) < R ? re - (rs + t * R) : R;
-        run.s = s; run.t = t; run.k = k;
-        run.r0 = w0 < rows ? w0 : rows;
-        run.r1 = w0 + WR < rows ? w0 + WR : rows;
-        run.za = cp[0] & ~3u;
-        run.j0 = cp[run.r0] - run.za;
-        run.j1 = cp[run.r1] - run.za;
-        // block 0 reads the published slice (constant for the whole kernel); x_full is written by this very kernel,
-        // behind the acquire that let this block start: L2 loads
-        if (k == 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t j = run.j0 + u * 32 + lane;
-                xv[u] = j < run.j1 ? __ldg(own + ci[j]) : (T)0;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t j = run.j0 + u * 32 + lane;
-                xv[u] = j < run.j1 ? __ldcg(x_full + ci[j]) : (T)0;
-            }
-        }
-    };
-    // products of the first round in place, further rounds of a long run, then the row sums; releases the stage
-    auto finish = [&](const Run &run, T (&xv)[U]) {
-        const uint32_t *cp = s_ptr + (size_t)run.s * PTRS;
-        const uint32_t *ci = s_ind + (size_t)run.s * sh.cap;
-        T *cv = s_val + (size_t)run.s * sh.cap;
-        const T *xb = run.k == 0 ? own : x_full;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t j = run.j0 + u * 32 + lane;
-            if (j < run.j1) cv[j] *= xv[u];
-        }
-        for (uint32_t base = run.j0 + 32 * U; base < run.j1; base += 32 * U) {       // warp-uniform trip count
-            T more[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t j = base + u * 32 + lane;
-                more[u] = j < run.j1 ? __ldcg(xb + ci[j]) : (T)0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t j = base + u * 32 + lane;
-                if (j < run.j1) cv[j] *= more[u];
-            }
-        }
-        __syncwarp();                                                // products of the run are in place
-        for (uint32_t i = run.r0 + lane; i < run.r1; i += 32) {
-            T acc = (T)0;
-            for (uint32_t j = cp[i] - run.za, e = cp[i + 1] - run.za; j < e; ++j) acc += cv[j];
-            T *slot = s_sum + (size_t)run.t * R + i;
-            *slot = run.k == 0 ? acc : *slot + acc;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // our writes to the stage, before the next bulk copy into it
-        __syncwarp();
-        if (lane == 0) gf_mbar_arrive(empty + run.s);
-    };
-    // have the slices of block k landed?  (acquire; lane 0 looks, the warp learns)
-    auto landed = [&](uint32_t k) {
-        int ok = 1;
-        if (lane == 0)
-            for (uint32_t o = gk.first[k]; o < gk.first[k + 1]; ++o) ok &= (int32_t)(ld_acquire_gpu(ready + o) - target) >= 0;
-        return __shfl_sync(0xffffffffu, ok, 0) != 0;
-    };
-
-    Run cur{}, nxt{};
-    T xa[U], xn[U];
     uint32_t s = 0, phase = 0;
-    if (stamp) timeline[1] = timeline[2] = global_timer_ns();
-    issue(0, 0, s, phase, cur, xa);
-    if (++s == sh.stages) { s = 0; phase ^= 1u; }
-    for (uint32_t k = 0; k < nb; ++k)
-        for (uint32_t t = 0; t < ntiles; ++t) {
-            const bool last = t + 1 == ntiles;
-            const uint32_t k2 = last ? k + 1 : k, t2 = last ? 0 : t + 1;
-            bool have = false;
-            if (k2 < nb) {
-                if (last && stamp) timeline[1 + 3 * k2] = global_timer_ns();                      // block k2: wait begins
-                if (!last || landed(k2)) {
-                    if (last && stamp) timeline[2 + 3 * k2] = global_timer_ns();                  // its slices have landed
-                    issue(k2, t2, s, phase, nxt, xn);
-                    have = true;
-                }
-            }
-            finish(cur, xa);
-            if (last && stamp) timeline[3 + 3 * k] = global_timer_ns();                           // block k done (this warp)
-            if (k2 < nb && !have) {
-                while (!landed(k2)) __nanosleep(64);
-                if (stamp) timeline[2 + 3 * k2] = global_timer_ns();
-                issue(k2, t2, s, phase, nxt, xn);
-            }
-            if (k2 < nb) {
-                if (++s == sh.stages) { s = 0; phase ^= 1u; }
-                cur = nxt;
-#pragma unroll
-                for (int u = 0; u < U; ++u) xa[u] = xn[u];
-            }
+    for (uint32_t k = 0; k < nb; ++k) {
+        if (stamp) timeline[1 + 3 * k] = global_timer_ns();                                           // block k: wait begins
+        if (k > 0) {
+            if (lane == 0)
+                for (uint32_t o = gk.first[k]; o < gk.first[k + 1]; ++o)
+                    while ((int32_t)(ld_acquire_gpu(ready + o) - target) < 0) __nanosleep(64);
+            __syncwarp();
         }
+        if (stamp) timeline[2 + 3 * k] = global_timer_ns();                                           // its slices have landed
+        for (uint32_t t = 0; t < ntiles; ++t) {
+            gf_mbar_wait(full + s, phase);
+            const uint32_t *cp = s_ptr + (size_t)s * PTRS;
+            const uint32_t *ci = s_ind + (size_t)s * sh.cap;
+            const T *cv = s_val + (size_t)s * sh.cap;
+            const uint32_t r = rs + t * R + rl;
+            const uint32_t za = cp[0] & ~3u;
+            uint32_t p0 = 0, e = 0;
+            if (r < re) { p0 = cp[rl] - za; e = cp[rl + 1] - za; }
+            T prev = (T)0;
+            if (k > 0 && sub == 0 && r < re) prev = y[r];              // in flight with the gathers
+            T acc = (T)0;
+            auto row_sum = [&](auto gather) {
+                for (uint32_t j = p0 + sub; j < e; j += U * LPR) {
+                    uint32_t col[U];
+                    T xv[U], v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) col[u] = j + u * LPR < e ? ci[j + u * LPR] : 0xffffffffu;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xv[u] = col[u] != 0xffffffffu ? gather(col[u]) : (T)0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) v[u] = j + u * LPR < e ? cv[j + u * LPR] : (T)0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc += j + u * LPR < e ? v[u] * xv[u] : (T)0;          // 0, never 0 * inf
+                }
+            };
+            // block 0 reads the published slice (constant for the whole kernel); x_full is written by this very kernel,
+            // behind the acquire that let this block start: L2 loads
+            if (k == 0) row_sum([&](uint32_t col) { return __ldg(own + col); });
+            else row_sum([&](uint32_t col) { return __ldcg(x_full + col); });
+            __syncwarp();
+            if (lane == 0) gf_mbar_arrive(empty + s);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (sub == 0 && r < re) y[r] = prev + acc;
+            if (++s == sh.stages) { s = 0; phase ^= 1u; }
+        }
+        if (stamp) timeline[3 + 3 * k] = global_timer_ns();                                           // block k done (this warp)
+    }
     // a fused barrier that gave up: NaN instead of sums over a half-written x (the status call reports it)
     const bool poisoned = gb.failed && *reinterpret_cast<const volatile uint32_t *>(gb.failed) != 0u;
-    for (uint32_t t = 0; t < ntiles; ++t) {                              // every lane writes the rows it summed
-        const uint32_t rows = re - (rs + t * R) < R ? re - (rs + t * R) : R;
-        const uint32_t r1 = w0 + WR < rows ? w0 + WR : rows;
-        for (uint32_t i = w0 + lane; i < r1; i += 32) y[rs + t * R + i] = poisoned ? (T)NAN : s_sum[(size_t)t * R + i];
-    }
+    if (poisoned && sub == 0)
+        for (uint32_t t = 0; t < ntiles; ++t) {                          // every lane poisons the rows it summed
+            const uint32_t r = rs + t * R + rl;
+            if (r < re) y[r] = (T)NAN;
+        }
     if (timeline && threadIdx.x == 0) atomicMax(timeline + 1 + 3 * nb, global_timer_ns());           // the last CTA to finish
 }
 
 }  // namespace
 
-// Launch shape: as many CTAs as stay resident (cooperative launch); the rows of a CTA (its shared-memory sums) shrink
-// as the CTAs per SM grow, so the two are found together.  tile_caps = the most entries any 64 / 128 / 256 / 512 / 1024
-// consecutive rows (starting at a multiple of 32) hold in one block.
-template <typename T, int TR>
-void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, uint32_t pstride, const uint32_t *bind,
+// Launch shape: three CTAs per SM (cooperative launch: all resident), two or three tile stages, within `smem_per_sm`
+// bytes of shared memory per SM.  The budget matters: what the kernel does not take stays L1, and L1 lines are where
+// the gathers in flight land — with 200 KB of staging the same gathers ran three times slower (profiles/
+// r2_spmv_notes.md).  Returns false when the tile does not fit the budget.  tile_caps = the most entries any 64 / 128 /
+// 256 / 512 / 1024 consecutive rows (starting at a multiple of 32) hold in one block.
+template <typename T, int LPR, int U>
+bool spmv_gather_fused_t(size_t smem_per_sm, spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, uint32_t pstride, const uint32_t *bind,
                          const T *bval, const uint32_t *tile_caps, const GatherPeers &gp, const GatherBlocks &gk, T *x_full,
                          T *y, uint32_t *ready, uint32_t epoch, const GatherBarrier &gb, unsigned long long *timeline) {
-    auto k = spmv_gather_fused_kernel<T, TR>;
-    constexpr uint32_t R = TR;
-    static_assert(R == 64 || R == 128 || R == 256 || R == 512 || R == 1024, "tile rows");
-    const uint32_t cap = (tile_caps[R == 64 ? 0 : R == 128 ? 1 : R == 256 ? 2 : R == 512 ? 3 : 4] + 6u + 3u) & ~3u;
+    auto k = spmv_gather_fused_kernel<T, LPR, U>;
+    constexpr uint32_t R = GF_THREADS / LPR;
+    static_assert(R == 64 || R == 128 || R == 256, "tile rows");
+    const uint32_t cap = (tile_caps[R == 64 ? 0 : R == 128 ? 1 : 2] + 6u + 3u) & ~3u;
     const char *pc = std::getenv("SPL_GATHER_CTAS_PER_SM");          // measurement knobs
     const char *ps = std::getenv("SPL_GATHER_STAGES");
     const int most = pc ? std::max(1, std::atoi(pc)) : 3;
@@ -463,9 +409,6 @@ void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, uint
         o += (size_t)stages * cap * sizeof(T);
         sh.off_ptr = (uint32_t)o;
         o += (size_t)stages * (R + 4) * sizeof(uint32_t);
-        o = (o + 15) & ~(size_t)15;
-        sh.off_sum = (uint32_t)o;
-        o += (size_t)sh.ntiles * R * sizeof(T);
         o = (o + 127) & ~(size_t)127;
         sh.off_ring = (uint32_t)o;
         o += GF_RING;
@@ -480,14 +423,13 @@ void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, uint
         for (uint32_t stages = ps ? (uint32_t)std::max(2, std::atoi(ps)) : 3u; stages >= 2 && ncta == 0; --stages) {
             const uint32_t ctas = (uint32_t)ctx->num_sms * (uint32_t)want;
             smem = shape(ctas, stages);
-            if (smem > 226 * 1024 / (size_t)want) continue;
+            if (smem > smem_per_sm / (size_t)want) continue;
             if (smem > 48 * 1024) SPL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int resident = 0;
             SPL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k, GF_CTA, smem));
             if (resident >= want) ncta = ctas;
         }
-    SPL_REQUIRE(ncta > 0, SPL_ERR_UNSUPPORTED,
-                "fused gather SpMV: a tile of the shard (or its row sums) does not fit in shared memory");
+    if (ncta == 0) return false;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ncta);
     cfg.blockDim = dim3(GF_CTA);
@@ -501,6 +443,7 @@ void spmv_gather_fused_t(spl_ctx *ctx, uint32_t nloc, const uint32_t *bptr, uint
     SPL_CUDA(cudaLaunchKernelEx(&cfg, k, nloc, bptr, pstride, bind, bval, gp, gk, x_full, y, ready, epoch * ncta, sh, gb,
                                 timeline));
     check_launch(ctx, "spmv_gather_fused");
+    return true;
 }
 
 void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int rank, const uint64_t *col_starts,
@@ -539,20 +482,28 @@ void spmv_gather_fused(spl_ctx *ctx, int dtype, uint32_t nloc, int world, int ra
     }
     // entries a row holds in the WIDEST block
     const double e = entries_per_row * (double)widest / (double)world;
-    auto go = [&](auto tag, auto rows) {
+    auto go = [&](auto tag, auto lpr, auto u, size_t smem_per_sm) {
         using T = decltype(tag);
-        spmv_gather_fused_t<T, decltype(rows)::value>(ctx, nloc, bptr, pstride, bind, (const T *)bval, tile_caps, gp, gk,
-                                                      (T *)x_full, (T *)y, ready, epoch, gb, timeline);
+        return spmv_gather_fused_t<T, decltype(lpr)::value, decltype(u)::value>(smem_per_sm, ctx, nloc, bptr, pstride, bind,
+                                                                               (const T *)bval, tile_caps, gp, gk, (T *)x_full,
+                                                                               (T *)y, ready, epoch, gb, timeline);
     };
-    // rows per tile so that a tile holds about 2048 entries: one round of eight gathers per consumer
-    const char *pl = std::getenv("SPL_GATHER_TILE_ROWS");            // measurement knob
-    const int rows = pl ? std::atoi(pl) : (e <= 3.0 ? 1024 : e <= 6.0 ? 512 : e <= 12.0 ? 256 : e <= 24.0 ? 128 : 64);
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I4 = std::integral_constant<int, 4>;
+    // lanes per row from the entries a row holds in the widest block; more lanes (a smaller tile) when the tile does
+    // not fit the shared-memory budget; as a last resort any tile that fits the SM at all
+    const char *pl = std::getenv("SPL_GATHER_LANES");                // measurement knobs
+    const char *pk = std::getenv("SPL_GATHER_SMEM_KB");
+    const size_t budget = (size_t)(pk ? std::max(16, std::atoi(pk)) : 128) * 1024;
+    const int lanes = pl ? std::atoi(pl) : (e <= 4.0 ? 1 : e <= 16.0 ? 2 : 4);
     auto pick = [&](auto tag) {
-        if (rows >= 1024) go(tag, std::integral_constant<int, 1024>{});
-        else if (rows >= 512) go(tag, std::integral_constant<int, 512>{});
-        else if (rows >= 256) go(tag, std::integral_constant<int, 256>{});
-        else if (rows >= 128) go(tag, std::integral_constant<int, 128>{});
-        else go(tag, std::integral_constant<int, 64>{});
+        for (size_t limit : {budget, (size_t)226 * 1024}) {
+            if (lanes <= 1 && go(tag, I1{}, I4{}, limit)) return;
+            if (lanes <= 2 && go(tag, I2{}, I4{}, limit)) return;
+            if (go(tag, I4{}, I4{}, limit)) return;
+        }
+        SPL_REQUIRE(false, SPL_ERR_UNSUPPORTED, "fused gather SpMV: 64 rows of one block of the shard do not fit in shared memory");
     };
     if (dtype == SPL_F32) pick(float{});
     else pick(double{});

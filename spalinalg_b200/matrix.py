@@ -84,6 +84,10 @@ class Context:
     def sync(self):
         self.check(self._lib.spl_ctx_sync(self._h))
 
+    def trim(self):
+        """Synchronise and hand the freed device memory in the library's pool back to the driver."""
+        self.check(self._lib.spl_ctx_trim(self._h))
+
     def launch_count(self) -> int:
         return int(self._lib.spl_launch_count(self._h))
 

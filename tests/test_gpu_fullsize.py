@@ -285,6 +285,10 @@ def test_wide_matrix_beyond_2_pow_32_entries():
     analytic band, transpose against the analytic transposed band, transpose twice = the matrix bit for bit,
     entry chunks past position 2^32, and the strictly-increasing assertion on an entry beyond 2^32.
     f32, 65 diagonals, n = 2^26: 4.36 G entries, 35 GB per copy."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    sp.default_context().trim()                              # what earlier tests left in the library's pool
     free, _ = torch.cuda.mem_get_info()
     if free < 150 * 2 ** 30:
         pytest.skip(f"needs ~150 GB of free device memory, {free / 2 ** 30:.0f} GB available")

@@ -137,9 +137,9 @@ def _worker(rank, world, port, out):
         xf32 = torch.empty(n, dtype=torch.float32, device="cuda")
         y32 = torch.empty(r1 - r0, dtype=torch.float32, device="cuda")
         D32.prepare_gather(torch)
-        for scale_x, tile_rows in ((1.0, None), (-3.0, None), (0.5, "64"), (2.0, "128"), (-1.0, "512"), (4.0, "1024")):
-            if tile_rows:                                       # every tile shape of the kernel, not only the one it picks
-                os.environ["SPL_GATHER_TILE_ROWS"] = tile_rows
+        for scale_x, lanes in ((1.0, None), (-3.0, None), (0.5, "1"), (2.0, "2"), (-1.0, "4")):
+            if lanes:                                           # every tile shape of the kernel, not only the one it picks
+                os.environ["SPL_GATHER_LANES"] = lanes
                 D32.prepare_gather(torch)                       # fresh counters: the shape decides the grid
             device_view(torch, xv32.local_ptr, r1 - r0, torch.float32).copy_(torch.from_numpy(np.float32(scale_x) * x32[r0:r1]))
             xv32.swap()
@@ -154,7 +154,7 @@ def _worker(rank, world, port, out):
             ok &= bool(np.array_equal(got_x[peers], (np.float32(scale_x) * x32)[peers]))      # the slices, bit for bit
             ok &= bool(np.all(np.abs(y32.cpu().numpy().astype(np.float64) - scale_x * yw32[r0:r1])
                               <= 1e-5 * abs(scale_x) * sc32[r0:r1] + 1e-30))
-        os.environ.pop("SPL_GATHER_TILE_ROWS", None)
+        os.environ.pop("SPL_GATHER_LANES", None)
         xv32.check()
         xv32.close(dist)
         assert ok, "fused gather SpMV (f32, unaligned slice) differs from the oracle"
