@@ -17,7 +17,7 @@ namespace spl {
 
 namespace {
 
-constexpr uint32_t kWideRepairMax = 64;      // longest output segment the transpose's repair pass ranks
+constexpr uint32_t kWideRepairMax = 256;      // longest output segment the transpose's repair pass ranks
 
 __device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *__restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
     while (lo < hi) {
@@ -243,9 +243,9 @@ wide_minor_scatter_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__re
     }
 }
 
-// LPS lanes own one output segment of at most 2*LPS entries and put it in ascending major order
+// LPS lanes own one output segment of at most EPL*LPS entries and put it in ascending major order
 // (the order of the reference's row-major sweep; majors are distinct inside a segment)
-template <typename VB, int LPS>
+template <typename VB, int LPS, int EPL>
 __global__ void __launch_bounds__(256)
 wide_segment_repair_kernel(const uint64_t *__restrict__ out_ptr, uint32_t nseg, uint32_t *__restrict__ out_ind,
                            VB *__restrict__ out_val) {
@@ -259,26 +259,30 @@ wide_segment_repair_kernel(const uint64_t *__restrict__ out_ptr, uint32_t nseg, 
         lo = __ldg(out_ptr + seg);
         len = (uint32_t)(__ldg(out_ptr + seg + 1) - lo);
     }
-    uint32_t r[2] = {0xffffffffu, 0xffffffffu};
-    VB v[2] = {};
+    uint32_t r[EPL];
+    VB v[EPL];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < EPL; ++u) {
         const uint32_t e = sub + u * LPS;
+        r[u] = 0xffffffffu;
+        v[u] = VB{};
         if (e < len) { r[u] = out_ind[lo + e]; v[u] = out_val[lo + e]; }
     }
-    uint32_t rank[2] = {0, 0};
+    uint32_t rank[EPL];
 #pragma unroll
-    for (int u2 = 0; u2 < 2; ++u2) {
+    for (int u = 0; u < EPL; ++u) rank[u] = 0;
 #pragma unroll
+    for (int u2 = 0; u2 < EPL; ++u2) {
+#pragma unroll 8
         for (int t = 0; t < LPS; ++t) {
             const uint32_t other = __shfl_sync(0xffffffffu, r[u2], group_base + t);
-            rank[0] += other < r[0];
-            rank[1] += other < r[1];
+#pragma unroll
+            for (int u = 0; u < EPL; ++u) rank[u] += other < r[u];
         }
     }
     __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < EPL; ++u) {
         const uint32_t e = sub + u * LPS;
         if (e < len) { out_ind[lo + rank[u]] = r[u]; out_val[lo + rank[u]] = v[u]; }
     }
@@ -299,7 +303,7 @@ void wide_recompress_t(spl_ctx *ctx, const spl_mat *in, spl_mat *out) {
     uint32_t longest = 0;
     read_back(ctx, ctx->d_scratch, &longest, 1);
     SPL_REQUIRE(longest <= kWideRepairMax, SPL_ERR_UNSUPPORTED,
-                "transpose of a matrix with 2^32 or more entries: output segments longer than 64 entries are not supported");
+                "transpose of a matrix with 2^32 or more entries: output segments longer than 256 entries are not supported");
     wide_exclusive_scan(ctx, counts, nminor, out->ptr64);
     const VB *val = static_cast<const VB *>(in->val);
     VB *oval = static_cast<VB *>(out->val);
@@ -316,11 +320,15 @@ void wide_recompress_t(spl_ctx *ctx, const spl_mat *in, spl_mat *out) {
     check_launch(ctx, "wide_minor_scatter");
     if (longest > 1) {
         if (longest <= 16)
-            wide_segment_repair_kernel<VB, 8><<<div_up((uint64_t)nminor * 8, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
+            wide_segment_repair_kernel<VB, 8, 2><<<div_up((uint64_t)nminor * 8, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
         else if (longest <= 32)
-            wide_segment_repair_kernel<VB, 16><<<div_up((uint64_t)nminor * 16, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
+            wide_segment_repair_kernel<VB, 16, 2><<<div_up((uint64_t)nminor * 16, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
+        else if (longest <= 64)
+            wide_segment_repair_kernel<VB, 32, 2><<<div_up((uint64_t)nminor * 32, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
+        else if (longest <= 128)
+            wide_segment_repair_kernel<VB, 32, 4><<<div_up((uint64_t)nminor * 32, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
         else
-            wide_segment_repair_kernel<VB, 32><<<div_up((uint64_t)nminor * 32, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
+            wide_segment_repair_kernel<VB, 32, 8><<<div_up((uint64_t)nminor * 32, 256), 256, 0, ctx->stream>>>(out->ptr64, nminor, out->ind, oval);
         check_launch(ctx, "wide_segment_repair");
     }
 }
