@@ -794,7 +794,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         except RuntimeError as e:
             sweep["blocks " + name] = str(e)[:60]
     for knob, value in (("SPL_GATHER_CTAS_PER_SM", "4"), ("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_LANES", "2"),
-                        ("SPL_GATHER_STAGES", "2")):
+                        ("SPL_GATHER_STAGES", "3")):
         os.environ[knob] = value
         D.prepare_gather(torch)                                          # fresh counters: the grid size may change
         label = f"{knob[11:].lower()} {value}"

@@ -420,7 +420,9 @@ bool spmv_gather_fused_t(size_t smem_per_sm, spl_ctx *ctx, uint32_t nloc, const 
         return o;
     };
     for (int want = most; want >= 1 && ncta == 0; --want)
-        for (uint32_t stages = ps ? (uint32_t)std::max(2, std::atoi(ps)) : 3u; stages >= 2 && ncta == 0; --stages) {
+        // two tile stages by default: a third measured 3 % faster on 8 GPUs (1.25 M rows per rank) and 36 % SLOWER on
+        // 2 GPUs (5 M rows per rank: 0.62 against 0.39 ms, profiles/r2_bench_n2.json); what it costs is L1
+        for (uint32_t stages = ps ? (uint32_t)std::max(2, std::atoi(ps)) : 2u; stages >= 2 && ncta == 0; --stages) {
             const uint32_t ctas = (uint32_t)ctx->num_sms * (uint32_t)want;
             smem = shape(ctas, stages);
             if (smem > smem_per_sm / (size_t)want) continue;
