@@ -817,7 +817,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
     out["sharded_spmv_peer_pull"] = {"workload": "same matrix; x all-gathered by one pull kernel over peer memory "
-                                                 "(device barrier + 128-bit NVLink reads), then the local SpMV",
+                                                 "(device barrier, then a TMA ring per CTA: NVLink reads), then the local SpMV",
                                      "ms": ms_pull, "gbps_algorithmic": b_ag / ms_pull / 1e6}
     xs.close(dist)
     del D, keep["D"], xg, yg, y_ag
