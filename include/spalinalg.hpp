@@ -45,6 +45,39 @@ template <typename T> struct Scalar;                       // src/scalar.rs:55-5
 template <> struct Scalar<float> { static constexpr int dtype = SPL_F32; };
 template <> struct Scalar<double> { static constexpr int dtype = SPL_F64; };
 
+// A fixed-length vector in page-locked host memory (spl_host_alloc), zero-initialised.  With PinnedVector
+// arguments matvec_into pipelines upload, product and download over row chunks (spl_spmv_host); std::vector
+// arguments give the same result through one staged copy each way.  An extension: the reference has no dense
+// vectors.
+template <typename T>
+class PinnedVector {
+public:
+    explicit PinnedVector(std::size_t n) : n_(n) {
+        void *p = nullptr;
+        if (spl_host_alloc(static_cast<std::uint64_t>(n * sizeof(T)), &p) != SPL_OK || !p)
+            throw DeviceError("spl_host_alloc failed: no CUDA device, or out of pinnable memory");
+        data_ = static_cast<T *>(p);
+        for (std::size_t i = 0; i < n_; ++i) data_[i] = T(0);
+    }
+    explicit PinnedVector(const std::vector<T> &x) : PinnedVector(x.size()) {
+        for (std::size_t i = 0; i < n_; ++i) data_[i] = x[i];
+    }
+    ~PinnedVector() { if (data_) spl_host_free(data_); }
+    PinnedVector(const PinnedVector &) = delete;
+    PinnedVector &operator=(const PinnedVector &) = delete;
+    PinnedVector(PinnedVector &&o) noexcept : data_(o.data_), n_(o.n_) { o.data_ = nullptr; o.n_ = 0; }
+    std::size_t size() const { return n_; }
+    T *data() { return data_; }
+    const T *data() const { return data_; }
+    T &operator[](std::size_t i) { return data_[i]; }
+    const T &operator[](std::size_t i) const { return data_[i]; }
+    const T *begin() const { return data_; }
+    const T *end() const { return data_ + n_; }
+private:
+    T *data_ = nullptr;
+    std::size_t n_ = 0;
+};
+
 // One spl_ctx per host thread (spl.h); created on first use on device 0.
 class Context {
 public:
@@ -406,6 +439,12 @@ public:
         std::vector<T> y(nrows_);
         ctx().check(spl_spmv_host(ctx().raw(), raw(), x.data(), y.data()));
         return y;
+    }
+    // the same into caller-owned page-locked vectors: pipelined over row chunks
+    void matvec_into(const PinnedVector<T> &x, PinnedVector<T> &y) const {
+        if (x.size() != ncols_) throw Panic("assertion `left == right` failed: self.ncols() == rhs.nrows()");
+        if (y.size() != nrows_) throw Panic("assertion `left == right` failed: self.nrows() == y.len()");
+        ctx().check(spl_spmv_host(ctx().raw(), raw(), x.data(), y.data()));
     }
     CooMatrix<T> to_coo() const {                                                         // coo.rs:629-705
         std::vector<std::uint64_t> r(nnz_), c(nnz_);

@@ -82,6 +82,15 @@ int spl_ctx_sync(spl_ctx *ctx);
  * driver (matrices and builders that are alive are untouched).  For callers about to allocate most of
  * the device themselves. */
 int spl_ctx_trim(spl_ctx *ctx);
+/* Page-locked host memory for the vectors of spl_spmv_host / spl_spmv_peer_host: with pinned x and y the
+ * upload, the product and the download are pipelined over row chunks; pageable vectors take one blocking
+ * copy each way (the result is the same).  spl_host_alloc / spl_host_free allocate such memory;
+ * spl_host_register / spl_host_unregister pin memory the caller already owns, in place (costs about as
+ * much as copying it: once per buffer, not per product).  No context: SPL_OK, SPL_ERR_ARG or SPL_ERR_CUDA. */
+int spl_host_alloc(uint64_t bytes, void **out);
+int spl_host_free(void *p);
+int spl_host_register(void *p, uint64_t bytes);
+int spl_host_unregister(void *p);
 const char *spl_last_error(const spl_ctx *ctx);
 /* After SPL_ERR_INVALID: 1-based ordinal of the failing assertion of
  * CsrMatrix::new (src/csr.rs:144-156) / CscMatrix::new (src/csc.rs:144-156):

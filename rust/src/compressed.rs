@@ -186,6 +186,17 @@ impl<T: Scalar> Compressed<T> {
         }));
         y
     }
+
+    /// `matvec` into a caller-owned vector.  With `PinnedVec`s for both (page-locked memory) the upload, the
+    /// product and the download are pipelined over row chunks; any other slices give the same result through
+    /// one staged copy each way.
+    pub fn matvec_into(&self, x: &[T], y: &mut [T]) {
+        assert_eq!(self.ncols, x.len());
+        assert_eq!(self.nrows, y.len());
+        with_ctx(|c| c.check(unsafe {
+            spl_spmv_host(c.raw(), self.raw(), x.as_ptr() as *const c_void, y.as_mut_ptr() as *mut c_void)
+        }));
+    }
 }
 
 impl<T: Scalar> std::fmt::Debug for Compressed<T> {

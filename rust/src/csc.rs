@@ -84,6 +84,8 @@ impl<T: Scalar> CscMatrix<T> {
     /// Extension: y = A x with dense host vectors (`&A * &X`, X n x 1, src/csc/ops/mul.rs:5-61); the first
     /// product builds the CSR form of the matrix on the device and keeps it.
     pub fn matvec(&self, x: &[T]) -> Vec<T> { self.0.matvec(x) }
+    /// `matvec` into `y`; pipelined when both are `PinnedVec`s.
+    pub fn matvec_into(&self, x: &[T], y: &mut [T]) { self.0.matvec_into(x, y) }
 
     pub(crate) fn inner(&self) -> &Compressed<T> { &self.0 }
     pub(crate) fn wrap(c: Compressed<T>) -> Self { CscMatrix(c) }

@@ -82,6 +82,8 @@ impl<T: Scalar> CsrMatrix<T> {
 
     /// Extension: y = A x with dense host vectors (`&A * &X`, X n x 1, src/csr/ops/mul.rs:5-60).
     pub fn matvec(&self, x: &[T]) -> Vec<T> { self.0.matvec(x) }
+    /// `matvec` into `y`; pipelined when both are `PinnedVec`s.
+    pub fn matvec_into(&self, x: &[T], y: &mut [T]) { self.0.matvec_into(x, y) }
 
     pub(crate) fn inner(&self) -> &Compressed<T> { &self.0 }
     pub(crate) fn wrap(c: Compressed<T>) -> Self { CsrMatrix(c) }

@@ -18,6 +18,10 @@ extern "C" {
     pub fn spl_ctx_destroy(ctx: *mut spl_ctx) -> c_int;
     pub fn spl_ctx_sync(ctx: *mut spl_ctx) -> c_int;
     pub fn spl_ctx_trim(ctx: *mut spl_ctx) -> c_int;
+    pub fn spl_host_alloc(bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn spl_host_free(p: *mut c_void) -> c_int;
+    pub fn spl_host_register(p: *mut c_void, bytes: u64) -> c_int;
+    pub fn spl_host_unregister(p: *mut c_void) -> c_int;
     pub fn spl_last_error(ctx: *const spl_ctx) -> *const c_char;
     pub fn spl_invalid_reason(ctx: *const spl_ctx) -> c_int;
     pub fn spl_launch_count(ctx: *const spl_ctx) -> u64;

@@ -7,6 +7,7 @@ pub mod coo;
 pub mod csc;
 pub mod csr;
 pub mod dok;
+pub mod pinned;
 pub mod scalar;
 
 mod compressed;
@@ -17,4 +18,5 @@ pub use coo::CooMatrix;
 pub use csc::CscMatrix;
 pub use csr::CsrMatrix;
 pub use dok::DokMatrix;
+pub use pinned::PinnedVec;
 pub use scalar::Scalar;

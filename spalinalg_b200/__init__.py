@@ -6,7 +6,7 @@ with `python -m spalinalg_b200.build`.  No CPU fallback.
 """
 from . import matrix
 from .matrix import (Context, CooMatrix, CscMatrix, CsrMatrix, DeviceError, DokMatrix, Panic, PinnedCooMatrix,
-                     default_context, set_default_context)
+                     default_context, pinned_empty, set_default_context)
 
 __all__ = ["Context", "CooMatrix", "CscMatrix", "CsrMatrix", "DokMatrix", "Panic", "DeviceError", "PinnedCooMatrix",
-           "default_context", "set_default_context"]
+           "default_context", "pinned_empty", "set_default_context"]

@@ -27,6 +27,10 @@ SIGNATURES = {
     "spl_ctx_destroy": (_i, [_vp]),
     "spl_ctx_sync": (_i, [_vp]),
     "spl_ctx_trim": (_i, [_vp]),
+    "spl_host_alloc": (_i, [_u64, _pp]),
+    "spl_host_free": (_i, [_vp]),
+    "spl_host_register": (_i, [_vp, _u64]),
+    "spl_host_unregister": (_i, [_vp]),
     "spl_last_error": (C.c_char_p, [_vp]),
     "spl_invalid_reason": (_i, [_vp]),
     "spl_launch_count": (_u64, [_vp]),

@@ -165,6 +165,34 @@ int spl_ctx_sync(spl_ctx *ctx) {
     API_END(ctx)
 }
 
+// page-locked host memory: no context, plain status codes
+int spl_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return SPL_ERR_ARG;
+    *out = nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? (size_t)bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return SPL_ERR_CUDA;
+    }
+    *out = p;
+    return SPL_OK;
+}
+int spl_host_free(void *p) {
+    if (!p) return SPL_OK;
+    if (cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return SPL_ERR_CUDA; }
+    return SPL_OK;
+}
+int spl_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return SPL_ERR_ARG;
+    if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return SPL_ERR_CUDA; }
+    return SPL_OK;
+}
+int spl_host_unregister(void *p) {
+    if (!p) return SPL_OK;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return SPL_ERR_CUDA; }
+    return SPL_OK;
+}
+
 int spl_ctx_trim(spl_ctx *ctx) {
     API_BEGIN(ctx)
     SPL_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -107,6 +107,34 @@ def set_default_context(ctx: Optional[Context]):
     _tls.ctx = ctx
 
 
+class _PinnedBlock:
+    """Owner of one spl_host_alloc block; freed when the last numpy view of it goes away."""
+
+    def __init__(self, nbytes: int):
+        self._lib = capi.load()
+        p = C.c_void_p()
+        status = self._lib.spl_host_alloc(max(int(nbytes), 1), C.byref(p))
+        if status != capi.SPL_OK or not p.value:
+            raise DeviceError("spl_host_alloc failed: no CUDA device, or out of pinnable memory")
+        self.addr = p.value
+
+    def __del__(self):
+        if getattr(self, "addr", None):
+            self._lib.spl_host_free(C.c_void_p(self.addr))
+            self.addr = None
+
+
+def pinned_empty(n: int, dtype=np.float64) -> np.ndarray:
+    """A 1-D numpy array of n values in page-locked host memory (spl_host_alloc).  Passed to matvec (x, and
+    out=) it lets spl_spmv_host pipeline the upload, the product and the download over row chunks; ordinary
+    arrays give the same result through one staged copy each way."""
+    dt = np.dtype(dtype)
+    block = _PinnedBlock(int(n) * dt.itemsize)
+    buf = (C.c_char * (int(n) * dt.itemsize)).from_address(block.addr)
+    buf._owner = block                                        # numpy keeps buf (its base) alive, buf keeps the block
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -756,14 +784,20 @@ class _Compressed:
         return type(self)._wrap(self._ctx, h)
 
 
-    def matvec(self, x: np.ndarray) -> np.ndarray:
+    def matvec(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """y = A x with host vectors (extension; reference route is `&A * &X`, X n x 1,
         src/csr/ops/mul.rs:5-60, src/csc/ops/mul.rs:5-61).  Uploads x, runs the SpMV kernel, downloads y.
-        On a CscMatrix the first product builds (and keeps) the CSR form on the device."""
+        On a CscMatrix the first product builds (and keeps) the CSR form on the device.  With x and out from
+        pinned_empty() the three steps are pipelined over row chunks."""
         x = np.ascontiguousarray(x, dtype=self._dtype)
         if len(x) != self._ncols:
             raise Panic("assertion `left == right` failed: self.ncols() == rhs.nrows()")
-        y = np.empty(self._nrows, self._dtype)
+        if out is not None:
+            if out.dtype != self._dtype or out.shape != (self._nrows,) or not out.flags.c_contiguous:
+                raise Panic("assertion `left == right` failed: self.nrows() == out.len()")
+            y = out
+        else:
+            y = np.empty(self._nrows, self._dtype)
         self._ctx.check(self._ctx._lib.spl_spmv_host(self._ctx._h, self._h, _ptr(x), _ptr(y)))
         return y
 

@@ -122,6 +122,11 @@ static int run() {
         CHECK(a.matvec(D{10, 20, 30}) == (D{70, 0, 180}));
         a.values_mut([](D &v) { for (auto &e : v) e *= 2; });                            // src/csr.rs:270-272
         CHECK(a.values() == (D{2, 4, 6, 8}) && a.matvec(D{10, 20, 30}) == (D{140, 0, 360}));
+        PinnedVector<double> px(D{10, 20, 30}), py(3);                                    // page-locked vectors (spl_host_alloc)
+        a.matvec_into(px, py);
+        CHECK(py[0] == 140 && py[1] == 0 && py[2] == 360);
+        PinnedVector<double> short_y(2);
+        CHECK(panics([&] { a.matvec_into(px, short_y); }));
         CHECK(panics([&] { (void)(x * a); }));                                             // mul.rs:9
     }
     {   // src/csc/ops/add.rs:77-100, src/csc/ops/sub.rs:77-103, src/csc/ops/neg.rs:25-36 (CSC twins), f32 values

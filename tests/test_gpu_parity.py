@@ -905,6 +905,14 @@ def test_spmv_host_pipelined_matches_device_product(kind):
     scale = orc.csr_spmv(n, a[0], a[1], np.abs(a[2]), np.abs(x))
     assert np.all(np.abs(hy.numpy() - want) <= 1e-12 * np.maximum(scale, 1e-300))
     assert np.array_equal(A.matvec(x), hy.numpy())          # pageable vectors: the plain path, same result
+    # the library's own page-locked vectors (spl_host_alloc) through the host mirror: the pipelined path again
+    px, py = sp.pinned_empty(m, np.float64), sp.pinned_empty(n, np.float64)
+    px[:] = x
+    py[:] = 7.0
+    assert A.matvec(px, out=py) is py and np.array_equal(py, hy.numpy())
+    with pytest.raises(sp.Panic):
+        A.matvec(px, out=sp.pinned_empty(n + 1, np.float64))
+    del px, py
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
