@@ -292,7 +292,11 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, uint3
                 const uint32_t lo = s_tlo[k * (ntiles + 1) + t], hi = s_tlo[k * (ntiles + 1) + t + 1];
                 if (i >= sh.stages) gf_mbar_wait(empty + s, phase ^ 1u);
                 const uint32_t za = lo & ~3u, zb = (hi + 3u) & ~3u;           // 16-byte aligned superset; the arrays carry slack
-                const uint32_t cnt = zb - za;
+                uint32_t cnt = zb - za;
+                if (cnt > sh.cap) {                        // tile_entries_max was too small: never overrun the stage — the
+                    atomicExch(gb.failed, 1u);             // tile is cut (the consumers clamp too) and y comes back as NaN
+                    cnt = sh.cap;
+                }
                 const uint32_t r0 = rs + t * R;
                 const uint32_t left = (pstride - r0) & ~3u;                   // pointer entries from r0 to the end of the block's array
                 const uint32_t np = left < PTRS ? left : PTRS;
@@ -336,7 +340,7 @@ spmv_gather_fused_kernel(uint32_t nloc, const uint32_t *__restrict__ bptr, uint3
             const uint32_t r = rs + t * R + rl;
             const uint32_t za = cp[0] & ~3u;
             uint32_t p0 = 0, e = 0;
-            if (r < re) { p0 = cp[rl] - za; e = cp[rl + 1] - za; }
+            if (r < re) { p0 = min(cp[rl] - za, sh.cap); e = min(cp[rl + 1] - za, sh.cap); }      // never past the stage
             T prev = (T)0;
             if (k > 0 && sub == 0 && r < re) prev = y[r];              // in flight with the gathers
             T acc = (T)0;
