@@ -646,6 +646,18 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
             ts.append(float(t.item()))
         return statistics.median(ts)
 
+    def agree(ok):
+        """The same verdict on every rank (a check that failed on one rank only must not leave the others waiting
+        in the next collective): True when it held everywhere."""
+        t = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def worst(v):
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def total(v, op=None):
         t = torch.tensor([v], device="cuda", dtype=torch.int64)
         dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
@@ -713,7 +725,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         keep["P"] = spd.DistCsrMatrix.from_device_triplets_peer(dist, torch, nr, nr, r_, c_, v_, ex)
     ms_p = timed_all(asm_peer)
     ex.check()
-    assert keep["P"].local.nnz() == keep["D"].local.nnz()
+    same_nnz = agree(keep["P"].local.nnz() == keep["D"].local.nnz())
     del keep["P"]
     D = keep["D"]
     nnz_d = total(D.local.nnz())
@@ -722,7 +734,8 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
                                "len": ln, "nnz_out": nnz_d, "ms": ms, "mnnz_per_s": ln / ms / 1e3}
     out["sharded_assembly_peer"] = {"workload": "same triplets; routing and exchange fused: the partition pass writes "
                                                 "into the owners' buffers over NVLink (peer memory), no all-to-all",
-                                    "len": ln, "nnz_out": nnz_d, "ms": ms_p, "mnnz_per_s": ln / ms_p / 1e3}
+                                    "len": ln, "nnz_out": nnz_d, "ms": ms_p if same_nnz else None,
+                                    "mnnz_per_s": ln / ms_p / 1e3 if same_nnz else None, "same_nnz_as_nccl_route": same_nnz}
     del r_, c_, v_
 
     # general (random-column) matrix: x exchanged (NCCL all-gather / pull over peer memory), then the local SpMV
@@ -748,7 +761,7 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     y_ag = yg.clone()
     ms_pull = timed_all(spmv_pull, reps=7, warm=3, batch=10)
     xs.check()
-    assert torch.equal(y_ag, yg), "pulled all-gather gives a different y"
+    pull_same = agree(torch.equal(y_ag, yg))                             # same kernel on the same x: bit for bit
     # the all-gather fused into the product: one persistent kernel, a copy warp per CTA pulls the slices over NVLink
     # (TMA bulk copies) while the compute warps work through the owner blocks
     D.prepare_gather(torch)
@@ -757,8 +770,8 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True)      # the barrier is part of the kernel
     ms_fused = timed_all(spmv_fused, reps=7, warm=3, batch=10)
     xs.check()
-    err = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-    assert err < 1e-5, f"fused gather SpMV differs from the all-gather product: {err}"
+    err = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+    fused_ok = err < 1e-5                                                # the same on every rank
     # where the time of one fused product goes: %globaltimer stamps from the kernel (first CTA)
     first = D._gather["first"]
     nb = len(first) - 1
@@ -789,8 +802,9 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         D.prepare_gather(torch, block_first=bf)
         try:
             sweep["blocks " + name] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
-            e2 = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-            assert e2 < 1e-5, f"fused gather SpMV, blocks {name}: differs from the all-gather product: {e2}"
+            e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+            if not e2 < 1e-5:
+                sweep["blocks " + name] = f"MISMATCH against the all-gather product: {e2:.3g}"
         except RuntimeError as e:
             sweep["blocks " + name] = str(e)[:60]
     for knob, value in (("SPL_GATHER_CTAS_PER_SM", "4"), ("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_LANES", "2"),
@@ -800,8 +814,9 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
         label = f"{knob[11:].lower()} {value}"
         try:
             sweep[label] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
-            e2 = float(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-            assert e2 < 1e-5, f"fused gather SpMV, {label}: differs from the all-gather product: {e2}"
+            e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+            if not e2 < 1e-5:
+                sweep[label] = f"MISMATCH against the all-gather product: {e2:.3g}"
         except RuntimeError as e:
             sweep[label] = str(e)[:60]
         os.environ.pop(knob, None)
@@ -810,15 +825,18 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
                                                     "the peers' slices of x over NVLink with TMA bulk copies, and the compute "
                                                     "warps multiplying the shard block by block (blocked by column owner, ring "
                                                     "order) as the slices land",
-                                        "ms": ms_fused, "gbps_algorithmic": b_ag / ms_fused / 1e6,
-                                        "max_rel_diff_vs_allgather": err, "block_first": first, "ms_variants": sweep,
+                                        "ms": ms_fused if fused_ok else None,      # no number for a product that is off
+                                        "gbps_algorithmic": b_ag / ms_fused / 1e6 if fused_ok else None,
+                                        "within_1e-5_of_allgather": fused_ok, "max_rel_diff_vs_allgather": err if err == err else None, "block_first": first, "ms_variants": sweep,
                                         "timeline_rank0_first_cta": stamps}
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
     out["sharded_spmv_peer_pull"] = {"workload": "same matrix; x all-gathered by one pull kernel over peer memory "
                                                  "(device barrier, then a TMA ring per CTA: NVLink reads), then the local SpMV",
-                                     "ms": ms_pull, "gbps_algorithmic": b_ag / ms_pull / 1e6}
+                                     "ms": ms_pull if pull_same else None,
+                                     "gbps_algorithmic": b_ag / ms_pull / 1e6 if pull_same else None,
+                                     "bit_identical_to_allgather": pull_same}
     xs.close(dist)
     del D, keep["D"], xg, yg, y_ag
     torch.cuda.empty_cache()
