@@ -762,73 +762,80 @@ def sharded_extras(torch, dist, sp, spd, ctx, A, n, r0, r1, rank, world):
     ms_pull = timed_all(spmv_pull, reps=7, warm=3, batch=10)
     xs.check()
     pull_same = agree(torch.equal(y_ag, yg))                             # same kernel on the same x: bit for bit
-    # the all-gather fused into the product: one persistent kernel, a copy warp per CTA pulls the slices over NVLink
-    # (TMA bulk copies) while the compute warps work through the owner blocks
-    D.prepare_gather(torch)
 
-    def spmv_fused():
-        D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True)      # the barrier is part of the kernel
-    ms_fused = timed_all(spmv_fused, reps=7, warm=3, batch=10)
-    xs.check()
-    err = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-    fused_ok = err < 1e-5                                                # the same on every rank
-    # where the time of one fused product goes: %globaltimer stamps from the kernel (first CTA)
-    first = D._gather["first"]
-    nb = len(first) - 1
-    tl = torch.zeros(2 + 3 * nb, dtype=torch.int64, device="cuda")
-    dist.barrier(); torch.cuda.synchronize()
-    for _ in range(6):                                                   # stamps of a product in the middle of a run of them:
-        spmv_fused()                                                     # a lone launch would mostly show how far apart the
-    D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())     # ranks' hosts are
-    for _ in range(3):
-        spmv_fused()
-    torch.cuda.synchronize()
-    t = tl.cpu().tolist()
-    t0 = t[1]                                                            # the first consumer warp starts
-    stamps = [{"block": k, "ring_offsets": [first[k], first[k + 1]], "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3,
-               "slices_landed_us": (t[2 + 3 * k] - t0) / 1e3, "block_done_us": (t[3 + 3 * k] - t0) / 1e3}
-              for k in range(nb)]
-    stamps.append({"last_cta_done_us": (t[1 + 3 * nb] - t0) / 1e3, "first_peer_arrived_copy_starts_us": (t[0] - t0) / 1e3})
-    # how the shard is blocked (one pass over the rows per block) and how many CTAs stay resident: measured per run,
-    # the library's defaults stand in the headline number above
-    sweep = {}
-    shapes = {"per_rank": list(range(world + 1)), "own|rest": [0, 1, world]}
-    if world >= 8:
-        shapes["1|1|2|4"] = [0, 1, 2, 4, 8]
-        shapes["1|1|1|1|2|2"] = [0, 1, 2, 3, 4, 6, 8]
-    for name, bf in shapes.items():
-        if bf == first or len(set(bf)) != len(bf):
-            continue
-        D.prepare_gather(torch, block_first=bf)
-        try:
-            sweep["blocks " + name] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
-            e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-            if not e2 < 1e-5:
-                sweep["blocks " + name] = f"MISMATCH against the all-gather product: {e2:.3g}"
-        except RuntimeError as e:
-            sweep["blocks " + name] = str(e)[:60]
-    for knob, value in (("SPL_GATHER_CTAS_PER_SM", "4"), ("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_LANES", "2"),
-                        ("SPL_GATHER_STAGES", "3")):
-        os.environ[knob] = value
-        D.prepare_gather(torch)                                          # fresh counters: the grid size may change
-        label = f"{knob[11:].lower()} {value}"
-        try:
-            sweep[label] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
-            e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
-            if not e2 < 1e-5:
-                sweep[label] = f"MISMATCH against the all-gather product: {e2:.3g}"
-        except RuntimeError as e:
-            sweep[label] = str(e)[:60]
-        os.environ.pop(knob, None)
-    xs.check()
-    out["sharded_spmv_gather_fused"] = {"workload": "same matrix; ONE kernel: the device barrier, one copy warp per CTA pulling "
-                                                    "the peers' slices of x over NVLink with TMA bulk copies, and the compute "
-                                                    "warps multiplying the shard block by block (blocked by column owner, ring "
-                                                    "order) as the slices land",
-                                        "ms": ms_fused if fused_ok else None,      # no number for a product that is off
-                                        "gbps_algorithmic": b_ag / ms_fused / 1e6 if fused_ok else None,
-                                        "within_1e-5_of_allgather": fused_ok, "max_rel_diff_vs_allgather": err if err == err else None, "block_first": first, "ms_variants": sweep,
-                                        "timeline_rank0_first_cta": stamps}
+    def fused_section():
+        # the all-gather fused into the product: one persistent kernel, a copy warp per CTA pulls the slices over NVLink
+        # (TMA bulk copies) while the compute warps work through the owner blocks
+        D.prepare_gather(torch)
+
+        def spmv_fused():
+            D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True)      # the barrier is part of the kernel
+        ms_fused = timed_all(spmv_fused, reps=7, warm=3, batch=10)
+        xs.check()
+        err = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+        fused_ok = err < 1e-5                                                # the same on every rank
+        # where the time of one fused product goes: %globaltimer stamps from the kernel (first CTA)
+        first = D._gather["first"]
+        nb = len(first) - 1
+        tl = torch.zeros(2 + 3 * nb, dtype=torch.int64, device="cuda")
+        dist.barrier(); torch.cuda.synchronize()
+        for _ in range(6):                                                   # stamps of a product in the middle of a run of them:
+            spmv_fused()                                                     # a lone launch would mostly show how far apart the
+        D.spmv_gather(xs, xg.data_ptr(), yg.data_ptr(), barrier=True, timeline_dev=tl.data_ptr())     # ranks' hosts are
+        for _ in range(3):
+            spmv_fused()
+        torch.cuda.synchronize()
+        t = tl.cpu().tolist()
+        t0 = t[1]                                                            # the first consumer warp starts
+        stamps = [{"block": k, "ring_offsets": [first[k], first[k + 1]], "wait_begins_us": (t[1 + 3 * k] - t0) / 1e3,
+                   "slices_landed_us": (t[2 + 3 * k] - t0) / 1e3, "block_done_us": (t[3 + 3 * k] - t0) / 1e3}
+                  for k in range(nb)]
+        stamps.append({"last_cta_done_us": (t[1 + 3 * nb] - t0) / 1e3, "first_peer_arrived_copy_starts_us": (t[0] - t0) / 1e3})
+        # how the shard is blocked (one pass over the rows per block) and how many CTAs stay resident: measured per run,
+        # the library's defaults stand in the headline number above
+        sweep = {}
+        shapes = {"per_rank": list(range(world + 1)), "own|rest": [0, 1, world]}
+        if world >= 8:
+            shapes["1|1|2|4"] = [0, 1, 2, 4, 8]
+            shapes["1|1|1|1|2|2"] = [0, 1, 2, 3, 4, 6, 8]
+        for name, bf in shapes.items():
+            if bf == first or len(set(bf)) != len(bf):
+                continue
+            D.prepare_gather(torch, block_first=bf)
+            try:
+                sweep["blocks " + name] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
+                e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+                if not e2 < 1e-5:
+                    sweep["blocks " + name] = f"MISMATCH against the all-gather product: {e2:.3g}"
+            except RuntimeError as e:
+                sweep["blocks " + name] = str(e)[:60]
+        for knob, value in (("SPL_GATHER_CTAS_PER_SM", "4"), ("SPL_GATHER_CTAS_PER_SM", "2"), ("SPL_GATHER_LANES", "2"),
+                            ("SPL_GATHER_STAGES", "3")):
+            os.environ[knob] = value
+            D.prepare_gather(torch)                                          # fresh counters: the grid size may change
+            label = f"{knob[11:].lower()} {value}"
+            try:
+                sweep[label] = timed_all(spmv_fused, reps=5, warm=2, batch=10)
+                e2 = worst(((yg - y_ag).abs().max() / (y_ag.abs().max() + 1e-30)).item())
+                if not e2 < 1e-5:
+                    sweep[label] = f"MISMATCH against the all-gather product: {e2:.3g}"
+            except RuntimeError as e:
+                sweep[label] = str(e)[:60]
+            os.environ.pop(knob, None)
+        xs.check()
+        return {"workload": "same matrix; ONE kernel: the device barrier, one copy warp per CTA pulling "
+                                                        "the peers' slices of x over NVLink with TMA bulk copies, and the compute "
+                                                        "warps multiplying the shard block by block (blocked by column owner, ring "
+                                                        "order) as the slices land",
+                                            "ms": ms_fused if fused_ok else None,      # no number for a product that is off
+                                            "gbps_algorithmic": b_ag / ms_fused / 1e6 if fused_ok else None,
+                                            "within_1e-5_of_allgather": fused_ok, "max_rel_diff_vs_allgather": err if err == err else None, "block_first": first, "ms_variants": sweep,
+                                            "timeline_rank0_first_cta": stamps}
+    try:
+        out["sharded_spmv_gather_fused"] = fused_section()
+    except RuntimeError as e:                                             # the library refused (same on every rank): say so
+        out["sharded_spmv_gather_fused"] = {"error": str(e)[:200]}
+        os.environ.pop("SPL_GATHER_CTAS_PER_SM", None); os.environ.pop("SPL_GATHER_LANES", None); os.environ.pop("SPL_GATHER_STAGES", None)
     out["sharded_spmv_allgather"] = {"workload": "config 3 matrix assembled above (random 16/row, f32), x all-gathered "
                                                  "with NCCL every step", "ms": ms, "gbps_algorithmic": b_ag / ms / 1e6,
                                      "x_bytes_received_per_rank": (nr - (d1 - d0)) * 4}
