@@ -93,3 +93,19 @@ def test_balanced_starts_follow_the_entries():
     # more ranks than non-empty bins: still a valid partition
     st = spd.balanced_starts([5, 0, 0, 0], 4, 16, 4)
     assert st[0] == 0 and st[-1] == 16 and all(b > a for a, b in zip(st, st[1:]))
+
+
+def test_gather_groups_block_the_shard_by_ring_offset(monkeypatch):
+    """Blocking of a general shard for the fused all-gather + SpMV (spl_spmv_gather_fused): block 0 is the
+    own slice alone, the peers follow in ring order, one block per rank unless SPL_GATHER_GROUPS groups them."""
+    from spalinalg_b200.dist import DistCsrMatrix as D
+    monkeypatch.delenv("SPL_GATHER_GROUPS", raising=False)
+    for world in (1, 2, 3, 8):
+        first = D.gather_groups(world)
+        assert first == list(range(world + 1))
+    monkeypatch.setenv("SPL_GATHER_GROUPS", "1,1,2,4")
+    assert D.gather_groups(8) == [0, 1, 2, 4, 8]
+    for bad, world in (("2,6", 8), ("1,1,2", 8), ("1,0,7", 8)):
+        monkeypatch.setenv("SPL_GATHER_GROUPS", bad)
+        with pytest.raises(ValueError):
+            D.gather_groups(world)
