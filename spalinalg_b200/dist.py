@@ -10,11 +10,14 @@ keeps GLOBAL column indices.  What moves between ranks, and how:
              among duplicates — and runs the single-GPU assembly (spl_mat_from_packed_dev).
              Bit-exact against the reference's From<&CooMatrix> on the whole matrix.
   SpMV       x stays where it lives.  Every rank keeps its slice of x in peer-visible memory
-             (CUDA IPC over NVLink/NVSwitch); spl_spmv_peer gathers each x[c] from the slice that
-             owns column c inside the SpMV kernel itself: no staging copy, no collective, and for a
-             banded or stencil matrix only the few halo columns ever cross NVLink.  Ordering between
-             iterations is a device-side flag barrier over the same peer memory (spl_peer_barrier).
-             General (random / power-law) matrices all-gather x with NCCL instead (sharding.py).
+             (CUDA IPC over NVLink/NVSwitch), twice (products read the published buffer, the rank
+             writes the other).  Banded / stencil shards: one small kernel is the device-side flag
+             barrier and copies the few halo columns next to the own slice (spl_peer_barrier_halo),
+             then the unsharded kernels run (spl_spmv_window); spl_spmv_peer, which gathers each
+             x[c] from the slice that owns column c inside the kernel, stays available.  General
+             (random / power-law) shards need the whole of x: ONE kernel pulls the peers' slices
+             with TMA bulk copies while it multiplies block by block (spl_spmv_gather_fused), or
+             x is pulled / all-gathered first (spl_peer_pull, NCCL in sharding.py).
   add/sub/neg  no exchange when the operands share the partition.
 
 torch.distributed is the plumbing (rendezvous, the all-to-all, object exchange of IPC handles);
@@ -326,9 +329,9 @@ class DistCsrMatrix:
     @staticmethod
     def gather_groups(world: int):
         """Default blocking of a shard for spmv_gather: ring offsets where blocks begin.  One block per rank (own
-        columns, then rank+1, rank+2, ...): the finest overlap of transfer and product; the kernel keeps eight gathers
-        in flight per lane however short a row's share of a block is.  SPL_GATHER_GROUPS=1,1,2,4 (widths) groups
-        consecutive peers into wider blocks (fewer passes over the rows, coarser overlap)."""
+        columns, then rank+1, rank+2, ...): the finest overlap of transfer and product (fastest measured on 8 GPUs).
+        SPL_GATHER_GROUPS=1,1,2,4 (widths) groups consecutive peers into wider blocks (fewer passes over the rows,
+        coarser overlap)."""
         env = os.environ.get("SPL_GATHER_GROUPS")
         widths = [1] * world
         if env:

@@ -326,7 +326,7 @@ def test_sharded_front_end_world1_nccl():
         ctx.sync()
         xv.check()
         assert np.all(np.abs(y.cpu().numpy() - yw) <= 1e-12 * sc + 1e-300)
-        # the fused gather kernel with a world of one: no copy CTAs, the own block only
+        # the fused gather kernel with a world of one: nothing to copy, the own block only
         D.prepare_gather(torch)
         xf = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
         y.fill_(7.0)

@@ -98,8 +98,8 @@ def _worker(rank, world, port, out):
         ok &= bool(np.all(np.abs(y.cpu().numpy() - yw[r0:r1]) <= 1e-12 * sc[r0:r1] + 1e-300))
         assert ok, "pulled all-gather SpMV differs from the oracle"
 
-        # general shards: the all-gather fused into the product (copy CTAs pull the slices over NVLink while
-        # the compute CTAs work through the owner blocks); two products on one set of flags, x changed between
+        # general shards: the all-gather fused into the product (a copy warp per CTA pulls the slices over NVLink
+        # while the consumer warps work through the owner blocks); two products on one set of flags, x changed between
         D.prepare_gather(torch)
         for scale_x in (1.0, -0.5):
             device_view(torch, xv.local_ptr, r1 - r0, torch.float64).copy_(torch.from_numpy(scale_x * x[r0:r1]))
