@@ -328,8 +328,9 @@ int spl_spmv_footprint(spl_ctx *ctx, const spl_mat *a, uint64_t *col_min, uint64
 /* All-gather of x by pulling over peer memory, for general (random / power-law) shards whose
  * gathers would be 4-byte NVLink transactions: one kernel copies every peer's slice
  * (slices[g] = x[starts[g] .. starts[g+1]), mapped with spl_peer_open) into the local full-length
- * vector x_full_dev with 128-bit coalesced loads; the own slice is not touched (keep it in place
- * or copy it yourself).  Order it with spl_peer_barrier like spl_spmv_peer. */
+ * vector x_full_dev with TMA bulk copies through a shared-memory ring (one thread per CTA; slices
+ * whose ends are not 16-byte aligned go value by value); the own slice is not touched (keep it in
+ * place or copy it yourself).  Order it with spl_peer_barrier like spl_spmv_peer. */
 int spl_peer_pull(spl_ctx *ctx, int dtype, int world, int rank, const uint64_t *starts,
                   const void *const *slices, void *x_full_dev);
 /* Row-sharded y_local = A_local * x with x left where it lives: x_slices[g] is rank
