@@ -122,3 +122,50 @@ def test_synthetic_generators():
     assert len(v) == (3 * 5 - 2) ** 3
     r, c, v = syn.banded(100, range(-4, 5))
     assert len(v) == 9 * 100 - 20
+
+
+def _c_declarations():
+    import re
+    h = open(os.path.join(ROOT, "include", "spl.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    h = re.sub(r"//[^\n]*", "", h)
+    out = {}
+    for name, args in re.findall(r"\b(?:int|uint64_t|const char \*)\s*(spl_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S):
+        out[name] = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+    return out
+
+
+def test_rust_and_python_bindings_follow_the_header():
+    """rust/src/ffi.rs (not compiled in this image) and spalinalg_b200/_capi.py declare every entry point of
+    include/spl.h with the same number of arguments, pointers where the header has pointers and integers of
+    the header's width where it has integers."""
+    import re
+    from spalinalg_b200 import _capi
+    c = _c_declarations()
+    assert len(c) >= 60
+    r = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    r = re.sub(r"//[^\n]*", "", r)
+    rust = {m.group(1): [a.strip() for a in m.group(2).split(",") if a.strip()]
+            for m in re.finditer(r"pub fn (spl_[a-z_0-9]+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", r, flags=re.S)}
+    assert set(rust) == set(c), (sorted(set(c) - set(rust)), sorted(set(rust) - set(c)))
+
+    def kind_c(a):
+        if "*" in a:
+            return "ptr"
+        t = a.rsplit(" ", 1)[0].replace("const ", "").strip()
+        return {"int": "i32", "uint32_t": "u32", "uint64_t": "u64", "double": "f64", "float": "f32"}[t]
+
+    def kind_rust(a):
+        t = a.split(":", 1)[1].strip()
+        if t.startswith("*"):
+            return "ptr"
+        return {"c_int": "i32", "u32": "u32", "u64": "u64", "f64": "f64", "f32": "f32"}[t]
+
+    for name, args in c.items():
+        assert [kind_c(a) for a in args] == [kind_rust(a) for a in rust[name]], name
+    sigs = {k: v for k, v in vars(_capi).items() if isinstance(v, dict) and "spl_ctx_create" in v}
+    assert len(sigs) == 1
+    table = next(iter(sigs.values()))
+    assert set(table) == set(c)
+    for name, (_res, argtypes) in table.items():
+        assert len(argtypes) == len(c[name]), name
