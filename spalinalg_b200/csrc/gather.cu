@@ -164,6 +164,7 @@ __device__ void gather_copy_warp(const GatherPeers &gp, T *x_full, uint32_t *rea
         const unsigned long long total = cum[G - 1];
         const unsigned long long mine = total > cta ? (total - cta + ncta - 1) / ncta : 0;
         int kl = 1, ks = 1, ksig = 1, kw = 0;
+        __threadfence();                                                               // the warp's element-path stores above
         for (; ksig < G && cum[ksig] <= cta; ++ksig) atomicAdd(ready + ksig, 1u);      // slices that hold no chunk of this CTA
         auto slice_of = [&](int k, const unsigned char *&src, unsigned char *&dst, unsigned long long &b16) {
             const int g = (gp.rank + k) % G;
