@@ -163,6 +163,43 @@ def _assemble_over_peers(dist, torch, fmt: int, nrows: int, ncols: int, row, col
     return h, starts
 
 
+def gather_block_layout(torch, ptr, col, val, starts, rank: int, first):
+    """The blocked form of a row shard that spl_spmv_gather_fused takes (plain tensor plumbing: runs on the
+    device for prepare_gather and on the CPU in the tests).  ptr: int64[nloc+1] row pointers of the shard,
+    col: int32 (uint32 bit pattern) GLOBAL columns, val: values; starts: column partition; first: ring offsets
+    where blocks begin (block b = columns owned by ranks rank+first[b] .. rank+first[b+1]-1, mod world).
+    Returns bptr int32[nblocks, stride] (absolute positions; every row padded to a multiple of 4 entries that
+    repeat the end position, plus 4), bind / bval (entries stably regrouped by block, row order and column
+    order kept inside a block, 4 entries of slack), stride, and caps = the most entries any 64 / 128 / 256 /
+    512 / 1024 consecutive rows starting at a multiple of 32 hold in one block."""
+    world = len(starts) - 1
+    nloc = int(ptr.numel()) - 1
+    nb = len(first) - 1
+    dev = col.device
+    rows = torch.repeat_interleave(torch.arange(nloc, device=dev), ptr[1:] - ptr[:-1])
+    bounds = torch.tensor(list(starts[1:-1]), device=dev, dtype=torch.int64)
+    owner = torch.searchsorted(bounds, col.long() & 0xFFFFFFFF, right=True)
+    offset = (owner - rank) % world
+    block = torch.searchsorted(torch.tensor(list(first[1:]), device=dev, dtype=torch.int64), offset, right=True).to(torch.int16)
+    order = torch.sort(block, stable=True).indices
+    bind = col[order].contiguous()
+    bval = val[order].contiguous()
+    key = block[order].long() * nloc + rows[order]
+    counts = torch.bincount(key, minlength=nb * nloc).view(nb, nloc)
+    base = torch.cumsum(counts.sum(1), 0) - counts.sum(1)                 # first position of every block
+    # the kernel fetches whole tiles with 16-byte bulk copies: pointer arrays padded to a multiple of 4 entries (the
+    # padding repeats the end position), four entries of slack behind the indices and values
+    stride = (nloc + 1 + 3) // 4 * 4 + 4
+    bptr = torch.zeros((nb, stride), dtype=torch.int64, device=dev)
+    bptr[:, 1:nloc + 1] = torch.cumsum(counts, 1)
+    bptr[:, nloc + 1:] = bptr[:, nloc:nloc + 1]
+    bptr += base[:, None]
+    pad = lambda t: torch.cat([t, torch.zeros(4, dtype=t.dtype, device=t.device)])
+    at = torch.arange(0, max(nloc, 1), 32, device=dev)
+    caps = [int((bptr[:, torch.clamp(at + w, max=nloc)] - bptr[:, at]).max().item()) for w in (64, 128, 256, 512, 1024)]
+    return {"bptr": bptr.to(torch.int32).contiguous(), "bind": pad(bind), "bval": pad(bval), "stride": stride, "caps": caps}
+
+
 class DistCsrMatrix:
     """Row block of a CSR matrix on this rank plus the partition it belongs to."""
 
@@ -363,31 +400,9 @@ class DistCsrMatrix:
         ptr = device_view(torch, p_ptr, nloc + 1, torch.int32).long()
         col = device_view(torch, p_ind, max(nnz, 1), torch.int32)[:nnz]
         val = device_view(torch, p_val, max(nnz, 1), tdt)[:nnz]
-        rows = torch.repeat_interleave(torch.arange(nloc, device=col.device), ptr[1:] - ptr[:-1])
-        bounds = torch.tensor(self.starts[1:-1], device=col.device, dtype=torch.int64)
-        owner = torch.searchsorted(bounds, col.long() & 0xFFFFFFFF, right=True)
-        offset = (owner - self.rank) % G
-        block_of = torch.searchsorted(torch.tensor(first[1:], device=col.device, dtype=torch.int64), offset, right=True)
-        block = block_of.to(torch.int16)
-        order = torch.sort(block, stable=True).indices
-        bind = col[order].contiguous()
-        bval = val[order].contiguous()
-        key = block[order].long() * nloc + rows[order]
-        counts = torch.bincount(key, minlength=nb * nloc).view(nb, nloc)
-        base = torch.cumsum(counts.sum(1), 0) - counts.sum(1)                 # first position of every block
-        # the kernel fetches whole tiles with 16-byte bulk copies: pointer arrays padded to a multiple of 4 entries (the
-        # padding repeats the end position), four entries of slack behind the indices and values
-        stride = (nloc + 1 + 3) // 4 * 4 + 4
-        bptr = torch.zeros((nb, stride), dtype=torch.int64, device=col.device)
-        bptr[:, 1:nloc + 1] = torch.cumsum(counts, 1)
-        bptr[:, nloc + 1:] = bptr[:, nloc:nloc + 1]
-        bptr += base[:, None]
-        pad = lambda t: torch.cat([t, torch.zeros(4, dtype=t.dtype, device=t.device)])
-        # most entries any 64 ... 1024 consecutive rows (from a multiple of 32) hold in one block
-        at = torch.arange(0, max(nloc, 1), 32, device=col.device)
-        caps = [int((bptr[:, torch.clamp(at + w, max=nloc)] - bptr[:, at]).max().item()) for w in (64, 128, 256, 512, 1024)]
-        self._gather = {"bptr": bptr.to(torch.int32).contiguous(), "bind": pad(bind), "bval": pad(bval), "first": first,
-                        "stride": stride, "caps": caps,
+        lay = gather_block_layout(torch, ptr, col, val, self.starts, self.rank, first)
+        self._gather = {"bptr": lay["bptr"], "bind": lay["bind"], "bval": lay["bval"], "first": first,
+                        "stride": lay["stride"], "caps": lay["caps"],
                         "ready": torch.zeros(capi.SPL_MAX_PEERS, dtype=torch.int32, device=col.device), "epoch": 0}
         torch.cuda.current_stream().synchronize()
 

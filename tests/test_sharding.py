@@ -109,3 +109,52 @@ def test_gather_groups_block_the_shard_by_ring_offset(monkeypatch):
         monkeypatch.setenv("SPL_GATHER_GROUPS", bad)
         with pytest.raises(ValueError):
             D.gather_groups(world)
+
+
+@pytest.mark.parametrize("world,first", [(1, [0, 1]), (2, [0, 1, 2]), (3, [0, 1, 2, 3]), (5, [0, 1, 3, 5]), (8, [0, 1, 2, 4, 8])])
+def test_gather_block_layout_is_the_shard_regrouped_by_column_owner(world, first):
+    """The blocked form spl_spmv_gather_fused takes (dist.gather_block_layout, the body of prepare_gather) on CPU
+    tensors: every entry of the shard appears once, in the block of its column's owner (ring order from the own
+    rank), rows and columns in order inside a block; the pointer arrays are padded as the kernel's 16-byte bulk
+    copies need; tile_entries_max bounds every tile; and the kernel's walk over the layout (block by block, row
+    by row) gives the shard's product."""
+    from spalinalg_b200.dist import gather_block_layout, partition_starts
+    rng = np.random.default_rng(world)
+    n = 2000 + world
+    starts = partition_starts(n, world)
+    x = rng.standard_normal(n)
+    for rank in range(world):
+        r0, r1 = starts[rank], starts[rank + 1]
+        nloc = r1 - r0
+        deg = rng.integers(0, 12, nloc)
+        deg[rng.integers(0, nloc, 3)] = 90                                   # a few long rows
+        ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+        col = np.concatenate([np.sort(rng.choice(n, d, replace=False)) for d in deg]).astype(np.int64)
+        val = rng.standard_normal(len(col))
+        lay = gather_block_layout(torch, torch.from_numpy(ptr), torch.from_numpy(col.astype(np.uint32).view(np.int32)),
+                                  torch.from_numpy(val), starts, rank, first)
+        nb, stride = len(first) - 1, lay["stride"]
+        bptr, bind, bval = lay["bptr"].numpy().astype(np.int64), lay["bind"].numpy().view(np.uint32).astype(np.int64), lay["bval"].numpy()
+        assert bptr.shape == (nb, stride) and stride % 4 == 0 and stride >= nloc + 1 + 3
+        assert len(bind) == len(col) + 4 and len(bval) == len(col) + 4
+        assert bptr[0, 0] == 0 and bptr[-1, nloc] == len(col)
+        assert np.all(bptr[:, nloc + 1:] == bptr[:, nloc:nloc + 1])        # padding repeats the end position
+        assert np.all(bptr[1:, 0] == bptr[:-1, nloc])                      # blocks follow each other
+        owner = np.searchsorted(np.asarray(starts[1:-1]), bind[:len(col)], side="right")
+        y = np.zeros(nloc)
+        seen = 0
+        for b in range(nb):
+            lo, hi = bptr[b, 0], bptr[b, nloc]
+            off = (owner[lo:hi] - rank) % world
+            assert np.all((off >= first[b]) & (off < first[b + 1]))        # the block holds its owners' columns only
+            for r in range(nloc):
+                a, e = bptr[b, r], bptr[b, r + 1]
+                assert np.all(np.diff(bind[a:e]) > 0)                      # ascending columns inside (block, row)
+                y[r] += float(np.dot(bval[a:e], x[bind[a:e]]))
+                seen += e - a
+            for w, cap in zip((64, 128, 256, 512, 1024), lay["caps"]):
+                for r in range(0, nloc, 32):
+                    assert bptr[b, min(r + w, nloc)] - bptr[b, r] <= cap
+        assert seen == len(col)
+        want = np.array([np.dot(val[ptr[r]:ptr[r + 1]], x[col[ptr[r]:ptr[r + 1]]]) for r in range(nloc)])
+        assert np.allclose(y, want, rtol=1e-12, atol=1e-12)
